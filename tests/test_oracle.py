@@ -1,0 +1,74 @@
+"""CPU: pin oracle/molkgnn_oracle.py against the fixtures produced by the UNMODIFIED reference (tools/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import molkgnn_oracle as orc
+from tests.helpers import load_golden, golden_params, golden_buckets, golden_argmax, check_argmax, rel_err
+
+
+def test_kat_cosine_docstring():
+    # the reference's only in-tree known-answer vector, kernels.py:161-170 -> tensor([1.000, 0.8729])
+    g = load_golden("kat_cosine")
+    out = orc.cosine_mean(torch.from_numpy(g["t1"]), torch.from_numpy(g["t2"]))
+    assert np.allclose(out.numpy(), g["out"], atol=1e-12)
+    assert np.allclose(out.numpy(), [1.0, 0.8729], atol=5e-5)
+
+
+def test_perm_tables():
+    g = load_golden("perms")
+    for d in range(1, 5):
+        assert np.array_equal(np.asarray(orc.perm_table(d)), g[f"d{d}"])
+    assert [len(orc.perm_table(d)) for d in range(1, 5)] == [1, 2, 6, 12]
+
+
+@pytest.mark.parametrize("name", ["bucket_a", "bucket_b"])
+def test_bucket_pass_bit_exact(name):
+    g = load_golden(name)
+    bk = orc.bucket_pass(g["edge_index"], int(g["num_nodes"]), g["p"], g["edge_attr"])
+    for d in range(1, 5):
+        for k in ["selected_index", "nei_index", "p_focal", "nei_p", "nei_edge_attr"]:
+            ref = g[f"{k}_deg{d}"]
+            got = bk[d][k]
+            assert got.shape == ref.shape, (k, d, got.shape, ref.shape)
+            assert np.array_equal(got, ref), (k, d)
+
+
+@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer"])
+def test_molgcn_forward_backward(name):
+    g = load_golden(name)
+    params = golden_params(g, requires_grad=True)
+    bk_np = orc.bucket_pass(g["edge_index"], g["x"].shape[0], g["p"], g["edge_attr"])
+    bk = orc.buckets_to_torch(bk_np)
+    gb = golden_buckets(g)
+    for d in range(1, 5):  # oracle bucket pass == what the reference consumed
+        for k in gb[d]:
+            assert torch.equal(bk[d][k], gb[d][k])
+    x = torch.from_numpy(g["x"]).clone().requires_grad_(True)
+    ei = torch.from_numpy(g["edge_index"])
+    # teacher-forced on the reference's arg-max so that a flip inside a tie class cannot cascade (hard part 1)
+    h, auxs = orc.molgcn_forward(params, x, ei, bk, return_aux=True, force_argmax=golden_argmax(g))
+    assert rel_err(h.detach(), g["h"]) < 1e-5
+    # arg-max permutation (tie-aware) against the reference's torch.max
+    tot = ex = 0
+    for li, aux in enumerate(auxs):
+        for d in range(1, 5):
+            if aux[d - 1] is None:
+                continue
+            n, e, _ = check_argmax(g[f"S_l{li}_d{d}"], g[f"argmax_l{li}_d{d}"], aux[d - 1]["argmax"])
+            tot += n
+            ex += e
+    assert ex / tot > 0.97
+    (h * torch.from_numpy(g["wout"])).sum().backward()
+    assert rel_err(x.grad, g["grad_x"]) < 2e-5
+    for li, layer in enumerate(params):
+        for d in range(4):
+            for nme in ["x_center", "x_support", "edge_attr_support"]:
+                ref = g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{nme}"]
+                assert rel_err(layer[d][nme].grad, ref) < 5e-5, (li, d, nme)
+            trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
+            refs = np.array([g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{t}"] for t in trip])
+            got = np.array([layer[d][t].grad.item() for t in trip])
+            assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (li, d, got, refs)
+            # parameters the reference never differentiates
+            assert f"grad_layers.{li}.trainable_kernelconv_set.{d}.p_support" not in g

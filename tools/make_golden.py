@@ -1,0 +1,170 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the build container.
+
+Runs only where /root/reference exists (the build container).  The reference is imported through the
+test-only ``tests/stubs/torch_geometric`` stand-in (torch_geometric is not installed, no network);
+``rdkit`` & co. are mocked because only ``wrapper.ToXAndPAndEdgeAttrForDeg`` (pure torch) is executed.
+
+    python tools/make_golden.py            # rewrites tests/golden/
+
+Fixtures
+  kat_cosine.npz        the reference's only in-tree known-answer vector (kernels.py:161-170), evaluated by
+                        KernelConv.calculate_average_similarity_score itself
+  perms.npz             KernelConv.permute applied to an index tensor -> the permutation tables (kernels.py:109-128)
+  bucket_*.npz          ToXAndPAndEdgeAttrForDeg per molecule + PyG collation semantics (wrapper.py:559-672)
+  molgcn_*.npz          MolGCN forward (+ torch.max spy: S tensor / argmax per layer & degree) and autograd grads
+"""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+sys.path.insert(0, os.path.join(ROOT, "tests", "stubs"))
+sys.path.insert(0, REF)
+sys.path.insert(0, ROOT)
+for m in ["rdkit", "rdkit.Chem", "rdkit.Chem.AllChem", "rdkit.RDLogger", "rdkit.Chem.EState",
+          "rdkit.Chem.rdMolDescriptors", "rdkit.Chem.rdPartialCharges", "rdkit.Chem.Crippen", "networkx",
+          "models.ChIRoNet.embedding_functions", "clearml"]:
+    sys.modules.setdefault(m, MagicMock())
+
+from torch_geometric.data import Data  # noqa: E402  (the stub)
+from models.MolKGNN.kernels import KernelConv  # noqa: E402
+from models.MolKGNN.KernelLayer import MolGCN  # noqa: E402
+import wrapper as ref_wrapper  # noqa: E402
+
+from molkgnn_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+DEG_KEYS = ["p_focal", "nei_p", "nei_edge_attr", "selected_index", "nei_index"]
+
+
+def ref_bucket_collated(mols):
+    """Reference transform per molecule, then PyG 2.0.x collation semantics for the 20 per-degree attributes."""
+    tr = ref_wrapper.ToXAndPAndEdgeAttrForDeg()
+    per = []
+    for m in mols:
+        d = Data(x=torch.from_numpy(m.x), p=torch.from_numpy(m.p), edge_index=torch.from_numpy(m.edge_index),
+                 edge_attr=torch.from_numpy(m.edge_attr))
+        per.append(tr(d))
+    out = {}
+    off = np.concatenate([[0], np.cumsum([m.num_nodes for m in mols])])
+    for d in range(1, 5):
+        for key in DEG_KEYS:
+            name = f"{key}_deg{d}"
+            parts = []
+            for i, dd in enumerate(per):
+                t = getattr(dd, name)
+                if t.numel() == 0:
+                    continue  # PyG cat of an empty 1-D float tensor is a no-op
+                if "index" in key:
+                    t = t + int(off[i])
+                parts.append(t)
+            if parts:
+                cat = torch.cat(parts, dim=-1 if "index" in key else 0)
+            else:
+                cat = torch.zeros(0)
+            out[name] = cat.numpy()
+    return out
+
+
+class MaxSpy(object):
+    def __init__(self):
+        self.records = []
+        self._orig = torch.max
+
+    def __enter__(self):
+        def spy(*a, **k):
+            r = self._orig(*a, **k)
+            if len(a) == 1 and k.get("dim", None) == 1 and a[0].dim() == 3:
+                self.records.append((a[0].detach().clone(), r[1].detach().clone()))
+            return r
+        torch.max = spy
+        return self
+
+    def __exit__(self, *a):
+        torch.max = self._orig
+
+
+def molgcn_case(name, n_mol, seed, num_layers, L1, LN, dup=0.5):
+    mols = synth.make_molecules(n_mol, seed=seed, dup_leaf_prob=dup)
+    b = synth.collate(mols)
+    bk = ref_bucket_collated(mols)
+    torch.manual_seed(seed)
+    net = MolGCN(num_layers=num_layers, num_kernel1_1hop=L1[0], num_kernel2_1hop=L1[1], num_kernel3_1hop=L1[2],
+                 num_kernel4_1hop=L1[3], num_kernel1_Nhop=LN[0], num_kernel2_Nhop=LN[1], num_kernel3_Nhop=LN[2],
+                 num_kernel4_Nhop=LN[3], x_dim=synth.X_DIM, p_dim=3, edge_attr_dim=synth.EDGE_DIM)
+    # de-symmetrise the scalar mixing weights so their gradients are exercised away from the 0.2/0.2/0.2 init
+    g = torch.Generator().manual_seed(seed + 7)
+    with torch.no_grad():
+        for layer in net.layers:
+            for kc in layer.trainable_kernelconv_set:
+                for w in (kc.support_attr_sc_weight, kc.center_attr_sc_weight, kc.edge_attr_support_sc_weight):
+                    w.add_(0.5 * torch.randn((), generator=g))
+    x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+    kw = dict(x=x, edge_index=torch.from_numpy(b["edge_index"]), edge_attr=torch.from_numpy(b["edge_attr"]),
+              p=torch.from_numpy(b["p"]), save_score=False)
+    for k, v in bk.items():
+        kw[k] = torch.from_numpy(v)
+    with MaxSpy() as spy:
+        h = net(**kw)
+    K = h.shape[1]
+    wout = torch.randn(h.shape, generator=torch.Generator().manual_seed(seed + 11))
+    (h * wout).sum().backward()
+    save = dict(x=b["x"], p=b["p"], edge_index=b["edge_index"], edge_attr=b["edge_attr"], batch=b["batch"],
+                h=h.detach().numpy(), wout=wout.numpy(), grad_x=x.grad.numpy(),
+                num_layers=np.int64(num_layers), L1=np.asarray(L1), LN=np.asarray(LN), seed=np.int64(seed))
+    for k, v in bk.items():
+        save["bk_" + k] = v
+    for k, v in net.state_dict().items():
+        save["param_" + k] = v.numpy()
+    for k, v in net.named_parameters():
+        if v.grad is not None:
+            save["grad_" + k] = v.grad.numpy()
+    # spy records arrive in (layer, degree) order for the non-empty buckets
+    it = iter(spy.records)
+    for li in range(num_layers):
+        for d in range(1, 5):
+            if bk[f"selected_index_deg{d}"].size == 0:
+                continue
+            S, am = next(it)
+            save[f"S_l{li}_d{d}"] = S.numpy()          # [L,P,n_d] fp32, as the reference computed it
+            save[f"argmax_l{li}_d{d}"] = am.numpy().astype(np.int64)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "N=", b["x"].shape[0], "E=", b["edge_index"].shape[1], "K=", K, "h.abs.mean=", float(h.abs().mean()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    # 1. docstring KAT (kernels.py:161-170)
+    kc = KernelConv(L=1, D=3, num_supports=1, node_attr_dim=3, edge_attr_dim=1)
+    t1 = torch.tensor([[[1, 2, 3], [3, 2, 1]], [[1, 2, 3], [3, 2, 1]]], dtype=torch.double)
+    t2 = torch.tensor([[[1, 2, 3], [3, 2, 1]], [[1, 2, 1], [1, 2, 1]]], dtype=torch.double)
+    r = kc.calculate_average_similarity_score(t1, t2, sim_dim=-1, avg_dim=-2)
+    np.savez(os.path.join(OUT, "kat_cosine.npz"), t1=t1.numpy(), t2=t2.numpy(), out=r.numpy())
+    print("KAT", r)
+    # 2. permutation tables
+    tabs = {}
+    for d in range(1, 5):
+        idx = torch.arange(d).view(1, d, 1)
+        tabs[f"d{d}"] = kc.permute(idx)[0, :, :, 0].numpy()
+    np.savez(os.path.join(OUT, "perms.npz"), **tabs)
+    # 3. bucket transform
+    for name, n_mol, seed in [("bucket_a", 12, 3), ("bucket_b", 5, 17)]:
+        mols = synth.make_molecules(n_mol, seed=seed)
+        b = synth.collate(mols)
+        bk = ref_bucket_collated(mols)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), p=b["p"], edge_index=b["edge_index"],
+                            edge_attr=b["edge_attr"], num_nodes=np.int64(b["x"].shape[0]), **bk)
+        print(name, {k: v.shape for k, v in bk.items() if "selected" in k})
+    # 4. MolGCN forward/backward
+    molgcn_case("molgcn_small", n_mol=6, seed=1, num_layers=2, L1=(3, 4, 5, 6), LN=(2, 3, 4, 5))
+    molgcn_case("molgcn_readme", n_mol=4, seed=2, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50))
+    molgcn_case("molgcn_1layer", n_mol=5, seed=5, num_layers=1, L1=(4, 4, 4, 4), LN=(4, 4, 4, 4))
+
+
+if __name__ == "__main__":
+    main()
