@@ -1,0 +1,155 @@
+/*
+ * molkgnn_b200 -- C-ABI of the B200-native MolKGNN molecular-kernel convolution.
+ *
+ * Drop-in boundary for ONE hot path of LanceKnight/MolKGNN: the KernelConv / BaseKernelSetConv /
+ * KernelSetConv stack driven by MolGCN, plus the degree-bucket pre-transform that feeds it.
+ * The reference has no native code; every entry point below cites the Python interface
+ * it replaces (paths relative to the reference repository).  Plain pointers and sizes only: all pointers
+ * are DEVICE pointers unless the name ends in _host; the caller owns every buffer (the library never
+ * allocates device memory); every call is asynchronous on `stream` (a cudaStream_t passed as void*)
+ * unless stated.  Return value: 0 = ok, <0 = error (molkgnn_last_error() gives the text, thread-local).
+ *
+ * Layouts
+ *   activations   x[N, ldx] fp32 row-major, ldx % 4 == 0, columns F..ldx-1 zero; xnorm[N] = ||x_row||_2
+ *   buckets       degree d in 1..4; bucket rows r = 0..n_d-1 are the nodes of out-degree d in ascending node id
+ *                 (wrapper.py:599-600); sel[boff_d + r] = node id; nei[eoff_d + r*d + j] = j-th neighbour in edge
+ *                 order (wrapper.py:567-572); ehat[(eoff_d + r*d + j) * 8 + c] = bond attribute row
+ *                 edge_attr[2*(eid/2)] (wrapper.py:586-591) divided by max(norm, 1e-8), zero padded to 8
+ *   scores        compact: sc_d[r * L_d + k] per degree bucket (sc + scoff[d-1]);  dense: sc[node * ld + koff_d + k]
+ *   argmax        uint8 per (r,k), same compact indexing: bits 0..6 = permutation index into the table of
+ *                 kernels.py:109-128, bit 7 = chirality sign negative (kernels.py:396-400)
+ *   packed params see molkgnn_packed_floats(): per degree, L2-normalised kernel rows in the order the kernels stage
+ *                 them in shared memory
+ */
+#ifndef MOLKGNN_B200_H_
+#define MOLKGNN_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOLKGNN_MAX_DEG 4
+#define MOLKGNN_EDGE_PAD 8      /* bond-attribute rows are padded to 8 floats (edge_attr_dim <= 8) */
+#define MOLKGNN_COS_EPS 1e-8f   /* torch.nn.CosineSimilarity eps, kernels.py:189 */
+
+/* Degree-bucket plan of one collated batch.  Device arrays are filled by molkgnn_bucket_build();
+ * n/boff/eoff are host copies of the per-degree counts (index d-1). */
+typedef struct molkgnn_plan {
+    int32_t N, E;
+    int32_t n[4];              /* nodes per degree bucket */
+    int32_t boff[4];           /* prefix of n      : bucket row offset into sel / tsign base for d=4 */
+    int32_t eoff[4];           /* prefix of n_d * d: offset into nei / nei_eid / ehat rows */
+    int32_t* deg;              /* [N]   out-degree                                   (wrapper.py:574-576) */
+    int32_t* pos;              /* [N]   row of the node inside its bucket */
+    int32_t* sel;              /* [N]   selected_index_deg1..4 concatenated          (wrapper.py:599-600) */
+    int32_t* nei;              /* [E]   nei_index_deg1..4 concatenated               (wrapper.py:567-572,611) */
+    int32_t* nei_eid;          /* [E]   edge id of (r,j) */
+    float*   ehat;             /* [E,8] normalised neighbour bond attributes          (wrapper.py:578-593) */
+    int8_t*  tsign;            /* [n_4] sign of p2.(p0 x p1) of the calibrated neighbour positions (kernels.py:336,356) */
+    int32_t* in_cnt;           /* [N]   in-degree */
+    int32_t* in_src;           /* [N,4] sources of the in-edges, edge order           (KernelLayer.py:119, PyG aggr='add') */
+    int32_t* in_j;             /* [N,4] position of this node inside the source's neighbour list */
+} molkgnn_plan_t;
+
+/* One KernelSetConv layer (kernels.py:754-781): raw parameters of the four KernelConv modules + packed workspace. */
+typedef struct molkgnn_layer {
+    int32_t F;                 /* node_attr_dim of this layer */
+    int32_t Fp;                /* F rounded up to a multiple of 4 (row stride of the packed kernel rows) */
+    int32_t Fe;                /* edge_attr_dim (<= 8) */
+    int32_t L[4];              /* kernels per degree (kernels.py:760) */
+    int32_t koff[4];           /* column offset of degree block in the [N,K] score matrix (kernels.py:725-727) */
+    int32_t K;                 /* sum(L) */
+    const float* x_center[4];            /* [L,F]      kernels.py:58  */
+    const float* x_support[4];           /* [L,d,F]    kernels.py:61  */
+    const float* edge_attr_support[4];   /* [L,d,Fe]   kernels.py:65  */
+    const float* p_support[4];           /* [L,d,3]    kernels.py:69  */
+    const float* w_support[4];           /* scalar support_attr_sc_weight       kernels.py:79 */
+    const float* w_center[4];            /* scalar center_attr_sc_weight        kernels.py:76 */
+    const float* w_edge[4];              /* scalar edge_attr_support_sc_weight  kernels.py:82 */
+    float* packed[4];                    /* workspace, molkgnn_packed_floats(d, L, Fp) floats each, 16-byte aligned */
+} molkgnn_layer_t;
+
+/* Parameter gradients of one layer, in the reference's own parameter layouts (what autograd would return). */
+typedef struct molkgnn_layer_grads {
+    float* x_center[4];
+    float* x_support[4];
+    float* edge_attr_support[4];
+    float* w_support[4];
+    float* w_center[4];
+    float* w_edge[4];
+} molkgnn_layer_grads_t;
+
+const char* molkgnn_last_error(void);
+int molkgnn_version(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int molkgnn_num_sms(void);
+
+/* ---- degree bucketing: replaces ToXAndPAndEdgeAttrForDeg.__call__ (wrapper.py:559-672) + PyG collation ---- */
+/* bytes of scratch needed by molkgnn_bucket_build */
+int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E);
+/* Builds the plan from a collated batch.  edge_index is the PyG [2,E] int64 tensor (row 0 = source).  SYNCHRONISES
+ * the stream once to bring the four bucket sizes to the host (plan->n/boff/eoff).  Fails (-3) if a node has
+ * out-degree outside 1..4 or in-degree > 4 (the reference silently mis-shapes its output, kernels.py:743-747). */
+int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                         const float* edge_attr, int32_t Fe, void* scratch, void* stream);
+/* Writes the reference-format attributes of degree d (int64 indices, raw fp32 gathers), bit-exact with
+ * wrapper.py:595-635 after PyG collation: selected_index[n_d], nei_index[n_d*d], p_focal[n_d,p_dim],
+ * nei_p[n_d,d,p_dim], nei_edge_attr[n_d,d,Fe].  Any output pointer may be NULL. */
+int molkgnn_bucket_export(const molkgnn_plan_t* plan, int32_t d, const float* p, int32_t p_dim,
+                          const float* edge_attr, int32_t Fe, int64_t* selected_index, int64_t* nei_index,
+                          float* p_focal, float* nei_p, float* nei_edge_attr, void* stream);
+/* Builds a plan from reference-format bucket tensors (the attributes a PyG batch already carries,
+ * kernels.py:628-645) instead of edge_index.  nei_p/p_focal/nei_edge_attr per degree as in the reference. */
+int molkgnn_plan_from_buckets(molkgnn_plan_t* plan, const int64_t* const selected_index[4],
+                              const int64_t* const nei_index[4], const float* const p_focal[4],
+                              const float* const nei_p[4], int32_t p_dim, const float* const nei_edge_attr[4],
+                              int32_t Fe, void* stream);
+
+/* ---- activations ---- */
+/* out[N,ldo] = x[N,ldx] zero padded (skipped if out == x), norm[N] = ||row||.  kernels.py:189-190 (norm half of cosine) */
+int molkgnn_pad_norm(const float* x, int32_t N, int32_t F, int32_t ldx, float* out, int32_t ldo, float* norm,
+                     void* stream);
+
+/* ---- parameters ---- */
+int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp);
+/* Normalises the kernel rows of one layer into layer->packed (cosine denominators of kernels.py:189-190 on the
+ * kernel side), evaluates the softmax mixing weights (kernels.py:402-412) and the support chirality signs
+ * (kernels.py:338-341) for every permutation. */
+int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream);
+
+/* ---- forward: KernelConv.calculate_total_score for the four buckets (kernels.py:353-425, 610-751) ---- */
+int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
+/* sc_mode 0: compact per-degree blocks at sc + scoff[d-1] (n_d*L_d floats each, scoff in floats);
+ * sc_mode 1: dense sc[node*ld_sc + koff_d + k] (only the L_d entries of the node's own block are written).
+ * argmax (compact, byte offsets = scoff) always receives the permutation actually used + chirality bit;
+ * argmax_free (nullable) receives the free-running arg-max; argmax_in (nullable) forces the permutation
+ * (parity harness / replay).  counter: one zero-initialised int32 of scratch per call. */
+int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                     const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
+                     const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
+                     int32_t* counter, void* stream);
+
+/* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
+/* h[i, koff_d + k] = sum over in-edges (j -> i) in edge order of sc_{deg j}[pos j, k]; columns K..ldh-1 zeroed;
+ * hnorm[i] = ||h_i|| (nullable). */
+int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* sc,
+                          const int64_t scoff[4], float* h, int32_t ldh, float* hnorm, void* stream);
+
+/* ---- backward (the reference uses autograd over kernels.py:353-425 and KernelLayer.py:119) ---- */
+int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+/* grad_mode 0: g[n,k] = grad[n*ldg + koff_d + k]                 (grad w.r.t. the dense score matrix)
+ * grad_mode 1: g[n,k] = sum_{i in nei(n)} grad[i*ldg + koff_d + k] (grad w.r.t. the propagated h: fuses propagate^T)
+ * coef: scratch, sum_d n_d*L_d floats (compact, offsets scoff).  partials: scratch of
+ * molkgnn_conv_bwd_partial_floats() floats.  grad_x (nullable) [N,ldgx] receives dL/dx including the cosine
+ * normalisation Jacobian; columns F..ldgx-1 zeroed.  grads (nullable members skipped) receives dL/dparam. */
+int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                     const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
+                     const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
+                     const molkgnn_layer_grads_t* grads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOLKGNN_B200_H_ */

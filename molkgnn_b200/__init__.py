@@ -1,0 +1,6 @@
+"""molkgnn_b200: B200-native (sm_100a) MolKGNN molecular-kernel convolution behind the reference's module API."""
+from .kernels import KernelConv, BaseKernelSetConv, KernelSetConv  # noqa: F401
+from .KernelLayer import MolGCN  # noqa: F401
+from .plan import BucketPlan, ToXAndPAndEdgeAttrForDeg  # noqa: F401
+
+__all__ = ["KernelConv", "BaseKernelSetConv", "KernelSetConv", "MolGCN", "BucketPlan", "ToXAndPAndEdgeAttrForDeg"]

@@ -1,0 +1,84 @@
+"""ctypes binding of the C-ABI in include/molkgnn_b200.h.  No CPU fallback: if the shared library is missing or a
+call fails this raises -- the product path is the CUDA path."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmolkgnn_b200.so")
+
+i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
+
+
+class Plan(C.Structure):
+    _fields_ = [("N", i32), ("E", i32), ("n", i32 * 4), ("boff", i32 * 4), ("eoff", i32 * 4),
+                ("deg", vp), ("pos", vp), ("sel", vp), ("nei", vp), ("nei_eid", vp), ("ehat", vp), ("tsign", vp),
+                ("in_cnt", vp), ("in_src", vp), ("in_j", vp)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("F", i32), ("Fp", i32), ("Fe", i32), ("L", i32 * 4), ("koff", i32 * 4), ("K", i32),
+                ("x_center", vp * 4), ("x_support", vp * 4), ("edge_attr_support", vp * 4), ("p_support", vp * 4),
+                ("w_support", vp * 4), ("w_center", vp * 4), ("w_edge", vp * 4), ("packed", vp * 4)]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [("x_center", vp * 4), ("x_support", vp * 4), ("edge_attr_support", vp * 4),
+                ("w_support", vp * 4), ("w_center", vp * 4), ("w_edge", vp * 4)]
+
+
+EXPORTS = {
+    "molkgnn_last_error": (C.c_char_p, []),
+    "molkgnn_version": (C.c_int, []),
+    "molkgnn_num_sms": (C.c_int, []),
+    "molkgnn_bucket_scratch_bytes": (i64, [i32, i32]),
+    "molkgnn_bucket_build": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
+    "molkgnn_bucket_export": (C.c_int, [C.POINTER(Plan), i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "molkgnn_plan_from_buckets": (C.c_int, [C.POINTER(Plan), vp * 4, vp * 4, vp * 4, vp * 4, i32, vp * 4, i32, vp]),
+    "molkgnn_pad_norm": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, vp]),
+    "molkgnn_packed_floats": (i64, [i32, i32, i32]),
+    "molkgnn_param_pack": (C.c_int, [C.POINTER(Layer), vp]),
+    "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
+    "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
+                                   vp, vp, vp]),
+    "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp]),
+    "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
+    "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
+                                   vp, i32, C.POINTER(LayerGrads), vp]),
+}
+
+_lib = None
+
+
+class MolKGNNError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MolKGNNError(
+                f"{LIB_PATH} not found: build the CUDA extension first (python -m molkgnn_b200.build). "
+                "molkgnn_b200 has no CPU fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            f = getattr(l, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise MolKGNNError(lib().molkgnn_last_error().decode())
+
+
+def ptr(t):
+    """device (or host) pointer of a torch tensor, None -> NULL"""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

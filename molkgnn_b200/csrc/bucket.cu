@@ -1,0 +1,359 @@
+// Degree bucketing of a collated PyG batch on the GPU: one CSR-to-degree-bucket pass.
+// Replaces ToXAndPAndEdgeAttrForDeg (reference wrapper.py:559-672) + PyG collation of its 20 attributes.
+//
+// Integer work, HBM/latency bound.  Four small launches:
+//   k_edge_slots   every edge claims a slot in its source's out-list and its target's in-list (<=4 each)
+//   k_node_prepare per node: sort the <=4 claimed edge ids (restores edge order, wrapper.py:567-572), degree class,
+//                  per-block class histogram
+//   k_scan_blocks  exclusive scan of the block histograms -> stable bucket positions (ascending node id,
+//                  wrapper.py:599-600) and the bucket sizes
+//   k_assign       writes sel / pos / nei / nei_eid / ehat / tsign / in-lists
+#include "common.cuh"
+
+namespace mk {
+
+constexpr int BT = 256;  // threads per block in the node kernels
+
+__global__ void k_edge_slots(const int64_t* __restrict__ ei, int E, int N, int* out_cnt, int* out_eid, int* in_cnt,
+                             int* in_eid, int* err) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= E) return;
+    long long u = ei[e], v = ei[(size_t)E + e];
+    if (u < 0 || u >= N || v < 0 || v >= N) { atomicOr(err, 1); return; }
+    int so = atomicAdd(&out_cnt[u], 1);
+    if (so < 4) out_eid[4 * u + so] = e; else atomicOr(err, 2);
+    int si = atomicAdd(&in_cnt[v], 1);
+    if (si < 4) in_eid[4 * v + si] = e; else atomicOr(err, 4);
+}
+
+__device__ __forceinline__ void sort4(int* a, int n) {
+    // tiny insertion sort, n <= 4
+    for (int i = 1; i < n; ++i) {
+        int key = a[i], j = i - 1;
+        while (j >= 0 && a[j] > key) { a[j + 1] = a[j]; --j; }
+        a[j + 1] = key;
+    }
+}
+
+__global__ void k_node_prepare(int N, const int* __restrict__ out_cnt, int* out_eid, const int* __restrict__ in_cnt,
+                               int* in_eid, int* deg, int* blk_counts, int* err) {
+    int v = blockIdx.x * BT + threadIdx.x;
+    int cls = -1;
+    if (v < N) {
+        int d = out_cnt[v];
+        deg[v] = d;
+        if (d >= 1 && d <= 4) {
+            cls = d - 1;
+            int a[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = j < d ? out_eid[4 * v + j] : 0x7fffffff;
+            sort4(a, d);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < d) out_eid[4 * v + j] = a[j];
+        } else {
+            cls = 4;
+            atomicOr(err, 8);
+        }
+        int di = min(in_cnt[v], 4);
+        int b[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = j < di ? in_eid[4 * v + j] : 0x7fffffff;
+        sort4(b, di);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) if (j < di) in_eid[4 * v + j] = b[j];
+    }
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        int cnt = __syncthreads_count(cls == c);
+        if (threadIdx.x == 0) blk_counts[blockIdx.x * 5 + c] = cnt;
+    }
+}
+
+// totals[0..3] = n_d, totals[4] = bad nodes, totals[5..8] = boff, totals[9..12] = eoff
+__global__ void k_scan_blocks(int nblk, const int* __restrict__ blk_counts, int* blk_off, int* totals) {
+    int c = threadIdx.x;
+    if (c < 5) {
+        int run = 0;
+        for (int b = 0; b < nblk; ++b) {
+            blk_off[b * 5 + c] = run;
+            run += blk_counts[b * 5 + c];
+        }
+        totals[c] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int bo = 0, eo = 0;
+        for (int d = 0; d < 4; ++d) {
+            totals[5 + d] = bo;
+            totals[9 + d] = eo;
+            bo += totals[d];
+            eo += totals[d] * (d + 1);
+        }
+    }
+}
+
+__global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int* __restrict__ deg,
+                         const int* __restrict__ out_eid, const int* __restrict__ in_cnt,
+                         const int* __restrict__ in_eid, const int* __restrict__ blk_off,
+                         const int* __restrict__ totals, const float* __restrict__ p, int p_dim,
+                         const float* __restrict__ edge_attr, int Fe, int* pos, int* sel, int* nei, int* nei_eid,
+                         float* ehat, int8_t* tsign, int* in_src, int* in_j) {
+    __shared__ int warp_cnt[BT / 32][4];
+    int v = blockIdx.x * BT + threadIdx.x;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int d = v < N ? deg[v] : 0;
+    int cls = (d >= 1 && d <= 4) ? d - 1 : -1;
+    int rank = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (cls == c) rank = __popc(m & ((1u << lane) - 1u));
+        if (lane == 0) warp_cnt[wid][c] = __popc(m);
+    }
+    __syncthreads();
+    if (cls < 0) return;
+    int r = blk_off[blockIdx.x * 5 + cls] + rank;
+    for (int w = 0; w < wid; ++w) r += warp_cnt[w][cls];
+    const int boff = totals[5 + cls], eoff = totals[9 + cls];
+    pos[v] = r;
+    sel[boff + r] = v;
+    int nb[4];
+    for (int j = 0; j < d; ++j) {
+        int e = out_eid[4 * v + j];
+        int u = (int)ei[(size_t)E + e];
+        nb[j] = u;
+        size_t row = (size_t)eoff + (size_t)r * d + j;
+        nei[row] = u;
+        nei_eid[row] = e;
+        // bond attributes of the undirected bond: row 2*(eid/2) (wrapper.py:586-591), normalised for the cosine
+        const float* ea = edge_attr + (size_t)(2 * (e / 2)) * Fe;
+        float t[EP];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < EP; ++c) { t[c] = c < Fe ? ea[c] : 0.f; ss += t[c] * t[c]; }
+        float nrm = fmaxf(sqrtf(ss), MOLKGNN_COS_EPS);
+#pragma unroll
+        for (int c = 0; c < EP; ++c) ehat[row * EP + c] = t[c] / nrm;
+    }
+    if (d == 4 && p_dim == 3) {
+        // sign of p2 . (p0 x p1) on neighbour coordinates calibrated by the focal atom (kernels.py:336,356)
+        float q[3][3];
+        for (int j = 0; j < 3; ++j)
+            for (int c = 0; c < 3; ++c) q[j][c] = __fsub_rn(p[(size_t)nb[j] * 3 + c], p[(size_t)v * 3 + c]);
+        float cx = __fsub_rn(__fmul_rn(q[0][1], q[1][2]), __fmul_rn(q[0][2], q[1][1]));
+        float cy = __fsub_rn(__fmul_rn(q[0][2], q[1][0]), __fmul_rn(q[0][0], q[1][2]));
+        float cz = __fsub_rn(__fmul_rn(q[0][0], q[1][1]), __fmul_rn(q[0][1], q[1][0]));
+        float dt = __fadd_rn(__fadd_rn(__fmul_rn(q[2][0], cx), __fmul_rn(q[2][1], cy)), __fmul_rn(q[2][2], cz));
+        tsign[r] = dt > 0.f ? 1 : (dt < 0.f ? -1 : 0);
+    }
+    int di = min(in_cnt[v], 4);
+    for (int t = 0; t < 4; ++t) {
+        int u = -1, jj = 0;
+        if (t < di) {
+            int e = in_eid[4 * v + t];
+            u = (int)ei[e];
+            for (int k = 0; k < 4; ++k) if (out_eid[4 * u + k] == e) jj = k;
+        }
+        in_src[4 * v + t] = u;
+        in_j[4 * v + t] = jj;
+    }
+}
+
+__global__ void k_export(int d, int n, int boff, int eoff, const int* __restrict__ sel, const int* __restrict__ nei,
+                         const int* __restrict__ nei_eid, const float* __restrict__ p, int p_dim,
+                         const float* __restrict__ edge_attr, int Fe, int64_t* selected_index, int64_t* nei_index,
+                         float* p_focal, float* nei_p, float* nei_edge_attr) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int v = sel[boff + r];
+    if (selected_index) selected_index[r] = v;
+    if (p_focal) for (int c = 0; c < p_dim; ++c) p_focal[(size_t)r * p_dim + c] = p[(size_t)v * p_dim + c];
+    for (int j = 0; j < d; ++j) {
+        size_t row = (size_t)eoff + (size_t)r * d + j;
+        int u = nei[row], e = nei_eid[row];
+        size_t o = (size_t)r * d + j;
+        if (nei_index) nei_index[o] = u;
+        if (nei_p) for (int c = 0; c < p_dim; ++c) nei_p[o * p_dim + c] = p[(size_t)u * p_dim + c];
+        if (nei_edge_attr)
+            for (int c = 0; c < Fe; ++c) nei_edge_attr[o * Fe + c] = edge_attr[(size_t)(2 * (e / 2)) * Fe + c];
+    }
+}
+
+// ---- plan from reference-format bucket tensors -------------------------------------------------------------
+__global__ void k_from_buckets(int d, int n, int boff, int eoff, const int64_t* __restrict__ selected_index,
+                               const int64_t* __restrict__ nei_index, const float* __restrict__ p_focal,
+                               const float* __restrict__ nei_p, int p_dim, const float* __restrict__ nei_ea, int Fe,
+                               int N, int* deg, int* pos, int* sel, int* nei, int* nei_eid, float* ehat, int8_t* tsign,
+                               int* in_cnt, int* in_key, int* err) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    long long v = selected_index[r];
+    if (v < 0 || v >= N) { atomicOr(err, 1); return; }
+    deg[v] = d;
+    pos[v] = r;
+    sel[boff + r] = (int)v;
+    for (int j = 0; j < d; ++j) {
+        size_t o = (size_t)r * d + j, row = (size_t)eoff + o;
+        long long u = nei_index[o];
+        if (u < 0 || u >= N) { atomicOr(err, 1); u = 0; }
+        nei[row] = (int)u;
+        nei_eid[row] = -1;
+        float t[EP];
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < EP; ++c) { t[c] = c < Fe ? nei_ea[o * Fe + c] : 0.f; ss += t[c] * t[c]; }
+        float nrm = fmaxf(sqrtf(ss), MOLKGNN_COS_EPS);
+#pragma unroll
+        for (int c = 0; c < EP; ++c) ehat[row * EP + c] = t[c] / nrm;
+        int si = atomicAdd(&in_cnt[u], 1);
+        if (si < 4) in_key[4 * u + si] = (int)(row);  // global neighbour-row id identifies (source bucket row, j)
+        else atomicOr(err, 4);
+    }
+    if (d == 4 && p_dim == 3 && tsign) {
+        float q[3][3];
+        for (int j = 0; j < 3; ++j)
+            for (int c = 0; c < 3; ++c)
+                q[j][c] = __fsub_rn(nei_p[((size_t)r * 4 + j) * 3 + c], p_focal[(size_t)r * 3 + c]);
+        float cx = __fsub_rn(__fmul_rn(q[0][1], q[1][2]), __fmul_rn(q[0][2], q[1][1]));
+        float cy = __fsub_rn(__fmul_rn(q[0][2], q[1][0]), __fmul_rn(q[0][0], q[1][2]));
+        float cz = __fsub_rn(__fmul_rn(q[0][0], q[1][1]), __fmul_rn(q[0][1], q[1][0]));
+        float dt = __fadd_rn(__fadd_rn(__fmul_rn(q[2][0], cx), __fmul_rn(q[2][1], cy)), __fmul_rn(q[2][2], cz));
+        tsign[r] = dt > 0.f ? 1 : (dt < 0.f ? -1 : 0);
+    }
+}
+
+// in_key holds neighbour-row ids; sort them (deterministic order) and decode into (source node, j)
+__global__ void k_from_buckets_inlists(int N, const int* __restrict__ in_cnt, int* in_key, const int* __restrict__ sel,
+                                       int4 boff, int4 eoff, int4 nd, int* in_src, int* in_j) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N) return;
+    int di = min(in_cnt[v], 4);
+    int a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = j < di ? in_key[4 * v + j] : 0x7fffffff;
+    sort4(a, di);
+    const int bo[4] = {boff.x, boff.y, boff.z, boff.w};
+    const int eo[4] = {eoff.x, eoff.y, eoff.z, eoff.w};
+    const int nn[4] = {nd.x, nd.y, nd.z, nd.w};
+    for (int t = 0; t < 4; ++t) {
+        int u = -1, jj = 0;
+        if (t < di) {
+            int row = a[t];
+            for (int d = 1; d <= 4; ++d) {
+                int lo = eo[d - 1], hi = lo + nn[d - 1] * d;
+                if (row >= lo && row < hi) {
+                    int o = row - lo;
+                    u = sel[bo[d - 1] + o / d];
+                    jj = o % d;
+                }
+            }
+        }
+        in_src[4 * v + t] = u;
+        in_j[4 * v + t] = jj;
+    }
+}
+
+}  // namespace mk
+
+using namespace mk;
+
+extern "C" int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E) {
+    int64_t nblk = (N + BT - 1) / BT;
+    // out_cnt[N] out_eid[4N] in_eid[4N] blk_counts[5*nblk] blk_off[5*nblk] totals[16] err[1]
+    return (int64_t)sizeof(int) * ((int64_t)N * 9 + nblk * 10 + 32);
+}
+
+extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                    const float* edge_attr, int32_t Fe, void* scratch, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int N = plan->N, E = plan->E;
+    MK_REQUIRE(N > 0 && E >= 0, "bucket_build: empty batch (N=%d E=%d)", N, E);
+    MK_REQUIRE(Fe >= 1 && Fe <= EP, "bucket_build: edge_attr_dim %d not in 1..%d", Fe, EP);
+    MK_REQUIRE(p_dim == 3, "bucket_build: only 3-D coordinates are supported (got %d)", p_dim);
+    const int nblk = (N + BT - 1) / BT;
+    int* s = (int*)scratch;
+    int* out_cnt = s;             s += N;
+    int* out_eid = s;             s += 4 * (size_t)N;
+    int* in_eid = s;              s += 4 * (size_t)N;
+    int* blk_counts = s;          s += 5 * (size_t)nblk;
+    int* blk_off = s;             s += 5 * (size_t)nblk;
+    int* totals = s;              s += 16;
+    int* err = s;
+    MK_CHECK_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int) * (size_t)N, st));
+    MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
+    MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 17, st));
+    if (E > 0)
+        k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, err);
+    k_node_prepare<<<nblk, BT, 0, st>>>(N, out_cnt, out_eid, plan->in_cnt, in_eid, plan->deg, blk_counts, err);
+    k_scan_blocks<<<1, 32, 0, st>>>(nblk, blk_counts, blk_off, totals);
+    int host[17];
+    MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 17, cudaMemcpyDeviceToHost, st));
+    MK_CHECK_CUDA(cudaStreamSynchronize(st));
+    MK_REQUIRE(host[16] == 0 && host[4] == 0,
+               "bucket_build: unsupported graph (flags=0x%x: 1=node id out of range, 2=out-degree>4, 4=in-degree>4, "
+               "8=node with out-degree 0 or >4; %d offending nodes)", host[16], host[4]);
+    for (int d = 0; d < 4; ++d) { plan->n[d] = host[d]; plan->boff[d] = host[5 + d]; plan->eoff[d] = host[9 + d]; }
+    k_assign<<<nblk, BT, 0, st>>>(N, E, edge_index, plan->deg, out_eid, plan->in_cnt, in_eid, blk_off, totals, p, p_dim,
+                                  edge_attr, Fe, plan->pos, plan->sel, plan->nei, plan->nei_eid, plan->ehat,
+                                  plan->tsign, plan->in_src, plan->in_j);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int molkgnn_bucket_export(const molkgnn_plan_t* plan, int32_t d, const float* p, int32_t p_dim,
+                                     const float* edge_attr, int32_t Fe, int64_t* selected_index, int64_t* nei_index,
+                                     float* p_focal, float* nei_p, float* nei_edge_attr, void* stream_) {
+    MK_REQUIRE(d >= 1 && d <= 4, "bucket_export: degree %d", d);
+    int n = plan->n[d - 1];
+    if (n == 0) return 0;
+    k_export<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(d, n, plan->boff[d - 1], plan->eoff[d - 1], plan->sel,
+                                                                plan->nei, plan->nei_eid, p, p_dim, edge_attr, Fe,
+                                                                selected_index, nei_index, p_focal, nei_p,
+                                                                nei_edge_attr);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int molkgnn_plan_from_buckets(molkgnn_plan_t* plan, const int64_t* const selected_index[4],
+                                         const int64_t* const nei_index[4], const float* const p_focal[4],
+                                         const float* const nei_p[4], int32_t p_dim,
+                                         const float* const nei_edge_attr[4], int32_t Fe, void* stream_) {
+    // plan->N, plan->n[] must be set by the caller (tensor shapes); boff/eoff are derived here.
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int N = plan->N;
+    MK_REQUIRE(Fe >= 1 && Fe <= EP, "plan_from_buckets: edge_attr_dim %d not in 1..%d", Fe, EP);
+    int bo = 0, eo = 0, tot = 0;
+    for (int d = 0; d < 4; ++d) {
+        plan->boff[d] = bo; plan->eoff[d] = eo;
+        bo += plan->n[d]; eo += plan->n[d] * (d + 1); tot += plan->n[d];
+    }
+    // nodes outside every bucket (deg 0) are allowed here: they only ever act as neighbours (KernelConv.forward)
+    MK_REQUIRE(tot <= N, "plan_from_buckets: buckets hold %d focal nodes but the batch has %d nodes", tot, N);
+    MK_REQUIRE(eo == plan->E, "plan_from_buckets: plan->E=%d but buckets hold %d neighbour rows", plan->E, eo);
+    // in_j doubles as the key scratch (4 ints per node) until the in-lists are decoded; err flag lives in in_cnt? no:
+    // use the last int of nei_eid's allocation is not safe either -> use a static device flag.
+    static int* d_err = nullptr;
+    if (!d_err) MK_CHECK_CUDA(cudaMalloc(&d_err, sizeof(int)));
+    MK_CHECK_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
+    MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
+    MK_CHECK_CUDA(cudaMemsetAsync(plan->deg, 0, sizeof(int) * (size_t)N, st));
+    MK_CHECK_CUDA(cudaMemsetAsync(plan->pos, 0, sizeof(int) * (size_t)N, st));
+    for (int d = 1; d <= 4; ++d) {
+        int n = plan->n[d - 1];
+        if (!n) continue;
+        k_from_buckets<<<(n + 127) / 128, 128, 0, st>>>(d, n, plan->boff[d - 1], plan->eoff[d - 1], selected_index[d - 1],
+                                                       nei_index[d - 1], p_focal[d - 1], nei_p[d - 1], p_dim,
+                                                       nei_edge_attr[d - 1], Fe, N, plan->deg, plan->pos, plan->sel,
+                                                       plan->nei, plan->nei_eid, plan->ehat, plan->tsign, plan->in_cnt,
+                                                       plan->in_j, d_err);
+    }
+    k_from_buckets_inlists<<<(N + 127) / 128, 128, 0, st>>>(
+        N, plan->in_cnt, plan->in_j, plan->sel, make_int4(plan->boff[0], plan->boff[1], plan->boff[2], plan->boff[3]),
+        make_int4(plan->eoff[0], plan->eoff[1], plan->eoff[2], plan->eoff[3]),
+        make_int4(plan->n[0], plan->n[1], plan->n[2], plan->n[3]), plan->in_src, plan->in_j);
+    int herr = 0;
+    MK_CHECK_CUDA(cudaMemcpyAsync(&herr, d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    MK_CHECK_CUDA(cudaStreamSynchronize(st));
+    MK_REQUIRE(herr == 0, "plan_from_buckets: invalid bucket tensors (flags=0x%x: 1=index out of range, 4=in-degree>4)", herr);
+    return 0;
+}

@@ -1,0 +1,102 @@
+// Shared helpers for the molkgnn_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/molkgnn_b200.h"
+
+namespace mk {
+
+void set_error(const char* fmt, ...);
+
+#define MK_CHECK_CUDA(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            mk::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return -2;                                                                   \
+        }                                                                                \
+    } while (0)
+
+#define MK_REQUIRE(cond, ...)                                                            \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            mk::set_error(__VA_ARGS__);                                                  \
+            return -1;                                                                   \
+        }                                                                                \
+    } while (0)
+
+constexpr int EP = MOLKGNN_EDGE_PAD;  // padded bond-attribute row
+
+// ---- permutation tables (kernels.py:109-128): lexicographic for d != 4, the 12 even ones for d == 4 ----
+template <int D> struct Perm;
+template <> struct Perm<1> {
+    static constexpr int P = 1;
+    __host__ __device__ static constexpr int at(int p, int j) { return 0; }
+};
+template <> struct Perm<2> {
+    static constexpr int P = 2;
+    __host__ __device__ static constexpr int at(int p, int j) { return p == 0 ? j : 1 - j; }
+};
+template <> struct Perm<3> {
+    static constexpr int P = 6;
+    __host__ __device__ static constexpr int at(int p, int j) {
+        constexpr int T[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+        return T[p][j];
+    }
+};
+template <> struct Perm<4> {
+    static constexpr int P = 12;
+    __host__ __device__ static constexpr int at(int p, int j) {
+        constexpr int T[12][4] = {{0, 1, 2, 3}, {0, 2, 3, 1}, {0, 3, 1, 2}, {1, 0, 3, 2}, {1, 2, 0, 3}, {1, 3, 2, 0},
+                                  {2, 0, 1, 3}, {2, 1, 3, 0}, {2, 3, 0, 1}, {3, 0, 2, 1}, {3, 1, 0, 2}, {3, 2, 1, 0}};
+        return T[p][j];
+    }
+};
+// packed code of permutation p: 2 bits per j -> s = perm[j]
+template <int D> __host__ __device__ constexpr uint32_t perm_code(int p) {
+    uint32_t c = 0;
+    for (int j = 0; j < D; ++j) c |= (uint32_t)Perm<D>::at(p, j) << (2 * j);
+    return c;
+}
+// packed code of the inverse permutation: 2 bits per s -> j with perm[j] == s
+template <int D> __host__ __device__ constexpr uint32_t perm_inv_code(int p) {
+    uint32_t c = 0;
+    for (int j = 0; j < D; ++j) c |= (uint32_t)j << (2 * Perm<D>::at(p, j));
+    return c;
+}
+__host__ __device__ inline int num_perms(int d) { return d == 1 ? 1 : d == 2 ? 2 : d == 3 ? 6 : 12; }
+
+// ---- packed (normalised) kernel-set layout of one degree; all offsets in floats ----
+struct PackedLayout {
+    int d, L, Fp;
+    int rows_x;   // (d+1)*L : support rows s*L+k (s<d), centre rows d*L+k
+    int64_t sup, es, norm, enorm, w, sign, total;
+    __host__ __device__ PackedLayout(int d_, int L_, int Fp_) : d(d_), L(L_), Fp(Fp_) {
+        rows_x = (d + 1) * L;
+        sup = 0;
+        es = sup + (int64_t)rows_x * Fp;
+        norm = es + (int64_t)d * L * EP;
+        enorm = norm + rows_x;
+        w = (enorm + d * L + 3) / 4 * 4;
+        sign = w + 8;
+        total = (sign + (L * 12 + 3) / 4 + 3) / 4 * 4;
+    }
+};
+// w block: [0]=ws [1]=wc [2]=we [3]=W=ws+wc+we [4..7] reserved
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+int device_num_sms();
+int device_max_smem_optin();
+
+}  // namespace mk

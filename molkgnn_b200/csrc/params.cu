@@ -1,0 +1,317 @@
+// Kernel-parameter side of the cosine similarities.
+//   k_param_pack      normalise kernel rows once per step (the kernel half of torch's cosine_similarity,
+//                     reference kernels.py:189-190), softmax mixing weights (kernels.py:402-412), chirality sign of
+//                     every permuted support (kernels.py:338-341) -> packed, smem-ready layout
+//   k_param_finalize  deterministic reduction of the per-CTA partial sums written by the backward kernel, chain
+//                     rule through the normalisation and the softmax weights, results in the reference's layouts
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace mk {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int device_num_sms() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
+}
+int device_max_smem_optin() {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return -1;
+    return n;
+}
+
+struct PackArgs {
+    int F, Fp, Fe;
+    int L[4];
+    int row_begin[5];  // block index ranges per degree: (2d+1)*L rows each, then 4 tail blocks
+    const float* x_center[4];
+    const float* x_support[4];
+    const float* edge_attr_support[4];
+    const float* p_support[4];
+    const float* w_support[4];
+    const float* w_center[4];
+    const float* w_edge[4];
+    float* packed[4];
+};
+
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = red[0] + red[1] + red[2] + red[3];
+    __syncthreads();
+    return t;
+}
+
+template <int D>
+__device__ void sup_signs(const float* __restrict__ ps, int L, int8_t* out) {
+    // sign of b2 . (b0 x b1) with b_j = p_support[k, perm[j]] (kernels.py:331-341), for every kernel and permutation
+    for (int i = threadIdx.x; i < L * Perm<D>::P; i += blockDim.x) {
+        int k = i / Perm<D>::P, pi = i % Perm<D>::P;
+        float b[3][3];
+        for (int j = 0; j < 3; ++j) {
+            int s = 0;
+#pragma unroll
+            for (int q = 0; q < Perm<D>::P; ++q)
+                if (q == pi) s = Perm<D>::at(q, j < D ? j : 0);
+            for (int c = 0; c < 3; ++c) b[j][c] = ps[((size_t)k * D + s) * 3 + c];
+        }
+        float cx = __fsub_rn(__fmul_rn(b[0][1], b[1][2]), __fmul_rn(b[0][2], b[1][1]));
+        float cy = __fsub_rn(__fmul_rn(b[0][2], b[1][0]), __fmul_rn(b[0][0], b[1][2]));
+        float cz = __fsub_rn(__fmul_rn(b[0][0], b[1][1]), __fmul_rn(b[0][1], b[1][0]));
+        float dt = __fadd_rn(__fadd_rn(__fmul_rn(b[2][0], cx), __fmul_rn(b[2][1], cy)), __fmul_rn(b[2][2], cz));
+        out[i] = dt > 0.f ? 1 : (dt < 0.f ? -1 : 0);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_param_pack(PackArgs a) {
+    __shared__ float red[4];
+    int b = blockIdx.x;
+    if (b >= a.row_begin[4]) {  // tail blocks: weights + support signs of degree d
+        int d = b - a.row_begin[4] + 1;
+        int L = a.L[d - 1];
+        if (L == 0) return;
+        PackedLayout pl(d, L, a.Fp);
+        float* pk = a.packed[d - 1];
+        if (threadIdx.x == 0) {
+            float es = expf(*a.w_support[d - 1]), ec = expf(*a.w_center[d - 1]), ee = expf(*a.w_edge[d - 1]);
+            float den = (es + ec) + ee;
+            float ws = es / den, wc = ec / den, we = ee / den;
+            float W = (ws + wc) + we;
+            pk[pl.w + 0] = ws; pk[pl.w + 1] = wc; pk[pl.w + 2] = we; pk[pl.w + 3] = W;
+            pk[pl.w + 4] = 0.f; pk[pl.w + 5] = 0.f; pk[pl.w + 6] = 0.f; pk[pl.w + 7] = 0.f;
+        }
+        if (d == 4) sup_signs<4>(a.p_support[3], L, reinterpret_cast<int8_t*>(pk + pl.sign));
+        return;
+    }
+    int d = 1;
+    while (b >= a.row_begin[d]) ++d;
+    int L = a.L[d - 1];
+    int row = b - a.row_begin[d - 1];  // 0 .. (2d+1)L-1 : support rows (s*L+k), centre rows, edge rows (s*L+k)
+    PackedLayout pl(d, L, a.Fp);
+    float* pk = a.packed[d - 1];
+    const float* src;
+    float* dst;
+    float* nrm_out;
+    int n, npad;
+    if (row < pl.rows_x) {
+        int s = row / L, k = row % L;
+        src = s < d ? a.x_support[d - 1] + ((size_t)k * d + s) * a.F : a.x_center[d - 1] + (size_t)k * a.F;
+        dst = pk + pl.sup + (size_t)row * a.Fp;
+        nrm_out = pk + pl.norm + row;
+        n = a.F; npad = a.Fp;
+    } else {
+        int er = row - pl.rows_x;
+        int s = er / L, k = er % L;
+        src = a.edge_attr_support[d - 1] + ((size_t)k * d + s) * a.Fe;
+        dst = pk + pl.es + (size_t)er * EP;
+        nrm_out = pk + pl.enorm + er;
+        n = a.Fe; npad = EP;
+    }
+    float ss = 0.f;
+    for (int i = threadIdx.x; i < n; i += 128) { float v = src[i]; ss += v * v; }
+    ss = block_sum_128(ss, red);
+    float nrm = sqrtf(ss);
+    float den = fmaxf(nrm, MOLKGNN_COS_EPS);
+    for (int i = threadIdx.x; i < npad; i += 128) dst[i] = i < n ? src[i] / den : 0.f;
+    if (threadIdx.x == 0) *nrm_out = nrm;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+struct FinArgs {
+    int F, Fp, Fe, FW;       // FW = Fp + EP : row width of the partial accumulators
+    int L[4];
+    int row_begin[5];        // blocks per degree: (d+1)*L rows
+    int ncta[4];             // number of partial copies per degree
+    int64_t part_off[4];     // float offset of degree d's partial block; copy c at + c*rows_x*FW
+    const float* partials;
+    const float* packed[4];
+    float* gx_center[4];
+    float* gx_support[4];
+    float* ge_support[4];
+    float* q;                // [sum rows] per-row Q contributions: q[row_begin[d]+row] (x part), and edge part after
+    int q_edge_off;          // offset of edge Q values
+};
+
+// one block (128 threads) per packed row; writes final dL/d(raw row) and per-row Q = sum(hat * G)
+__global__ void __launch_bounds__(128) k_param_finalize(FinArgs a) {
+    __shared__ float red[4];
+    int b = blockIdx.x;
+    int d = 1;
+    while (b >= a.row_begin[d]) ++d;
+    int L = a.L[d - 1];
+    int row = b - a.row_begin[d - 1];
+    PackedLayout pl(d, L, a.Fp);
+    const float* pk = a.packed[d - 1];
+    const int s = row / L, k = row % L;
+    const bool is_center = (s == d);
+    const float ws = pk[pl.w + 0], wc = pk[pl.w + 1], we = pk[pl.w + 2], W = pk[pl.w + 3];
+    const size_t stride = (size_t)pl.rows_x * a.FW;
+    const float* part = a.partials + a.part_off[d - 1] + (size_t)row * a.FW;
+    const int nc = a.ncta[d - 1];
+    // ---- node-attribute part ----
+    {
+        const float* hat = pk + pl.sup + (size_t)row * a.Fp;
+        float dot = 0.f;
+        float g[4];  // up to 512 features per thread-strided loop: keep values in registers for the second pass
+        int cnt = 0;
+        for (int f = threadIdx.x; f < a.Fp; f += 128, ++cnt) {
+            float acc = 0.f;
+            for (int c = 0; c < nc; ++c) acc += part[c * stride + f];
+            if (cnt < 4) g[cnt] = acc;
+            dot += acc * hat[f];
+        }
+        dot = block_sum_128(dot, red);
+        const float nrm = pk[pl.norm + row];
+        const float coef = (is_center ? wc : ws / (float)d) / W;
+        float* out = is_center ? (a.gx_center[d - 1] ? a.gx_center[d - 1] + (size_t)k * a.F : nullptr)
+                               : (a.gx_support[d - 1] ? a.gx_support[d - 1] + ((size_t)k * d + s) * a.F : nullptr);
+        cnt = 0;
+        for (int f = threadIdx.x; f < a.Fp; f += 128, ++cnt) {
+            float G;
+            if (cnt < 4) G = g[cnt];
+            else { G = 0.f; for (int c = 0; c < nc; ++c) G += part[c * stride + f]; }
+            float v = nrm > MOLKGNN_COS_EPS ? (G - dot * hat[f]) / nrm : G / MOLKGNN_COS_EPS;
+            if (out && f < a.F) out[f] = coef * v;
+        }
+        if (threadIdx.x == 0) a.q[b] = is_center ? dot : dot / (float)d;
+    }
+    // ---- bond-attribute part (support rows only) ----
+    if (!is_center) {
+        const float* hat = pk + pl.es + (size_t)row * EP;
+        float G = 0.f, h = 0.f;
+        if (threadIdx.x < EP) {
+            for (int c = 0; c < nc; ++c) G += part[c * stride + a.Fp + threadIdx.x];
+            h = hat[threadIdx.x];
+        }
+        float dot = block_sum_128(G * h, red);
+        const float nrm = pk[pl.enorm + row];
+        if (threadIdx.x < a.Fe && a.ge_support[d - 1]) {
+            float v = nrm > MOLKGNN_COS_EPS ? (G - dot * h) / nrm : G / MOLKGNN_COS_EPS;
+            a.ge_support[d - 1][((size_t)k * d + s) * a.Fe + threadIdx.x] = (we / (float)d / W) * v;
+        }
+        if (threadIdx.x == 0) a.q[a.q_edge_off + b] = dot / (float)d;
+    }
+}
+
+struct ThetaArgs {
+    int L[4];
+    int row_begin[5];
+    int Fp;
+    int q_edge_off;
+    const float* q;
+    const float* packed[4];
+    float* gw_support[4];
+    float* gw_center[4];
+    float* gw_edge[4];
+};
+
+// d(theta_i) = (w_i/W) * (Q_i - sum_j (w_j/W) Q_j),  Q_i = sum_{n,k} g*chi*T_i   (T = S*, C, E);  one block per degree
+__global__ void __launch_bounds__(128) k_theta(ThetaArgs a) {
+    __shared__ float red[4];
+    int d = blockIdx.x + 1;
+    int L = a.L[d - 1];
+    if (L == 0) return;
+    PackedLayout pl(d, L, a.Fp);
+    const float* pk = a.packed[d - 1];
+    float qs = 0.f, qc = 0.f, qe = 0.f;
+    int base = a.row_begin[d - 1];
+    for (int r = threadIdx.x; r < pl.rows_x; r += 128) {
+        if (r < d * L) { qs += a.q[base + r]; qe += a.q[a.q_edge_off + base + r]; }
+        else qc += a.q[base + r];
+    }
+    qs = block_sum_128(qs, red);
+    qc = block_sum_128(qc, red);
+    qe = block_sum_128(qe, red);
+    if (threadIdx.x == 0) {
+        const float ws = pk[pl.w + 0], wc = pk[pl.w + 1], we = pk[pl.w + 2], W = pk[pl.w + 3];
+        float mean = (ws * qs + wc * qc + we * qe) / W;
+        if (a.gw_support[d - 1]) *a.gw_support[d - 1] = ws / W * (qs - mean);
+        if (a.gw_center[d - 1]) *a.gw_center[d - 1] = wc / W * (qc - mean);
+        if (a.gw_edge[d - 1]) *a.gw_edge[d - 1] = we / W * (qe - mean);
+    }
+}
+
+// entry used by conv_bwd.cu
+int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, const int64_t part_off[4],
+                          const int ncta[4], float* q_scratch, const molkgnn_layer_grads_t* grads, cudaStream_t st) {
+    FinArgs fa;
+    ThetaArgs ta;
+    fa.F = layer->F; fa.Fp = layer->Fp; fa.Fe = layer->Fe; fa.FW = layer->Fp + EP;
+    int rb = 0;
+    for (int d = 0; d < 4; ++d) {
+        fa.L[d] = ta.L[d] = layer->L[d];
+        fa.row_begin[d] = ta.row_begin[d] = rb;
+        rb += (d + 2) * layer->L[d];
+        fa.ncta[d] = ncta[d];
+        fa.part_off[d] = part_off[d];
+        fa.packed[d] = ta.packed[d] = layer->packed[d];
+        fa.gx_center[d] = grads->x_center[d];
+        fa.gx_support[d] = grads->x_support[d];
+        fa.ge_support[d] = grads->edge_attr_support[d];
+        ta.gw_support[d] = grads->w_support[d];
+        ta.gw_center[d] = grads->w_center[d];
+        ta.gw_edge[d] = grads->w_edge[d];
+    }
+    fa.row_begin[4] = ta.row_begin[4] = rb;
+    fa.partials = partials;
+    fa.q = q_scratch;
+    fa.q_edge_off = ta.q_edge_off = rb;
+    ta.q = q_scratch;
+    ta.Fp = layer->Fp;
+    if (rb == 0) return 0;
+    k_param_finalize<<<rb, 128, 0, st>>>(fa);
+    k_theta<<<4, 128, 0, st>>>(ta);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace mk
+
+using namespace mk;
+
+extern "C" const char* molkgnn_last_error(void) { return mk::g_err; }
+extern "C" int molkgnn_version(void) { return 100; }
+extern "C" int molkgnn_num_sms(void) { return device_num_sms(); }
+
+extern "C" int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp) {
+    if (d < 1 || d > 4 || L < 0 || Fp < 4 || Fp % 4) return -1;
+    return PackedLayout(d, L, Fp).total;
+}
+
+extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
+    PackArgs a;
+    MK_REQUIRE(layer->Fp % 4 == 0 && layer->Fp >= layer->F, "param_pack: Fp=%d must be a multiple of 4 >= F=%d",
+               layer->Fp, layer->F);
+    MK_REQUIRE(layer->Fe >= 1 && layer->Fe <= EP, "param_pack: edge_attr_dim %d not in 1..%d", layer->Fe, EP);
+    a.F = layer->F; a.Fp = layer->Fp; a.Fe = layer->Fe;
+    int rb = 0;
+    for (int d = 0; d < 4; ++d) {
+        a.L[d] = layer->L[d];
+        a.row_begin[d] = rb;
+        rb += (2 * (d + 1) + 1) * layer->L[d];
+        a.x_center[d] = layer->x_center[d];
+        a.x_support[d] = layer->x_support[d];
+        a.edge_attr_support[d] = layer->edge_attr_support[d];
+        a.p_support[d] = layer->p_support[d];
+        a.w_support[d] = layer->w_support[d];
+        a.w_center[d] = layer->w_center[d];
+        a.w_edge[d] = layer->w_edge[d];
+        a.packed[d] = layer->packed[d];
+    }
+    a.row_begin[4] = rb;
+    k_param_pack<<<rb + 4, 128, 0, (cudaStream_t)stream_>>>(a);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}

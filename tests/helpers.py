@@ -73,3 +73,51 @@ def golden_argmax(g):
         out.append([torch.from_numpy(g[f"argmax_l{li}_d{d}"]) if f"argmax_l{li}_d{d}" in g else None
                     for d in range(1, 5)])
     return out
+
+
+# ---- GPU-side helpers -------------------------------------------------------------------------------------------
+def compact_from_kernel_major(per_degree, device):
+    """[argmax [L_d,n_d] or None x4] -> uint8 compact vector (degree blocks, row-major [n_d, L_d])."""
+    parts = []
+    for a in per_degree:
+        if a is None:
+            continue
+        parts.append(torch.as_tensor(a).t().contiguous().reshape(-1).to(torch.uint8))
+    if not parts:
+        return torch.zeros(1, dtype=torch.uint8, device=device)
+    return torch.cat(parts).to(device)
+
+
+def kernel_major_from_compact(vec, n, Ls):
+    """inverse of compact_from_kernel_major: -> list of 4 tensors [L_d, n_d] (None for empty buckets)."""
+    out, off = [], 0
+    vec = vec.cpu()
+    for d in range(4):
+        cnt = n[d] * Ls[d]
+        out.append(vec[off:off + cnt].reshape(n[d], Ls[d]).t().contiguous() if cnt else None)
+        off += cnt
+    return out
+
+
+def module_from_golden(g, device):
+    import molkgnn_b200 as mk
+    L1, LN = [int(v) for v in g["L1"]], [int(v) for v in g["LN"]]
+    net = mk.MolGCN(num_layers=int(g["num_layers"]), num_kernel1_1hop=L1[0], num_kernel2_1hop=L1[1],
+                    num_kernel3_1hop=L1[2], num_kernel4_1hop=L1[3], num_kernel1_Nhop=LN[0], num_kernel2_Nhop=LN[1],
+                    num_kernel3_Nhop=LN[2], num_kernel4_Nhop=LN[3], x_dim=g["x"].shape[1], p_dim=3,
+                    edge_attr_dim=g["edge_attr"].shape[1])
+    sd = {k[len("param_"):]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("param_")}
+    missing, unexpected = net.load_state_dict(sd, strict=True)
+    return net.to(device)
+
+
+def params_from_module(net, dtype=torch.float32, requires_grad=False):
+    """MolGCN module -> oracle parameter structure (CPU)."""
+    out = []
+    for layer in net.layers:
+        lp = []
+        for kc in layer.trainable_kernelconv_set:
+            lp.append({n: getattr(kc, n).detach().cpu().to(dtype).clone().requires_grad_(requires_grad)
+                       for n in PARAM_NAMES})
+        out.append(lp)
+    return out

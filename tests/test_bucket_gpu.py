@@ -1,0 +1,118 @@
+"""GPU: the CUDA degree-bucket pass against the reference transform's golden output and the oracle (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import molkgnn_oracle as orc
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+KEYS = ["selected_index", "nei_index", "p_focal", "nei_p", "nei_edge_attr"]
+
+
+def _plan(ei, p, ea, n):
+    from molkgnn_b200 import BucketPlan
+    dev = torch.device("cuda")
+    return BucketPlan.from_edge_index(torch.from_numpy(ei).to(dev), torch.from_numpy(p).to(dev),
+                                      torch.from_numpy(ea).to(dev), n)
+
+
+@pytest.mark.parametrize("name", ["bucket_a", "bucket_b"])
+def test_bucket_golden_bit_exact(name):
+    g = load_golden(name)
+    plan = _plan(g["edge_index"], g["p"], g["edge_attr"], int(g["num_nodes"]))
+    p, ea = torch.from_numpy(g["p"]).cuda(), torch.from_numpy(g["edge_attr"]).cuda()
+    for d in range(1, 5):
+        ref_n = g[f"selected_index_deg{d}"].shape[0]
+        assert plan.n[d - 1] == ref_n
+        if ref_n == 0:
+            continue
+        out = plan.export(d, p, ea)
+        for k in KEYS:
+            ref = g[f"{k}_deg{d}"]
+            got = out[k].cpu().numpy()
+            assert got.dtype == ref.dtype, (k, got.dtype, ref.dtype)
+            assert got.shape == ref.shape, (k, d, got.shape, ref.shape)
+            assert np.array_equal(got, ref), (k, d)
+
+
+@pytest.mark.parametrize("n_mol,seed", [(1, 0), (64, 1), (1024, 2)])
+def test_bucket_vs_oracle(n_mol, seed):
+    from molkgnn_b200 import synth
+    b = synth.make_batch(n_mol, seed=seed)
+    N = b["x"].shape[0]
+    ref = orc.bucket_pass(b["edge_index"], N, b["p"], b["edge_attr"])
+    plan = _plan(b["edge_index"], b["p"], b["edge_attr"], N)
+    assert np.array_equal(plan.deg.cpu().numpy(), ref["deg"])
+    p, ea = torch.from_numpy(b["p"]).cuda(), torch.from_numpy(b["edge_attr"]).cuda()
+    for d in range(1, 5):
+        assert plan.n[d - 1] == ref[d]["selected_index"].shape[0]
+        if plan.n[d - 1] == 0:
+            continue
+        out = plan.export(d, p, ea)
+        for k in KEYS:
+            assert np.array_equal(out[k].cpu().numpy(), ref[d][k]), (k, d)
+    # in-lists: sources of in-edges in edge order + position inside the source's neighbour list
+    ei = b["edge_index"]
+    order = np.argsort(ei[1], kind="stable")
+    in_src = plan.in_src.cpu().numpy()
+    in_cnt = plan.in_cnt.cpu().numpy()
+    assert np.array_equal(in_cnt, np.bincount(ei[1], minlength=N))
+    ptr = np.concatenate([[0], np.cumsum(in_cnt)])
+    for v in np.random.default_rng(0).integers(0, N, size=min(N, 200)):
+        assert np.array_equal(in_src[v, :in_cnt[v]], ei[0][order[ptr[v]:ptr[v + 1]]])
+
+
+def test_shuffled_edge_order():
+    """edge_index that is not grouped by source: neighbours must still come out in edge order (wrapper.py:567-572)."""
+    from molkgnn_b200 import synth
+    b = synth.make_batch(32, seed=5)
+    rng = np.random.default_rng(1)
+    E = b["edge_index"].shape[1]
+    # permute BONDS (pairs of rows) so that the 2*(eid//2) bond-row convention still holds
+    perm = rng.permutation(E // 2)
+    idx = np.stack([2 * perm, 2 * perm + 1], 1).reshape(-1)
+    ei, ea = b["edge_index"][:, idx], b["edge_attr"][idx]
+    N = b["x"].shape[0]
+    ref = orc.bucket_pass(ei, N, b["p"], ea)
+    plan = _plan(np.ascontiguousarray(ei), b["p"], np.ascontiguousarray(ea), N)
+    p, eat = torch.from_numpy(b["p"]).cuda(), torch.from_numpy(np.ascontiguousarray(ea)).cuda()
+    for d in range(1, 5):
+        if plan.n[d - 1] == 0:
+            continue
+        out = plan.export(d, p, eat)
+        for k in KEYS:
+            assert np.array_equal(out[k].cpu().numpy(), ref[d][k]), (k, d)
+
+
+def test_transform_drop_in():
+    from molkgnn_b200 import ToXAndPAndEdgeAttrForDeg, synth
+
+    class Bag(object):
+        pass
+    g = load_golden("bucket_b")
+    d = Bag()
+    d.x = torch.zeros(int(g["num_nodes"]), 28)
+    d.p, d.edge_index, d.edge_attr = (torch.from_numpy(g[k]) for k in ["p", "edge_index", "edge_attr"])
+    d = ToXAndPAndEdgeAttrForDeg()(d)
+    for deg in range(1, 5):
+        for k in KEYS:
+            got = getattr(d, f"{k}_deg{deg}")
+            assert not got.is_cuda
+            if g[f"{k}_deg{deg}"].size:
+                assert np.array_equal(got.numpy(), g[f"{k}_deg{deg}"])
+
+
+def test_rejects_bad_degree():
+    from molkgnn_b200 import BucketPlan
+    from molkgnn_b200._lib import MolKGNNError
+    # star with 5 leaves: centre has degree 5
+    src = [0, 1, 0, 2, 0, 3, 0, 4, 0, 5]
+    dst = [1, 0, 2, 0, 3, 0, 4, 0, 5, 0]
+    ei = torch.tensor([src, dst], dtype=torch.int64).cuda()
+    with pytest.raises(MolKGNNError):
+        BucketPlan.from_edge_index(ei, torch.zeros(6, 3).cuda(), torch.ones(10, 7).cuda(), 6)
+    # isolated node (degree 0)
+    ei = torch.tensor([[0, 1], [1, 0]], dtype=torch.int64).cuda()
+    with pytest.raises(MolKGNNError):
+        BucketPlan.from_edge_index(ei, torch.zeros(3, 3).cuda(), torch.ones(2, 7).cuda(), 3)

@@ -1,0 +1,258 @@
+"""GPU parity tests proper: the CUDA conv stack (through the C-ABI, via the drop-in modules) against
+  (a) the golden fixtures produced by the UNMODIFIED reference (tests/golden, tools/make_golden.py) and
+  (b) the CPU oracle on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star): degree buckets and arg-max permutation indices exact -- arg-max up to the
+reference's own tie classes (hard part 1: structurally tied permutations are decided by fp32 rounding of
+ATen's dot-product order, which no other implementation can reproduce); scores and gradients within 1e-5 relative (fp32),
+measured as max |err| / max |ref| per tensor.  Mixing-weight gradients (which cancel to ~0 across the softmax triple)
+are judged relative to the largest magnitude of their triple at 1e-4.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import molkgnn_oracle as orc
+from tests.helpers import (load_golden, golden_argmax, check_argmax, rel_err, compact_from_kernel_major,
+                           kernel_major_from_compact, module_from_golden, params_from_module)
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+DEV = "cuda"
+
+
+def _to_dev(b):
+    return dict(x=torch.from_numpy(b["x"]).to(DEV), p=torch.from_numpy(b["p"]).to(DEV),
+                edge_index=torch.from_numpy(b["edge_index"]).to(DEV), edge_attr=torch.from_numpy(b["edge_attr"]).to(DEV))
+
+
+def _check_param_grads(net, ref_grad, tol=TOL):
+    """ref_grad(li, d, name) -> reference gradient (numpy / tensor)"""
+    for li, layer in enumerate(net.layers):
+        for d, kc in enumerate(layer.trainable_kernelconv_set):
+            for nme in ["x_center", "x_support", "edge_attr_support"]:
+                got = getattr(kc, nme).grad
+                assert got is not None, (li, d, nme)
+                assert rel_err(got.cpu(), ref_grad(li, d, nme)) < tol, (li, d, nme)
+            trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
+            refs = np.array([float(ref_grad(li, d, t)) for t in trip])
+            got = np.array([getattr(kc, t).grad.item() for t in trip])
+            assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (li, d, got, refs)
+            # never differentiated by the reference
+            for nme in ["p_support", "length_sc_weight", "angle_sc_weight"]:
+                assert getattr(kc, nme).grad is None
+
+
+@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer"])
+def test_molgcn_vs_reference_golden(name):
+    g = load_golden(name)
+    net = module_from_golden(g, DEV)
+    b = _to_dev(g)
+    x = b["x"].clone().requires_grad_(True)
+    plan = net.build_plan(b["edge_index"], b["p"], b["edge_attr"], x.shape[0])
+    forced = [compact_from_kernel_major(a, DEV) for a in golden_argmax(g)]
+    aux = {}
+    h = net(x=x, edge_index=b["edge_index"], edge_attr=b["edge_attr"], p=b["p"], save_score=False, plan=plan,
+            argmax_in=forced, aux=aux)
+    assert h.shape == g["h"].shape
+    assert rel_err(h.detach().cpu(), g["h"]) < TOL
+    # free-running arg-max of every layer/degree vs the reference's torch.max (layer inputs are teacher-forced)
+    tot = ex = 0
+    for li, layer in enumerate(net.layers):
+        free = kernel_major_from_compact(aux["argmax_free"][li], plan.n, layer.num_kernel_list)
+        used = kernel_major_from_compact(aux["argmax"][li], plan.n, layer.num_kernel_list)
+        for d in range(1, 5):
+            if free[d - 1] is None:
+                continue
+            n_, e_, _ = check_argmax(g[f"S_l{li}_d{d}"], g[f"argmax_l{li}_d{d}"], free[d - 1])
+            tot += n_
+            ex += e_
+            assert torch.equal(used[d - 1] & 0x7f, torch.from_numpy(g[f"argmax_l{li}_d{d}"]).to(torch.uint8))
+    assert ex / tot > 0.97, (ex, tot)
+    (h * torch.from_numpy(g["wout"]).to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), g["grad_x"]) < TOL
+    _check_param_grads(net, lambda li, d, n: g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{n}"])
+
+
+def _oracle_run(net, b, wout, force=None):
+    params = params_from_module(net, requires_grad=True)
+    N = b["x"].shape[0]
+    bk = orc.buckets_to_torch(orc.bucket_pass(b["edge_index"], N, b["p"], b["edge_attr"]))
+    x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+    h, auxs = orc.molgcn_forward(params, x, torch.from_numpy(b["edge_index"]), bk, return_aux=True, force_argmax=force)
+    (h * wout).sum().backward()
+    return h.detach(), x.grad, params, auxs
+
+
+@pytest.mark.parametrize("n_mol,layers,L1,LN,seed", [
+    (48, 3, (10, 20, 30, 50), (10, 20, 30, 50), 11),      # README shape, a few tiles per degree
+    (300, 2, (3, 5, 7, 9), (4, 6, 8, 10), 12),            # odd kernel counts: partial kernel groups, K % 4 != 0
+    (16, 2, (1, 1, 1, 1), (1, 2, 1, 2), 13),              # minimum kernel counts
+])
+def test_molgcn_vs_oracle(n_mol, layers, L1, LN, seed):
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    b = synth.make_batch(n_mol, seed=seed)
+    torch.manual_seed(seed)
+    net = mk.MolGCN(layers, *L1, *LN, x_dim=28, p_dim=3, edge_attr_dim=7)
+    with torch.no_grad():
+        for layer in net.layers:
+            for kc in layer.trainable_kernelconv_set:
+                for w in (kc.support_attr_sc_weight, kc.center_attr_sc_weight, kc.edge_attr_support_sc_weight):
+                    w.add_(0.5 * torch.randn(()))
+    wout = torch.randn(b["x"].shape[0], sum(LN) if layers > 1 else sum(L1))
+    # oracle free-running first: its arg-max is then forced onto the GPU run (tie classes checked separately)
+    h_ref, gx_ref, params_ref, auxs = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    x = d["x"].clone().requires_grad_(True)
+    plan = net.build_plan(d["edge_index"], d["p"], d["edge_attr"], x.shape[0])
+    forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+    aux = {}
+    h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, plan=plan,
+            argmax_in=forced, aux=aux)
+    assert rel_err(h.detach().cpu(), h_ref) < TOL
+    tot = ex = 0
+    for li, layer in enumerate(net.layers):
+        free = kernel_major_from_compact(aux["argmax_free"][li], plan.n, layer.num_kernel_list)
+        for dd in range(1, 5):
+            if free[dd - 1] is None:
+                continue
+            n_, e_, _ = check_argmax(auxs[li][dd - 1]["S"].detach(), auxs[li][dd - 1]["argmax"], free[dd - 1])
+            tot += n_
+            ex += e_
+    assert ex / tot > 0.97, (ex, tot)
+    (h * wout.to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), gx_ref) < TOL
+    _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
+
+
+def test_free_running_is_deterministic_and_close():
+    """Without teacher forcing the run is deterministic (bitwise equal twice) and differs from the oracle only
+    downstream of tie flips: the bulk of the output matches to 1e-5."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    b = synth.make_batch(64, seed=21)
+    torch.manual_seed(21)
+    net = mk.MolGCN(3, 10, 20, 30, 50, 10, 20, 30, 50, x_dim=28, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], 110)
+    h_ref, gx_ref, _, _ = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    outs = []
+    for _ in range(2):
+        x = d["x"].clone().requires_grad_(True)
+        h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False)
+        (h * wout.to(DEV)).sum().backward()
+        outs.append((h.detach().clone(), x.grad.clone(), [p.grad.clone() for p in net.parameters() if p.grad is not None]))
+        net.zero_grad()
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+    for a, c in zip(outs[0][2], outs[1][2]):
+        assert torch.equal(a, c)
+    err = (outs[0][0].cpu() - h_ref).abs() / h_ref.abs().max()
+    assert (err < TOL).float().mean() > 0.9
+
+
+def test_kernel_set_conv_layer_dense():
+    """KernelSetConv.forward with the reference protocol (data= bag carrying the precomputed per-degree tensors)."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    from molkgnn_b200.kernels import _Bag
+    b = synth.make_batch(40, seed=31)
+    N = b["x"].shape[0]
+    bk_np = orc.bucket_pass(b["edge_index"], N, b["p"], b["edge_attr"])
+    bk = orc.buckets_to_torch(bk_np)
+    torch.manual_seed(3)
+    layer = mk.KernelSetConv(4, 6, 8, 10, D=3, node_attr_dim=28, edge_attr_dim=7)
+    lp = [{n: getattr(kc, n).detach().clone().requires_grad_(True) for n in
+           ["x_center", "x_support", "edge_attr_support", "p_support", "support_attr_sc_weight",
+            "center_attr_sc_weight", "edge_attr_support_sc_weight"]} for kc in layer.trainable_kernelconv_set]
+    for is_last in (False, True):
+        xr = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+        sc_ref, aux_ref = orc.kernel_set_conv_forward(lp, xr, bk, is_last_layer=is_last, return_aux=True)
+        layer = layer.to(DEV)
+        data = _Bag(x=torch.from_numpy(b["x"]).to(DEV).requires_grad_(True), p=torch.from_numpy(b["p"]).to(DEV),
+                    edge_index=torch.from_numpy(b["edge_index"]).to(DEV),
+                    edge_attr=torch.from_numpy(b["edge_attr"]).to(DEV))
+        for d in range(1, 5):
+            for k, v in bk[d].items():
+                setattr(data, f"{k}_deg{d}", v.to(DEV))
+        forced = compact_from_kernel_major([None if a is None else a["argmax"] for a in aux_ref], DEV)
+        sc = layer(is_last_layer=is_last, data=data, save_score=False, argmax_in=forced)
+        assert sc.shape == (N, 28)
+        assert rel_err(sc.detach().cpu(), sc_ref.detach()) < TOL
+        # block sparsity: a degree-d node is non-zero only inside its own degree block (kernels.py:725-727)
+        deg = torch.from_numpy(bk_np["deg"])
+        offs = [0, 4, 10, 18, 28]
+        for d in range(1, 5):
+            rows = sc.detach().cpu()[deg == d]
+            mask = torch.ones(28, dtype=torch.bool)
+            mask[offs[d - 1]:offs[d]] = False
+            assert (rows[:, mask] == 0).all()
+        w = torch.randn(N, 28, generator=torch.Generator().manual_seed(1))
+        (sc * w.to(DEV)).sum().backward()
+        (sc_ref * w).sum().backward()
+        assert rel_err(data.x.grad.cpu(), xr.grad) < TOL
+        for d, kc in enumerate(layer.trainable_kernelconv_set):
+            for nme in ["x_center", "x_support", "edge_attr_support"]:
+                assert rel_err(getattr(kc, nme).grad.cpu(), lp[d][nme].grad) < TOL, (d, nme)
+        layer.zero_grad()
+        for prm in lp:
+            for v in prm.values():
+                v.grad = None
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4])
+def test_kernel_conv_single_bucket(deg):
+    """KernelConv.forward, the reference's per-degree entry (kernels.py:428-448): kwargs protocol, [L,n] output."""
+    import molkgnn_b200 as mk
+    torch.manual_seed(deg)
+    n, L, F = 37, 7, 28
+    kc = mk.KernelConv(L=L, D=3, num_supports=deg, node_attr_dim=F, edge_attr_dim=7)
+    prm = {k: getattr(kc, k).detach().clone() for k in
+           ["x_center", "x_support", "edge_attr_support", "p_support", "support_attr_sc_weight",
+            "center_attr_sc_weight", "edge_attr_support_sc_weight"]}
+    x_focal, p_focal = torch.randn(n, F), torch.randn(n, 3)
+    x_nei, p_nei = torch.randn(n, deg, F), torch.randn(n, deg, 3)
+    if deg >= 2:
+        x_nei[::5, 1] = x_nei[::5, 0]   # duplicate neighbours: tied permutations + chirality gate
+    ea = torch.rand(n, deg, 7) + 0.1
+    for is_last in (False, True):
+        ref, aux = orc.kernel_conv_forward(prm, x_focal, p_focal, x_nei, p_nei, ea, is_last_layer=is_last,
+                                           return_aux=True)
+        kc = kc.to(DEV)
+        out = kc(is_last_layer=is_last, x_focal=x_focal.to(DEV), p_focal=p_focal.to(DEV), x_neighbor=x_nei.to(DEV),
+                 p_neighbor=p_nei.to(DEV), edge_attr_neighbor=ea.to(DEV))
+        assert out.shape == (L, n)
+        # free-running here: compare only where the oracle's arg-max gap is clear
+        S = aux["S"].double()
+        top2 = S.topk(min(2, S.shape[1]), dim=1).values
+        clear = (top2[:, 0] - top2[:, -1] > 1e-5) if S.shape[1] > 1 else torch.ones_like(top2[:, 0], dtype=torch.bool)
+        err = (out.detach().cpu() - ref).abs() / ref.abs().max()
+        assert (err[clear] < TOL).all()
+    with pytest.raises(Exception):
+        kc(is_last_layer=False, x_focal=x_focal.to(DEV), p_focal=torch.zeros(n, 2, device=DEV),
+           x_neighbor=x_nei.to(DEV), p_neighbor=p_nei.to(DEV), edge_attr_neighbor=ea.to(DEV))
+
+
+def test_wide_layer_chunked_paths():
+    """Wide kernel sets (BASELINE config 3 shape, fewer layers/molecules): kernel set does not fit in shared memory,
+    so the feature-chunked forward, kernel-ranged backward and multi-pass input-gradient paths are exercised."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    b = synth.make_batch(6, seed=41)
+    torch.manual_seed(41)
+    L = (40, 80, 120, 200)
+    net = mk.MolGCN(2, *L, *L, x_dim=28, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], 440)
+    h_ref, gx_ref, params_ref, auxs = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    x = d["x"].clone().requires_grad_(True)
+    forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+    h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, argmax_in=forced)
+    assert rel_err(h.detach().cpu(), h_ref) < TOL
+    (h * wout.to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), gx_ref) < TOL
+    _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
