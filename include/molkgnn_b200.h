@@ -83,6 +83,8 @@ typedef struct molkgnn_layer_grads {
 
 const char* molkgnn_last_error(void);
 int molkgnn_version(void);
+/* number of kernels this library has launched so far in the process (bench.py reports it as gpu_launches) */
+int64_t molkgnn_launch_count(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
 int molkgnn_num_sms(void);
 
@@ -143,11 +145,13 @@ int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgn
  * grad_mode 1: g[n,k] = sum_{i in nei(n)} grad[i*ldg + koff_d + k] (grad w.r.t. the propagated h: fuses propagate^T)
  * coef: scratch, sum_d n_d*L_d floats (compact, offsets scoff).  partials: scratch of
  * molkgnn_conv_bwd_partial_floats() floats.  grad_x (nullable) [N,ldgx] receives dL/dx including the cosine
- * normalisation Jacobian; columns F..ldgx-1 zeroed.  grads (nullable members skipped) receives dL/dparam. */
+ * normalisation Jacobian; columns F..ldgx-1 zeroed.  grads (nullable members skipped) receives dL/dparam.
+ * phases: bit 0 = k_bwd_w (coef + per-CTA partial sums), bit 1 = parameter finalize, bit 2 = k_bwd_x (grad_x);
+ * 7 runs everything; the split exists so that a profiler can time the three kernels separately. */
 int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
                      const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
-                     const molkgnn_layer_grads_t* grads, void* stream);
+                     const molkgnn_layer_grads_t* grads, int32_t phases, void* stream);
 
 #ifdef __cplusplus
 }

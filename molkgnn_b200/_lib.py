@@ -30,6 +30,7 @@ EXPORTS = {
     "molkgnn_last_error": (C.c_char_p, []),
     "molkgnn_version": (C.c_int, []),
     "molkgnn_num_sms": (C.c_int, []),
+    "molkgnn_launch_count": (i64, []),
     "molkgnn_bucket_scratch_bytes": (i64, [i32, i32]),
     "molkgnn_bucket_build": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
     "molkgnn_bucket_export": (C.c_int, [C.POINTER(Plan), i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
@@ -43,7 +44,7 @@ EXPORTS = {
     "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp]),
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
-                                   vp, i32, C.POINTER(LayerGrads), vp]),
+                                   vp, i32, C.POINTER(LayerGrads), i32, vp]),
 }
 
 _lib = None

@@ -75,6 +75,7 @@ extern "C" int molkgnn_pad_norm(const float* x, int32_t N, int32_t F, int32_t ld
                                 void* stream_) {
     MK_REQUIRE(ldo >= F, "pad_norm: ldo=%d < F=%d", ldo, F);
     if (N == 0) return 0;
+    count_launches(1);
     k_pad_norm<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(x, N, F, ldx, out, ldo, norm);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -91,6 +92,7 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
     if (a.N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream_;
     const int grid = (a.N + 7) / 8;
+    count_launches(1);
     if (ldh <= 32 * 1) k_propagate_fwd<1><<<grid, 256, 0, st>>>(a);
     else if (ldh <= 32 * 4) k_propagate_fwd<4><<<grid, 256, 0, st>>>(a);
     else if (ldh <= 32 * 8) k_propagate_fwd<8><<<grid, 256, 0, st>>>(a);

@@ -152,7 +152,8 @@ __global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int
         if (t < di) {
             int e = in_eid[4 * v + t];
             u = (int)ei[e];
-            for (int k = 0; k < 4; ++k) if (out_eid[4 * u + k] == e) jj = k;
+            const int du = min(deg[u], 4);   // slots >= deg[u] are uninitialised scratch
+            for (int k = 0; k < du; ++k) if (out_eid[4 * u + k] == e) jj = k;
         }
         in_src[4 * v + t] = u;
         in_j[4 * v + t] = jj;
@@ -282,6 +283,7 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     MK_CHECK_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 17, st));
+    count_launches(E > 0 ? 4 : 3);
     if (E > 0)
         k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, err);
     k_node_prepare<<<nblk, BT, 0, st>>>(N, out_cnt, out_eid, plan->in_cnt, in_eid, plan->deg, blk_counts, err);
@@ -306,6 +308,7 @@ extern "C" int molkgnn_bucket_export(const molkgnn_plan_t* plan, int32_t d, cons
     MK_REQUIRE(d >= 1 && d <= 4, "bucket_export: degree %d", d);
     int n = plan->n[d - 1];
     if (n == 0) return 0;
+    count_launches(1);
     k_export<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream_>>>(d, n, plan->boff[d - 1], plan->eoff[d - 1], plan->sel,
                                                                 plan->nei, plan->nei_eid, p, p_dim, edge_attr, Fe,
                                                                 selected_index, nei_index, p_focal, nei_p,
@@ -341,12 +344,14 @@ extern "C" int molkgnn_plan_from_buckets(molkgnn_plan_t* plan, const int64_t* co
     for (int d = 1; d <= 4; ++d) {
         int n = plan->n[d - 1];
         if (!n) continue;
+        count_launches(1);
         k_from_buckets<<<(n + 127) / 128, 128, 0, st>>>(d, n, plan->boff[d - 1], plan->eoff[d - 1], selected_index[d - 1],
                                                        nei_index[d - 1], p_focal[d - 1], nei_p[d - 1], p_dim,
                                                        nei_edge_attr[d - 1], Fe, N, plan->deg, plan->pos, plan->sel,
                                                        plan->nei, plan->nei_eid, plan->ehat, plan->tsign, plan->in_cnt,
                                                        plan->in_j, d_err);
     }
+    count_launches(1);
     k_from_buckets_inlists<<<(N + 127) / 128, 128, 0, st>>>(
         N, plan->in_cnt, plan->in_j, plan->sel, make_int4(plan->boff[0], plan->boff[1], plan->boff[2], plan->boff[3]),
         make_int4(plan->eoff[0], plan->eoff[1], plan->eoff[2], plan->eoff[3]),

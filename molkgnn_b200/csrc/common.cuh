@@ -96,6 +96,7 @@ __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<floa
 
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+void count_launches(int n);
 int device_num_sms();
 int device_max_smem_optin();
 

@@ -418,6 +418,7 @@ static int launch_bwd_x(const BwdXArgs& a, int grid, int64_t smem, cudaStream_t 
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_x<LPN, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s_attr = smem;
     }
+    count_launches(1);
     k_bwd_x<LPN, NACC><<<grid, BX_THREADS, smem, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -452,7 +453,7 @@ extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, c
 extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                                 const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode,
                                 const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials,
-                                float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, void* stream_) {
+                                float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, int32_t phases, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (init_dev()) return -1;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_bwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
@@ -478,23 +479,24 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     w.sel = plan->sel; w.nei = plan->nei; w.ehat = plan->ehat;
     w.grad = grad; w.ldg = ldg; w.grad_mode = grad_mode;
     w.argmax = argmax; w.coef = coef; w.partials = partials;
-    if (cb > 0) {
+    if (cb > 0 && (phases & 1)) {
         static int64_t s_attr = 0;
         if (smem_w > s_attr) {
             MK_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
             s_attr = smem_w;
         }
+        count_launches(1);
         k_bwd_w<<<cb, BW_THREADS, smem_w, st>>>(w);
         MK_CHECK_CUDA(cudaGetLastError());
     }
     // ---------------- parameter gradients ----------------
-    if (grads) {
+    if (grads && (phases & 2)) {
         // degrees without nodes: their parameter gradients are exactly zero (ncta == 0 -> finalize sums nothing)
         int rc = launch_param_finalize(layer, partials, part_off, ncta, partials + po, grads, st);
         if (rc) return rc;
     }
     // ---------------- k_bwd_x ----------------
-    if (grad_x && plan->N > 0) {
+    if (grad_x && plan->N > 0 && (phases & 4)) {
         BwdXArgs b;
         b.x = x; b.xnorm = xnorm; b.ldx = ldx;
         b.deg = plan->deg; b.pos = plan->pos; b.in_cnt = plan->in_cnt; b.in_src = plan->in_src; b.in_j = plan->in_j;

@@ -431,6 +431,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         s_attr = smem;
     }
     const int grid = std::min(tb, s_sms);
+    count_launches(1);
     k_conv_fwd<<<grid, FWD_THREADS, smem, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;

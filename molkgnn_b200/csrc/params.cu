@@ -18,6 +18,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static long long g_launches = 0;
+void count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
+long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 int device_num_sms() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -273,6 +277,7 @@ int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, c
     if (rb == 0) return 0;
     k_param_finalize<<<rb, 128, 0, st>>>(fa);
     k_theta<<<4, 128, 0, st>>>(ta);
+    count_launches(2);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -284,6 +289,8 @@ using namespace mk;
 extern "C" const char* molkgnn_last_error(void) { return mk::g_err; }
 extern "C" int molkgnn_version(void) { return 100; }
 extern "C" int molkgnn_num_sms(void) { return device_num_sms(); }
+namespace mk { long long launches(); }
+extern "C" int64_t molkgnn_launch_count(void) { return mk::launches(); }
 
 extern "C" int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp) {
     if (d < 1 || d > 4 || L < 0 || Fp < 4 || Fp % 4) return -1;
@@ -312,6 +319,7 @@ extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
     }
     a.row_begin[4] = rb;
     k_param_pack<<<rb + 4, 128, 0, (cudaStream_t)stream_>>>(a);
+    count_launches(1);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,0 +1,60 @@
+"""Molecule-sharded data parallelism for the conv stack.
+
+Molecules are independent graphs, so the forward needs no communication: every rank runs the full kernels on its own
+shard (parameters replicated).  The only exchange is ONE all-reduce per step of a flat fp32 bucket holding the
+kernel-parameter gradients (0.49 MB for the base stack): NCCL over NVLink 5 / NVSwitch on GPUs, gloo in the CPU tests.
+Parameters that never receive a gradient (p_support, length/angle weights) are not in the bucket.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+GRAD_PARAM_SUFFIXES = ("x_center", "x_support", "edge_attr_support", "support_attr_sc_weight",
+                       "center_attr_sc_weight", "edge_attr_support_sc_weight")
+
+
+def shard_bounds(num_nodes_per_molecule, world):
+    """Contiguous molecule ranges balanced by atom count -> list of (first_molecule, last_molecule_exclusive)."""
+    import numpy as np
+    sizes = np.asarray(num_nodes_per_molecule, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(sizes)])
+    total = csum[-1]
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(csum, total * r / world, side="left")))
+    cuts.append(len(sizes))
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+
+
+class GradBucket(object):
+    """Flat all-reduce bucket over the gradients of the kernel parameters of a module."""
+
+    def __init__(self, module, world=None, average=True, group=None):
+        self.params = [p for n, p in module.named_parameters()
+                       if p.requires_grad and n.rsplit(".", 1)[-1] in GRAD_PARAM_SUFFIXES]
+        self.numel = sum(p.numel() for p in self.params)
+        self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        self.average = average
+        self.group = group
+        self.flat = None
+
+    def allreduce(self):
+        """sum (or mean) the gradients over ranks; afterwards every p.grad is a view into the reduced flat bucket"""
+        ps = [p for p in self.params if p.grad is not None]
+        if not ps:
+            return None
+        flat = torch.cat([p.grad.reshape(-1) for p in ps])
+        if self.world > 1:
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            if self.average:
+                flat.div_(self.world)
+        off = 0
+        for p in ps:
+            n = p.numel()
+            p.grad = flat[off:off + n].view_as(p)
+            off += n
+        self.flat = flat
+        return flat

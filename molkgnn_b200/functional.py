@@ -13,6 +13,41 @@ from . import _lib
 from ._lib import ptr, stream_ptr, check
 from .plan import BucketPlan
 
+# optional CUDA-event profiler (bench.py): name -> list of (start, end) events recorded on the launching stream
+_PROF = None
+_PROF_NAMES = None
+
+
+def profile_start(names=None):
+    global _PROF, _PROF_NAMES
+    _PROF, _PROF_NAMES = {}, (None if names is None else set(names))
+
+
+def profile_stop():
+    """-> {name: (launches, total_ms)}; synchronises."""
+    global _PROF
+    torch.cuda.synchronize()
+    out = {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in (_PROF or {}).items()}
+    _PROF = None
+    return out
+
+
+class _timed(object):
+    def __init__(self, name):
+        self.on = _PROF is not None and (_PROF_NAMES is None or name in _PROF_NAMES)
+        self.name = name
+
+    def __enter__(self):
+        if self.on:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            self.e.record()
+            _PROF.setdefault(self.name, []).append((self.s, self.e))
+
 PARAMS_PER_DEGREE = ("x_center", "x_support", "edge_attr_support", "p_support", "support_attr_sc_weight",
                      "center_attr_sc_weight", "edge_attr_support_sc_weight")
 
@@ -74,7 +109,8 @@ class LayerPack(object):
         self.device = device
 
     def pack(self):
-        check(_lib.lib().molkgnn_param_pack(C.byref(self.c), stream_ptr()))
+        with _timed("param_pack"):
+            check(_lib.lib().molkgnn_param_pack(C.byref(self.c), stream_ptr()))
         return self
 
 
@@ -97,7 +133,8 @@ def pad_norm(x, Fp):
         out = x
     else:
         out = torch.empty(N, Fp, dtype=torch.float32, device=x.device)
-    check(_lib.lib().molkgnn_pad_norm(ptr(x), N, F, ldx, ptr(out), out.stride(0), ptr(norm), stream_ptr()))
+    with _timed("pad_norm"):
+        check(_lib.lib().molkgnn_pad_norm(ptr(x), N, F, ldx, ptr(out), out.stride(0), ptr(norm), stream_ptr()))
     return out, norm
 
 
@@ -118,9 +155,10 @@ def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=Fal
         argmax_in = argmax_in.to(device=dev, dtype=torch.uint8).contiguous()
         if argmax_in.numel() != max(tot, 1) and argmax_in.numel() != tot:
             raise _lib.MolKGNNError("argmax_in has the wrong size")
-    check(_lib.lib().molkgnn_conv_fwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm),
-                                      1 if is_last else 0, ptr(sc), 1 if dense else 0, ld, _i64x4(scoff), ptr(argmax),
-                                      ptr(free), ptr(argmax_in), ptr(counter), stream_ptr()))
+    with _timed("conv_fwd"):
+        check(_lib.lib().molkgnn_conv_fwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm),
+                                          1 if is_last else 0, ptr(sc), 1 if dense else 0, ld, _i64x4(scoff),
+                                          ptr(argmax), ptr(free), ptr(argmax_in), ptr(counter), stream_ptr()))
     return sc, argmax, free
 
 
@@ -128,8 +166,9 @@ def propagate_forward(plan: BucketPlan, pack: LayerPack, sc):
     scoff, _ = plan.scoff(pack.L)
     h = torch.empty(plan.N, pack.Kp, dtype=torch.float32, device=sc.device)
     hnorm = torch.empty(plan.N, dtype=torch.float32, device=sc.device)
-    check(_lib.lib().molkgnn_propagate_fwd(C.byref(plan.c), C.byref(pack.c), ptr(sc), _i64x4(scoff), ptr(h), pack.Kp,
-                                           ptr(hnorm), stream_ptr()))
+    with _timed("propagate_fwd"):
+        check(_lib.lib().molkgnn_propagate_fwd(C.byref(plan.c), C.byref(pack.c), ptr(sc), _i64x4(scoff), ptr(h),
+                                               pack.Kp, ptr(hnorm), stream_ptr()))
     return h, hnorm
 
 
@@ -164,9 +203,13 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
             grads.append(g)
     if grad.stride(1) != 1:
         grad = grad.contiguous()
-    check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
-                             grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials), ptr(gx),
-                             pack.Fp if need_gx else 0, C.byref(gc) if gc is not None else None, stream_ptr()))
+    # one C call runs all three kernels; under the profiler they are issued separately so each can be timed
+    for name, ph in ((("conv_bwd", 7),) if _PROF is None else (("bwd_w", 1), ("param_finalize", 2), ("bwd_x", 4))):
+        with _timed(name):
+            check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
+                                     grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials),
+                                     ptr(gx), pack.Fp if need_gx else 0, C.byref(gc) if gc is not None else None, ph,
+                                     stream_ptr()))
     return gx, grads
 
 

@@ -145,7 +145,7 @@ class BaseKernelSetConv(Module):
         if len(argv) != 0:
             raise Exception('Kernel does not take positional argument, use keyword argument instead. e.g. '
                             'model(data=data)')
-        if len(kwargv) == 2:
+        if 'data' in kwargv:   # reference: len(kwargv) == 2, i.e. data= and save_score= (kernels.py:622)
             g = lambda k: getattr(kwargv['data'], k)  # noqa: E731
         else:
             g = lambda k: kwargv[k]  # noqa: E731

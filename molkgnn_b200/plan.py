@@ -61,8 +61,10 @@ class BucketPlan(object):
         self = cls(num_nodes, E, edge_index.device)
         L = _lib.lib()
         scratch = torch.empty(int(L.molkgnn_bucket_scratch_bytes(self.N, E)), dtype=torch.uint8, device=self.device)
-        check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
-                                     edge_attr.shape[1], ptr(scratch), stream_ptr()))
+        from .functional import _timed
+        with _timed("bucket_build"):
+            check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
+                                         edge_attr.shape[1], ptr(scratch), stream_ptr()))
         self.n = list(self.c.n)
         self._keep = (edge_index, p, edge_attr)
         return self

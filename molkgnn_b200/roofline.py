@@ -45,3 +45,30 @@ def stack_flops(E, n, x_dim, L1, LN, num_layers, Fe=7):
         bwd += b
         F = sum(L)
     return fwd, bwd
+
+
+def kernel_bytes_per_step(kernel, N, E, n, x_dim, L1, LN, num_layers, Fe=7):
+    """Share of the per-layer algorithmic bytes (formulas above) that one kernel class is responsible for, summed
+    over the layers of one step.  Intermediates of the unfused design (compact scores, coefficients, per-CTA partial
+    sums, the second read of x in the input-gradient kernel) are NOT counted: they lower the achieved fraction."""
+    tot = 0
+    F = x_dim
+    for i in range(num_layers):
+        L = L1 if i == 0 else LN
+        K = sum(L)
+        am = sum(nd * ld for nd, ld in zip(n, L))
+        topo = 4 * E + 4 * N
+        if kernel == "conv_fwd":
+            tot += 4 * N * F + 4 * E * Fe + topo + am + (12 * N if i == num_layers - 1 else 0)
+        elif kernel == "propagate_fwd":
+            tot += 4 * N * K
+        elif kernel == "bwd_w":
+            tot += 4 * N * K + 4 * N * F + am + 4 * E * Fe + topo
+        elif kernel == "bwd_x":
+            tot += 4 * N * F
+        elif kernel == "bucket_build":
+            tot += (16 * E + 12 * N + 4 * E * Fe) if i == 0 else 0
+        else:
+            tot += 0
+        F = K
+    return tot

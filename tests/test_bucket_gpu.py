@@ -59,8 +59,16 @@ def test_bucket_vs_oracle(n_mol, seed):
     in_cnt = plan.in_cnt.cpu().numpy()
     assert np.array_equal(in_cnt, np.bincount(ei[1], minlength=N))
     ptr = np.concatenate([[0], np.cumsum(in_cnt)])
-    for v in np.random.default_rng(0).integers(0, N, size=min(N, 200)):
-        assert np.array_equal(in_src[v, :in_cnt[v]], ei[0][order[ptr[v]:ptr[v + 1]]])
+    in_j = plan.in_j.cpu().numpy()
+    oorder = np.argsort(ei[0], kind="stable")
+    optr = np.concatenate([[0], np.cumsum(ref["deg"])])
+    sample = set(np.random.default_rng(0).integers(0, N, size=min(N, 200)).tolist()) | set(range(min(N, 40)))
+    for v in sample:
+        eids = order[ptr[v]:ptr[v + 1]]
+        assert np.array_equal(in_src[v, :in_cnt[v]], ei[0][eids])
+        for t, e in enumerate(eids):       # in_j = rank of the edge inside its source's (edge ordered) out-list
+            u = ei[0][e]
+            assert oorder[optr[u] + in_j[v, t]] == e, (v, t)
 
 
 def test_shuffled_edge_order():
