@@ -94,6 +94,22 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
+// x / y for a divisor whose reciprocal ry = RN(1/y) is known: one product, one exact residual, one correction
+// (Markstein).  Bit-identical to IEEE division for operands in the normal range, without the MUFU/FCHK sequence and
+// its slow path that `x / y` compiles to.
+__device__ __forceinline__ float div_by(float x, float y, float ry) {
+    const float q = x * ry;
+    const float r = fmaf(-y, q, x);
+    return fmaf(r, ry, q);
+}
+// mean over d items: true division by d (torch.mean), exact scalings for d = 1, 2, 4
+template <int D> __device__ __forceinline__ float div_deg(float x) {
+    if (D == 1) return x;
+    if (D == 2) return x * 0.5f;
+    if (D == 4) return x * 0.25f;
+    return div_by(x, 3.0f, 0x1.555556p-2f);
+}
+
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 void count_launches(int n);

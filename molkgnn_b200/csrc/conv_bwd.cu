@@ -56,6 +56,8 @@ __device__ __forceinline__ void bwd_w_body(const BwdWArgs& a, unsigned char* sme
     float* coefS = reinterpret_cast<float*>(smem + a.sm_coef);
     unsigned char* permS = smem + a.sm_perm;
     int* rowNode = reinterpret_cast<int*>(smem + a.sm_rownode);
+    float* rowNrm = reinterpret_cast<float*>(rowNode + (D + 1) * TN);
+    float* rowRinv = rowNrm + (D + 1) * TN;
     __shared__ unsigned char invcode[16];
     if (tid < P) {
         uint32_t code = 0;
@@ -90,6 +92,9 @@ __device__ __forceinline__ void bwd_w_body(const BwdWArgs& a, unsigned char* sme
                     int node = -1;
                     if (r < n) node = j < D ? a.nei[(size_t)eoff + (size_t)r * D + j] : a.sel[boff + r];
                     rowNode[i] = node;
+                    const float nrm = node >= 0 ? fmaxf(a.xnorm[node], MOLKGNN_COS_EPS) : 1.0f;
+                    rowNrm[i] = nrm;
+                    rowRinv[i] = 1.0f / nrm;
                 }
                 __syncthreads();
                 // ---- incoming gradient -> a[n,k] = chi * g ----
@@ -111,28 +116,44 @@ __device__ __forceinline__ void bwd_w_body(const BwdWArgs& a, unsigned char* sme
                     permS[nl * c.LKc + kk] = invcode[am & 0x7f];
                     if (fc == 0) a.coef[cidx] = av;
                 }
-                // ---- stage [xhat | ehat] rows (chunk f0 .. f0+FC of the FW-wide row) ----
-                for (int row = warp; row < (D + 1) * TN; row += NW) {
-                    const int node = rowNode[row];
-                    const int j = row / TN, nl = row % TN;
-                    float* dst = As + (size_t)row * fsw;
-                    if (node >= 0) {
-                        const float inv = fmaxf(a.xnorm[node], MOLKGNN_COS_EPS);
-                        const float* src = a.x + (size_t)node * a.ldx;
-                        const float* esrc = a.ehat + ((size_t)eoff + (size_t)(node0 + nl) * D + j) * EP;
-                        for (int q = lane; q < FCq; q += 32) {
-                            const int w = f0 + 4 * q;
-                            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (w < a.Fp) {
-                                v = ld4(src + w);
-                                v.x = v.x / inv; v.y = v.y / inv; v.z = v.z / inv; v.w = v.w / inv;
-                            } else if (w < a.FW && j < D) {
-                                v = ld4(esrc + (w - a.Fp));
+                // ---- stage [xhat | ehat] rows (chunk f0 .. f0+FC of the FW-wide row); UNR rows in flight per warp ----
+                {
+                    constexpr int UNR = 8;
+                    const int nrows = (D + 1) * TN;
+                    for (int q = lane; q < FCq; q += 32) {
+                        const int w = f0 + 4 * q;
+                        for (int row0 = warp; row0 < nrows; row0 += NW * UNR) {
+                            float4 v[UNR];
+                            float ri[UNR], nr[UNR];
+#pragma unroll
+                            for (int u = 0; u < UNR; ++u) {
+                                const int row = row0 + u * NW;
+                                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                ri[u] = 1.f; nr[u] = 1.f;
+                                if (row < nrows) {
+                                    const int node = rowNode[row];
+                                    const int j = row / TN, nl = row - j * TN;
+                                    if (node >= 0) {
+                                        if (w < a.Fp) {
+                                            ri[u] = rowRinv[row]; nr[u] = rowNrm[row];
+                                            v[u] = ld4(a.x + (size_t)node * a.ldx + w);
+                                        } else if (w < a.FW && j < D) {
+                                            v[u] = ld4(a.ehat + ((size_t)eoff + (size_t)(node0 + nl) * D + j) * EP + (w - a.Fp));
+                                        }
+                                    }
+                                }
                             }
-                            st4(dst + 4 * q, v);
+#pragma unroll
+                            for (int u = 0; u < UNR; ++u) {
+                                const int row = row0 + u * NW;
+                                if (row < nrows) {
+                                    float4 o;
+                                    o.x = div_by(v[u].x, nr[u], ri[u]); o.y = div_by(v[u].y, nr[u], ri[u]);
+                                    o.z = div_by(v[u].z, nr[u], ri[u]); o.w = div_by(v[u].w, nr[u], ri[u]);
+                                    st4(As + (size_t)row * fsw + 4 * q, o);
+                                }
+                            }
                         }
-                    } else {
-                        for (int q = lane; q < FCq; q += 32) st4(dst + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
                     }
                 }
                 __syncthreads();
@@ -227,7 +248,7 @@ static int64_t bwd_w_configure(const molkgnn_layer_t* layer, int budget, BwdWArg
             mA = std::max<int64_t>(mA, (int64_t)(d + 1) * TN * fsw * 4);
             mC = std::max<int64_t>(mC, (int64_t)TN * LKc * 4);
             mP = std::max<int64_t>(mP, ((int64_t)TN * LKc + 15) / 16 * 16);
-            mR = std::max<int64_t>(mR, (int64_t)(d + 1) * TN * 4);
+            mR = std::max<int64_t>(mR, (int64_t)(d + 1) * TN * 12);   // node id + clamped norm + reciprocal
         }
         int64_t off = 0;
         a->sm_A = (int)off; off += mA;
@@ -369,6 +390,7 @@ __global__ void __launch_bounds__(BX_THREADS, 1) k_bwd_x(const __grid_constant__
             // chain rule through xhat = x / max(|x|, eps):  gx = (g - (xhat.g) xhat) / |x|
             const float nrm = a.xnorm[v];
             const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
+            const float rden = 1.0f / den;
             float4 xh[NACC];
             float dot = 0.f;
 #pragma unroll
@@ -377,7 +399,8 @@ __global__ void __launch_bounds__(BX_THREADS, 1) k_bwd_x(const __grid_constant__
                 xh[c] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (q < FQ) {
                     float4 xv = ld4(a.x + (size_t)v * a.ldx + 4 * q);
-                    xh[c] = make_float4(xv.x / den, xv.y / den, xv.z / den, xv.w / den);
+                    xh[c] = make_float4(div_by(xv.x, den, rden), div_by(xv.y, den, rden), div_by(xv.z, den, rden),
+                                        div_by(xv.w, den, rden));
                     dot += acc[c].x * xh[c].x + acc[c].y * xh[c].y + acc[c].z * xh[c].z + acc[c].w * xh[c].w;
                 }
             }
@@ -389,9 +412,9 @@ __global__ void __launch_bounds__(BX_THREADS, 1) k_bwd_x(const __grid_constant__
                 const int q = gl + c * LPN;
                 if (q < FQ) {
                     float4 g;
-                    if (clamped) g = make_float4(acc[c].x / den, acc[c].y / den, acc[c].z / den, acc[c].w / den);
-                    else g = make_float4((acc[c].x - dot * xh[c].x) / den, (acc[c].y - dot * xh[c].y) / den,
-                                         (acc[c].z - dot * xh[c].z) / den, (acc[c].w - dot * xh[c].w) / den);
+                    if (clamped) g = make_float4(acc[c].x * rden, acc[c].y * rden, acc[c].z * rden, acc[c].w * rden);
+                    else g = make_float4((acc[c].x - dot * xh[c].x) * rden, (acc[c].y - dot * xh[c].y) * rden,
+                                         (acc[c].z - dot * xh[c].z) * rden, (acc[c].w - dot * xh[c].w) * rden);
                     const int f = 4 * q;
                     if (f + 0 >= a.F) g.x = 0.f;
                     if (f + 1 >= a.F) g.y = 0.f;

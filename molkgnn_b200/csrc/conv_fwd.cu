@@ -19,14 +19,15 @@
 
 namespace mk {
 
-constexpr int FWD_THREADS = 320;
+constexpr int FWD_THREADS = 256;   // 8 warps = 2 per scheduler: the register file allows 255 registers per thread
 constexpr int FWD_WARPS = FWD_THREADS / 32;
 
 template <int D> struct FwdTile;   // register tile: RN node slots x RK kernels per lane
-template <> struct FwdTile<1> { static constexpr int RN = 2, RK = 2; };
-template <> struct FwdTile<2> { static constexpr int RN = 2, RK = 4; };
-template <> struct FwdTile<3> { static constexpr int RN = 2, RK = 3; };
-template <> struct FwdTile<4> { static constexpr int RN = 1, RK = 5; };
+// tuned so that the README kernel counts 10/20/30/50 give 8 (node set, kernel group) items per tile = one per warp
+template <> struct FwdTile<1> { static constexpr int RN = 2, RK = 3; };
+template <> struct FwdTile<2> { static constexpr int RN = 2, RK = 5; };
+template <> struct FwdTile<3> { static constexpr int RN = 2, RK = 4; };
+template <> struct FwdTile<4> { static constexpr int RN = 1, RK = 7; };
 
 struct FwdCfg {
     int LKc;   // kernels per range
@@ -34,6 +35,8 @@ struct FwdCfg {
     int sets;  // node sets (32*RN nodes) per tile
     int TN;    // nodes per tile
     int KGc;   // kernel groups per full range
+    // byte offsets into dynamic shared memory (the layout is per degree; B rows start at 0)
+    int sm_A, sm_E, sm_ES, sm_rownode, sm_rinv, sm_dup;
 };
 
 struct FwdArgs {
@@ -48,7 +51,6 @@ struct FwdArgs {
     float* sc; int sc_mode; int ld_sc; long long scoff[4];
     uint8_t* argmax; uint8_t* argmax_free; const uint8_t* argmax_in;
     int* counter;
-    int sm_B, sm_A, sm_E, sm_ES, sm_rownode, sm_dup;   // byte offsets into dynamic smem
 };
 
 __device__ __forceinline__ void fma4(float& acc, const float4& a, const float4& b) {
@@ -74,12 +76,14 @@ __device__ __forceinline__ void fwd_tile(const FwdArgs& a, unsigned char* smem, 
     const PackedLayout pl(D, L, a.Fp);
     const float* __restrict__ pk = a.packed[D - 1];
 
-    float* Bs = reinterpret_cast<float*>(smem + a.sm_B);
-    float* As = reinterpret_cast<float*>(smem + a.sm_A);
-    float* Es = reinterpret_cast<float*>(smem + a.sm_E);
-    float* ESs = reinterpret_cast<float*>(smem + a.sm_ES);
-    int* rowNode = reinterpret_cast<int*>(smem + a.sm_rownode);
-    unsigned char* dupf = smem + a.sm_dup;
+    float* Bs = reinterpret_cast<float*>(smem);
+    float* As = reinterpret_cast<float*>(smem + c.sm_A);
+    float* Es = reinterpret_cast<float*>(smem + c.sm_E);
+    float* ESs = reinterpret_cast<float*>(smem + c.sm_ES);
+    int* rowNode = reinterpret_cast<int*>(smem + c.sm_rownode);
+    float* rowRinv = reinterpret_cast<float*>(smem + c.sm_rinv);
+    float* rowNrm = rowRinv + (D + 1) * c.TN;
+    unsigned char* dupf = smem + c.sm_dup;
 
     const int eoff = a.eoff[D - 1], boff = a.boff[D - 1];
     // ---- tile set-up: row -> node table, neighbour bond rows, support bond rows ----
@@ -88,6 +92,10 @@ __device__ __forceinline__ void fwd_tile(const FwdArgs& a, unsigned char* smem, 
         int node = -1;
         if (r < n) node = j < D ? a.nei[(size_t)eoff + (size_t)r * D + j] : a.sel[boff + r];
         rowNode[i] = node;
+        // 1 / max(||x||, eps): the node half of the cosine denominators (kernels.py:189-190)
+        const float nrm = node >= 0 ? fmaxf(a.xnorm[node], MOLKGNN_COS_EPS) : 1.0f;
+        rowNrm[i] = nrm;
+        rowRinv[i] = 1.0f / nrm;
     }
     {
         const int nvalid = min(TN, n - node0) * D * EP;
@@ -136,28 +144,46 @@ __device__ __forceinline__ void fwd_tile(const FwdArgs& a, unsigned char* smem, 
     const int nitems = c.sets * KG;
     const int FC = a.FC, FCq = FC / 4, fsa = a.fsa;
     const float ws = pk[pl.w + 0], wc = pk[pl.w + 1], we = pk[pl.w + 2], W = pk[pl.w + 3];
+    const float rW = 1.0f / W;
 
     float acc[RN][RK][D][D];
     float accc[RN][RK];
 
     auto stage = [&](int fc) {
         const int f0 = fc * FC;
-        for (int row = warp; row < (D + 1) * TN; row += FWD_WARPS) {
-            const int node = rowNode[row];
-            float* dst = As + (size_t)row * fsa;
-            if (node >= 0) {
-                const float inv = fmaxf(a.xnorm[node], MOLKGNN_COS_EPS);
-                const float* src = a.x + (size_t)node * a.ldx + f0;
-                for (int q = lane; q < FCq; q += 32) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (f0 + 4 * q < a.Fp) {
-                        v = ld4(src + 4 * q);
-                        v.x = v.x / inv; v.y = v.y / inv; v.z = v.z / inv; v.w = v.w / inv;
+        // gather the neighbour / focal rows: a warp covers one row per quad-column pass (coalesced float4), UNR rows
+        // in flight per warp so that the dependent global loads overlap instead of serialising
+        constexpr int UNR = 8;
+        const int nrows = (D + 1) * TN;
+        for (int q = lane; q < FCq; q += 32) {
+            const bool fin = f0 + 4 * q < a.Fp;
+            for (int row0 = warp; row0 < nrows; row0 += FWD_WARPS * UNR) {
+                float4 v[UNR];
+                float ri[UNR], nr[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int row = row0 + u * FWD_WARPS;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    ri[u] = 0.f;
+                    nr[u] = 1.f;
+                    if (row < nrows) {
+                        const int node = rowNode[row];
+                        ri[u] = rowRinv[row];
+                        nr[u] = rowNrm[row];
+                        if (node >= 0 && fin) v[u] = ld4(a.x + (size_t)node * a.ldx + f0 + 4 * q);
                     }
-                    st4(dst + 4 * q, v);
                 }
-            } else {
-                for (int q = lane; q < FCq; q += 32) st4(dst + 4 * q, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int row = row0 + u * FWD_WARPS;
+                    if (row < nrows) {
+                        // x / max(||x||, eps) with the precomputed reciprocal: product, exact residual, correction
+                        float4 o;
+                        o.x = div_by(v[u].x, nr[u], ri[u]); o.y = div_by(v[u].y, nr[u], ri[u]);
+                        o.z = div_by(v[u].z, nr[u], ri[u]); o.w = div_by(v[u].w, nr[u], ri[u]);
+                        st4(As + (size_t)row * fsa + 4 * q, o);
+                    }
+                }
             }
         }
         if (restage_B) {
@@ -242,7 +268,7 @@ __device__ __forceinline__ void fwd_tile(const FwdArgs& a, unsigned char* smem, 
                     float s = acc[r][k][0][Perm<D>::at(p, 0)];
 #pragma unroll
                     for (int j = 1; j < D; ++j) s += acc[r][k][j][Perm<D>::at(p, j)];
-                    s = s / (float)D;
+                    s = div_deg<D>(s);
                     if (p == 0 || s > best) { best = s; bi = p; }   // first maximum wins (torch.max, kernels.py:373)
                     if (p == forced) used = s;
                 }
@@ -264,8 +290,8 @@ __device__ __forceinline__ void fwd_tile(const FwdArgs& a, unsigned char* smem, 
                     fma4(dd, e1, s1);
                     esum = j == 0 ? dd : esum + dd;
                 }
-                const float E = esum / (float)D;
-                float sc = ((best * ws + accc[r][k] * wc) + E * we) / W;
+                const float E = div_deg<D>(esum);
+                float sc = div_by((best * ws + accc[r][k] * wc) + E * we, W, rW);
                 uint8_t am = (uint8_t)bi;
                 if (D == 4 && a.is_last) {
                     // chirality (kernels.py:279-350): +1 if any two neighbours are identical, else sign agreement
@@ -324,7 +350,8 @@ static int fwd_rk(int d) { return d == 1 ? FwdTile<1>::RK : d == 2 ? FwdTile<2>:
 
 static int odd_quads(int fl) { return ((fl / 4) % 2 == 0) ? fl + 4 : fl; }
 
-// Chooses chunking so that everything fits in `budget` bytes of shared memory.  Returns total bytes or -1.
+// Chooses chunking so that everything fits in `budget` bytes of shared memory.  The layout is per degree (a CTA works
+// on one degree at a time); returns the maximum over degrees of the bytes needed, or -1.
 static int64_t fwd_configure(const molkgnn_layer_t* layer, int budget, FwdArgs* a) {
     const int Fp = layer->Fp;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -332,45 +359,38 @@ static int64_t fwd_configure(const molkgnn_layer_t* layer, int budget, FwdArgs* 
         const int FC = resident ? Fp : (Fp > 64 ? 64 : Fp);
         const int nfc = (Fp + FC - 1) / FC;
         const int fsa = odd_quads(FC);
-        int64_t mB = 0, mA = 0, mE = 0, mES = 0, mRN = 0, mDup = 16;
+        int64_t total = 0;
         bool ok = true;
         for (int d = 1; d <= 4; ++d) {
             const int L = layer->L[d - 1];
             FwdCfg& c = a->cfg[d - 1];
-            if (L == 0) { c = FwdCfg{1, 0, 1, 32 * fwd_rn(d), 1}; continue; }
             const int RN = fwd_rn(d), RK = fwd_rk(d);
-            int LKc = resident ? L : std::min(L, FWD_WARPS * RK);
-            int KGc = (LKc + RK - 1) / RK;
+            if (L == 0) { c = FwdCfg{1, 0, 1, 32 * RN, 1, 0, 0, 0, 0, 0, 0}; continue; }
+            const int LKc = resident ? L : std::min(L, FWD_WARPS * RK);
+            const int KGc = (LKc + RK - 1) / RK;
+            // with several feature chunks the accumulators of an item live across chunks: one item per warp
             int sets = std::max(1, FWD_WARPS / KGc);
-            int64_t need;
+            int64_t need = 0;
             while (true) {
-                int TN = sets * 32 * RN;
-                need = (int64_t)(d + 1) * LKc * FC * 4 + (int64_t)(d + 1) * TN * fsa * 4 + (int64_t)TN * d * EP * 4 +
-                       (int64_t)d * LKc * EP * 4 + (int64_t)(d + 1) * TN * 4 + TN + 64;
+                const int TN = sets * 32 * RN;
+                int64_t off = (int64_t)(d + 1) * LKc * FC * 4;                 // B rows
+                c.sm_A = (int)off;       off += (int64_t)(d + 1) * TN * fsa * 4;
+                c.sm_E = (int)off;       off += (int64_t)TN * d * EP * 4;
+                c.sm_ES = (int)off;      off += (int64_t)d * LKc * EP * 4;
+                c.sm_rownode = (int)off; off += (int64_t)(d + 1) * TN * 4;
+                c.sm_rinv = (int)off;    off += (int64_t)(d + 1) * TN * 8;     // reciprocal + clamped norm
+                c.sm_dup = (int)off;     off += (TN + 15) / 16 * 16;
+                need = off;
                 if (need <= budget || sets == 1) break;
                 --sets;
             }
             if (need > budget) { ok = false; break; }
-            const int TN = sets * 32 * RN;
-            c.LKc = LKc; c.nkr = (L + LKc - 1) / LKc; c.sets = sets; c.TN = TN; c.KGc = KGc;
-            mB = std::max<int64_t>(mB, (int64_t)(d + 1) * LKc * FC * 4);
-            mA = std::max<int64_t>(mA, (int64_t)(d + 1) * TN * fsa * 4);
-            mE = std::max<int64_t>(mE, (int64_t)TN * d * EP * 4);
-            mES = std::max<int64_t>(mES, (int64_t)d * LKc * EP * 4);
-            mRN = std::max<int64_t>(mRN, (int64_t)(d + 1) * TN * 4);
-            mDup = std::max<int64_t>(mDup, (TN + 15) / 16 * 16);
+            c.LKc = LKc; c.nkr = (L + LKc - 1) / LKc; c.sets = sets; c.TN = sets * 32 * RN; c.KGc = KGc;
+            total = std::max(total, need);
         }
         if (!ok) continue;
-        int64_t off = 0;
-        a->sm_B = (int)off; off += mB;
-        a->sm_A = (int)off; off += mA;
-        a->sm_E = (int)off; off += mE;
-        a->sm_ES = (int)off; off += mES;
-        a->sm_rownode = (int)off; off += mRN;
-        a->sm_dup = (int)off; off += mDup;
-        if (off > budget) continue;   // per-degree maxima do not fit together
         a->FC = FC; a->nfc = nfc; a->fsa = fsa;
-        return off;
+        return std::max<int64_t>(total, 16);
     }
     return -1;
 }
