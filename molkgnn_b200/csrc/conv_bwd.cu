@@ -266,7 +266,7 @@ static int64_t bwd_w_configure(const molkgnn_layer_t* layer, int budget, BwdWArg
 // =============================================================================================================
 // k_bwd_x
 // =============================================================================================================
-constexpr int BX_THREADS = 512;
+constexpr int BX_THREADS = 1024;   // 32 warps: the resident kernel rows allow one CTA per SM, so TLP comes from the block
 
 struct BwdXArgs {
     const float* x; const float* xnorm; int ldx;
@@ -337,41 +337,62 @@ __global__ void __launch_bounds__(BX_THREADS, 1) k_bwd_x(const __grid_constant__
 #pragma unroll
         for (int c = 0; c < NACC; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int cnt = valid ? min(a.in_cnt[v], 4) : 0;
-        // t = -1: focal term; t >= 0: neighbourhoods of the in-neighbours, edge order
-        for (int t = -1; t < cnt; ++t) {
-            int u, j = 0;
-            if (t < 0) { u = valid ? v : -1; } else { u = a.in_src[4 * v + t]; j = a.in_j[4 * v + t]; }
-            if (u < 0) continue;
-            const int d = a.deg[u];
-            if (d < 1 || d > 4) continue;   // node outside every bucket (only possible for plans built from buckets)
-            const int L = a.L[d - 1];
+        // ---- role table: role 0 = focal term, roles 1..cnt = neighbourhoods of the in-neighbours (edge order).
+        // Lane r of the node group fetches role r's metadata, so the dependent loads of all roles overlap. ----
+        int m_off = -1, m_j = 0, m_d = 0;      // m_off: offset of the role's coefficient row (floats), -1 = none
+        if (valid && gl <= cnt) {
+            int u = v;
+            if (gl > 0) { u = a.in_src[4 * v + gl - 1]; m_j = a.in_j[4 * v + gl - 1]; }
+            if (u >= 0) {
+                m_d = a.deg[u];
+                if (m_d >= 1 && m_d <= 4 && a.L[m_d - 1] > 0 && a.khi[m_d - 1] > a.klo[m_d - 1])
+                    m_off = (int)(a.scoff[m_d - 1] + (long long)a.pos[u] * a.L[m_d - 1]);
+            }
+        }
+        for (int t = 0; t <= cnt; ++t) {
+            const int off = __shfl_sync(gmask, m_off, grp * LPN + t);
+            const int j = __shfl_sync(gmask, m_j, grp * LPN + t);
+            const int d = __shfl_sync(gmask, m_d, grp * LPN + t);
+            if (off < 0) continue;
             const int klo = a.klo[d - 1], khi = a.khi[d - 1], LK = khi - klo;
-            if (L == 0 || LK <= 0) continue;
-            const size_t cbase = (size_t)a.scoff[d - 1] + (size_t)a.pos[u] * L;
-            const float scale = t < 0 ? wsc[d - 1][1] : wsc[d - 1][0];
-            const float* rows = Bs + (size_t)a.sm_row0[d - 1] * Fp;
-            for (int k0 = klo; k0 < khi; k0 += LPN) {
-                float my_a = 0.f;
-                int my_s = 0;
-                if (k0 + gl < khi) {
-                    my_a = a.coef[cbase + k0 + gl] * scale;
-                    if (t >= 0) my_s = (permtab[d - 1][a.argmax[cbase + k0 + gl] & 0x7f] >> (2 * j)) & 3;
-                    else my_s = d;   // centre rows sit after the d support blocks
-                }
-                const int lim = min(LPN, khi - k0);
-                for (int i = 0; i < lim; ++i) {
-                    const float av = __shfl_sync(gmask, my_a, grp * LPN + i);
-                    const int s = __shfl_sync(gmask, my_s, grp * LPN + i);
-                    const float* rp = rows + (size_t)(s * LK + (k0 - klo) + i) * Fp;
+            const float scale = t == 0 ? wsc[d - 1][1] : wsc[d - 1][0];
+            const float* rows = Bs + (size_t)a.sm_row0[d - 1] * Fp + 4 * gl;
+            const unsigned pj = 2 * j;
+            // batches of KB kernels: every lane of the group holds KB/LPN (coefficient, row offset) pairs
+            constexpr int KB = 32, MR = KB / LPN;
+            for (int k0 = klo; k0 < khi; k0 += KB) {
+                float my_a[MR];
+                int my_r[MR];
 #pragma unroll
-                    for (int c = 0; c < NACC; ++c) {
-                        const int q = gl + c * LPN;
-                        if (q < FQ) {
-                            const float4 b = ld4(rp + 4 * q);
-                            acc[c].x = fmaf(av, b.x, acc[c].x);
-                            acc[c].y = fmaf(av, b.y, acc[c].y);
-                            acc[c].z = fmaf(av, b.z, acc[c].z);
-                            acc[c].w = fmaf(av, b.w, acc[c].w);
+                for (int m = 0; m < MR; ++m) {
+                    const int k = k0 + m * LPN + gl;
+                    my_a[m] = 0.f;
+                    my_r[m] = 0;
+                    if (k < khi) {
+                        my_a[m] = a.coef[off + k] * scale;
+                        // centre rows sit after the d support blocks; supports: s = perm[pi][j]
+                        const int s = t == 0 ? d : (permtab[d - 1][a.argmax[off + k] & 0x7f] >> pj) & 3;
+                        my_r[m] = (s * LK + (k - klo)) * Fp;
+                    }
+                }
+                // coefficients beyond khi are zero and point at row 0: no branches in the FMA loop
+#pragma unroll
+                for (int m = 0; m < MR; ++m) {
+                    if (k0 + m * LPN >= khi) break;
+#pragma unroll 4
+                    for (int i = 0; i < LPN; ++i) {
+                        const float av = __shfl_sync(gmask, my_a[m], grp * LPN + i);
+                        const int ro = __shfl_sync(gmask, my_r[m], grp * LPN + i);
+                        const float* rp = rows + ro;
+#pragma unroll
+                        for (int c = 0; c < NACC; ++c) {
+                            if (gl + c * LPN < FQ) {
+                                const float4 b = ld4(rp + 4 * c * LPN);
+                                acc[c].x = fmaf(av, b.x, acc[c].x);
+                                acc[c].y = fmaf(av, b.y, acc[c].y);
+                                acc[c].z = fmaf(av, b.z, acc[c].z);
+                                acc[c].w = fmaf(av, b.w, acc[c].w);
+                            }
                         }
                     }
                 }
@@ -560,13 +581,15 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                 const int npc = (BX_THREADS / 32) * 4;
                 rc = launch_bwd_x<8, 1>(b, std::min(g_sms, (plan->N + npc - 1) / npc), smem, st);
             } else if (FQ <= 16) {
+                const int npc = (BX_THREADS / 32) * 4;
+                rc = launch_bwd_x<8, 2>(b, std::min(g_sms, (plan->N + npc - 1) / npc), smem, st);
+            } else if (FQ <= 32) {
                 const int npc = (BX_THREADS / 32) * 2;
-                rc = launch_bwd_x<16, 1>(b, std::min(g_sms, (plan->N + npc - 1) / npc), smem, st);
+                rc = launch_bwd_x<16, 2>(b, std::min(g_sms, (plan->N + npc - 1) / npc), smem, st);
             } else {
                 const int npc = BX_THREADS / 32;
                 const int grid = std::min(g_sms, (plan->N + npc - 1) / npc);
-                if (FQ <= 32) rc = launch_bwd_x<32, 1>(b, grid, smem, st);
-                else if (FQ <= 64) rc = launch_bwd_x<32, 2>(b, grid, smem, st);
+                if (FQ <= 64) rc = launch_bwd_x<32, 2>(b, grid, smem, st);
                 else if (FQ <= 128) rc = launch_bwd_x<32, 4>(b, grid, smem, st);
                 else { MK_REQUIRE(false, "conv_bwd: node_attr_dim %d > 512 not supported", layer->F); }
             }
