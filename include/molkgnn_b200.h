@@ -153,6 +153,13 @@ int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, c
                      const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
                      const molkgnn_layer_grads_t* grads, int32_t phases, void* stream);
 
+/* ---- diagnostics ---- */
+/* Known-answer test of the tcgen05 (UMMA) plumbing: D[128,N] (fp32) = A * B^T on the tensor cores, one CTA.
+ * A, B: fp16.  a_mn = 0: A is [128,K] row-major (K-major operand); a_mn = 1: A is [K,128] row-major (MN-major
+ * operand); same for B with N.  swap = 1 exchanges the two stride fields of the descriptors (diagnostic only). */
+int molkgnn_tc_selftest(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
+                        int32_t swap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
