@@ -133,6 +133,10 @@ int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, c
                      const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                      int32_t* counter, void* stream);
 
+/* Selects the forward kernel: 1 = tcgen05 tensor-core kernel (default; falls back to 0 for layers whose kernel set does
+ * not fit shared memory), 0 = fp32 SIMT kernel.  Returns the previous setting (-1 = not yet chosen). */
+int molkgnn_set_fwd_path(int path);
+
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
 /* h[i, koff_d + k] = sum over in-edges (j -> i) in edge order of sc_{deg j}[pos j, k]; columns K..ldh-1 zeroed;
  * hnorm[i] = ||h_i|| (nullable). */

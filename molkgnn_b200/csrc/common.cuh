@@ -80,8 +80,24 @@ struct PackedLayout {
         enorm = norm + rows_x;
         w = (enorm + d * L + 3) / 4 * 4;
         sign = w + 8;
-        total = (sign + (L * 12 + 3) / 4 + 3) / 4 * 4;
+        const int64_t base_total = (sign + (L * 12 + 3) / 4 + 3) / 4 * 4;
+        // tensor-core operand images (fp16 hi/lo pairs in the interleaved UMMA layout of tc.cuh), 128-byte aligned
+        Fk = (Fp + 15) / 16 * 16;
+        DS = d == 3 ? 4 : d;
+        KSpad = (L * DS + 15) / 16 * 16 + 16;   // + one spare 16-row block: kernel ranges may over-read up to 15 rows
+        Lpad = (L + 15) / 16 * 16;
+        tc = (base_total + 31) / 32 * 32;
+        tc_sup_bytes = (int64_t)(KSpad / 8) * (Fk / 8) * 128;
+        tc_cen_bytes = (int64_t)(Lpad / 8) * (Fk / 8) * 128;
+        total = tc + (2 * tc_sup_bytes + 2 * tc_cen_bytes) / 4;
     }
+    int Fk, DS, KSpad, Lpad;
+    int64_t tc, tc_sup_bytes, tc_cen_bytes;
+    // byte offsets of the four images from (char*)(packed + tc)
+    __host__ __device__ int64_t tc_sup_hi() const { return 0; }
+    __host__ __device__ int64_t tc_sup_lo() const { return tc_sup_bytes; }
+    __host__ __device__ int64_t tc_cen_hi() const { return 2 * tc_sup_bytes; }
+    __host__ __device__ int64_t tc_cen_lo() const { return 2 * tc_sup_bytes + tc_cen_bytes; }
 };
 // w block: [0]=ws [1]=wc [2]=we [3]=W=ws+wc+we [4..7] reserved
 

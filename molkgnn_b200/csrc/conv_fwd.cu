@@ -15,6 +15,7 @@
 // If the kernel set or a node tile does not fit in shared memory (wide layers) the feature dimension is processed
 // in chunks with the accumulators kept in registers, and kernels in ranges.
 #include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace mk {
@@ -395,9 +396,23 @@ static int64_t fwd_configure(const molkgnn_layer_t* layer, int budget, FwdArgs* 
     return -1;
 }
 
+int launch_conv_fwd_tc(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                       const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
+                       const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
+                       int32_t* counter, cudaStream_t st);
+
 }  // namespace mk
 
 using namespace mk;
+
+// 1 = tensor-core kernel (default), 0 = fp32 SIMT kernel (also the automatic choice for layers whose kernel set does
+// not fit the resident tensor-core design).  MOLKGNN_FWD=simt in the environment selects 0 at load time.
+static int g_fwd_path = -1;
+extern "C" int molkgnn_set_fwd_path(int path) {
+    const int old = g_fwd_path;
+    g_fwd_path = path ? 1 : 0;
+    return old;
+}
 
 extern "C" int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer) {
     FwdArgs a;
@@ -418,6 +433,15 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         s_budget = device_max_smem_optin();
         s_sms = device_num_sms();
         MK_REQUIRE(s_budget > 0 && s_sms > 0, "conv_fwd: no CUDA device");
+    }
+    if (g_fwd_path < 0) {
+        const char* e = getenv("MOLKGNN_FWD");
+        g_fwd_path = (e && e[0] == 's') ? 0 : 1;
+    }
+    if (g_fwd_path == 1) {
+        const int rc = launch_conv_fwd_tc(plan, layer, x, ldx, xnorm, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
+                                          argmax_free, argmax_in, counter, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
     }
     FwdArgs a;
     const int64_t smem = fwd_configure(layer, s_budget - 1024, &a);

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace mk {
 
@@ -130,6 +131,52 @@ __global__ void __launch_bounds__(128) k_param_pack(PackArgs a) {
     float den = fmaxf(nrm, MOLKGNN_COS_EPS);
     for (int i = threadIdx.x; i < npad; i += 128) dst[i] = i < n ? src[i] / den : 0.f;
     if (threadIdx.x == 0) *nrm_out = nrm;
+}
+
+// fp16 (hi, lo) images of the normalised kernel rows in the interleaved UMMA operand layout (tc.cuh): support image rows
+// k*DS + s (DS = 4 for d = 3, else d; unused rows zero), centre image rows k.  One thread per (row, 8-column chunk).
+struct PackTcArgs {
+    int Fp;
+    int L[4];
+    int item_begin[5];
+    float* packed[4];
+};
+
+__global__ void __launch_bounds__(256) k_param_pack_tc(PackTcArgs a) {
+    const int it = blockIdx.x * 256 + threadIdx.x;
+    if (it >= a.item_begin[4]) return;
+    int d = 1;
+    while (it >= a.item_begin[d]) ++d;
+    const int L = a.L[d - 1];
+    const PackedLayout pl(d, L, a.Fp);
+    const int nch = pl.Fk / 8;
+    const int local = it - a.item_begin[d - 1];
+    int row = local / nch;
+    const int c = local % nch;
+    float* pk = a.packed[d - 1];
+    unsigned char* img = reinterpret_cast<unsigned char*>(pk + pl.tc);
+    const float* src = nullptr;
+    int64_t hi_off, lo_off;
+    if (row < pl.KSpad) {
+        const int k = row / pl.DS, s = row % pl.DS;
+        if (k < L && s < d) src = pk + pl.sup + ((size_t)s * L + k) * a.Fp;
+        hi_off = pl.tc_sup_hi(); lo_off = pl.tc_sup_lo();
+    } else {
+        row -= pl.KSpad;
+        if (row < L) src = pk + pl.sup + ((size_t)d * L + row) * a.Fp;
+        hi_off = pl.tc_cen_hi(); lo_off = pl.tc_cen_lo();
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        const int col = 8 * c + t;
+        const float v = (src && col < a.Fp) ? src[col] : 0.f;
+        tc::split_h(v, hi[t], lo[t]);
+    }
+    const uint32_t off = tc::il_off(row, 8 * c, pl.Fk);
+    *reinterpret_cast<uint4*>(img + hi_off + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(img + lo_off + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -321,5 +368,23 @@ extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
     k_param_pack<<<rb + 4, 128, 0, (cudaStream_t)stream_>>>(a);
     count_launches(1);
     MK_CHECK_CUDA(cudaGetLastError());
+    PackTcArgs t;
+    t.Fp = layer->Fp;
+    int ib = 0;
+    for (int d = 0; d < 4; ++d) {
+        t.L[d] = layer->L[d];
+        t.packed[d] = layer->packed[d];
+        t.item_begin[d] = ib;
+        if (layer->L[d] > 0) {
+            const PackedLayout pl(d + 1, layer->L[d], layer->Fp);
+            ib += (pl.KSpad + pl.Lpad) * (pl.Fk / 8);
+        }
+    }
+    t.item_begin[4] = ib;
+    if (ib > 0) {
+        k_param_pack_tc<<<(ib + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(t);
+        count_launches(1);
+        MK_CHECK_CUDA(cudaGetLastError());
+    }
     return 0;
 }

@@ -21,6 +21,16 @@ TOL = 1e-5
 DEV = "cuda"
 
 
+@pytest.fixture(autouse=True, params=["tc", "simt"])
+def fwd_path(request):
+    """Every test runs twice: with the tcgen05 tensor-core forward (default product path) and with the fp32 SIMT
+    forward (the path wide layers fall back to)."""
+    from molkgnn_b200 import _lib
+    old = _lib.lib().molkgnn_set_fwd_path(1 if request.param == "tc" else 0)
+    yield request.param
+    _lib.lib().molkgnn_set_fwd_path(1 if old != 0 else 0)
+
+
 def _to_dev(b):
     return dict(x=torch.from_numpy(b["x"]).to(DEV), p=torch.from_numpy(b["p"]).to(DEV),
                 edge_index=torch.from_numpy(b["edge_index"]).to(DEV), edge_attr=torch.from_numpy(b["edge_attr"]).to(DEV))
