@@ -33,6 +33,7 @@ extern "C" {
 #define MOLKGNN_MAX_DEG 4
 #define MOLKGNN_EDGE_PAD 8      /* bond-attribute rows are padded to 8 floats (edge_attr_dim <= 8) */
 #define MOLKGNN_COS_EPS 1e-8f   /* torch.nn.CosineSimilarity eps, kernels.py:189 */
+#define MOLKGNN_TILE_NODES 128  /* nodes per molecule tile = one tcgen05 N / TMEM column block */
 
 /* Degree-bucket plan of one collated batch.  Device arrays are filled by molkgnn_bucket_build();
  * n/boff/eoff are host copies of the per-degree counts (index d-1). */
@@ -51,6 +52,13 @@ typedef struct molkgnn_plan {
     int32_t* in_cnt;           /* [N]   in-degree */
     int32_t* in_src;           /* [N,4] sources of the in-edges, edge order           (KernelLayer.py:119, PyG aggr='add') */
     int32_t* in_j;             /* [N,4] position of this node inside the source's neighbour list */
+    /* molecule tiles (tile kernels): consecutive node ranges that no edge crosses, each <= MOLKGNN_TILE_NODES nodes.
+     * Filled by molkgnn_bucket_build(); n_tiles == 0 means "no tiling" (a molecule larger than the tile, or a plan
+     * built from bucket tensors) and the bucket-order kernels are used instead. */
+    int32_t* tile_start;       /* [n_tiles + 1] first node of every tile; tile_start[n_tiles] = N (capacity N/32 + 4) */
+    int32_t n_tiles;
+    int32_t tile_max_nodes;    /* largest tile */
+    int32_t tile_max_deg[4];   /* largest number of degree-d nodes in one tile */
 } molkgnn_plan_t;
 
 /* One KernelSetConv layer (kernels.py:754-781): raw parameters of the four KernelConv modules + packed workspace. */
@@ -69,6 +77,8 @@ typedef struct molkgnn_layer {
     const float* w_center[4];            /* scalar center_attr_sc_weight        kernels.py:76 */
     const float* w_edge[4];              /* scalar edge_attr_support_sc_weight  kernels.py:82 */
     float* packed[4];                    /* workspace, molkgnn_packed_floats(d, L, Fp) floats each, 16-byte aligned */
+    void* tile_img;                      /* workspace, molkgnn_tile_img_bytes(layer) bytes, 128-byte aligned (nullable:
+                                            disables the tile kernels for this layer) */
 } molkgnn_layer_t;
 
 /* Parameter gradients of one layer, in the reference's own parameter layouts (what autograd would return). */
@@ -120,6 +130,9 @@ int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp);
  * kernel side), evaluates the softmax mixing weights (kernels.py:402-412) and the support chirality signs
  * (kernels.py:338-341) for every permutation. */
 int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream);
+/* bytes of the fp16 (hi, lo) tensor-core operand images of the whole kernel set used by the tile kernels;
+ * 0 if the layer is not eligible (too many kernels per degree for two 128-row blocks per role, or F > 240) */
+int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer);
 
 /* ---- forward: KernelConv.calculate_total_score for the four buckets (kernels.py:353-425, 610-751) ---- */
 int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);

@@ -12,13 +12,15 @@ i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 class Plan(C.Structure):
     _fields_ = [("N", i32), ("E", i32), ("n", i32 * 4), ("boff", i32 * 4), ("eoff", i32 * 4),
                 ("deg", vp), ("pos", vp), ("sel", vp), ("nei", vp), ("nei_eid", vp), ("ehat", vp), ("tsign", vp),
-                ("in_cnt", vp), ("in_src", vp), ("in_j", vp)]
+                ("in_cnt", vp), ("in_src", vp), ("in_j", vp),
+                ("tile_start", vp), ("n_tiles", i32), ("tile_max_nodes", i32), ("tile_max_deg", i32 * 4)]
 
 
 class Layer(C.Structure):
     _fields_ = [("F", i32), ("Fp", i32), ("Fe", i32), ("L", i32 * 4), ("koff", i32 * 4), ("K", i32),
                 ("x_center", vp * 4), ("x_support", vp * 4), ("edge_attr_support", vp * 4), ("p_support", vp * 4),
-                ("w_support", vp * 4), ("w_center", vp * 4), ("w_edge", vp * 4), ("packed", vp * 4)]
+                ("w_support", vp * 4), ("w_center", vp * 4), ("w_edge", vp * 4), ("packed", vp * 4),
+                ("tile_img", vp)]
 
 
 class LayerGrads(C.Structure):
@@ -38,6 +40,7 @@ EXPORTS = {
     "molkgnn_pad_norm": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "molkgnn_packed_floats": (i64, [i32, i32, i32]),
     "molkgnn_param_pack": (C.c_int, [C.POINTER(Layer), vp]),
+    "molkgnn_tile_img_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
                                    vp, vp, vp]),

@@ -15,11 +15,16 @@ namespace mk {
 constexpr int BT = 256;  // threads per block in the node kernels
 
 __global__ void k_edge_slots(const int64_t* __restrict__ ei, int E, int N, int* out_cnt, int* out_eid, int* in_cnt,
-                             int* in_eid, int* err) {
+                             int* in_eid, int* far, int* err) {
     int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= E) return;
     long long u = ei[e], v = ei[(size_t)E + e];
     if (u < 0 || u >= N || v < 0 || v >= N) { atomicOr(err, 1); return; }
+    // furthest node reached from the lower end of the edge: a tile boundary may not fall inside (lo, hi]
+    {
+        const int lo = (int)(u < v ? u : v), hi = (int)(u < v ? v : u);
+        if (hi > lo) atomicMax(&far[lo], hi);
+    }
     int so = atomicAdd(&out_cnt[u], 1);
     if (so < 4) out_eid[4 * u + so] = e; else atomicOr(err, 2);
     int si = atomicAdd(&in_cnt[v], 1);
@@ -160,6 +165,77 @@ __global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int
     }
 }
 
+// ---- molecule tiles ------------------------------------------------------------------------------------------------
+// tinfo: [0] widest gap between consecutive valid cuts (= largest molecule), [1] flags (1 = an edge spans >= 128 nodes),
+//        [2] n_tiles, [3] largest tile, [4..7] largest number of degree-1..4 nodes in one tile
+constexpr int TILE_CAP = MOLKGNN_TILE_NODES;
+constexpr int TILE_MIN_STRIDE = 32;
+
+// cutpos[c] = c if no edge crosses the boundary in front of node c (c = 0..N), else -1
+__global__ void __launch_bounds__(256) k_valid_cuts(int N, const int* __restrict__ far, int* cutpos, int* tinfo) {
+    __shared__ int f[256 + TILE_CAP];
+    const int B = blockIdx.x * 256;
+    for (int i = threadIdx.x; i < 256 + TILE_CAP; i += 256) {
+        const int u = B - TILE_CAP + i;
+        int r = -1;
+        if (u >= 0 && u < N) {
+            r = max(far[u], u);
+            if (r - u >= TILE_CAP) atomicOr(&tinfo[1], 1);
+        }
+        f[i] = r;
+    }
+    __syncthreads();
+    const int c = B + threadIdx.x;
+    if (c > N) return;
+    int m = -1;   // edges that could cross start at one of the TILE_CAP - 1 nodes in front of c (longer spans are flagged)
+#pragma unroll 8
+    for (int i = 0; i < TILE_CAP; ++i) m = max(m, f[threadIdx.x + i]);
+    cutpos[c] = (m < c) ? c : -1;
+}
+
+__global__ void __launch_bounds__(256) k_cut_gaps(int N, const int* __restrict__ cutpos, int* tinfo) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    int gap = 0;
+    if (c > 0 && c <= N && cutpos[c] >= 0) {
+        int q = c - 1;
+        while (q > 0 && cutpos[q] < 0 && c - q <= 2 * TILE_CAP) --q;   // bounded: anything wider disables tiling anyway
+        gap = c - q;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gap = max(gap, __shfl_xor_sync(0xffffffffu, gap, o));
+    if ((threadIdx.x & 31) == 0 && gap > 0) atomicMax(&tinfo[0], gap);
+}
+
+// tile i starts at the last valid cut <= i * S with S = TILE_CAP + 1 - (largest molecule): every tile then holds whole
+// molecules and at most TILE_CAP nodes
+__global__ void __launch_bounds__(128) k_tile_starts(int N, int cap, const int* __restrict__ cutpos,
+                                                     const int* __restrict__ deg, int* tile_start, int* tinfo) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int gap = tinfo[0];
+    const int S = TILE_CAP + 1 - gap;
+    if (S < TILE_MIN_STRIDE || (tinfo[1] & 1)) {
+        if (i == 0) tinfo[2] = 0;
+        return;
+    }
+    const int T = (N + S - 1) / S;
+    if (i == 0) tinfo[2] = T;
+    if (i > T || i >= cap) return;
+    int a = (int)min((long long)i * S, (long long)N);
+    while (a > 0 && cutpos[a] < 0) --a;
+    tile_start[i] = a;
+    if (i == T) return;
+    int b = (int)min((long long)(i + 1) * S, (long long)N);
+    while (b > 0 && cutpos[b] < 0) --b;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int v = a; v < b; ++v) {
+        const int d = deg[v];
+        if (d >= 1 && d <= 4) ++cnt[d - 1];
+    }
+    atomicMax(&tinfo[3], b - a);
+#pragma unroll
+    for (int d = 0; d < 4; ++d) atomicMax(&tinfo[4 + d], cnt[d]);
+}
+
 __global__ void k_export(int d, int n, int boff, int eoff, const int* __restrict__ sel, const int* __restrict__ nei,
                          const int* __restrict__ nei_eid, const float* __restrict__ p, int p_dim,
                          const float* __restrict__ edge_attr, int Fe, int64_t* selected_index, int64_t* nei_index,
@@ -260,8 +336,9 @@ using namespace mk;
 
 extern "C" int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E) {
     int64_t nblk = (N + BT - 1) / BT;
-    // out_cnt[N] out_eid[4N] in_eid[4N] blk_counts[5*nblk] blk_off[5*nblk] totals[16] err[1]
-    return (int64_t)sizeof(int) * ((int64_t)N * 9 + nblk * 10 + 32);
+    // out_cnt[N] out_eid[4N] in_eid[4N] blk_counts[5*nblk] blk_off[5*nblk] totals[16] err[1] tinfo[8] (32 ints)
+    // far[N] cutpos[N+1]
+    return (int64_t)sizeof(int) * ((int64_t)N * 11 + nblk * 10 + 64);
 }
 
 extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
@@ -279,18 +356,36 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     int* blk_counts = s;          s += 5 * (size_t)nblk;
     int* blk_off = s;             s += 5 * (size_t)nblk;
     int* totals = s;              s += 16;
-    int* err = s;
+    int* err = s;                 s += 1;
+    int* tinfo = s;               s += 15;     // totals .. tinfo are one 32-int block copied to the host
+    int* far = s;                 s += N;
+    int* cutpos = s;
+    const bool tiles = plan->tile_start != nullptr;
+    const int tile_cap = N / TILE_MIN_STRIDE + 4;
     MK_CHECK_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
-    MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 17, st));
-    count_launches(E > 0 ? 4 : 3);
+    MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 32, st));
+    MK_CHECK_CUDA(cudaMemsetAsync(far, 0, sizeof(int) * (size_t)N, st));
+    count_launches((E > 0 ? 4 : 3) + (tiles ? 3 : 0));
     if (E > 0)
-        k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, err);
+        k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, far, err);
     k_node_prepare<<<nblk, BT, 0, st>>>(N, out_cnt, out_eid, plan->in_cnt, in_eid, plan->deg, blk_counts, err);
     k_scan_blocks<<<1, 32, 0, st>>>(nblk, blk_counts, blk_off, totals);
-    int host[17];
-    MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 17, cudaMemcpyDeviceToHost, st));
+    if (tiles) {
+        k_valid_cuts<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, far, cutpos, tinfo);
+        k_cut_gaps<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, cutpos, tinfo);
+        k_tile_starts<<<(tile_cap + 127) / 128, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
+    }
+    int host[32];
+    MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
     MK_CHECK_CUDA(cudaStreamSynchronize(st));
+    plan->n_tiles = 0; plan->tile_max_nodes = 0;
+    for (int d = 0; d < 4; ++d) plan->tile_max_deg[d] = 0;
+    if (tiles && host[17 + 2] > 0 && host[17 + 2] < tile_cap && host[17 + 3] <= TILE_CAP) {
+        plan->n_tiles = host[17 + 2];
+        plan->tile_max_nodes = host[17 + 3];
+        for (int d = 0; d < 4; ++d) plan->tile_max_deg[d] = host[17 + 4 + d];
+    }
     MK_REQUIRE(host[16] == 0 && host[4] == 0,
                "bucket_build: unsupported graph (flags=0x%x: 1=node id out of range, 2=out-degree>4, 4=in-degree>4, "
                "8=node with out-degree 0 or >4; %d offending nodes)", host[16], host[4]);
@@ -323,6 +418,8 @@ extern "C" int molkgnn_plan_from_buckets(molkgnn_plan_t* plan, const int64_t* co
                                          const float* const nei_edge_attr[4], int32_t Fe, void* stream_) {
     // plan->N, plan->n[] must be set by the caller (tensor shapes); boff/eoff are derived here.
     cudaStream_t st = (cudaStream_t)stream_;
+    plan->n_tiles = 0; plan->tile_max_nodes = 0;     // bucket tensors carry no node order guarantees: no tiling
+    for (int d = 0; d < 4; ++d) plan->tile_max_deg[d] = 0;
     const int N = plan->N;
     MK_REQUIRE(Fe >= 1 && Fe <= EP, "plan_from_buckets: edge_attr_dim %d not in 1..%d", Fe, EP);
     int bo = 0, eo = 0, tot = 0;

@@ -400,6 +400,10 @@ int launch_conv_fwd_tc(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer,
                        const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                        const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                        int32_t* counter, cudaStream_t st);
+int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                         const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
+                         const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
+                         int32_t* counter, cudaStream_t st);
 
 }  // namespace mk
 
@@ -410,7 +414,7 @@ using namespace mk;
 static int g_fwd_path = -1;
 extern "C" int molkgnn_set_fwd_path(int path) {
     const int old = g_fwd_path;
-    g_fwd_path = path ? 1 : 0;
+    g_fwd_path = path < 0 ? 0 : path > 2 ? 2 : path;
     return old;
 }
 
@@ -436,9 +440,14 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     }
     if (g_fwd_path < 0) {
         const char* e = getenv("MOLKGNN_FWD");
-        g_fwd_path = (e && e[0] == 's') ? 0 : 1;
+        g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)
     }
-    if (g_fwd_path == 1) {
+    if (g_fwd_path == 2) {
+        const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, xnorm, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
+                                            argmax_free, argmax_in, counter, st);
+        if (rc != 0) return rc < 0 ? rc : 0;
+    }
+    if (g_fwd_path >= 1) {
         const int rc = launch_conv_fwd_tc(plan, layer, x, ldx, xnorm, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                           argmax_free, argmax_in, counter, st);
         if (rc != 0) return rc < 0 ? rc : 0;

@@ -179,6 +179,46 @@ __global__ void __launch_bounds__(256) k_param_pack_tc(PackTcArgs a) {
     *reinterpret_cast<uint4*>(img + lo_off + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// fp16 (hi, lo) images of the whole kernel set for the tile kernels: TileRows order, unscaled split (common.cuh).
+struct PackTileArgs {
+    int Fp, Fk;
+    int L[4];
+    const float* packed[4];
+    unsigned char* img;
+};
+
+__global__ void __launch_bounds__(256) k_param_pack_tile(PackTileArgs a) {
+    const int nch = a.Fk / 8;
+    const int it = blockIdx.x * 256 + threadIdx.x;
+    if (it >= 2 * TileRows::ROWS * nch) return;
+    const int c = it % nch;
+    const int row = (it / nch) % TileRows::ROWS;
+    const int role = it / (nch * TileRows::ROWS);
+    const TileRows tr(a.L);
+    int d, k, slot;
+    tr.describe(role, row, d, k, slot);
+    const float* src = nullptr;
+    if (d > 0) {
+        const int L = a.L[d - 1];
+        const PackedLayout pl(d, L, a.Fp);
+        src = a.packed[d - 1] + pl.sup + ((size_t)(slot < 4 ? slot : d) * L + k) * a.Fp;
+    }
+    __align__(16) __half2 hi[4];
+    __align__(16) __half2 lo[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int col = 8 * c + 2 * t;
+        const float v0 = (src && col < a.Fp) ? src[col] : 0.f;
+        const float v1 = (src && col + 1 < a.Fp) ? src[col + 1] : 0.f;
+        tc::split_u2(v0, v1, hi[t], lo[t]);
+    }
+    const int64_t one = tile_img_bytes_one(a.Fk);
+    unsigned char* base = a.img + (int64_t)role * 2 * one;
+    const uint32_t off = tc::il_off(row, 8 * c, a.Fk);
+    *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(base + one + off) = *reinterpret_cast<const uint4*>(lo);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 struct FinArgs {
     int F, Fp, Fe, FW;       // FW = Fp + EP : row width of the partial accumulators
@@ -344,6 +384,19 @@ extern "C" int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp) {
     return PackedLayout(d, L, Fp).total;
 }
 
+namespace mk {
+// tile kernels are eligible when both roles fit their 256 rows and the images + a node tile fit shared memory
+bool tile_layer_ok(const molkgnn_layer_t* layer) {
+    const TileRows tr(layer->L);
+    return tr.fits() && tile_fk(layer->Fp) <= 112 && layer->K > 0;
+}
+}  // namespace mk
+
+extern "C" int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer) {
+    if (!tile_layer_ok(layer)) return 0;
+    return 4 * tile_img_bytes_one(tile_fk(layer->Fp));
+}
+
 extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
     PackArgs a;
     MK_REQUIRE(layer->Fp % 4 == 0 && layer->Fp >= layer->F, "param_pack: Fp=%d must be a multiple of 4 >= F=%d",
@@ -383,6 +436,17 @@ extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
     t.item_begin[4] = ib;
     if (ib > 0) {
         k_param_pack_tc<<<(ib + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(t);
+        count_launches(1);
+        MK_CHECK_CUDA(cudaGetLastError());
+    }
+    if (layer->tile_img && tile_layer_ok(layer)) {
+        MK_REQUIRE((reinterpret_cast<uintptr_t>(layer->tile_img) & 127) == 0, "param_pack: tile_img must be 128-byte aligned");
+        PackTileArgs ta;
+        ta.Fp = layer->Fp; ta.Fk = tile_fk(layer->Fp);
+        for (int d = 0; d < 4; ++d) { ta.L[d] = layer->L[d]; ta.packed[d] = layer->packed[d]; }
+        ta.img = reinterpret_cast<unsigned char*>(layer->tile_img);
+        const int items = 2 * TileRows::ROWS * (ta.Fk / 8);
+        k_param_pack_tile<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(ta);
         count_launches(1);
         MK_CHECK_CUDA(cudaGetLastError());
     }

@@ -62,6 +62,11 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // this warp's 32 TMEM lanes (warp w of the CTA owns lanes 32*(w%4) ..), `n` consecutive 32-bit columns from `col`
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t v;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+    return v;
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
@@ -111,6 +116,13 @@ constexpr float LO_UNSCALE = 1.0f / 2048.0f;
 __device__ __forceinline__ void split_h(float v, __half& hi, __half& lo) {
     hi = __float2half_rn(v);
     lo = __float2half_rn((v - __half2float(hi)) * LO_SCALE);
+}
+
+// unscaled split: v ~= hi + lo (lo usually subnormal; |error| <= 2^-25 absolute for |v| <= 1)
+__device__ __forceinline__ void split_u2(float a, float b, __half2& hi, __half2& lo) {
+    hi = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(hi);
+    lo = __floats2half2_rn(a - hf.x, b - hf.y);
 }
 
 }  // namespace tc

@@ -103,6 +103,9 @@ class LayerPack(object):
             self.packed.append(pk)
             c.packed[d] = pk.data_ptr()
         c.K = koff
+        nb = int(L.molkgnn_tile_img_bytes(C.byref(c)))
+        self.tile_img = torch.empty(nb, dtype=torch.uint8, device=device) if nb > 0 else None
+        c.tile_img = self.tile_img.data_ptr() if nb > 0 else None
         self.K, self.Kp = koff, _rup4(koff)
         self.koff = [int(c.koff[d]) for d in range(4)]
         self.c = c
@@ -144,7 +147,7 @@ def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=Fal
     dev = x.device
     argmax = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev)
     free = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev) if want_free else None
-    counter = torch.empty(1, dtype=torch.int32, device=dev)
+    counter = torch.empty(4, dtype=torch.int32, device=dev)
     if dense:
         sc = torch.zeros(plan.N, pack.Kp, dtype=torch.float32, device=dev)
         ld = pack.Kp

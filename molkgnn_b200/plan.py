@@ -39,12 +39,14 @@ class BucketPlan(object):
         self.in_cnt = torch.empty(self.N, **i32)
         self.in_src = torch.empty(self.N, 4, **i32)
         self.in_j = torch.empty(self.N, 4, **i32)
+        self.tile_start = torch.empty(self.N // 32 + 4, **i32)      # molecule tiles (filled by molkgnn_bucket_build)
         c = _lib.Plan()
         c.N, c.E = self.N, self.E
-        for name in ("deg", "pos", "sel", "nei", "nei_eid", "ehat", "tsign", "in_cnt", "in_src", "in_j"):
+        for name in ("deg", "pos", "sel", "nei", "nei_eid", "ehat", "tsign", "in_cnt", "in_src", "in_j", "tile_start"):
             setattr(c, name, getattr(self, name).data_ptr())
         self.c = c
         self.n = [0, 0, 0, 0]
+        self.n_tiles = 0
 
     # ---- constructors -------------------------------------------------------------------------------------
     @classmethod
@@ -66,6 +68,7 @@ class BucketPlan(object):
             check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
                                          edge_attr.shape[1], ptr(scratch), stream_ptr()))
         self.n = list(self.c.n)
+        self.n_tiles = int(self.c.n_tiles)          # 0: no molecule tiling (bucket-order kernels are used)
         self._keep = (edge_index, p, edge_attr)
         return self
 

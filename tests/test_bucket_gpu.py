@@ -124,3 +124,28 @@ def test_rejects_bad_degree():
     ei = torch.tensor([[0, 1], [1, 0]], dtype=torch.int64).cuda()
     with pytest.raises(MolKGNNError):
         BucketPlan.from_edge_index(ei, torch.zeros(3, 3).cuda(), torch.ones(2, 7).cuda(), 3)
+
+
+@pytest.mark.parametrize("n_mol,seed", [(1, 0), (7, 3), (300, 1), (4096, 2)])
+def test_molecule_tiles(n_mol, seed):
+    """Tiles are consecutive node ranges of whole molecules (no edge crosses a boundary), at most 128 nodes each."""
+    from molkgnn_b200 import synth
+    b = synth.make_batch(n_mol, seed=seed)
+    N = b["x"].shape[0]
+    plan = _plan(b["edge_index"], b["p"], b["edge_attr"], N)
+    T = plan.n_tiles
+    assert T > 0
+    ts = plan.tile_start.cpu().numpy()[:T + 1]
+    assert ts[0] == 0 and ts[T] == N
+    assert np.all(np.diff(ts) >= 0) and np.diff(ts).max() <= 128
+    assert plan.c.tile_max_nodes == np.diff(ts).max()
+    tile_of = np.searchsorted(ts[1:], np.arange(N), side="right")
+    ei = b["edge_index"]
+    assert np.array_equal(tile_of[ei[0]], tile_of[ei[1]])
+    deg = plan.deg.cpu().numpy()
+    for d in range(1, 5):
+        cnt = np.bincount(tile_of[deg == d], minlength=T)
+        assert plan.c.tile_max_deg[d - 1] == cnt.max()
+    # packing efficiency: tiles hold whole molecules of <= 32 atoms, so they are at least 128 - 31 - 31 nodes wide on average
+    if n_mol >= 300:
+        assert np.diff(ts).mean() > 90

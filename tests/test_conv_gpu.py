@@ -21,14 +21,17 @@ TOL = 1e-5
 DEV = "cuda"
 
 
-@pytest.fixture(autouse=True, params=["tc", "simt"])
+PATHS = {"simt": 0, "bucket_tc": 1, "tile": 2}
+
+
+@pytest.fixture(autouse=True, params=["tile", "bucket_tc", "simt"])
 def fwd_path(request):
-    """Every test runs twice: with the tcgen05 tensor-core forward (default product path) and with the fp32 SIMT
-    forward (the path wide layers fall back to)."""
+    """Every test runs three times: with the molecule-tile tcgen05 forward (default product path), with the
+    bucket-order tcgen05 forward (plans without tiles) and with the fp32 SIMT forward (wide layers)."""
     from molkgnn_b200 import _lib
-    old = _lib.lib().molkgnn_set_fwd_path(1 if request.param == "tc" else 0)
+    old = _lib.lib().molkgnn_set_fwd_path(PATHS[request.param])
     yield request.param
-    _lib.lib().molkgnn_set_fwd_path(1 if old != 0 else 0)
+    _lib.lib().molkgnn_set_fwd_path(2 if old < 0 else old)
 
 
 def _to_dev(b):
