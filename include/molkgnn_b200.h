@@ -59,6 +59,9 @@ typedef struct molkgnn_plan {
     int32_t n_tiles;
     int32_t tile_max_nodes;    /* largest tile */
     int32_t tile_max_deg[4];   /* largest number of degree-d nodes in one tile */
+    void*    tile_meta;        /* [N/32 + 4] records of molkgnn_tile_meta_bytes() bytes: per-tile node lists, local neighbour
+                                  ids, bucket rows, in-lists (csrc/tile.cuh TileMetaG) */
+    float*   ehat_node;        /* [E,8] the rows of ehat in node order (tile-contiguous) */
 } molkgnn_plan_t;
 
 /* One KernelSetConv layer (kernels.py:754-781): raw parameters of the four KernelConv modules + packed workspace. */
@@ -99,6 +102,8 @@ int64_t molkgnn_launch_count(void);
 int molkgnn_num_sms(void);
 
 /* ---- degree bucketing: replaces ToXAndPAndEdgeAttrForDeg.__call__ (wrapper.py:559-672) + PyG collation ---- */
+/* size of one per-tile metadata record (plan->tile_meta) */
+int64_t molkgnn_tile_meta_bytes(void);
 /* bytes of scratch needed by molkgnn_bucket_build */
 int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E);
 /* Builds the plan from a collated batch.  edge_index is the PyG [2,E] int64 tensor (row 0 = source).  SYNCHRONISES
@@ -133,6 +138,11 @@ int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream);
 /* bytes of the fp16 (hi, lo) tensor-core operand images of the whole kernel set used by the tile kernels;
  * 0 if the layer is not eligible (too many kernels per degree for two 128-row blocks per role, or F > 240) */
 int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer);
+/* Normalised fp16 (hi, lo) images of the activations in tile order, the tensor-core operand of the tile kernels:
+ * ximg holds plan->n_tiles records of molkgnn_tile_ximg_bytes() bytes.  Built once per layer, read by forward and backward. */
+int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                            const float* xnorm, void* ximg, void* stream);
 
 /* ---- forward: KernelConv.calculate_total_score for the four buckets (kernels.py:353-425, 610-751) ---- */
 int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
@@ -140,14 +150,17 @@ int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
  * sc_mode 1: dense sc[node*ld_sc + koff_d + k] (only the L_d entries of the node's own block are written).
  * argmax (compact, byte offsets = scoff) always receives the permutation actually used + chirality bit;
  * argmax_free (nullable) receives the free-running arg-max; argmax_in (nullable) forces the permutation
- * (parity harness / replay).  counter: one zero-initialised int32 of scratch per call. */
+ * (parity harness / replay).  counter: 8 int32 of scratch per call.  ximg (nullable): the activations' fp16 images
+ * from molkgnn_tile_ximg_build(); with them, a plan that carries molecule tiles and an eligible layer the molecule-tile
+ * tcgen05 kernel runs, otherwise the bucket-order kernels. */
 int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                      const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
-                     int32_t* counter, void* stream);
+                     int32_t* counter, const void* ximg, void* stream);
 
-/* Selects the forward kernel: 1 = tcgen05 tensor-core kernel (default; falls back to 0 for layers whose kernel set does
- * not fit shared memory), 0 = fp32 SIMT kernel.  Returns the previous setting (-1 = not yet chosen). */
+/* Selects the forward kernel: 2 = molecule-tile tcgen05 kernel (default; needs ximg, a tiled plan and an eligible layer,
+ * else falls back to 1), 1 = bucket-order tcgen05 kernel (falls back to 0 for layers whose kernel set does not fit shared
+ * memory), 0 = fp32 SIMT kernel.  Returns the previous setting (-1 = not yet chosen). */
 int molkgnn_set_fwd_path(int path);
 
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */

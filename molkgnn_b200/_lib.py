@@ -13,7 +13,8 @@ class Plan(C.Structure):
     _fields_ = [("N", i32), ("E", i32), ("n", i32 * 4), ("boff", i32 * 4), ("eoff", i32 * 4),
                 ("deg", vp), ("pos", vp), ("sel", vp), ("nei", vp), ("nei_eid", vp), ("ehat", vp), ("tsign", vp),
                 ("in_cnt", vp), ("in_src", vp), ("in_j", vp),
-                ("tile_start", vp), ("n_tiles", i32), ("tile_max_nodes", i32), ("tile_max_deg", i32 * 4)]
+                ("tile_start", vp), ("n_tiles", i32), ("tile_max_nodes", i32), ("tile_max_deg", i32 * 4),
+                ("tile_meta", vp), ("ehat_node", vp)]
 
 
 class Layer(C.Structure):
@@ -34,6 +35,9 @@ EXPORTS = {
     "molkgnn_num_sms": (C.c_int, []),
     "molkgnn_launch_count": (i64, []),
     "molkgnn_bucket_scratch_bytes": (i64, [i32, i32]),
+    "molkgnn_tile_meta_bytes": (i64, []),
+    "molkgnn_tile_ximg_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
+    "molkgnn_tile_ximg_build": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp]),
     "molkgnn_bucket_build": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
     "molkgnn_bucket_export": (C.c_int, [C.POINTER(Plan), i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     "molkgnn_plan_from_buckets": (C.c_int, [C.POINTER(Plan), vp * 4, vp * 4, vp * 4, vp * 4, i32, vp * 4, i32, vp]),
@@ -43,7 +47,7 @@ EXPORTS = {
     "molkgnn_tile_img_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
-                                   vp, vp, vp]),
+                                   vp, vp, vp, vp]),
     "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp]),
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),

@@ -9,6 +9,7 @@
 //                  wrapper.py:599-600) and the bucket sizes
 //   k_assign       writes sel / pos / nei / nei_eid / ehat / tsign / in-lists
 #include "common.cuh"
+#include "tile.cuh"
 
 namespace mk {
 
@@ -236,6 +237,92 @@ __global__ void __launch_bounds__(128) k_tile_starts(int N, int cap, const int* 
     for (int d = 0; d < 4; ++d) atomicMax(&tinfo[4 + d], cnt[d]);
 }
 
+// per-tile metadata record + bond rows in node order (one block of 128 threads per tile, thread = local node)
+__global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restrict__ tile_start, const int* __restrict__ deg,
+                                                      const int* __restrict__ pos, const int* __restrict__ nei,
+                                                      const float* __restrict__ ehat, const int8_t* __restrict__ tsign,
+                                                      const int* __restrict__ in_cnt, const int* __restrict__ in_src,
+                                                      const int* __restrict__ in_j, const int* __restrict__ blk_off,
+                                                      const int* __restrict__ totals, TileMetaG* meta, float* ehat_node) {
+    __shared__ int wsum[4][6];
+    __shared__ int s_e0;
+    const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t0 = tile_start[tile], t1 = tile_start[tile + 1];
+    const int nn = t1 - t0;
+    TileMetaG* m = meta + tile;
+    // first bond slot of the tile = sum of the degrees of all nodes in front of it: whole 256-node blocks from the
+    // class histogram of the bucket pass, the rest by a block reduction
+    const int b0 = t0 / BT;
+    int part = 0;
+    for (int v = b0 * BT + tid; v < t0; v += TNODES) part += deg[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) wsum[warp][5] = part;
+    int d = 0, R = 0, base = 0;
+    if (tid < nn) {
+        d = deg[t0 + tid];
+        R = pos[t0 + tid];
+        base = totals[9 + d - 1] + R * d;
+    }
+    int rank[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const unsigned mk_ = __ballot_sync(0xffffffffu, d == c + 1);
+        rank[c] = __popc(mk_ & ((1u << lane) - 1u));
+        if (lane == 0) wsum[warp][c] = __popc(mk_);
+    }
+    int incl = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp][4] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int e0 = wsum[0][5] + wsum[1][5] + wsum[2][5] + wsum[3][5];
+        for (int c = 0; c < 4; ++c) e0 += (c + 1) * blk_off[b0 * 5 + c];
+        s_e0 = e0;
+        m->t0 = t0; m->nn = nn; m->e0 = e0;
+        m->ne = wsum[0][4] + wsum[1][4] + wsum[2][4] + wsum[3][4];
+        for (int c = 0; c < 4; ++c) m->cnt[c] = wsum[0][c] + wsum[1][c] + wsum[2][c] + wsum[3][c];
+    }
+    __syncthreads();
+    int soff = incl - d;
+    int loff = d > 0 ? rank[d - 1] : 0;
+    for (int w = 0; w < warp; ++w) {
+        soff += wsum[w][4];
+        if (d > 0) loff += wsum[w][d - 1];
+    }
+    uint32_t w_nl = 0, w_in = 0;
+    unsigned char ij[4] = {0, 0, 0, 0};
+    int ic = 0;
+    if (tid < nn) {
+        m->list[d - 1][loff] = (unsigned char)tid;
+        for (int j = 0; j < d; ++j) {
+            w_nl |= (uint32_t)((nei[(size_t)base + j] - t0) & 0xff) << (8 * j);
+            const float4* src = reinterpret_cast<const float4*>(ehat + ((size_t)base + j) * EP);
+            float4* dst = reinterpret_cast<float4*>(ehat_node + ((size_t)s_e0 + soff + j) * EP);
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
+        ic = min(in_cnt[t0 + tid], 4);
+        for (int t = 0; t < ic; ++t) {
+            w_in |= (uint32_t)((in_src[4 * (size_t)(t0 + tid) + t] - t0) & 0xff) << (8 * t);
+            ij[t] = (unsigned char)in_j[4 * (size_t)(t0 + tid) + t];
+        }
+    }
+    m->nl[tid] = w_nl;
+    m->posl[tid] = R;
+    m->eslot[tid] = (unsigned short)soff;
+    m->degl[tid] = (unsigned char)d;
+    m->tsg[tid] = (d == 4) ? tsign[R] : 0;
+    m->inl[tid] = w_in;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) m->inj[tid][t] = ij[t];
+    m->incnt[tid] = (unsigned char)ic;
+}
+
 __global__ void k_export(int d, int n, int boff, int eoff, const int* __restrict__ sel, const int* __restrict__ nei,
                          const int* __restrict__ nei_eid, const float* __restrict__ p, int p_dim,
                          const float* __restrict__ edge_attr, int Fe, int64_t* selected_index, int64_t* nei_index,
@@ -393,9 +480,19 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     k_assign<<<nblk, BT, 0, st>>>(N, E, edge_index, plan->deg, out_eid, plan->in_cnt, in_eid, blk_off, totals, p, p_dim,
                                   edge_attr, Fe, plan->pos, plan->sel, plan->nei, plan->nei_eid, plan->ehat,
                                   plan->tsign, plan->in_src, plan->in_j);
+    if (plan->n_tiles > 0 && plan->tile_meta && plan->ehat_node) {
+        count_launches(1);
+        k_tile_meta<<<plan->n_tiles, TNODES, 0, st>>>(N, plan->tile_start, plan->deg, plan->pos, plan->nei, plan->ehat,
+                                                    plan->tsign, plan->in_cnt, plan->in_src, plan->in_j, blk_off, totals,
+                                                    reinterpret_cast<TileMetaG*>(plan->tile_meta), plan->ehat_node);
+    } else {
+        plan->n_tiles = 0;
+    }
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
+
+extern "C" int64_t molkgnn_tile_meta_bytes(void) { return (int64_t)sizeof(TileMetaG); }
 
 extern "C" int molkgnn_bucket_export(const molkgnn_plan_t* plan, int32_t d, const float* p, int32_t p_dim,
                                      const float* edge_attr, int32_t Fe, int64_t* selected_index, int64_t* nei_index,

@@ -101,46 +101,6 @@ struct PackedLayout {
 };
 // w block: [0]=ws [1]=wc [2]=we [3]=W=ws+wc+we [4..7] reserved
 
-// ---- tile kernels: the kernel rows of one layer as two "roles" of 256 tensor-core rows (two 128-row UMMA M blocks) ----
-// Rows come in groups of 4 consecutive lanes so that the permutation search of one (node, kernel) pair is a 4-lane
-// shuffle exchange:
-//   role 0: degree-4 kernels, group k = support rows s = 0..3; after them the degree-4 centre rows, one per lane
-//   role 1: degree-3 groups (s0, s1, s2, centre), degree-2 groups (s0, s1, centre, -), degree-1 groups (s0, centre, -, -)
-// slot: 0..3 = support row s, 4 = centre row; d = 0 marks an unused row.
-struct TileRows {
-    int L1, L2, L3, L4;
-    static constexpr int ROWS = 256;
-    __host__ __device__ TileRows(const int* L) : L1(L[0]), L2(L[1]), L3(L[2]), L4(L[3]) {}
-    __host__ __device__ bool fits() const { return 5 * L4 <= ROWS && 4 * (L1 + L2 + L3) <= ROWS; }
-    __host__ __device__ int rows_used(int role) const { return role == 0 ? 5 * L4 : 4 * (L1 + L2 + L3); }
-    __host__ __device__ void describe(int role, int r, int& d, int& k, int& slot) const {
-        d = 0; k = 0; slot = 0;
-        if (role == 0) {
-            if (r < 4 * L4) { d = 4; k = r >> 2; slot = r & 3; }
-            else if (r < 5 * L4) { d = 4; k = r - 4 * L4; slot = 4; }
-            return;
-        }
-        const int g = r >> 2, t = r & 3;
-        int dd = 0, kk = 0;
-        if (g < L3) { dd = 3; kk = g; }
-        else if (g < L3 + L2) { dd = 2; kk = g - L3; }
-        else if (g < L3 + L2 + L1) { dd = 1; kk = g - L3 - L2; }
-        if (dd == 0 || t > dd) return;
-        d = dd; k = kk; slot = t < dd ? t : 4;
-    }
-    // row of (degree d, kernel k, slot) inside its role
-    __host__ __device__ int row_of(int d, int k, int slot) const {
-        if (d == 4) return slot < 4 ? 4 * k + slot : 4 * L4 + k;
-        const int g = d == 3 ? k : d == 2 ? L3 + k : L3 + L2 + k;
-        return 4 * g + (slot < 4 ? slot : d);
-    }
-};
-// Images of one layer: [role 0 hi][role 0 lo][role 1 hi][role 1 lo], each 256 rows x Fk fp16 in the interleaved UMMA
-// layout of tc.cuh; v = hi + lo with BOTH halves unscaled (lo is usually an fp16 subnormal, which tcgen05 honours), so a
-// single fp32 accumulator receives hi*hi + lo*hi + hi*lo.
-__host__ __device__ inline int tile_fk(int Fp) { return (Fp + 15) / 16 * 16; }
-__host__ __device__ inline int64_t tile_img_bytes_one(int Fk) { return (int64_t)(TileRows::ROWS / 8) * (Fk / 8) * 128; }
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

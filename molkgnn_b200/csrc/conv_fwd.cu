@@ -401,7 +401,7 @@ int launch_conv_fwd_tc(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer,
                        const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                        int32_t* counter, cudaStream_t st);
 int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
-                         const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
+                         const void* ximg, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                          int32_t* counter, cudaStream_t st);
 
@@ -428,7 +428,7 @@ extern "C" int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer) {
 extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                                 const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                                 const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free,
-                                const uint8_t* argmax_in, int32_t* counter, void* stream_) {
+                                const uint8_t* argmax_in, int32_t* counter, const void* ximg, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_fwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "conv_fwd: x must be 16-byte aligned");
@@ -443,7 +443,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)
     }
     if (g_fwd_path == 2) {
-        const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, xnorm, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
+        const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                             argmax_free, argmax_in, counter, st);
         if (rc != 0) return rc < 0 ? rc : 0;
     }

@@ -3,25 +3,25 @@
 // assembly of BaseKernelSetConv.forward (kernels.py:519-548, 674-747) for plans that carry molecule tiles.
 //
 // Formulation.  A tile is a run of <= 128 consecutive nodes holding whole molecules, so every neighbour of a tile node
-// is itself a tile node.  Per tile ONE dense GEMM on the tensor cores gives every cosine the layer needs,
-//        T[(k,s), v] = shat[k,s,:] . xhat[v,:]            (M = kernel rows, N = tile nodes, K = F)
-// with the kernel rows on the TMEM lanes and the nodes on the TMEM columns: the d x d similarity tile of a
-// (node, kernel) pair is then rows (k,0..d-1) = 4 adjacent lanes, columns nei(n,0..d-1) -- a thread reads "its" row at
-// its node's neighbour columns straight from TMEM (tcgen05.ld, one column per load) and there is no gather of
-// neighbour feature rows at all: x is read once per role, contiguously.  fp32 accuracy: both operands are split into
-// unscaled fp16 pairs v = hi + lo and three UMMAs per K step (hi*hi, lo*hi, hi*lo) accumulate into one fp32 accumulator.
+// is itself a tile node.  Per (kernel block, tile) ONE dense GEMM on the tensor cores gives every cosine needed,
+//        T[row, v] = khat[row,:] . xhat[v,:]              (M = 128 kernel rows, N = tile nodes, K = F)
+// with no gather of neighbour feature rows: the normalised fp16 images of x are built once per layer in tile order
+// (k_x_images) and fetched with one bulk async copy per tile visit, like the per-tile metadata (k_tile_meta, bucket.cu).
+// fp32 accuracy: both operands are unscaled fp16 pairs v = hi + lo, three UMMAs per K step (hi*hi, lo*hi, hi*lo) into one
+// fp32 accumulator.
 //
-// The kernel rows do not fit shared memory together with a node tile, so they are split into two roles (TileRows,
-// common.cuh: role 0 = degree 4, role 1 = degrees 3, 2, 1); every persistent CTA runs role 0 over a dynamic queue of
-// tiles with that role's images resident in shared memory, then role 1.  Per tile: x rows -> normalised fp16 images in
-// shared memory, 2 x (F/16) x 3 UMMAs into one of two TMEM accumulator sets (the next tile's MMAs overlap the second
-// half of the current tile's epilogue), and the epilogue: per (node, kernel) the 4 lanes of a kernel exchange rows by
-// shuffle, each evaluates its share of the permutations in the reference's arithmetic (sequential mean, first-max
-// arg-max kernels.py:373), then bond cosine at the arg-max (kernels.py:382-390), chirality (kernels.py:279-350) and the
-// softmax mix (kernels.py:402-425).
+// Block-major persistent kernel (tile.cuh): a CTA keeps one kernel block's images resident in shared memory, pulls tiles
+// from a queue and per tile: (1) waits for the tile's MMAs, (2) starts the bulk copies of the next tile (the x image
+// buffer is free as soon as the MMAs are done), (3) dumps the 128 x N accumulator TMEM -> shared memory ([column][row],
+// conflict free both ways), (4) runs the epilogue with ONE THREAD PER (node, kernel) PAIR: the d x d similarity tile is
+// 16 / 9 / 4 / 1 shared-memory reads, then exactly the reference arithmetic in registers -- sequential mean per
+// permutation, first-max arg-max (kernels.py:373), bond cosine at the arg-max (kernels.py:382-390), chirality
+// (kernels.py:279-350), softmax mix (kernels.py:402-425).  The next tile's MMAs are issued between the two halves of the
+// epilogue and run on the second TMEM accumulator.
 #include <algorithm>
 #include "common.cuh"
 #include "tc.cuh"
+#include "tile.cuh"
 
 namespace mk {
 
@@ -29,48 +29,146 @@ bool tile_layer_ok(const molkgnn_layer_t* layer);
 
 constexpr int TF_THREADS = 512;
 constexpr int TF_WARPS = TF_THREADS / 32;
-constexpr int TNODES = MOLKGNN_TILE_NODES;      // 128
-constexpr int TF_ESLOTS = 4 * TNODES;           // neighbour (bond) slots of a tile
 
-// per-tile metadata in shared memory (two copies: the next tile is prepared while the current one is still in its epilogue)
-struct __align__(128) TileMeta {
-    float ehat[TF_ESLOTS][EP];        // normalised bond rows of the role's nodes, slot = eslot[n] + j
-    uint32_t nl[TNODES];              // 4 local neighbour ids, 8 bits each
-    int posl[TNODES];                 // bucket row R of the node
-    unsigned short eslot[TNODES];
-    unsigned char list[4][TNODES];    // local ids of the degree-d nodes, ascending
-    signed char tsg[TNODES];          // degree-4 only: sign of the neighbour triple product
-    unsigned char dup[TNODES];        // degree-4 only: two identical neighbour rows (chirality gate)
-    int cnt[4];
-    int t0, nn;
-    int wcnt[4][5];                   // scratch: per-warp counts (4 degrees + slots)
+// ---- normalised fp16 images of the activations in tile order --------------------------------------------------------
+struct XImgArgs {
+    const float* x; const float* xnorm; int ldx;
+    int Fp, Fk;
+    const int* tile_start;
+    unsigned char* ximg;
+    int x_one;
+};
+
+__global__ void __launch_bounds__(512) k_x_images(const XImgArgs a) {
+    const int tile = blockIdx.x, tid = threadIdx.x;
+    const int t0 = a.tile_start[tile], nn = a.tile_start[tile + 1] - t0;
+    const int r = tid & (TNODES - 1), cg = tid >> 7;
+    const bool ok = r < nn;
+    float rinv = 0.f;
+    const float* xr = a.x;
+    if (ok) {
+        rinv = 1.0f / fmaxf(a.xnorm[t0 + r], MOLKGNN_COS_EPS);
+        xr = a.x + (size_t)(t0 + r) * a.ldx;
+    }
+    unsigned char* Xhi = a.ximg + (size_t)tile * 2 * a.x_one;
+    unsigned char* Xlo = Xhi + a.x_one;
+    const int nch = a.Fk >> 3;
+    constexpr int UNR = 4;
+    for (int c0 = cg; c0 < nch; c0 += 4 * UNR) {
+        float4 v[UNR][2];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int c = c0 + 4 * u;
+            v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok && c < nch) {
+                if (8 * c + 4 <= a.Fp) v[u][0] = ld4(xr + 8 * c);
+                if (8 * c + 8 <= a.Fp) v[u][1] = ld4(xr + 8 * c + 4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int c = c0 + 4 * u;
+            if (c < nch) {
+                __align__(16) __half2 hi[4];
+                __align__(16) __half2 lo[4];
+                tc::split_u2(v[u][0].x * rinv, v[u][0].y * rinv, hi[0], lo[0]);
+                tc::split_u2(v[u][0].z * rinv, v[u][0].w * rinv, hi[1], lo[1]);
+                tc::split_u2(v[u][1].x * rinv, v[u][1].y * rinv, hi[2], lo[2]);
+                tc::split_u2(v[u][1].z * rinv, v[u][1].w * rinv, hi[3], lo[3]);
+                const uint32_t off = tc::il_off(r, 8 * c, a.Fk);
+                *reinterpret_cast<uint4*>(Xhi + off) = *reinterpret_cast<const uint4*>(hi);
+                *reinterpret_cast<uint4*>(Xlo + off) = *reinterpret_cast<const uint4*>(lo);
+            }
+        }
+    }
+}
+
+// ---- forward kernel ------------------------------------------------------------------------------------------------------
+struct __align__(128) TileBuf {          // one in-flight tile: metadata record + its bond rows
+    TileMetaG m;
+    float ehat[TILE_ESLOTS][EP];
 };
 
 struct FwdTileArgs {
-    const float* x; const float* xnorm; int ldx;
+    const float* x; int ldx;
     int F, Fp, Fk;
-    const int* deg; const int* pos; const int* nei; const float* ehat; const int8_t* tsign;
-    const int* tile_start; int n_tiles;
-    int n[4], boff[4], eoff[4], L[4], koff[4];
+    const TileMetaG* meta; const float* ehat_node;
+    const unsigned char* ximg;
+    int n_tiles;
+    int L[4], koff[4];
     const float* packed[4];
     const unsigned char* img;
-    int img_one;                      // bytes of one image (hi or lo) of one role
+    TileBlocks tb;
+    int img_one, x_one;
     int is_last;
     float* sc; int sc_mode; int ld_sc; long long scoff[4];
     uint8_t* argmax; uint8_t* argmax_free; const uint8_t* argmax_in;
-    int* counter;                     // [2] tile queues
-    int sm_img, sm_x, sm_meta;        // byte offsets into dynamic shared memory
-    int x_one;                        // bytes of one node-tile image
+    int* counter;                     // [TILE_MAXB] tile queues
+    int sm_img, sm_x, sm_dump, sm_buf, sm_es, sm_dup;   // byte offsets into dynamic shared memory
 };
 
-// per-lane description of "its" kernel row, fixed for a whole role
-struct LaneRow {
-    int d, k, slot;                   // d = 0: unused lane
-    float es[EP];                     // normalised bond support row (support lanes)
+// segment constants kept in shared memory for the epilogue
+struct SegConst {
     float ws, wc, we, W, rW;
-    uint32_t pc[3];                   // packed permutation codes of the permutations this lane evaluates
-    const int8_t* supsign;            // degree 4: chirality sign of every (kernel, permutation)
+    int d, k0, nk, rowbase, L;
+    int es_off;                       // float4 offset of the segment's bond-support table [slot][half][kl]
+    float rnk;                        // 1 / nk
+    const int8_t* supsign;
 };
+
+__device__ __forceinline__ void tf_copy16(unsigned char* dst, const unsigned char* src, int64_t bytes) {
+    for (int64_t i = (int64_t)threadIdx.x * 16; i < bytes; i += (int64_t)TF_THREADS * 16)
+        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+}
+
+// thread 0: metadata record, bond rows and node images of `tile` -> buffer, all completing on `bar`
+__device__ __forceinline__ void tf_issue_copy(const FwdTileArgs& a, unsigned char* smem, TileBuf* buf, int tile, uint64_t* bar) {
+    const TileMetaG* g = a.meta + tile;
+    const int e0 = g->e0, ne = g->ne;          // two scalar loads ahead of the copies (L2 hits: the plan is small)
+    const uint32_t eb = (uint32_t)ne * EP * 4u;
+    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + eb + 2u * (uint32_t)a.x_one);
+    bulk_g2s(&buf->m, g, (uint32_t)sizeof(TileMetaG), bar);
+    if (eb) bulk_g2s(&buf->ehat[0][0], a.ehat_node + (size_t)e0 * EP, eb, bar);
+    bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
+}
+
+// thread 0: (Fk/16) K steps x 3 UMMAs into accumulator `set`
+__device__ __forceinline__ void tf_issue_mma(const FwdTileArgs& a, unsigned char* smem, int nn, uint32_t tmem, int set,
+                                             uint64_t* bar) {
+    const uint32_t sbo = (uint32_t)(a.Fk >> 3) * 128u;
+    const uint32_t ihi = tc::smem_u32(smem + a.sm_img), ilo = ihi + (uint32_t)a.img_one;
+    const uint32_t xhi = tc::smem_u32(smem + a.sm_x), xlo = xhi + (uint32_t)a.x_one;
+    const int N = max(16, (nn + 15) & ~15);
+    const uint32_t idesc = tc::idesc_f16(128, N, 0, 0);
+    const uint32_t d = tmem + (uint32_t)(set * TNODES);
+    const int nks = a.Fk >> 4;
+    for (int ks = 0; ks < nks; ++ks) {
+        const uint32_t o = (uint32_t)ks * 256u;
+        const uint64_t dAh = tc::smem_desc(ihi + o, 128u, sbo), dAl = tc::smem_desc(ilo + o, 128u, sbo);
+        const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
+        tc::umma_f16(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
+        tc::umma_f16(d, dAl, dBh, idesc, 1u);
+        tc::umma_f16(d, dAh, dBl, idesc, 1u);
+    }
+    tc::umma_commit(bar);
+}
+
+// accumulator set -> dump[column][row]: warp (quadrant q, column block cb) moves 32 rows x 32 columns
+__device__ __forceinline__ void tf_dump(float* dump, uint32_t tmem, int set, int nn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp & 3, cb = warp >> 2;
+    if (cb * 32 >= nn) return;
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * TNODES + cb * 32);
+    tc::tmem_ld16(taddr, v);
+    tc::tmem_ld16(taddr + 16, v + 16);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+    float* dst = dump + (size_t)(cb * 32) * 128 + q * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]);
+}
 
 template <int D> __device__ __forceinline__ uint32_t perm_code_rt(int p) {
     uint32_t c = 0;
@@ -78,424 +176,241 @@ template <int D> __device__ __forceinline__ uint32_t perm_code_rt(int p) {
     for (int q = 0; q < Perm<D>::P; ++q) if (q == p) c = perm_code<D>(q);
     return c;
 }
-template <int D> __device__ __forceinline__ uint32_t perm_inv_code_rt(int p) {
-    uint32_t c = 0;
-#pragma unroll
-    for (int q = 0; q < Perm<D>::P; ++q) if (q == p) c = perm_inv_code<D>(q);
-    return c;
-}
 
-__device__ __forceinline__ void tf_copy16(unsigned char* dst, const unsigned char* src, int64_t bytes) {
-    for (int64_t i = (int64_t)threadIdx.x * 16; i < bytes; i += (int64_t)TF_THREADS * 16)
-        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
-}
-
-__device__ __forceinline__ size_t tf_sc_index(const FwdTileArgs& a, int d, int R, int L, int k, int node) {
-    return a.sc_mode == 0 ? (size_t)a.scoff[d - 1] + (size_t)R * L + k : (size_t)node * a.ld_sc + a.koff[d - 1] + k;
-}
-
-// ---- tile preparation: metadata + normalised fp16 images of the tile's x rows ---------------------------------------
-__device__ __forceinline__ void tf_prepare(const FwdTileArgs& a, unsigned char* smem, TileMeta* mt, int tile, int role) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int t0 = a.tile_start[tile], t1 = a.tile_start[tile + 1];
-    const int nn = t1 - t0;
-    // (1) node-tile images: thread (row r, column group cg); 8 consecutive rows x 16 B are contiguous in the layout
-    {
-        const int r = tid & (TNODES - 1), cg = tid >> 7;
-        const bool ok = r < nn;
-        float rinv = 0.f;
-        const float* xr = a.x;
-        if (ok) {
-            rinv = 1.0f / fmaxf(a.xnorm[t0 + r], MOLKGNN_COS_EPS);
-            xr = a.x + (size_t)(t0 + r) * a.ldx;
-        }
-        unsigned char* Xhi = smem + a.sm_x;
-        unsigned char* Xlo = Xhi + a.x_one;
-        const int nch = a.Fk >> 3;
-        constexpr int UNR = 4;
-        for (int c0 = cg; c0 < nch; c0 += 4 * UNR) {
-            float4 v[UNR][2];
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int c = c0 + 4 * u;
-                v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ok && c < nch) {
-                    if (8 * c + 4 <= a.Fp) v[u][0] = ld4(xr + 8 * c);
-                    if (8 * c + 8 <= a.Fp) v[u][1] = ld4(xr + 8 * c + 4);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < UNR; ++u) {
-                const int c = c0 + 4 * u;
-                if (c < nch) {
-                    __align__(16) __half2 hi[4];
-                    __align__(16) __half2 lo[4];
-                    tc::split_u2(v[u][0].x * rinv, v[u][0].y * rinv, hi[0], lo[0]);
-                    tc::split_u2(v[u][0].z * rinv, v[u][0].w * rinv, hi[1], lo[1]);
-                    tc::split_u2(v[u][1].x * rinv, v[u][1].y * rinv, hi[2], lo[2]);
-                    tc::split_u2(v[u][1].z * rinv, v[u][1].w * rinv, hi[3], lo[3]);
-                    const uint32_t off = tc::il_off(r, 8 * c, a.Fk);
-                    *reinterpret_cast<uint4*>(Xhi + off) = *reinterpret_cast<const uint4*>(hi);
-                    *reinterpret_cast<uint4*>(Xlo + off) = *reinterpret_cast<const uint4*>(lo);
-                }
-            }
-        }
-    }
-    // (2) per-node metadata (threads 0..127 = local node id)
-    int d = 0, R = 0, base = 0, rank[4] = {0, 0, 0, 0}, srank = 0;
-    bool mine = false;
-    if (tid < TNODES) {
-        if (tid < nn) {
-            d = a.deg[t0 + tid];
-            R = a.pos[t0 + tid];
-            base = a.eoff[d - 1] + R * d;
-        }
-        mine = d > 0 && (role == 0 ? d == 4 : d <= 3) && a.L[d - 1] > 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const unsigned m = __ballot_sync(0xffffffffu, mine && d == c + 1);
-            rank[c] = __popc(m & ((1u << lane) - 1u));
-            if (lane == 0) mt->wcnt[warp][c] = __popc(m);
-        }
-        // exclusive prefix of the bond slots inside the warp
-        int s = mine ? d : 0;
-        int incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        srank = incl - s;
-        if (lane == 31) mt->wcnt[warp][4] = incl;
-    }
-    __syncthreads();
-    if (tid < TNODES) {
-        int soff = srank;
-        int loff[4] = {rank[0], rank[1], rank[2], rank[3]};
-        for (int w = 0; w < warp; ++w) {
-            soff += mt->wcnt[w][4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) loff[c] += mt->wcnt[w][c];
-        }
-        if (tid == 0) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) mt->cnt[c] = mt->wcnt[0][c] + mt->wcnt[1][c] + mt->wcnt[2][c] + mt->wcnt[3][c];
-            mt->t0 = t0; mt->nn = nn;
-        }
-        if (mine) {
-            mt->list[d - 1][loff[d - 1]] = (unsigned char)tid;
-            mt->posl[tid] = R;
-            mt->eslot[tid] = (unsigned short)soff;
-            uint32_t w = 0;
-            for (int j = 0; j < d; ++j) {
-                const int u = a.nei[(size_t)base + j] - t0;
-                w |= (uint32_t)(u & 0xff) << (8 * j);
-                const float4* src = reinterpret_cast<const float4*>(a.ehat + ((size_t)base + j) * EP);
-                float4* dst = reinterpret_cast<float4*>(&mt->ehat[soff + j][0]);
-                dst[0] = __ldg(src);
-                dst[1] = __ldg(src + 1);
-            }
-            mt->nl[tid] = w;
-            if (d == 4) mt->tsg[tid] = a.is_last ? a.tsign[R] : 0;
-        }
-    }
-    // (3) chirality gate of the degree-4 nodes: any two of the four neighbour feature rows bit-equal (torch.equal,
-    //     kernels.py:310-317); one warp per node, raw rows from global memory
-    if (role == 0 && a.is_last) {
-        __syncthreads();
-        const int n4 = mt->cnt[3];
-        for (int i = warp; i < n4; i += TF_WARPS) {
-            const int nl_ = mt->list[3][i];
-            const uint32_t w = mt->nl[nl_];
-            unsigned neq = 0;
-            for (int f = lane; f < a.F; f += 32) {
-                float v[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = a.x[(size_t)(t0 + ((w >> (8 * j)) & 0xff)) * a.ldx + f];
-                int b = 0;
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-#pragma unroll
-                    for (int q = p + 1; q < 4; ++q, ++b) if (!(v[p] == v[q])) neq |= 1u << b;
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) neq |= __shfl_xor_sync(0xffffffffu, neq, o);
-            if (lane == 0) mt->dup[nl_] = (neq != 0x3fu) ? 1 : 0;
-        }
-    }
-}
-
-// one thread: 2 M blocks x (Fk/16) K steps x 3 UMMAs into accumulator set `set`
-__device__ __forceinline__ void tf_issue(const FwdTileArgs& a, unsigned char* smem, int role, int nn, uint32_t tmem,
-                                         int set, uint64_t* bar) {
-    const TileRows tr(a.L);
-    const int used = tr.rows_used(role);
-    const int nmb = used > 128 ? 2 : 1;
-    const uint32_t sbo = (uint32_t)(a.Fk >> 3) * 128u;
-    const uint32_t ihi = tc::smem_u32(smem + a.sm_img), ilo = ihi + (uint32_t)a.img_one;
-    const uint32_t xhi = tc::smem_u32(smem + a.sm_x), xlo = xhi + (uint32_t)a.x_one;
-    const int N = max(16, (nn + 15) & ~15);
-    const uint32_t idesc = tc::idesc_f16(128, N, 0, 0);
-    const int nks = a.Fk >> 4;
-    for (int mb = 0; mb < nmb; ++mb) {
-        const uint32_t d = tmem + (uint32_t)(set * 256 + mb * 128);
-        const uint32_t ro = (uint32_t)mb * 16u * sbo;      // 128 rows = 16 row groups
-        for (int ks = 0; ks < nks; ++ks) {
-            const uint32_t o = (uint32_t)ks * 256u;
-            const uint64_t dAh = tc::smem_desc(ihi + ro + o, 128u, sbo), dAl = tc::smem_desc(ilo + ro + o, 128u, sbo);
-            const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
-            tc::umma_f16(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
-            tc::umma_f16(d, dAl, dBh, idesc, 1u);
-            tc::umma_f16(d, dAh, dBl, idesc, 1u);
-        }
-    }
-    tc::umma_commit(bar);
-}
-
-// ---- epilogue ------------------------------------------------------------------------------------------------------
-// Degree-4 centre rows: C[n,k] parked in the score slot of (n,k); the leader lane of the kernel reads it back.
-__device__ __forceinline__ void tf_centre_pass(const FwdTileArgs& a, const TileMeta* mt, const LaneRow& lr, uint32_t tb,
-                                               int slice, int nslices) {
-    const bool cen = lr.d == 4 && lr.slot == 4;
-    if (!__any_sync(0xffffffffu, cen)) return;
-    const int n4 = mt->cnt[3], L = a.L[3];
-    for (int i = slice; i < n4; i += nslices) {
-        const int nl_ = mt->list[3][i];
-        uint32_t v = tc::tmem_ld1(tb + (uint32_t)nl_);
-        tc::tmem_ld_wait();
-        asm volatile("" : "+r"(v) :: "memory");
-        if (cen) a.sc[tf_sc_index(a, 4, mt->posl[nl_], L, lr.k, mt->t0 + nl_)] = __uint_as_float(v);
-    }
-}
-
-// all (node, kernel) pairs of the degree-D nodes list[i0], list[i0 + istep], ... (< i1) against this warp's kernel rows
+// one (node, kernel) pair: the reference arithmetic on its d x d similarity tile
 template <int D>
-__device__ __forceinline__ void tf_visit(const FwdTileArgs& a, const TileMeta* mt, const LaneRow& lr, uint32_t tb,
-                                         int i0, int i1, int istep) {
-    constexpr int P = Perm<D>::P, PPL = P / D;
-    const int lane = threadIdx.x & 31;
-    const bool act = lr.d == D;
-    if (!__any_sync(0xffffffffu, act)) return;
-    const bool sup = act && lr.slot < D;
-    const bool leader = sup && lr.slot == 0;
-    const int gbase = lane & ~3;
-    const int L = a.L[D - 1];
-    const float NEG = -3.0e38f;
-    for (int i = i0; i < i1; i += istep) {
-        const int nl_ = mt->list[D - 1][i];
-        const uint32_t nw = mt->nl[nl_];
-        const int R = mt->posl[nl_];
-        const int e0 = mt->eslot[nl_];
-        const size_t cidx = (size_t)a.scoff[D - 1] + (size_t)R * L + lr.k;
-        const size_t oidx = tf_sc_index(a, D, R, L, lr.k, mt->t0 + nl_);
-        float cdot = 0.f;
-        if (D == 4 && leader) cdot = __ldcg(a.sc + oidx);
-        int forced = -1;
-        if (a.argmax_in && act) forced = a.argmax_in[cidx] & 0x7f;
-        // this lane's kernel row at the D neighbour columns (and at the node's own column for the centre row)
-        uint32_t tv[D], tcen = 0;
+__device__ __forceinline__ void tf_pair(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
+                                        const unsigned char* dupf, const SegConst& sg, int nl_, int kl) {
+    constexpr int P = Perm<D>::P;
+    const TileMetaG& m = tb->m;
+    const uint32_t nw = m.nl[nl_];
+    const int R = m.posl[nl_];
+    const int e0 = m.eslot[nl_];
+    const int k = sg.k0 + kl;
+    const float* col0 = dump + sg.rowbase + kl;
+    float T[D][D];
 #pragma unroll
-        for (int j = 0; j < D; ++j) tv[j] = tc::tmem_ld1(tb + ((nw >> (8 * j)) & 0xffu));
-        if (D < 4) tcen = tc::tmem_ld1(tb + (uint32_t)nl_);
-        tc::tmem_ld_wait();
+    for (int j = 0; j < D; ++j) {
+        const float* c = col0 + ((nw >> (8 * j)) & 0xffu) * 128;
 #pragma unroll
-        for (int j = 0; j < D; ++j) asm volatile("" : "+r"(tv[j]) :: "memory");   // consumers stay behind the wait
-        asm volatile("" : "+r"(tcen) :: "memory");
-        float t[D];
+        for (int s = 0; s < D; ++s) T[j][s] = c[s * sg.nk];
+    }
+    const float cdot = col0[nl_ * 128 + D * sg.nk];
+    const size_t cidx = (size_t)a.scoff[D - 1] + (size_t)R * sg.L + k;
+    const int forced = a.argmax_in ? (a.argmax_in[cidx] & 0x7f) : -1;
+    // mean over j for every permutation: sequential sum, then true division (kernels.py:194)
+    float best = 0.f, used = 0.f;
+    int bi = 0;
 #pragma unroll
-        for (int j = 0; j < D; ++j) t[j] = __uint_as_float(tv[j]);
-        // mean over j for this lane's permutations (pi(0) = slot): sequential sum, true division (kernels.py:194)
-        float val[PPL];
+    for (int p = 0; p < P; ++p) {
+        float s = T[0][Perm<D>::at(p, 0)];
 #pragma unroll
-        for (int q = 0; q < PPL; ++q) {
-            float s = t[0];
+        for (int j = 1; j < D; ++j) s += T[j][Perm<D>::at(p, j)];
+        s = div_deg<D>(s);
+        if (p == 0 || s > best) { best = s; bi = p; }   // first maximum wins (torch.max, kernels.py:373)
+        if (p == forced) used = s;
+    }
+    if (a.argmax_free) a.argmax_free[cidx] = (uint8_t)bi;
+    if (forced >= 0 && forced < P) { bi = forced; best = used; }
+    // bond-attribute cosine at the chosen permutation (kernels.py:382-390)
+    const uint32_t code = perm_code_rt<D>(bi);
+    float esum = 0.f;
 #pragma unroll
-            for (int j = 1; j < D; ++j) s += __shfl_sync(0xffffffffu, t[j], gbase + (int)((lr.pc[q] >> (2 * j)) & 3u));
-            val[q] = div_deg<D>(s);
-        }
-        float best = NEG;
-        int bi = 127;
-        if (sup) {
-            best = val[0]; bi = PPL * lr.slot;
-#pragma unroll
-            for (int q = 1; q < PPL; ++q) if (val[q] > best) { best = val[q]; bi = PPL * lr.slot + q; }   // first max wins
-        }
-        if (D > 1) {
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const int obi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ob > best || (ob == best && obi < bi)) { best = ob; bi = obi; }
+    for (int j = 0; j < D; ++j) {
+        const int s = (code >> (2 * j)) & 3;
+        const float4 e0v = *reinterpret_cast<const float4*>(&tb->ehat[e0 + j][0]);
+        const float4 e1v = *reinterpret_cast<const float4*>(&tb->ehat[e0 + j][4]);
+        const float4 s0 = estab[sg.es_off + (s * 2 + 0) * sg.nk + kl];
+        const float4 s1 = estab[sg.es_off + (s * 2 + 1) * sg.nk + kl];
+        float dd = 0.f;
+        dd = fmaf(e0v.x, s0.x, dd); dd = fmaf(e0v.y, s0.y, dd); dd = fmaf(e0v.z, s0.z, dd); dd = fmaf(e0v.w, s0.w, dd);
+        dd = fmaf(e1v.x, s1.x, dd); dd = fmaf(e1v.y, s1.y, dd); dd = fmaf(e1v.z, s1.z, dd); dd = fmaf(e1v.w, s1.w, dd);
+        esum = j == 0 ? dd : esum + dd;
+    }
+    const float E = div_deg<D>(esum);
+    float sc = div_by((best * sg.ws + cdot * sg.wc) + E * sg.we, sg.W, sg.rW);
+    uint8_t am = (uint8_t)bi;
+    if (D == 4 && a.is_last) {
+        // chirality (kernels.py:279-350): +1 if any two neighbours are identical, else sign agreement
+        int chi = 1;
+        if (!dupf[nl_]) chi = (m.tsg[nl_] == sg.supsign[k * 12 + bi]) ? 1 : -1;
+        if (chi < 0) { sc = -sc; am |= 0x80; }
+    }
+    a.argmax[cidx] = am;
+    const size_t oidx = a.sc_mode == 0 ? cidx : (size_t)(m.t0 + nl_) * a.ld_sc + a.koff[D - 1] + k;
+    a.sc[oidx] = sc;
+}
+
+// the block's pairs (segment-major, then node, then kernel), strided over the CTA; part 0 / 1 = first / second half
+__device__ __forceinline__ void tf_epilogue(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
+                                            const unsigned char* dupf, const SegConst* segs, int nseg, int part) {
+    for (int si = 0; si < nseg; ++si) {
+        const SegConst sg = segs[si];
+        const int cnt = tb->m.cnt[sg.d - 1];
+        const int np = cnt * sg.nk;
+        const int half = min(np, ((np / 2 + TF_THREADS - 1) / TF_THREADS) * TF_THREADS);   // whole CTA strides first
+        const int p0 = part == 0 ? 0 : half, p1 = part == 0 ? half : np;
+        for (int p = p0 + (int)threadIdx.x; p < p1; p += TF_THREADS) {
+            const int ni = (int)(((float)p + 0.5f) * sg.rnk);
+            const int kl = p - ni * sg.nk;
+            const int nl_ = tb->m.list[sg.d - 1][ni];
+            switch (sg.d) {
+                case 1: tf_pair<1>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
+                case 2: tf_pair<2>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
+                case 3: tf_pair<3>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
+                default: tf_pair<4>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
             }
-        }
-        if (a.argmax_in) {          // teacher forcing (parity harness / replay): warp-uniform branch
-            float mv = 0.f;
-#pragma unroll
-            for (int q = 0; q < PPL; ++q) if (forced == PPL * lr.slot + q) mv = val[q];
-            const int fl = (forced >= 0 && forced < P) ? forced / PPL : 0;
-            const float used = __shfl_sync(0xffffffffu, mv, gbase + fl);
-            if (leader && a.argmax_free) a.argmax_free[cidx] = (uint8_t)bi;
-            if (forced >= 0 && forced < P) { bi = forced; best = used; }
-        } else if (leader && a.argmax_free) {
-            a.argmax_free[cidx] = (uint8_t)bi;
-        }
-        if (bi >= P) bi = 0;        // unused lanes: keep the table lookups in range
-        // bond-attribute cosine at the chosen permutation (kernels.py:382-390): support lane s pairs with neighbour
-        // j = pi^-1(s); the leader sums the D terms in neighbour order
-        const uint32_t code = perm_code_rt<D>(bi);
-        const uint32_t inv = perm_inv_code_rt<D>(bi);
-        float dj = 0.f;
-        if (sup) {
-            const int j = (int)((inv >> (2 * lr.slot)) & 3u);
-            const float4 q0 = *reinterpret_cast<const float4*>(&mt->ehat[e0 + j][0]);
-            const float4 q1 = *reinterpret_cast<const float4*>(&mt->ehat[e0 + j][4]);
-            dj = fmaf(q0.x, lr.es[0], dj); dj = fmaf(q0.y, lr.es[1], dj); dj = fmaf(q0.z, lr.es[2], dj); dj = fmaf(q0.w, lr.es[3], dj);
-            dj = fmaf(q1.x, lr.es[4], dj); dj = fmaf(q1.y, lr.es[5], dj); dj = fmaf(q1.z, lr.es[6], dj); dj = fmaf(q1.w, lr.es[7], dj);
-        }
-        float esum = 0.f;
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const float v = __shfl_sync(0xffffffffu, dj, gbase + (int)((code >> (2 * j)) & 3u));
-            esum = j == 0 ? v : esum + v;
-        }
-        if (D < 4) cdot = __shfl_sync(0xffffffffu, __uint_as_float(tcen), gbase + D);
-        if (leader) {
-            const float E = div_deg<D>(esum);
-            float sc = div_by((best * lr.ws + cdot * lr.wc) + E * lr.we, lr.W, lr.rW);
-            uint8_t am = (uint8_t)bi;
-            if (D == 4 && a.is_last) {
-                // chirality (kernels.py:279-350): +1 if any two neighbours are identical, else sign agreement
-                int chi = 1;
-                if (!mt->dup[nl_]) chi = (mt->tsg[nl_] == lr.supsign[lr.k * 12 + bi]) ? 1 : -1;
-                if (chi < 0) { sc = -sc; am |= 0x80; }
-            }
-            a.argmax[cidx] = am;
-            a.sc[oidx] = sc;
         }
     }
 }
 
-__device__ __forceinline__ void tf_epilogue(const FwdTileArgs& a, const TileMeta* mt, const LaneRow& lr, uint32_t tb,
-                                            int role, int slice, int nslices, int part) {
-    // the node list of every degree is cut in two parts: the next tile is prepared between them
-    if (role == 0) {
-        const int c = mt->cnt[3], h = (c + 1) >> 1;
-        tf_visit<4>(a, mt, lr, tb, (part ? h : 0) + slice, part ? c : h, nslices);
-    } else {
-        int c = mt->cnt[2], h = (c + 1) >> 1;
-        tf_visit<3>(a, mt, lr, tb, (part ? h : 0) + slice, part ? c : h, nslices);
-        c = mt->cnt[1]; h = (c + 1) >> 1;
-        tf_visit<2>(a, mt, lr, tb, (part ? h : 0) + slice, part ? c : h, nslices);
-        c = mt->cnt[0]; h = (c + 1) >> 1;
-        tf_visit<1>(a, mt, lr, tb, (part ? h : 0) + slice, part ? c : h, nslices);
-    }
-}
-
-__device__ __forceinline__ void tf_lane_row(const FwdTileArgs& a, int role, int row, LaneRow& lr) {
-    const TileRows tr(a.L);
-    tr.describe(role, row, lr.d, lr.k, lr.slot);
+// chirality gate of the degree-4 nodes of a tile: any two of the four neighbour feature rows bit-equal (torch.equal,
+// kernels.py:310-317); one warp per node, raw rows from global memory
+__device__ __forceinline__ void tf_dup_flags(const FwdTileArgs& a, const TileBuf* tb, unsigned char* dupf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n4 = tb->m.cnt[3], t0 = tb->m.t0;
+    for (int i = warp; i < n4; i += TF_WARPS) {
+        const int nl_ = tb->m.list[3][i];
+        const uint32_t w = tb->m.nl[nl_];
+        unsigned neq = 0;
+        for (int f = lane; f < a.F; f += 32) {
+            float v[4];
 #pragma unroll
-    for (int c = 0; c < EP; ++c) lr.es[c] = 0.f;
-    lr.ws = lr.wc = lr.we = 0.f; lr.W = 1.f; lr.rW = 1.f;
-    lr.pc[0] = lr.pc[1] = lr.pc[2] = 0;
-    lr.supsign = nullptr;
-    if (lr.d == 0) return;
-    const int L = a.L[lr.d - 1];
-    const PackedLayout pl(lr.d, L, a.Fp);
-    const float* pk = a.packed[lr.d - 1];
-    lr.ws = pk[pl.w + 0]; lr.wc = pk[pl.w + 1]; lr.we = pk[pl.w + 2]; lr.W = pk[pl.w + 3];
-    lr.rW = 1.0f / lr.W;
-    lr.supsign = reinterpret_cast<const int8_t*>(pk + pl.sign);
-    if (lr.slot < 4) {
-        const float* es = pk + pl.es + (size_t)(lr.slot * L + lr.k) * EP;
+            for (int j = 0; j < 4; ++j) v[j] = a.x[(size_t)(t0 + ((w >> (8 * j)) & 0xff)) * a.ldx + f];
+            int b = 0;
 #pragma unroll
-        for (int c = 0; c < EP; ++c) lr.es[c] = es[c];
-        const int ppl = num_perms(lr.d) / lr.d;
-        for (int q = 0; q < ppl; ++q) {
-            const int p = ppl * lr.slot + q;
-            lr.pc[q] = lr.d == 4 ? perm_code_rt<4>(p) : lr.d == 3 ? perm_code_rt<3>(p) : lr.d == 2 ? perm_code_rt<2>(p) : 0u;
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = p + 1; q < 4; ++q, ++b) if (!(v[p] == v[q])) neq |= 1u << b;
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) neq |= __shfl_xor_sync(0xffffffffu, neq, o);
+        if (lane == 0) dupf[nl_] = (neq != 0x3fu) ? 1 : 0;
     }
 }
 
 __global__ void __launch_bounds__(TF_THREADS, 1) k_conv_fwd_tile(const __grid_constant__ FwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bar_mma[2], bar_cp[2];
     __shared__ uint32_t tslot;
     __shared__ int s_tile[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = warp & 3, mb = (warp >> 2) & 1, slice = warp >> 3;
-    constexpr int NSL = TF_WARPS / 8;
-    if (tid == 0) { tc::mbar_init(&bars[0], 1); tc::mbar_init(&bars[1], 1); tc::fence_mbar_init(); }
-    if (warp == 0) tc::tmem_alloc(&tslot, 512);
+    __shared__ SegConst s_seg[TILE_MAXSEG];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (tid == 0) {
+        tc::mbar_init(&bar_mma[0], 1); tc::mbar_init(&bar_mma[1], 1);
+        tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tslot, 256);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tslot;
-    TileMeta* meta = reinterpret_cast<TileMeta*>(smem + a.sm_meta);
-    uint32_t phase[2] = {0u, 0u};
+    TileBuf* bufs = reinterpret_cast<TileBuf*>(smem + a.sm_buf);
+    float* dump = reinterpret_cast<float*>(smem + a.sm_dump);
+    float4* estab = reinterpret_cast<float4*>(smem + a.sm_es);
+    unsigned char* dupf = smem + a.sm_dup;
+    uint32_t ph_mma[2] = {0u, 0u}, ph_cp[2] = {0u, 0u};
 
-    for (int role = 0; role < 2; ++role) {
-        const TileRows tr(a.L);
-        if (tr.rows_used(role) == 0) continue;
-        __syncthreads();                       // previous role completely finished (its MMAs were all waited for)
-        tf_copy16(smem + a.sm_img, a.img + (size_t)role * 2 * a.img_one, 2 * (int64_t)a.img_one);
-        LaneRow lr;
-        tf_lane_row(a, role, mb * 128 + q * 32 + lane, lr);
-        if (tid == 0) s_tile[0] = atomicAdd(a.counter + role, 1);
-        __syncthreads();
-        int t = s_tile[0];
-        int set = 0;
-        if (t < a.n_tiles) {
-            tf_prepare(a, smem, &meta[0], t, role);
-            tc::fence_async_smem();
-            __syncthreads();
-            if (tid == 0) {
-                tc::fence_after_sync();
-                tf_issue(a, smem, role, meta[0].nn, tmem, 0, &bars[0]);
+    for (int blk = 0; blk < a.tb.nb; ++blk) {
+        __syncthreads();                       // previous block completely finished
+        // ---- block set-up: images, segment constants, bond-support table [slot][half][kernel] ----
+        tf_copy16(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2 * (int64_t)a.img_one);
+        const int nseg = a.tb.nseg[blk];
+        bool has4 = false;
+        {
+            int es_off = 0;
+            for (int si = 0; si < nseg; ++si) {
+                const TileSeg sg = a.tb.seg[blk][si];
+                const int L = a.L[sg.d - 1];
+                const PackedLayout pl(sg.d, L, a.Fp);
+                const float* pk = a.packed[sg.d - 1];
+                if (sg.d == 4) has4 = true;
+                if (tid == 0) {
+                    SegConst c;
+                    c.ws = pk[pl.w + 0]; c.wc = pk[pl.w + 1]; c.we = pk[pl.w + 2]; c.W = pk[pl.w + 3];
+                    c.rW = 1.0f / c.W;
+                    c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
+                    c.es_off = es_off; c.rnk = 1.0f / (float)sg.nk;
+                    c.supsign = reinterpret_cast<const int8_t*>(pk + pl.sign);
+                    s_seg[si] = c;
+                }
+                for (int i = tid; i < sg.d * 2 * sg.nk; i += TF_THREADS) {
+                    const int kl = i % sg.nk, sh = i / sg.nk;          // sh = slot * 2 + half
+                    estab[es_off + i] =
+                        *reinterpret_cast<const float4*>(pk + pl.es + (size_t)((sh >> 1) * L + sg.k0 + kl) * EP + (sh & 1) * 4);
+                }
+                es_off += sg.d * 2 * sg.nk;
             }
         }
-        while (t < a.n_tiles) {
-            const TileMeta* mt = &meta[set];
-            if (tid == 0) s_tile[1] = atomicAdd(a.counter + role, 1);
-            tc::mbar_wait(&bars[set], phase[set]);
-            phase[set] ^= 1u;
+        if (tid == 0) s_tile[0] = atomicAdd(a.counter + blk, 1);
+        tc::fence_async_smem();                // images were written through the generic proxy, the MMAs read them
+        __syncthreads();
+        int t = s_tile[0];
+        int cur = 0;
+        if (t < a.n_tiles && tid == 0) {
+            tf_issue_copy(a, smem, &bufs[0], t, &bar_cp[0]);
+            tc::mbar_wait(&bar_cp[0], ph_cp[0]);
             tc::fence_after_sync();
-            const uint32_t tb = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 256 + mb * 128);
-            if (role == 0) tf_centre_pass(a, mt, lr, tb, slice, NSL);
-            __syncthreads();                   // centre scores parked; next tile id published
+            tf_issue_mma(a, smem, bufs[0].m.nn, tmem, 0, &bar_mma[0]);
+        }
+        while (t < a.n_tiles) {
+            const TileBuf* tb = &bufs[cur];
+            if (tid == 0) s_tile[1] = atomicAdd(a.counter + blk, 1);
+            tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);      // metadata of this tile visible to every thread
+            ph_cp[cur] ^= 1u;
+            tc::mbar_wait(&bar_mma[cur], ph_mma[cur]);    // accumulator ready, x image buffer free
+            ph_mma[cur] ^= 1u;
+            tc::fence_after_sync();
+            __syncthreads();                              // next tile id published
             const int tn = s_tile[1];
-            tf_epilogue(a, mt, lr, tb, role, slice, NSL, 0);
+            if (tn < a.n_tiles && tid == 0) tf_issue_copy(a, smem, &bufs[cur ^ 1], tn, &bar_cp[cur ^ 1]);
+            tf_dump(dump, tmem, cur, tb->m.nn);
+            if (has4 && a.is_last) tf_dup_flags(a, tb, dupf);
             tc::fence_before_sync();
-            __syncthreads();                   // every warp is past the previous tile: its metadata / TMEM set are free
-            if (tn < a.n_tiles) {
-                tf_prepare(a, smem, &meta[set ^ 1], tn, role);
-                tc::fence_async_smem();
-                __syncthreads();
-                if (tid == 0) {
-                    tc::fence_after_sync();
-                    tf_issue(a, smem, role, meta[set ^ 1].nn, tmem, set ^ 1, &bars[set ^ 1]);
-                }
+            __syncthreads();                              // dump complete
+            tf_epilogue(a, tb, dump, estab, dupf, s_seg, nseg, 0);
+            if (tn < a.n_tiles && tid == 0) {
+                tc::mbar_wait(&bar_cp[cur ^ 1], ph_cp[cur ^ 1]);
+                tc::fence_after_sync();
+                tf_issue_mma(a, smem, bufs[cur ^ 1].m.nn, tmem, cur ^ 1, &bar_mma[cur ^ 1]);
             }
-            tf_epilogue(a, mt, lr, tb, role, slice, NSL, 1);
-            tc::fence_before_sync();
+            tf_epilogue(a, tb, dump, estab, dupf, s_seg, nseg, 1);
+            __syncthreads();                              // dump and this tile's buffer are free again
             t = tn;
-            set ^= 1;
+            cur ^= 1;
         }
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
+static bool tile_plan_ok(const molkgnn_plan_t* plan) {
+    return plan->n_tiles > 0 && plan->tile_start && plan->tile_meta && plan->ehat_node && plan->tile_max_nodes <= TNODES;
+}
+
+int launch_x_images(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                    const float* xnorm, void* ximg, cudaStream_t st) {
+    XImgArgs a;
+    a.x = x; a.xnorm = xnorm; a.ldx = ldx;
+    a.Fp = layer->Fp; a.Fk = tile_fk(layer->Fp);
+    a.tile_start = plan->tile_start;
+    a.ximg = reinterpret_cast<unsigned char*>(ximg);
+    a.x_one = tile_img_one(a.Fk);
+    count_launches(1);
+    k_x_images<<<plan->n_tiles, 512, 0, st>>>(a);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // returns 1 if launched, 0 if the plan / layer is not eligible (caller falls back to the bucket-order kernels), <0 on error
 int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
-                         const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
+                         const void* ximg, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                          int32_t* counter, cudaStream_t st) {
-    if (plan->n_tiles <= 0 || !plan->tile_start || !layer->tile_img || !tile_layer_ok(layer)) return 0;
-    if (plan->tile_max_nodes > TNODES) return 0;
+    if (!ximg || !tile_plan_ok(plan) || !layer->tile_img || !tile_layer_ok(layer)) return 0;
     static int s_budget = 0, s_sms = 0;
     if (!s_budget) {
         s_budget = device_max_smem_optin();
@@ -503,19 +418,21 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         MK_REQUIRE(s_budget > 0 && s_sms > 0, "conv_fwd_tile: no CUDA device");
     }
     FwdTileArgs a;
-    a.x = x; a.xnorm = xnorm; a.ldx = ldx;
+    a.x = x; a.ldx = ldx;
     a.F = layer->F; a.Fp = layer->Fp; a.Fk = tile_fk(layer->Fp);
-    a.deg = plan->deg; a.pos = plan->pos; a.nei = plan->nei; a.ehat = plan->ehat; a.tsign = plan->tsign;
-    a.tile_start = plan->tile_start; a.n_tiles = plan->n_tiles;
+    a.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
+    a.ehat_node = plan->ehat_node;
+    a.ximg = reinterpret_cast<const unsigned char*>(ximg);
+    a.n_tiles = plan->n_tiles;
     for (int d = 0; d < 4; ++d) {
-        a.n[d] = plan->n[d]; a.boff[d] = plan->boff[d]; a.eoff[d] = plan->eoff[d];
         a.L[d] = layer->L[d]; a.koff[d] = layer->koff[d];
         a.packed[d] = layer->packed[d];
         a.scoff[d] = scoff[d];
     }
+    if (!a.tb.build(layer->L)) return 0;
     a.img = reinterpret_cast<const unsigned char*>(layer->tile_img);
-    a.img_one = (int)tile_img_bytes_one(a.Fk);
-    a.x_one = (int)tc::il_tile_bytes(TNODES, a.Fk);
+    a.img_one = tile_img_one(a.Fk);
+    a.x_one = tile_img_one(a.Fk);
     a.is_last = is_last_layer;
     a.sc = sc; a.sc_mode = sc_mode; a.ld_sc = ld_sc;
     a.argmax = argmax; a.argmax_free = argmax_free; a.argmax_in = argmax_in;
@@ -523,9 +440,12 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     int64_t off = 0;
     a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
     a.sm_x = (int)off; off += 2 * (int64_t)a.x_one;
-    a.sm_meta = (int)off; off += 2 * (int64_t)((sizeof(TileMeta) + 127) / 128 * 128);
+    a.sm_dump = (int)off; off += (int64_t)TNODES * 128 * 4;
+    a.sm_buf = (int)off; off += 2 * (int64_t)sizeof(TileBuf);
+    a.sm_es = (int)off; off += 128 * 32;        // <= 128 support rows x 8 floats per block
+    a.sm_dup = (int)off; off += 128;
     if (off > s_budget - 1024) return 0;
-    MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int), st));
+    MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, TILE_MAXB * sizeof(int), st));
     static int64_t s_attr = 0;
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
@@ -539,3 +459,19 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 }
 
 }  // namespace mk
+
+using namespace mk;
+
+extern "C" int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    if (!tile_plan_ok(plan) || !tile_layer_ok(layer)) return 0;
+    return 2 * (int64_t)tile_img_one(tile_fk(layer->Fp));
+}
+
+extern "C" int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                                       const float* xnorm, void* ximg, void* stream_) {
+    MK_REQUIRE(tile_plan_ok(plan) && tile_layer_ok(layer), "tile_ximg_build: plan or layer is not eligible for the tile kernels");
+    MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "tile_ximg_build: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
+    MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0,
+               "tile_ximg_build: x must be 16-byte and ximg 128-byte aligned");
+    return launch_x_images(plan, layer, x, ldx, xnorm, ximg, (cudaStream_t)stream_);
+}

@@ -8,6 +8,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "tc.cuh"
+#include "tile.cuh"
 
 namespace mk {
 
@@ -179,29 +180,33 @@ __global__ void __launch_bounds__(256) k_param_pack_tc(PackTcArgs a) {
     *reinterpret_cast<uint4*>(img + lo_off + off) = *reinterpret_cast<const uint4*>(lo);
 }
 
-// fp16 (hi, lo) images of the whole kernel set for the tile kernels: TileRows order, unscaled split (common.cuh).
+// fp16 (hi, lo) images of the kernel blocks for the tile kernels (tile.cuh): block b at img + b * 2 * tile_img_one(Fk),
+// hi image then lo image, rows in TileBlocks order, unscaled split.  One thread per (block, row, 8-column chunk).
 struct PackTileArgs {
     int Fp, Fk;
     int L[4];
+    TileBlocks tb;
     const float* packed[4];
     unsigned char* img;
 };
 
-__global__ void __launch_bounds__(256) k_param_pack_tile(PackTileArgs a) {
+__global__ void __launch_bounds__(256) k_param_pack_tile(const __grid_constant__ PackTileArgs a) {
     const int nch = a.Fk / 8;
     const int it = blockIdx.x * 256 + threadIdx.x;
-    if (it >= 2 * TileRows::ROWS * nch) return;
+    if (it >= a.tb.nb * 128 * nch) return;
     const int c = it % nch;
-    const int row = (it / nch) % TileRows::ROWS;
-    const int role = it / (nch * TileRows::ROWS);
-    const TileRows tr(a.L);
-    int d, k, slot;
-    tr.describe(role, row, d, k, slot);
+    const int row = (it / nch) % 128;
+    const int blk = it / (nch * 128);
     const float* src = nullptr;
-    if (d > 0) {
-        const int L = a.L[d - 1];
-        const PackedLayout pl(d, L, a.Fp);
-        src = a.packed[d - 1] + pl.sup + ((size_t)(slot < 4 ? slot : d) * L + k) * a.Fp;
+    for (int sgi = 0; sgi < a.tb.nseg[blk]; ++sgi) {
+        const TileSeg sg = a.tb.seg[blk][sgi];
+        const int r = row - sg.rowbase;
+        if (r >= 0 && r < sg.nk * (sg.d + 1)) {
+            const int slot = r / sg.nk, k = sg.k0 + r % sg.nk;
+            const int L = a.L[sg.d - 1];
+            const PackedLayout pl(sg.d, L, a.Fp);
+            src = a.packed[sg.d - 1] + pl.sup + ((size_t)slot * L + k) * a.Fp;   // packed rows: s*L+k supports, d*L+k centre
+        }
     }
     __align__(16) __half2 hi[4];
     __align__(16) __half2 lo[4];
@@ -212,8 +217,8 @@ __global__ void __launch_bounds__(256) k_param_pack_tile(PackTileArgs a) {
         const float v1 = (src && col + 1 < a.Fp) ? src[col + 1] : 0.f;
         tc::split_u2(v0, v1, hi[t], lo[t]);
     }
-    const int64_t one = tile_img_bytes_one(a.Fk);
-    unsigned char* base = a.img + (int64_t)role * 2 * one;
+    const int one = tile_img_one(a.Fk);
+    unsigned char* base = a.img + (size_t)blk * 2 * one;
     const uint32_t off = tc::il_off(row, 8 * c, a.Fk);
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(base + one + off) = *reinterpret_cast<const uint4*>(lo);
@@ -385,16 +390,17 @@ extern "C" int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp) {
 }
 
 namespace mk {
-// tile kernels are eligible when both roles fit their 256 rows and the images + a node tile fit shared memory
+// tile kernels are eligible when the kernel rows fit TILE_MAXB blocks and one block + a node tile fit shared memory
 bool tile_layer_ok(const molkgnn_layer_t* layer) {
-    const TileRows tr(layer->L);
-    return tr.fits() && tile_fk(layer->Fp) <= 112 && layer->K > 0;
+    TileBlocks tb;
+    return layer->K > 0 && tile_fk(layer->Fp) <= 112 && tb.build(layer->L);
 }
 }  // namespace mk
 
 extern "C" int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer) {
-    if (!tile_layer_ok(layer)) return 0;
-    return 4 * tile_img_bytes_one(tile_fk(layer->Fp));
+    TileBlocks tb;
+    if (!tile_layer_ok(layer) || !tb.build(layer->L)) return 0;
+    return (int64_t)tb.nb * 2 * tile_img_one(tile_fk(layer->Fp));
 }
 
 extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
@@ -444,8 +450,9 @@ extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
         PackTileArgs ta;
         ta.Fp = layer->Fp; ta.Fk = tile_fk(layer->Fp);
         for (int d = 0; d < 4; ++d) { ta.L[d] = layer->L[d]; ta.packed[d] = layer->packed[d]; }
+        ta.tb.build(layer->L);
         ta.img = reinterpret_cast<unsigned char*>(layer->tile_img);
-        const int items = 2 * TileRows::ROWS * (ta.Fk / 8);
+        const int items = ta.tb.nb * 128 * (ta.Fk / 8);
         k_param_pack_tile<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(ta);
         count_launches(1);
         MK_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,91 @@
+// Shared infrastructure of the molecule-tile kernels (conv_fwd_tile.cu, conv_bwd_tile.cu, bucket.cu, params.cu).
+//
+// A TILE is a run of <= 128 consecutive nodes that holds whole molecules (no edge crosses its boundary): one tcgen05 N
+// block / 128 TMEM columns.  The kernel rows of a layer are packed into BLOCKS of <= 128 rows (one UMMA M block = the 128
+// TMEM lanes); a block holds segments, a segment holds kernels k0..k0+nk-1 of one degree d in slot-major order:
+//        row = rowbase + slot * nk + (k - k0),   slot 0..d-1 = support row s, slot d = centre row.
+// The tile kernels run block-major: a persistent CTA keeps ONE block's fp16 images resident in shared memory and pulls
+// tiles from a queue.
+#pragma once
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace mk {
+
+constexpr int TNODES = MOLKGNN_TILE_NODES;      // 128
+constexpr int TILE_ESLOTS = 4 * TNODES;         // bond slots of a tile (node order)
+constexpr int TILE_MAXB = 8;                    // blocks per layer
+constexpr int TILE_MAXSEG = 4;                  // segments per block (one per degree)
+
+struct TileSeg { int d, k0, nk, rowbase; };
+
+struct TileBlocks {
+    int nb;
+    int nseg[TILE_MAXB];
+    int rows[TILE_MAXB];
+    TileSeg seg[TILE_MAXB][TILE_MAXSEG];
+    // A degree's kernels are split evenly over the fewest blocks that hold them; a later (smaller) degree shares the
+    // last block only if it fits there completely.  Base model 10/20/30/50: [d4 k0-24] [d4 k25-49] [d3] [d2, d1].
+    __host__ __device__ bool build(const int* L) {
+        nb = 0;
+        for (int b = 0; b < TILE_MAXB; ++b) { nseg[b] = 0; rows[b] = 0; }
+        for (int d = 4; d >= 1; --d) {
+            const int Ld = L[d - 1];
+            if (Ld <= 0) continue;
+            const int per = 128 / (d + 1);                       // kernels per empty block
+            if (nb > 0 && rows[nb - 1] + Ld * (d + 1) <= 128 && nseg[nb - 1] < TILE_MAXSEG) {
+                TileSeg& sg = seg[nb - 1][nseg[nb - 1]++];
+                sg.d = d; sg.k0 = 0; sg.nk = Ld; sg.rowbase = rows[nb - 1];
+                rows[nb - 1] += Ld * (d + 1);
+                continue;
+            }
+            const int need = (Ld + per - 1) / per;
+            if (nb + need > TILE_MAXB) return false;
+            int k0 = 0;
+            for (int i = 0; i < need; ++i) {
+                const int nk = (Ld - k0 + (need - i) - 1) / (need - i);
+                TileSeg& sg = seg[nb][0];
+                sg.d = d; sg.k0 = k0; sg.nk = nk; sg.rowbase = 0;
+                nseg[nb] = 1; rows[nb] = nk * (d + 1);
+                ++nb;
+                k0 += nk;
+            }
+        }
+        return nb > 0;
+    }
+};
+
+__host__ __device__ inline int tile_fk(int Fp) { return (Fp + 15) / 16 * 16; }
+// one fp16 image (hi or lo) of a 128-row block / of a node tile: [16 row groups][Fk/8 chunks][8 rows][8 elements]
+__host__ __device__ inline int tile_img_one(int Fk) { return 16 * (Fk / 8) * 128; }
+// Images in global memory: kernel blocks [block][hi | lo]; node tiles [tile][hi | lo].  v = hi + lo, BOTH halves unscaled
+// (lo is usually an fp16 subnormal, which tcgen05 honours): one fp32 accumulator receives hi*hi + lo*hi + hi*lo.
+
+// Per-tile metadata, built once per batch by k_tile_meta (bucket.cu) and fetched with one bulk copy per tile visit.
+struct __align__(16) TileMetaG {
+    int t0, nn;                       // first node, number of nodes
+    int e0, ne;                       // first bond slot in ehat_node, number of slots
+    int cnt[4];                       // nodes per degree
+    uint32_t nl[TNODES];              // 4 local neighbour ids, 8 bits each (neighbour order = edge order)
+    int posl[TNODES];                 // bucket row R of the node
+    unsigned short eslot[TNODES];     // local slot of the node's first bond
+    unsigned char degl[TNODES];
+    unsigned char list[4][TNODES];    // local ids of the degree-d nodes, ascending
+    signed char tsg[TNODES];          // degree 4: sign of the neighbour triple product (kernels.py:336)
+    uint32_t inl[TNODES];             // 4 local in-neighbour ids (sources of the in-edges, edge order), 8 bits each
+    unsigned char inj[TNODES][4];     // position of this node in that source's neighbour list
+    unsigned char incnt[TNODES];
+};
+static_assert(sizeof(TileMetaG) % 16 == 0, "TileMetaG must be a multiple of 16 bytes");
+
+// ---- bulk async copy global -> shared with mbarrier completion ---------------------------------------------------------
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// size % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(tc::smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+
+}  // namespace mk

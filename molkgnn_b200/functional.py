@@ -141,13 +141,28 @@ def pad_norm(x, Fp):
     return out, norm
 
 
-def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=False, argmax_in=None, want_free=False):
+def x_images(plan: BucketPlan, pack: LayerPack, x, xnorm):
+    """Normalised fp16 (hi, lo) images of the activations in tile order (tensor-core operand of the tile kernels), or
+    None when the plan carries no molecule tiles / the layer is not eligible."""
+    L = _lib.lib()
+    one = int(L.molkgnn_tile_ximg_bytes(C.byref(plan.c), C.byref(pack.c))) if pack.tile_img is not None else 0
+    if one <= 0:
+        return None
+    ximg = torch.empty(plan.n_tiles * one, dtype=torch.uint8, device=x.device)
+    with _timed("x_images"):
+        check(L.molkgnn_tile_ximg_build(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(ximg),
+                                        stream_ptr()))
+    return ximg
+
+
+def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=False, argmax_in=None, want_free=False,
+                 ximg=None):
     """-> (sc, argmax_used_u8, argmax_free_u8 or None).  sc compact [sum n_d L_d] or dense zero-filled [N,Kp]."""
     scoff, tot = plan.scoff(pack.L)
     dev = x.device
     argmax = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev)
     free = torch.empty(max(tot, 1), dtype=torch.uint8, device=dev) if want_free else None
-    counter = torch.empty(4, dtype=torch.int32, device=dev)
+    counter = torch.empty(8, dtype=torch.int32, device=dev)
     if dense:
         sc = torch.zeros(plan.N, pack.Kp, dtype=torch.float32, device=dev)
         ld = pack.Kp
@@ -161,7 +176,8 @@ def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=Fal
     with _timed("conv_fwd"):
         check(_lib.lib().molkgnn_conv_fwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm),
                                           1 if is_last else 0, ptr(sc), 1 if dense else 0, ld, _i64x4(scoff),
-                                          ptr(argmax), ptr(free), ptr(argmax_in), ptr(counter), stream_ptr()))
+                                          ptr(argmax), ptr(free), ptr(argmax_in), ptr(counter), ptr(ximg),
+                                          stream_ptr()))
     return sc, argmax, free
 
 
@@ -236,7 +252,7 @@ class KernelSetConvFn(torch.autograd.Function):
         pack = LayerPack(params, x.shape[1], Fe, x.device).pack()
         xp, xnorm = pad_norm(x.detach(), pack.Fp)
         sc, argmax, free = conv_forward(plan, pack, xp, xnorm, is_last, dense=True, argmax_in=argmax_in,
-                                        want_free=aux is not None)
+                                        want_free=aux is not None, ximg=x_images(plan, pack, xp, xnorm))
         if aux is not None:
             aux["argmax"], aux["argmax_free"] = argmax, free
         ctx.plan, ctx.pack = plan, pack
@@ -269,9 +285,10 @@ class MolGCNFn(torch.autograd.Function):
             pack = LayerPack(params, F, Fe, dev).pack()
             if i == 0:
                 h, hnorm = pad_norm(x.detach(), pack.Fp)
+            ximg = x_images(plan, pack, h, hnorm)
             sc, argmax, free = conv_forward(plan, pack, h, hnorm, i == nl - 1, dense=False,
                                             argmax_in=None if argmax_in is None else argmax_in[i],
-                                            want_free=aux is not None)
+                                            want_free=aux is not None, ximg=ximg)
             if aux is not None:
                 aux.setdefault("argmax", []).append(argmax)
                 aux.setdefault("argmax_free", []).append(free)
