@@ -177,11 +177,24 @@ int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgn
  * molkgnn_conv_bwd_partial_floats() floats.  grad_x (nullable) [N,ldgx] receives dL/dx including the cosine
  * normalisation Jacobian; columns F..ldgx-1 zeroed.  grads (nullable members skipped) receives dL/dparam.
  * phases: bit 0 = k_bwd_w (coef + per-CTA partial sums), bit 1 = parameter finalize, bit 2 = k_bwd_x (grad_x);
- * 7 runs everything; the split exists so that a profiler can time the three kernels separately. */
+ * 7 runs everything; the split exists so that a profiler can time the three kernels separately.
+ *
+ * Molecule-tile tensor-core path (default when eligible): runs when ximg (molkgnn_tile_ximg_build of this layer's x) and
+ * grad_absmax (device scalar = max |grad|, e.g. from molkgnn_absmax or the gx_absmax of the layer above) are given, the
+ * plan carries tiles, the layer is eligible and ldgx == Fp.  scratch: N * roundup(Fp,16) floats (partial input gradients
+ * between kernel blocks).  gx_absmax (nullable, device scalar) receives max |grad_x|.  Then phase bit 0 runs the whole
+ * backward kernel (coefficients, parameter partial sums AND grad_x), bit 2 is a no-op and coef is unused. */
 int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
                      const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
-                     const molkgnn_layer_grads_t* grads, int32_t phases, void* stream);
+                     const molkgnn_layer_grads_t* grads, int32_t phases, const void* ximg, const float* grad_absmax,
+                     float* scratch, float* gx_absmax, void* stream);
+/* out[0] = max |x[i]|, i < n (x 16-byte aligned): the scale of the fp16 coefficient operand of the tile backward */
+int molkgnn_absmax(const float* x, int64_t n, float* out, void* stream);
+/* 1 = molecule-tile tensor-core backward when eligible (default), 0 = bucket-order SIMT kernels; returns the old value */
+int molkgnn_set_bwd_path(int path);
+/* how often each path ran so far: forward tile / forward other / backward tile / backward other */
+void molkgnn_path_counts(int64_t out[4]);
 
 /* ---- diagnostics ---- */
 /* Known-answer test of the tcgen05 (UMMA) plumbing: D[128,N] (fp32) = A * B^T on the tensor cores, one CTA.

@@ -53,7 +53,10 @@ EXPORTS = {
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),
     "molkgnn_tc_selftest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
-                                   vp, i32, C.POINTER(LayerGrads), i32, vp]),
+                                   vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp, vp, vp]),
+    "molkgnn_absmax": (C.c_int, [vp, i64, vp, vp]),
+    "molkgnn_set_bwd_path": (C.c_int, [C.c_int]),
+    "molkgnn_path_counts": (None, [i64 * 4]),
 }
 
 _lib = None

@@ -246,10 +246,12 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
                                                       const int* __restrict__ totals, TileMetaG* meta, float* ehat_node) {
     __shared__ int wsum[4][6];
     __shared__ int s_e0;
+    __shared__ int s_gcnt[16], s_goff[17], s_gfill[16];
     const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = tile_start[tile], t1 = tile_start[tile + 1];
     const int nn = t1 - t0;
     TileMetaG* m = meta + tile;
+    if (tid < 16) { s_gcnt[tid] = 0; s_gfill[tid] = 0; }
     // first bond slot of the tile = sum of the degrees of all nodes in front of it: whole 256-node blocks from the
     // class histogram of the bucket pass, the rest by a block reduction
     const int b0 = t0 / BT;
@@ -297,8 +299,22 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
     uint32_t w_nl = 0, w_in = 0;
     unsigned char ij[4] = {0, 0, 0, 0};
     int ic = 0;
+    int crank[4] = {0, 0, 0, 0};
     if (tid < nn) {
         m->list[d - 1][loff] = (unsigned char)tid;
+        for (int j = 0; j < d; ++j) {
+            // rank of the edge (tid, j) among the in-edges of its target whose source has the same degree
+            const int v = nei[(size_t)base + j];
+            const int icv = min(in_cnt[v], 4);
+            int r = 0;
+            for (int t = 0; t < icv; ++t) {
+                const int u = in_src[4 * (size_t)v + t];
+                if (u == t0 + tid && in_j[4 * (size_t)v + t] == j) break;
+                if (deg[u] == d) ++r;
+            }
+            crank[j] = min(r, 3);
+            atomicAdd(&s_gcnt[(d - 1) * 4 + crank[j]], 1);
+        }
         for (int j = 0; j < d; ++j) {
             w_nl |= (uint32_t)((nei[(size_t)base + j] - t0) & 0xff) << (8 * j);
             const float4* src = reinterpret_cast<const float4*>(ehat + ((size_t)base + j) * EP);
@@ -321,6 +337,23 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
 #pragma unroll
     for (int t = 0; t < 4; ++t) m->inj[tid][t] = ij[t];
     m->incnt[tid] = (unsigned char)ic;
+    m->lidx[tid] = (unsigned char)loff;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int g = 0; g < 16; ++g) { s_goff[g] = run; run += s_gcnt[g]; }
+        s_goff[16] = run;
+        for (int dd = 0; dd < 4; ++dd)
+            for (int r = 0; r < 5; ++r) m->eoffs[dd][r] = s_goff[min(dd * 4 + r, 16)];
+    }
+    __syncthreads();
+    if (tid < nn) {
+        for (int j = 0; j < d; ++j) {
+            const int g = (d - 1) * 4 + crank[j];
+            const int slot = s_goff[g] + atomicAdd(&s_gfill[g], 1);
+            m->elist[slot] = (unsigned short)((tid << 2) | j);
+        }
+    }
 }
 
 __global__ void k_export(int d, int n, int boff, int eoff, const int* __restrict__ sel, const int* __restrict__ nei,

@@ -15,7 +15,16 @@
 namespace mk {
 
 int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, const int64_t part_off[4],
-                          const int ncta[4], float* q_scratch, const molkgnn_layer_grads_t* grads, cudaStream_t st);
+                          const int ncta[4], float* q_scratch, const molkgnn_layer_grads_t* grads, int prescaled,
+                          cudaStream_t st);
+int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                         const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
+                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* partials,
+                         float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4], int ncta[4],
+                         int64_t* part_total, bool do_launch, cudaStream_t st);
+int tile_bwd_grid(const molkgnn_plan_t* plan);
+bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+long long g_path_counts[4] = {0, 0, 0, 0};   // forward tile / other, backward tile / other
 
 // =============================================================================================================
 // k_bwd_w
@@ -473,6 +482,15 @@ static int launch_bwd_x(const BwdXArgs& a, int grid, int64_t smem, cudaStream_t 
 using namespace mk;
 
 static int g_budget = 0, g_sms = 0;
+static int g_bwd_path = 1;   // 1 = molecule-tile tensor-core backward when eligible, 0 = bucket-order SIMT kernels
+extern "C" int molkgnn_set_bwd_path(int path) {
+    const int old = g_bwd_path;
+    g_bwd_path = path ? 1 : 0;
+    return old;
+}
+extern "C" void molkgnn_path_counts(int64_t out[4]) {
+    for (int i = 0; i < 4; ++i) out[i] = g_path_counts[i];
+}
 static int init_dev() {
     if (!g_budget) {
         g_budget = device_max_smem_optin();
@@ -486,22 +504,41 @@ extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, c
     if (init_dev()) return -1;
     int ncta[4];
     bwd_w_partition(plan, layer, g_sms, ncta);
-    int64_t tot = 0, rows = 0;
+    int64_t tot = 0, rows = 0, tot_tile = 0;
+    const int tgrid = tile_bwd_ok(plan, layer) ? tile_bwd_grid(plan) : 0;
     for (int d = 0; d < 4; ++d) {
         tot += (int64_t)ncta[d] * (d + 2) * layer->L[d] * (layer->Fp + EP);
+        tot_tile += (int64_t)tgrid * (d + 2) * layer->L[d] * (layer->Fp + EP);
         rows += (int64_t)(d + 2) * layer->L[d];
     }
-    return tot + 2 * rows + 16;
+    return std::max(tot, tot_tile) + 2 * rows + 16;
 }
 
 extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                                 const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode,
                                 const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials,
-                                float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, int32_t phases, void* stream_) {
+                                float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, int32_t phases,
+                                const void* ximg, const float* grad_absmax, float* scratch, float* gx_absmax,
+                                void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (init_dev()) return -1;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_bwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE(!grad_x || (ldgx % 4 == 0 && ldgx >= layer->Fp), "conv_bwd: ldgx=%d must be a multiple of 4 >= Fp", ldgx);
+    // ---------------- molecule-tile tensor-core path ----------------
+    if (ximg && grad_absmax && g_bwd_path != 0 && (!grad_x || ldgx == layer->Fp)) {
+        int64_t t_off[4], t_total = 0;
+        int t_ncta[4];
+        const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, grad_absmax, argmax, scoff,
+                                            partials, scratch, grad_x, ldgx, gx_absmax, t_off, t_ncta, &t_total,
+                                            (phases & 1) != 0, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            if (phases & 1) ++g_path_counts[2];
+            if (grads && (phases & 2)) return launch_param_finalize(layer, partials, t_off, t_ncta, partials + t_total, grads, 1, st);
+            return 0;
+        }
+    }
+    if (phases & 1) ++g_path_counts[3];
     // ---------------- k_bwd_w ----------------
     BwdWArgs w;
     const int64_t smem_w = bwd_w_configure(layer, g_budget - 1024, &w);
@@ -536,7 +573,7 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     // ---------------- parameter gradients ----------------
     if (grads && (phases & 2)) {
         // degrees without nodes: their parameter gradients are exactly zero (ncta == 0 -> finalize sums nothing)
-        int rc = launch_param_finalize(layer, partials, part_off, ncta, partials + po, grads, st);
+        int rc = launch_param_finalize(layer, partials, part_off, ncta, partials + po, grads, 0, st);
         if (rc) return rc;
     }
     // ---------------- k_bwd_x ----------------
@@ -593,6 +630,10 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                 else if (FQ <= 128) rc = launch_bwd_x<32, 4>(b, grid, smem, st);
                 else { MK_REQUIRE(false, "conv_bwd: node_attr_dim %d > 512 not supported", layer->F); }
             }
+            if (rc) return rc;
+        }
+        if (gx_absmax) {
+            const int rc = molkgnn_absmax(grad_x, (int64_t)plan->N * ldgx, gx_absmax, stream_);
             if (rc) return rc;
         }
     }

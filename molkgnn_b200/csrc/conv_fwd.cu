@@ -405,6 +405,8 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                          int32_t* counter, cudaStream_t st);
 
+extern long long g_path_counts[4];
+
 }  // namespace mk
 
 using namespace mk;
@@ -445,8 +447,10 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     if (g_fwd_path == 2) {
         const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                             argmax_free, argmax_in, counter, st);
+        if (rc > 0) ++g_path_counts[0];
         if (rc != 0) return rc < 0 ? rc : 0;
     }
+    ++g_path_counts[1];
     if (g_fwd_path >= 1) {
         const int rc = launch_conv_fwd_tc(plan, layer, x, ldx, xnorm, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                           argmax_free, argmax_in, counter, st);

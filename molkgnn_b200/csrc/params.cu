@@ -238,6 +238,7 @@ struct FinArgs {
     float* ge_support[4];
     float* q;                // [sum rows] per-row Q contributions: q[row_begin[d]+row] (x part), and edge part after
     int q_edge_off;          // offset of edge Q values
+    int prescaled;           // node-attribute partial sums already carry the mixing factor (tile backward)
 };
 
 // one block (128 threads) per packed row; writes final dL/d(raw row) and per-row Q = sum(hat * G)
@@ -271,13 +272,23 @@ __global__ void __launch_bounds__(128) k_param_finalize(FinArgs a) {
         dot = block_sum_128(dot, red);
         const float nrm = pk[pl.norm + row];
         const float coef = (is_center ? wc : ws / (float)d) / W;
+        if (a.prescaled) {   // the tile backward accumulates coef * G: recover G (the chain rule below is written for it)
+            const float rc = 1.0f / coef;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) g[c] *= rc;
+            dot *= rc;
+        }
         float* out = is_center ? (a.gx_center[d - 1] ? a.gx_center[d - 1] + (size_t)k * a.F : nullptr)
                                : (a.gx_support[d - 1] ? a.gx_support[d - 1] + ((size_t)k * d + s) * a.F : nullptr);
         cnt = 0;
         for (int f = threadIdx.x; f < a.Fp; f += 128, ++cnt) {
             float G;
             if (cnt < 4) G = g[cnt];
-            else { G = 0.f; for (int c = 0; c < nc; ++c) G += part[c * stride + f]; }
+            else {
+                G = 0.f;
+                for (int c = 0; c < nc; ++c) G += part[c * stride + f];
+                if (a.prescaled) G *= 1.0f / coef;
+            }
             float v = nrm > MOLKGNN_COS_EPS ? (G - dot * hat[f]) / nrm : G / MOLKGNN_COS_EPS;
             if (out && f < a.F) out[f] = coef * v;
         }
@@ -341,8 +352,10 @@ __global__ void __launch_bounds__(128) k_theta(ThetaArgs a) {
 
 // entry used by conv_bwd.cu
 int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, const int64_t part_off[4],
-                          const int ncta[4], float* q_scratch, const molkgnn_layer_grads_t* grads, cudaStream_t st) {
+                          const int ncta[4], float* q_scratch, const molkgnn_layer_grads_t* grads, int prescaled,
+                          cudaStream_t st) {
     FinArgs fa;
+    fa.prescaled = prescaled;
     ThetaArgs ta;
     fa.F = layer->F; fa.Fp = layer->Fp; fa.Fe = layer->Fe; fa.FW = layer->Fp + EP;
     int rb = 0;

@@ -75,6 +75,12 @@ struct __align__(16) TileMetaG {
     uint32_t inl[TNODES];             // 4 local in-neighbour ids (sources of the in-edges, edge order), 8 bits each
     unsigned char inj[TNODES][4];     // position of this node in that source's neighbour list
     unsigned char incnt[TNODES];
+    unsigned char lidx[TNODES];       // index of the node inside list[deg - 1]
+    // neighbour slots (node << 2 | j) grouped by (degree d of the node, rank r): r = number of earlier in-edges of the
+    // same target whose source also has degree d.  Two slots of one group never share a target, so the backward scatter
+    // into (kernel row, target column) is collision free inside a group; groups of higher rank accumulate.
+    unsigned short elist[TILE_ESLOTS];
+    int eoffs[4][5];                  // elist range of group (d, r): [eoffs[d-1][r], eoffs[d-1][r+1])
 };
 static_assert(sizeof(TileMetaG) % 16 == 0, "TileMetaG must be a multiple of 16 bytes");
 

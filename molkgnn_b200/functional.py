@@ -191,8 +191,23 @@ def propagate_forward(plan: BucketPlan, pack: LayerPack, sc):
     return h, hnorm
 
 
-def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, argmax, need_gx, need_gparams):
-    """-> (gx [N,Fp] or None, list of 4 dicts of parameter grads or None)."""
+def absmax(t):
+    """device scalar max |t| (scale of the tile backward's fp16 coefficient operand)"""
+    out = torch.empty(1, dtype=torch.float32, device=t.device)
+    with _timed("absmax"):
+        check(_lib.lib().molkgnn_absmax(ptr(t), t.numel(), ptr(out), stream_ptr()))
+    return out
+
+
+def path_counts():
+    a = (C.c_int64 * 4)()
+    _lib.lib().molkgnn_path_counts(a)
+    return dict(fwd_tile=int(a[0]), fwd_other=int(a[1]), bwd_tile=int(a[2]), bwd_other=int(a[3]))
+
+
+def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, argmax, need_gx, need_gparams,
+                  ximg=None, grad_absmax=None):
+    """-> (gx [N,Fp] or None, list of 4 dicts of parameter grads or None, device scalar max|gx| or None)."""
     L = _lib.lib()
     dev = x.device
     scoff, tot = plan.scoff(pack.L)
@@ -220,16 +235,22 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
             gc.w_center[d] = g["w"].data_ptr() + 4
             gc.w_edge[d] = g["w"].data_ptr() + 8
             grads.append(g)
-    if grad.stride(1) != 1:
+    if grad.stride(1) != 1 or grad.data_ptr() % 16:
         grad = grad.contiguous()
+    scratch = gmax = None
+    if ximg is not None:
+        if grad_absmax is None:
+            grad_absmax = absmax(grad) if grad.is_contiguous() else absmax(grad.contiguous())
+        scratch = torch.empty(plan.N * ((pack.Fp + 15) // 16 * 16), dtype=torch.float32, device=dev)
+        gmax = torch.empty(1, dtype=torch.float32, device=dev) if need_gx else None
     # one C call runs all three kernels; under the profiler they are issued separately so each can be timed
     for name, ph in ((("conv_bwd", 7),) if _PROF is None else (("bwd_w", 1), ("param_finalize", 2), ("bwd_x", 4))):
         with _timed(name):
             check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
                                      grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials),
                                      ptr(gx), pack.Fp if need_gx else 0, C.byref(gc) if gc is not None else None, ph,
-                                     stream_ptr()))
-    return gx, grads
+                                     ptr(ximg), ptr(grad_absmax), ptr(scratch), ptr(gmax), stream_ptr()))
+    return gx, grads, gmax
 
 
 def _flatten_param_grads(grads, pack, needs):
@@ -251,8 +272,10 @@ class KernelSetConvFn(torch.autograd.Function):
     def forward(ctx, x, plan, params, Fe, is_last, argmax_in, aux, *flat):
         pack = LayerPack(params, x.shape[1], Fe, x.device).pack()
         xp, xnorm = pad_norm(x.detach(), pack.Fp)
+        ximg = x_images(plan, pack, xp, xnorm)
         sc, argmax, free = conv_forward(plan, pack, xp, xnorm, is_last, dense=True, argmax_in=argmax_in,
-                                        want_free=aux is not None, ximg=x_images(plan, pack, xp, xnorm))
+                                        want_free=aux is not None, ximg=ximg)
+        ctx.ximg = ximg
         if aux is not None:
             aux["argmax"], aux["argmax_free"] = argmax, free
         ctx.plan, ctx.pack = plan, pack
@@ -266,7 +289,8 @@ class KernelSetConvFn(torch.autograd.Function):
         xp, xnorm, argmax = ctx.saved_tensors
         pack = ctx.pack
         need_gp = any(ctx.needs_input_grad[7:])
-        gx, grads = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float(), 0, argmax, ctx.need_gx, need_gp)
+        gx, grads, _ = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float(), 0, argmax, ctx.need_gx, need_gp,
+                                     ximg=ctx.ximg)
         flat = _flatten_param_grads(grads, pack, ctx.needs_input_grad[7:])
         return (gx[:, :ctx.F] if gx is not None else None, None, None, None, None, None, None, *flat)
 
@@ -279,7 +303,7 @@ class MolGCNFn(torch.autograd.Function):
         dev = x.device
         nl = len(layer_params)
         F = x.shape[1]
-        packs, saved = [], []
+        packs, saved, ximgs = [], [], []
         h, hnorm = None, None
         for i, params in enumerate(layer_params):
             pack = LayerPack(params, F, Fe, dev).pack()
@@ -294,10 +318,11 @@ class MolGCNFn(torch.autograd.Function):
                 aux.setdefault("argmax_free", []).append(free)
                 aux.setdefault("sc", []).append(sc)
             saved += [h, hnorm, argmax]
+            ximgs.append(ximg)
             h, hnorm = propagate_forward(plan, pack, sc)
             packs.append(pack)
             F = pack.K
-        ctx.plan, ctx.packs = plan, packs
+        ctx.plan, ctx.packs, ctx.ximgs = plan, packs, ximgs
         ctx.save_for_backward(*saved)
         ctx.need_gx = x.requires_grad
         ctx.F0 = x.shape[1]
@@ -310,12 +335,14 @@ class MolGCNFn(torch.autograd.Function):
         nl = len(packs)
         needs = ctx.needs_input_grad[6:]
         g = grad_h.float()
+        gmax = None
         flat_all = [None] * (nl * 28)
         for i in range(nl - 1, -1, -1):
             xp, xnorm, argmax = saved[3 * i:3 * i + 3]
             need_gp = any(needs[28 * i:28 * (i + 1)])
             need_gx = ctx.need_gx if i == 0 else True
-            gx, grads = conv_backward(ctx.plan, packs[i], xp, xnorm, g, 1, argmax, need_gx, need_gp)
+            gx, grads, gmax = conv_backward(ctx.plan, packs[i], xp, xnorm, g, 1, argmax, need_gx, need_gp,
+                                            ximg=ctx.ximgs[i], grad_absmax=gmax)
             flat_all[28 * i:28 * (i + 1)] = _flatten_param_grads(grads, packs[i], None)
             g = gx
         return (g[:, :ctx.F0] if g is not None else None, None, None, None, None, None, *flat_all)

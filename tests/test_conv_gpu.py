@@ -30,8 +30,10 @@ def fwd_path(request):
     bucket-order tcgen05 forward (plans without tiles) and with the fp32 SIMT forward (wide layers)."""
     from molkgnn_b200 import _lib
     old = _lib.lib().molkgnn_set_fwd_path(PATHS[request.param])
+    oldb = _lib.lib().molkgnn_set_bwd_path(1 if request.param == "tile" else 0)   # tile backward with the tile forward
     yield request.param
     _lib.lib().molkgnn_set_fwd_path(2 if old < 0 else old)
+    _lib.lib().molkgnn_set_bwd_path(oldb)
 
 
 def _to_dev(b):
@@ -54,6 +56,25 @@ def _check_param_grads(net, ref_grad, tol=TOL):
             # never differentiated by the reference
             for nme in ["p_support", "length_sc_weight", "angle_sc_weight"]:
                 assert getattr(kc, nme).grad is None
+
+
+def test_tile_kernels_are_the_default_path(fwd_path):
+    """The base model on a tiled plan must run the molecule-tile tcgen05 kernels (no silent fall back)."""
+    if fwd_path != "tile":
+        pytest.skip("path selection is only asserted for the default path")
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth, functional
+    b = _to_dev(synth.make_batch(64, seed=11))
+    torch.manual_seed(0)
+    net = mk.MolGCN(3, 10, 20, 30, 50, 10, 20, 30, 50, x_dim=28, p_dim=3, edge_attr_dim=7).to(DEV)
+    before = functional.path_counts()
+    x = b["x"].clone().requires_grad_(True)
+    h = net(x=x, edge_index=b["edge_index"], edge_attr=b["edge_attr"], p=b["p"], save_score=False)
+    h.sum().backward()
+    torch.cuda.synchronize()
+    after = functional.path_counts()
+    assert after["fwd_tile"] - before["fwd_tile"] == 3 and after["fwd_other"] == before["fwd_other"]
+    assert after["bwd_tile"] - before["bwd_tile"] == 3 and after["bwd_other"] == before["bwd_other"]
 
 
 @pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer"])
