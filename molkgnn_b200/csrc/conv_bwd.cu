@@ -19,9 +19,9 @@ int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, c
                           cudaStream_t st);
 int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
-                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* partials,
-                         float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4], int ncta[4],
-                         int64_t* part_total, bool do_launch, cudaStream_t st);
+                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* coef,
+                         float* partials, float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4],
+                         int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st);
 int tile_bwd_grid(const molkgnn_plan_t* plan);
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 long long g_path_counts[4] = {0, 0, 0, 0};   // forward tile / other, backward tile / other
@@ -529,7 +529,7 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         int64_t t_off[4], t_total = 0;
         int t_ncta[4];
         const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, grad_absmax, argmax, scoff,
-                                            partials, scratch, grad_x, ldgx, gx_absmax, t_off, t_ncta, &t_total,
+                                            coef, partials, scratch, grad_x, ldgx, gx_absmax, t_off, t_ncta, &t_total,
                                             (phases & 1) != 0, st);
         if (rc < 0) return rc;
         if (rc == 1) {

@@ -41,7 +41,7 @@ struct BwdTileArgs {
     const unsigned char* img;
     TileBlocks tb;
     int img_one, x_one;
-    const float* grad; int ldg; int grad_mode;
+    const float* coef;                 // chi * g per (node, kernel) pair, compact bucket order (k_coef)
     const uint8_t* argmax; long long scoff[4];
     const float* grad_absmax;          // device scalar: max |grad|
     float* partials; long long part_off[4]; int FW;
@@ -138,6 +138,37 @@ __device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char
     tc::umma_commit(bar);
 }
 
+// coef[pair] = chi * g for every (node, kernel) pair in compact bucket order (streaming, fully occupied: keeps the gather
+// of the incoming gradient rows out of the tile kernel's critical path)
+struct CoefArgs {
+    const int* sel; const int* nei;
+    int n[4], boff[4], eoff[4], L[4], koff[4];
+    long long scoff[4], tot;
+    const float* grad; int ldg; int grad_mode;
+    const uint8_t* argmax;
+    float* coef;
+};
+
+__global__ void __launch_bounds__(256) k_coef(const CoefArgs a) {
+    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.tot) return;
+    int d = 4;
+    while (d > 1 && i < a.scoff[d - 1]) --d;
+    const int L = a.L[d - 1];
+    const long long li = i - a.scoff[d - 1];
+    const int R = (int)(li / L), k = (int)(li - (long long)R * L);
+    const int col = a.koff[d - 1] + k;
+    float g;
+    if (a.grad_mode == 0) {
+        g = a.grad[(size_t)a.sel[a.boff[d - 1] + R] * a.ldg + col];
+    } else {
+        const int* nb = a.nei + (size_t)a.eoff[d - 1] + (size_t)R * d;
+        g = a.grad[(size_t)nb[0] * a.ldg + col];
+        for (int j = 1; j < d; ++j) g += a.grad[(size_t)nb[j] * a.ldg + col];
+    }
+    a.coef[i] = (a.argmax[i] & 0x80) ? -g : g;
+}
+
 __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_constant__ BwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_mma, bar_cp[2];
@@ -232,17 +263,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     const int kl = p - ni * sg.nk;
                     const int nl_ = m.list[sg.d - 1][ni];
                     const int k = sg.k0 + kl;
-                    const int col = a.koff[sg.d - 1] + k;
-                    float g;
-                    if (a.grad_mode == 0) {
-                        g = a.grad[(size_t)(t0 + nl_) * a.ldg + col];
-                    } else {
-                        const uint32_t nw = m.nl[nl_];
-                        g = a.grad[(size_t)(t0 + (nw & 0xff)) * a.ldg + col];
-                        for (int j = 1; j < sg.d; ++j) g += a.grad[(size_t)(t0 + ((nw >> (8 * j)) & 0xff)) * a.ldg + col];
-                    }
-                    const uint8_t am = a.argmax[(size_t)a.scoff[sg.d - 1] + (size_t)m.posl[nl_] * sg.L + k];
-                    const float av = ((am & 0x80) ? -g : g) * rscale;
+                    const size_t cidx = (size_t)a.scoff[sg.d - 1] + (size_t)m.posl[nl_] * sg.L + k;
+                    const float av = a.coef[cidx] * rscale;
+                    const uint8_t am = a.argmax[cidx];
                     a_s[abase[si] + p] = av;
                     am_s[abase[si] + p] = am & 0x7f;
                     __half hi, lo;
@@ -318,91 +341,105 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 tb_issue_mma(a, smem, nn, rows, first, tmem, &bar_mma);
             }
             first = false;
+            // ---- (E) dxh epilogue: lane = node, 32 columns per warp.  Loads that do not depend on the tensor cores go first ----
+            const bool lastb = blk + 1 == a.tb.nb;
+            const int v = q * 32 + lane;
+            const int f0 = cpart * 32;
+            const bool colok = f0 < a.Fk;
+            const bool rowok = v < nn;
+            const int nf = min(32, a.Fk - f0);            // columns of this part (multiple of 16, or <= 0)
+            float dv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dv[i] = 0.f;
+            float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
+            if (blk > 0 && rowok && colok) {              // partial sums of the previous kernel blocks
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nf) {
+                        const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
+                        dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
+                    }
+                }
+            }
+            float nrm = 1.f;
+            if (lastb && rowok) nrm = a.xnorm[t0 + v];
             tc::mbar_wait(&bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc::fence_after_sync();
             // the tensor cores are done with Wt: clear it for the next tile (ordered by the barrier that ends this tile)
             for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
             const int tnext = tile + gridDim.x;
-            if (tid == 0 && tnext < a.n_tiles)
+            if (!lastb && tid == 0 && tnext < a.n_tiles)
                 tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
-            // ---- (E) dxh epilogue: lane = node, 32 columns per warp ----
-            {
-                const int v = q * 32 + lane;
-                const int f0 = cpart * 32;
-                const bool colok = f0 < a.Fk;
-                float dv[32];
-                if (colok) {
-                    uint32_t u[32];
-                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)f0;
-                    tc::tmem_ld16(taddr, u);
-                    if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
-                    else {
+            if (colok) {
+                uint32_t u[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)f0;
+                tc::tmem_ld16(taddr, u);
+                if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
+                else {
 #pragma unroll
-                        for (int i = 16; i < 32; ++i) u[i] = 0u;
-                    }
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = __uint_as_float(u[i]) * scale; }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) dv[i] = 0.f;
+                    for (int i = 16; i < 32; ++i) u[i] = 0u;
                 }
-                const bool rowok = v < nn;
-                const int nf = min(32, a.Fk - f0);            // columns of this part (multiple of 16 or <= 0)
-                float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
-                if (blk > 0 && rowok && colok) {
+                tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (i < nf) {
-                            const float4 o = *reinterpret_cast<const float4*>(sp + i);
-                            dv[i] += o.x; dv[i + 1] += o.y; dv[i + 2] += o.z; dv[i + 3] += o.w;
+                for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = fmaf(__uint_as_float(u[i]), scale, dv[i]); }
+            }
+            if (!lastb) {
+                if (rowok && colok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        if (i < nf) __stcg(reinterpret_cast<float4*>(sp + i), make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]));
+                }
+            } else {
+                // chain rule through xhat = x / max(|x|, eps):  gx = (g - (xhat . g) xhat) / |x|;  xhat = hi + lo from the
+                // node images still resident in shared memory
+                float xh[32];
+                float dot = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) xh[i] = 0.f;
+                if (colok) {
+                    const unsigned char* Xhi = smem + a.sm_x;
+                    const unsigned char* Xlo = Xhi + a.x_one;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (8 * c < nf) {
+                            const uint32_t off = tc::il_off(v, f0 + 8 * c, a.Fk);
+                            const uint4 h4 = *reinterpret_cast<const uint4*>(Xhi + off);
+                            const uint4 l4 = *reinterpret_cast<const uint4*>(Xlo + off);
+                            const __half2* hh = reinterpret_cast<const __half2*>(&h4);
+                            const __half2* ll = reinterpret_cast<const __half2*>(&l4);
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const float2 fh = __half22float2(hh[t]), fl = __half22float2(ll[t]);
+                                xh[8 * c + 2 * t] = fh.x + fl.x;
+                                xh[8 * c + 2 * t + 1] = fh.y + fl.y;
+                            }
                         }
                     }
-                }
-                if (blk + 1 < a.tb.nb) {
-                    if (rowok && colok) {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4)
-                            if (i < nf) *reinterpret_cast<float4*>(sp + i) = make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]);
-                    }
-                } else if (a.gx) {
-                    // chain rule through xhat = x / max(|x|, eps):  gx = (g - (xhat . g) xhat) / |x|
-                    float nrm = 1.f, den = 1.f, rden = 1.f;
-                    float xh[32];
-                    float dot = 0.f;
-                    if (rowok) {
-                        nrm = a.xnorm[t0 + v];
-                        den = fmaxf(nrm, MOLKGNN_COS_EPS);
-                        rden = 1.0f / den;
-                    }
-                    const float* xr = a.x + (size_t)(t0 + v) * a.ldx + f0;
+                    for (int i = 0; i < 32; ++i) dot = fmaf(dv[i], xh[i], dot);
+                }
+                red[cpart * 128 + v] = dot;
+                __syncthreads();
+                if (tid == 0 && tnext < a.n_tiles)      // every thread has read its xhat: the image buffer may be refilled
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
+                dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
+                const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
+                const float rden = 1.0f / den;
+                const bool clamped = !(nrm > MOLKGNN_COS_EPS);
+                if (a.gx && rowok && colok) {
+                    float* out = a.gx + (size_t)(t0 + v) * a.ldgx + f0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rowok && colok && f0 + i + 4 <= a.Fp) xv = ld4(xr + i);
-                        xh[i] = div_by(xv.x, den, rden); xh[i + 1] = div_by(xv.y, den, rden);
-                        xh[i + 2] = div_by(xv.z, den, rden); xh[i + 3] = div_by(xv.w, den, rden);
-                        dot += dv[i] * xh[i] + dv[i + 1] * xh[i + 1] + dv[i + 2] * xh[i + 2] + dv[i + 3] * xh[i + 3];
-                    }
-                    red[cpart * 128 + v] = dot;
-                    __syncthreads();
-                    dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
-                    const bool clamped = !(nrm > MOLKGNN_COS_EPS);
-                    if (rowok && colok) {
-                        float* out = a.gx + (size_t)(t0 + v) * a.ldgx + f0;
+                        if (f0 + i + 4 <= a.Fp) {
+                            float o[4];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            if (f0 + i + 4 <= a.Fp) {
-                                float o[4];
-#pragma unroll
-                                for (int c = 0; c < 4; ++c) {
-                                    o[c] = clamped ? dv[i + c] * rden : (dv[i + c] - dot * xh[i + c]) * rden;
-                                    if (f0 + i + c >= a.F) o[c] = 0.f;
-                                    gmax_local = fmaxf(gmax_local, fabsf(o[c]));
-                                }
-                                st4(out + i, make_float4(o[0], o[1], o[2], o[3]));
+                            for (int c = 0; c < 4; ++c) {
+                                o[c] = clamped ? dv[i + c] * rden : (dv[i + c] - dot * xh[i + c]) * rden;
+                                if (f0 + i + c >= a.F) o[c] = 0.f;
+                                gmax_local = fmaxf(gmax_local, fabsf(o[c]));
                             }
+                            st4(out + i, make_float4(o[0], o[1], o[2], o[3]));
                         }
                     }
                 }
@@ -507,9 +544,9 @@ bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
 // returns 1 if launched, 0 if not eligible, <0 on error.  part_off / ncta describe the partial copies for k_param_finalize.
 int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
-                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* partials,
-                         float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4], int ncta[4],
-                         int64_t* part_total, bool do_launch, cudaStream_t st) {
+                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* coef,
+                         float* partials, float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4],
+                         int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st) {
     if (!ximg || !grad_absmax || !tile_bwd_ok(plan, layer)) return 0;
     static int s_budget = 0;
     if (!s_budget) {
@@ -540,7 +577,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.img = reinterpret_cast<const unsigned char*>(layer->tile_img);
     a.img_one = tile_img_one(a.Fk);
     a.x_one = tile_img_one(a.Fk);
-    a.grad = grad; a.ldg = ldg; a.grad_mode = grad_mode;
+    a.coef = coef;
     a.argmax = argmax;
     a.grad_absmax = grad_absmax;
     a.partials = partials;
@@ -573,6 +610,24 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         s_attr = off;
     }
     if (gx_absmax) MK_CHECK_CUDA(cudaMemsetAsync(gx_absmax, 0, sizeof(float), st));
+    {
+        CoefArgs c;
+        c.sel = plan->sel; c.nei = plan->nei;
+        long long tot = 0;
+        for (int d = 0; d < 4; ++d) {
+            c.n[d] = plan->n[d]; c.boff[d] = plan->boff[d]; c.eoff[d] = plan->eoff[d];
+            c.L[d] = layer->L[d]; c.koff[d] = layer->koff[d]; c.scoff[d] = scoff[d];
+            tot = std::max<long long>(tot, scoff[d] + (long long)plan->n[d] * layer->L[d]);
+        }
+        c.tot = tot;
+        c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode;
+        c.argmax = argmax; c.coef = coef;
+        if (tot > 0) {
+            count_launches(1);
+            k_coef<<<(int)((tot + 255) / 256), 256, 0, st>>>(c);
+            MK_CHECK_CUDA(cudaGetLastError());
+        }
+    }
     count_launches(1);
     k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
