@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
     for (int t = 0; t < 4; ++t) m->inj[tid][t] = ij[t];
     m->incnt[tid] = (unsigned char)ic;
     m->lidx[tid] = (unsigned char)loff;
+    m->cr[tid] = (unsigned char)(crank[0] | (crank[1] << 2) | (crank[2] << 4) | (crank[3] << 6));
     __syncthreads();
     if (tid == 0) {
         int run = 0;

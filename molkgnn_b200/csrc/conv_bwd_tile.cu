@@ -2,23 +2,29 @@
 // over kernels.py:353-425 and KernelLayer.py:119; gradients are routed through the SAVED arg-max permutation.
 //
 // Formulation (tile.cuh: tiles of <= 128 nodes holding whole molecules, kernel rows in blocks of <= 128).  For one
-// (block, tile) the sparse coefficient matrix
+// (tile, block) the sparse coefficient matrix
 //        Wt[row, v] = sum over (n, j, k): nei(n,j) = v, row = (k, pi*_{n,k}(j))   of   alpha_d * chi*g[n,k] / scale
 //                   (+ centre rows: Wt[(c,k), n] = beta_d * chi*g[n,k] / scale)
 // is built in shared memory as an fp16 (hi, lo) tensor-core operand, and two GEMMs consume it:
-//        G[row, f]   += Wt[row, :] . xhat[:, f]        kernel-parameter gradients, accumulated in TMEM over all tiles of the CTA
-//        dxh[v, f]    = Wt[:, v]^T . khat[:, f]        gradient w.r.t. the normalised input rows, per tile
-// g[n,k] is the incoming gradient (optionally summed over the node's neighbours = transpose of propagate, KernelLayer.py:119),
-// chi the saved chirality sign, alpha_d = w_s/(d W), beta_d = w_c/W the softmax mixing factors (kernels.py:402-425) and
-// `scale` a power of two derived from max|grad| so that every entry fits fp16 comfortably; both operands are unscaled
-// (hi, lo) splits, three UMMAs per K step, fp32 accumulation.
+//        G_b[row, f] += Wt[row, :] . xhat[:, f]        kernel-parameter gradients: TMEM resident over ALL tiles of the CTA
+//        dxh[v, f]   += Wt[:, v]^T . khat_b[:, f]      gradient w.r.t. the normalised input rows: TMEM resident over the
+//                                                      blocks of one tile
+// g[n,k] is the incoming gradient (optionally summed over the node's neighbours = transpose of propagate,
+// KernelLayer.py:119), chi the saved chirality sign, alpha_d = w_s/(d W), beta_d = w_c/W the softmax mixing factors
+// (kernels.py:402-425) and `scale` a power of two derived from max|grad| so that every entry fits fp16 comfortably; both
+// operands are unscaled (hi, lo) splits, three UMMAs per K step, fp32 accumulation.
 //
-// Wt is built by scatter with one thread per (neighbour slot, kernel); slots are pre-grouped by collision rank
-// (k_tile_meta, bucket.cu) so that group 0 is a plain store and the few higher groups read-modify-write after a barrier:
-// deterministic, no atomics.  Bond-attribute gradients (8 floats per support row) accumulate in registers.  The partial
-// dxh of the kernel blocks are summed through an L2-resident scratch in fixed block order by the same CTA (static tile
-// assignment); the last block applies d(x/|x|)/dx and writes grad_x.  k_param_finalize (params.cu) reduces the per-CTA
-// copies of G in fixed order.
+//   k_coef_bond      streaming pre-pass in bucket order: coef = chi * g per (node, kernel) pair (the gather of the
+//                    incoming gradient rows stays out of the tile kernel's critical path) and the bond-attribute support
+//                    gradients (8 floats per support row) as one partial copy per CTA
+//   k_conv_bwd_tile  tile-major persistent kernel over a subset of <= 2 kernel blocks (TMEM: 2 x G_b + dxh = 336 of the
+//                    512 columns; a layer with 4 blocks runs it twice and the first launch hands its partial dxh to the
+//                    second through `scratch`).  Per (tile, block): Wt by scatter with one thread per (node, kernel) pair;
+//                    neighbour slots are pre-grouped by collision rank (k_tile_meta, bucket.cu) so that rank 0 is a plain
+//                    store and the few higher ranks read-modify-write after a barrier -- deterministic, no atomics;
+//                    then 48 UMMAs.  The block's images stream through shared memory by bulk copy.  Per tile one dxh
+//                    epilogue; the last launch applies d(x/|x|)/dx and writes grad_x.
+// k_param_finalize (params.cu) reduces the per-CTA copies in fixed order.
 #include <algorithm>
 #include "common.cuh"
 #include "tc.cuh"
@@ -29,100 +35,192 @@ namespace mk {
 bool tile_layer_ok(const molkgnn_layer_t* layer);
 
 constexpr int TB_THREADS = 512;
-constexpr int TB_WARPS = TB_THREADS / 32;
 constexpr int WT_ONE = 16 * 16 * 128;          // one fp16 image of the 128 x 128 coefficient block
+constexpr int CB_TN = 64;                      // nodes per step of k_coef_bond
+constexpr int CB_THREADS = 256;
+constexpr int CB_MAXR = 4;                     // support rows per thread of k_coef_bond (L * d <= 1024)
 
+// =============================================================================================================
+// k_coef_bond
+// =============================================================================================================
+struct CoefArgs {
+    const int* sel; const int* nei; const float* ehat;
+    int n[4], boff[4], eoff[4], L[4], koff[4];
+    long long scoff[4];
+    const float* grad; int ldg; int grad_mode;
+    const uint8_t* argmax;
+    float* coef;
+    float* partials; long long part_off[4]; int FW, Fp;
+    int G;                                     // CTAs (= partial copies) per degree
+};
+
+template <int D>
+__device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, unsigned char* invS, int c) {
+    const int L = a.L[D - 1], n = a.n[D - 1];
+    const int tid = threadIdx.x;
+    const int eoff = a.eoff[D - 1], koff = a.koff[D - 1];
+    const int nrows = L * D;
+    float acc[CB_MAXR][EP];
+#pragma unroll
+    for (int r = 0; r < CB_MAXR; ++r)
+#pragma unroll
+        for (int e = 0; e < EP; ++e) acc[r][e] = 0.f;
+    const int ntiles = (n + CB_TN - 1) / CB_TN;
+    for (int t = c; t < ntiles; t += a.G) {
+        const int R0 = t * CB_TN;
+        const int nv = min(CB_TN, n - R0);
+        __syncthreads();
+        for (int i = tid; i < nv * L; i += CB_THREADS) {
+            const int nl = i / L, k = i - nl * L;
+            const int col = koff + k;
+            const int R = R0 + nl;
+            float g;
+            if (a.grad_mode == 0) {
+                g = a.grad[(size_t)a.sel[a.boff[D - 1] + R] * a.ldg + col];
+            } else {
+                const int* nb = a.nei + (size_t)eoff + (size_t)R * D;
+                g = a.grad[(size_t)nb[0] * a.ldg + col];
+#pragma unroll
+                for (int j = 1; j < D; ++j) g += a.grad[(size_t)nb[j] * a.ldg + col];
+            }
+            const size_t cidx = (size_t)a.scoff[D - 1] + (size_t)R * L + k;
+            const uint8_t am = a.argmax[cidx];
+            const float av = (am & 0x80) ? -g : g;
+            a.coef[cidx] = av;
+            coefS[i] = av;
+            uint32_t inv = 0;
+#pragma unroll
+            for (int p = 0; p < Perm<D>::P; ++p) if (p == (am & 0x7f)) inv = perm_inv_code<D>(p);
+            invS[i] = (unsigned char)inv;
+        }
+        __syncthreads();
+        // bond-attribute support gradients: thread owns rows (s, k), sums over the nodes in fixed order
+#pragma unroll
+        for (int r = 0; r < CB_MAXR; ++r) {
+            const int row = tid + r * CB_THREADS;
+            if (row < nrows) {
+                const int s = row / L, k = row - s * L;
+                for (int nl = 0; nl < nv; ++nl) {
+                    const float av = coefS[nl * L + k];
+                    const int j = (invS[nl * L + k] >> (2 * s)) & 3;
+                    const float* e = a.ehat + ((size_t)eoff + (size_t)(R0 + nl) * D + j) * EP;
+                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(e)), e1 = __ldg(reinterpret_cast<const float4*>(e + 4));
+                    acc[r][0] = fmaf(av, e0.x, acc[r][0]); acc[r][1] = fmaf(av, e0.y, acc[r][1]);
+                    acc[r][2] = fmaf(av, e0.z, acc[r][2]); acc[r][3] = fmaf(av, e0.w, acc[r][3]);
+                    acc[r][4] = fmaf(av, e1.x, acc[r][4]); acc[r][5] = fmaf(av, e1.y, acc[r][5]);
+                    acc[r][6] = fmaf(av, e1.z, acc[r][6]); acc[r][7] = fmaf(av, e1.w, acc[r][7]);
+                }
+            }
+        }
+    }
+    const int rows_x = (D + 1) * L;
+    float* part = a.partials + a.part_off[D - 1] + (size_t)c * rows_x * a.FW + a.Fp;
+#pragma unroll
+    for (int r = 0; r < CB_MAXR; ++r) {
+        const int row = tid + r * CB_THREADS;
+        if (row < nrows) {
+            st4(part + (size_t)row * a.FW, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
+            st4(part + (size_t)row * a.FW + 4, make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
+        }
+    }
+    for (int row = nrows + tid; row < rows_x; row += CB_THREADS) {   // centre rows carry no bond part
+        st4(part + (size_t)row * a.FW, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4(part + (size_t)row * a.FW + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+}
+
+__global__ void __launch_bounds__(CB_THREADS) k_coef_bond(const __grid_constant__ CoefArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_c[];
+    const int d = blockIdx.x / a.G + 1, c = blockIdx.x % a.G;
+    const int L = a.L[d - 1];
+    if (L == 0) return;
+    float* coefS = reinterpret_cast<float*>(smem_c);
+    unsigned char* invS = smem_c + (size_t)CB_TN * L * 4;
+    switch (d) {
+        case 1: coef_bond_body<1>(a, coefS, invS, c); break;
+        case 2: coef_bond_body<2>(a, coefS, invS, c); break;
+        case 3: coef_bond_body<3>(a, coefS, invS, c); break;
+        default: coef_bond_body<4>(a, coefS, invS, c); break;
+    }
+}
+
+// =============================================================================================================
+// k_conv_bwd_tile
+// =============================================================================================================
 struct BwdTileArgs {
-    const float* x; const float* xnorm; int ldx;
+    const float* xnorm;
     int F, Fp, Fk;
-    const TileMetaG* meta; const float* ehat_node; const unsigned char* ximg; int n_tiles;
-    int L[4], koff[4];
+    const TileMetaG* meta; const unsigned char* ximg; int n_tiles;
+    int L[4];
     const float* packed[4];
     const unsigned char* img;
     TileBlocks tb;
     int img_one, x_one;
-    const float* coef;                 // chi * g per (node, kernel) pair, compact bucket order (k_coef)
+    const float* coef;                 // chi * g per (node, kernel) pair, compact bucket order (k_coef_bond)
     const uint8_t* argmax; long long scoff[4];
     const float* grad_absmax;          // device scalar: max |grad|
     float* partials; long long part_off[4]; int FW;
-    float* scratch;                    // [N, Fk] partial dxh between kernel blocks
+    float* scratch;                    // [N, Fk] partial dxh handed from the first launch to the second
     float* gx; int ldgx;
     float* gx_absmax;                  // device scalar (nullable): max |grad_x|, for the next layer down
-    int ne_cap, a_cap, buf_bytes;
-    int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
+    int nbl, blist[2];                 // kernel blocks of this launch
+    int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
+    int a_cap, buf_bytes;
+    int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am;
 };
 
 struct BSeg {
     float alpha, beta;                 // w_s/(d W), w_c/W
-    int d, k0, nk, rowbase, L, abase;
+    int d, k0, nk, rowbase, L;
     float rnk;
 };
 
-__device__ __forceinline__ void tb_copy16(unsigned char* dst, const unsigned char* src, int64_t bytes) {
-    for (int64_t i = (int64_t)threadIdx.x * 16; i < bytes; i += (int64_t)TB_THREADS * 16)
-        *reinterpret_cast<uint4*>(dst + i) = *reinterpret_cast<const uint4*>(src + i);
+__device__ __forceinline__ void wt_store(unsigned char* wt, int row, int col, float v) {
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+    const uint32_t off = tc::il_off(row, col, 128);
+    *reinterpret_cast<__half*>(wt + off) = hi;
+    *reinterpret_cast<__half*>(wt + WT_ONE + off) = lo;
+}
+__device__ __forceinline__ void wt_add(unsigned char* wt, int row, int col, float v) {
+    const uint32_t off = tc::il_off(row, col, 128);
+    __half* ph = reinterpret_cast<__half*>(wt + off);
+    __half* pl = reinterpret_cast<__half*>(wt + WT_ONE + off);
+    v += __half2float(*ph) + __half2float(*pl);
+    const __half hi = __float2half_rn(v);
+    *ph = hi;
+    *pl = __float2half_rn(v - __half2float(hi));
 }
 
-__device__ __forceinline__ uint32_t tb_perm_code(int d, int p) {
-    uint32_t c = 0;
-    if (d == 4) {
-#pragma unroll
-        for (int q = 0; q < 12; ++q) if (q == p) c = perm_code<4>(q);
-    } else if (d == 3) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) if (q == p) c = perm_code<3>(q);
-    } else if (d == 2) {
-        c = p == 0 ? perm_code<2>(0) : perm_code<2>(1);
-    }
-    return c;
-}
-__device__ __forceinline__ uint32_t tb_perm_inv_code(int d, int p) {
-    uint32_t c = 0;
-    if (d == 4) {
-#pragma unroll
-        for (int q = 0; q < 12; ++q) if (q == p) c = perm_inv_code<4>(q);
-    } else if (d == 3) {
-#pragma unroll
-        for (int q = 0; q < 6; ++q) if (q == p) c = perm_inv_code<3>(q);
-    } else if (d == 2) {
-        c = p == 0 ? perm_inv_code<2>(0) : perm_inv_code<2>(1);
-    }
-    return c;
-}
-
-__device__ __forceinline__ void tb_split(float v, __half& hi, __half& lo) {
-    hi = __float2half_rn(v);
-    lo = __float2half_rn(v - __half2float(hi));
-}
-
-// thread 0: metadata record, bond rows and node images of `tile`
+// thread 0: metadata record and node images of `tile`
 __device__ __forceinline__ void tb_issue_copy(const BwdTileArgs& a, unsigned char* smem, unsigned char* buf, int tile,
                                               uint64_t* bar) {
-    const TileMetaG* g = a.meta + tile;
-    const int e0 = g->e0, ne = g->ne;
-    const uint32_t eb = (uint32_t)ne * EP * 4u;
-    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + eb + 2u * (uint32_t)a.x_one);
-    bulk_g2s(buf, g, (uint32_t)sizeof(TileMetaG), bar);
-    if (eb) bulk_g2s(buf + sizeof(TileMetaG), a.ehat_node + (size_t)e0 * EP, eb, bar);
+    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + 2u * (uint32_t)a.x_one);
+    bulk_g2s(buf, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
     bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
 }
+// thread 0: images of kernel block `blk`
+__device__ __forceinline__ void tb_issue_img(const BwdTileArgs& a, unsigned char* smem, int blk, uint64_t* bar) {
+    mbar_expect_tx(bar, 2u * (uint32_t)a.img_one);
+    bulk_g2s(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2u * (uint32_t)a.img_one, bar);
+}
 
-// thread 0: G (TMEM columns 0..Fk) += Wt . xhat ;  dxh (TMEM columns 128..128+Fk) = Wt^T . khat
-__device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char* smem, int nn, int rows, bool first,
-                                             uint32_t tmem, uint64_t* bar) {
+// thread 0: G_bi (TMEM columns bi*128 ..) += Wt . xhat ;  dxh (TMEM columns 256 ..) (+)= Wt^T . khat
+__device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char* smem, int nn, int rows, int bi,
+                                             bool g_fresh, uint32_t tmem, uint64_t* bar) {
     const uint32_t whi = tc::smem_u32(smem + a.sm_wt), wlo = whi + WT_ONE;
     const uint32_t xhi = tc::smem_u32(smem + a.sm_x), xlo = xhi + (uint32_t)a.x_one;
     const uint32_t ihi = tc::smem_u32(smem + a.sm_img), ilo = ihi + (uint32_t)a.img_one;
     const uint32_t fgrp = (uint32_t)(a.Fk >> 3) * 128u;      // bytes of one 8-row group of an [R x Fk] image
     const uint32_t idesc_g = tc::idesc_f16(128, a.Fk, 0, 1);  // A = Wt K-major (K = node), B = xhat MN-major (N = feature)
     const uint32_t idesc_x = tc::idesc_f16(128, a.Fk, 1, 1);  // A = Wt MN-major (M = node, K = row), B = khat MN-major
-    const uint32_t dG = tmem, dX = tmem + 128u;
+    const uint32_t dG = tmem + (uint32_t)bi * 128u, dX = tmem + 256u;
     // G: K = nodes, 16 per step.  Wt K-major: +256 B per step (two 8-column chunks); xhat MN-major: +2 row groups per step
     const int nkg = (max(16, (nn + 15) & ~15)) >> 4;
     for (int ks = 0; ks < nkg; ++ks) {
         const uint64_t dAh = tc::smem_desc(whi + ks * 256u, 128u, 2048u), dAl = tc::smem_desc(wlo + ks * 256u, 128u, 2048u);
         const uint64_t dBh = tc::smem_desc(xhi + ks * 2u * fgrp, fgrp, 128u), dBl = tc::smem_desc(xlo + ks * 2u * fgrp, fgrp, 128u);
-        tc::umma_f16(dG, dAh, dBh, idesc_g, (first && ks == 0) ? 0u : 1u);
+        tc::umma_f16(dG, dAh, dBh, idesc_g, (g_fresh && ks == 0) ? 0u : 1u);
         tc::umma_f16(dG, dAl, dBh, idesc_g, 1u);
         tc::umma_f16(dG, dAh, dBl, idesc_g, 1u);
     }
@@ -131,66 +229,59 @@ __device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char
     for (int ks = 0; ks < nkx; ++ks) {
         const uint64_t dAh = tc::smem_desc(whi + ks * 4096u, 2048u, 128u), dAl = tc::smem_desc(wlo + ks * 4096u, 2048u, 128u);
         const uint64_t dBh = tc::smem_desc(ihi + ks * 2u * fgrp, fgrp, 128u), dBl = tc::smem_desc(ilo + ks * 2u * fgrp, fgrp, 128u);
-        tc::umma_f16(dX, dAh, dBh, idesc_x, ks == 0 ? 0u : 1u);
+        tc::umma_f16(dX, dAh, dBh, idesc_x, (bi == 0 && ks == 0) ? 0u : 1u);
         tc::umma_f16(dX, dAl, dBh, idesc_x, 1u);
         tc::umma_f16(dX, dAh, dBl, idesc_x, 1u);
     }
     tc::umma_commit(bar);
 }
 
-// coef[pair] = chi * g for every (node, kernel) pair in compact bucket order (streaming, fully occupied: keeps the gather
-// of the incoming gradient rows out of the tile kernel's critical path)
-struct CoefArgs {
-    const int* sel; const int* nei;
-    int n[4], boff[4], eoff[4], L[4], koff[4];
-    long long scoff[4], tot;
-    const float* grad; int ldg; int grad_mode;
-    const uint8_t* argmax;
-    float* coef;
-};
-
-__global__ void __launch_bounds__(256) k_coef(const CoefArgs a) {
-    const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.tot) return;
-    int d = 4;
-    while (d > 1 && i < a.scoff[d - 1]) --d;
-    const int L = a.L[d - 1];
-    const long long li = i - a.scoff[d - 1];
-    const int R = (int)(li / L), k = (int)(li - (long long)R * L);
-    const int col = a.koff[d - 1] + k;
-    float g;
-    if (a.grad_mode == 0) {
-        g = a.grad[(size_t)a.sel[a.boff[d - 1] + R] * a.ldg + col];
-    } else {
-        const int* nb = a.nei + (size_t)a.eoff[d - 1] + (size_t)R * d;
-        g = a.grad[(size_t)nb[0] * a.ldg + col];
-        for (int j = 1; j < d; ++j) g += a.grad[(size_t)nb[j] * a.ldg + col];
-    }
-    a.coef[i] = (a.argmax[i] & 0x80) ? -g : g;
-}
-
 __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_constant__ BwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma, bar_cp[2];
+    __shared__ uint64_t bar_mma, bar_img, bar_cp[2];
     __shared__ uint32_t tslot;
-    __shared__ BSeg s_seg[TILE_MAXSEG];
+    __shared__ BSeg s_seg[2][TILE_MAXSEG];
+    __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
-        tc::mbar_init(&bar_mma, 1);
+        tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_img, 1);
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc(&tslot, 256);
+    if (warp == 0) tc::tmem_alloc(&tslot, 512);
+    if (tid < 48) {
+        const int d = tid / 12 + 1, p = tid % 12;
+        uint32_t code = 0;
+        if (d == 2) code = p < 2 ? perm_code<2>(p) : 0;
+        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_code<3>(q); }
+        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
+        s_lut[d - 1][p] = (unsigned char)code;
+    }
+    if (tid >= 64 && tid < 64 + 2 * TILE_MAXSEG) {
+        const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
+        if (bi < a.nbl && si < a.tb.nseg[a.blist[bi]]) {
+            const TileSeg sg = a.tb.seg[a.blist[bi]][si];
+            const int L = a.L[sg.d - 1];
+            const PackedLayout pl(sg.d, L, a.Fp);
+            const float* pk = a.packed[sg.d - 1];
+            BSeg c;
+            c.alpha = pk[pl.w + 0] / pk[pl.w + 3] / (float)sg.d;
+            c.beta = pk[pl.w + 1] / pk[pl.w + 3];
+            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
+            c.rnk = 1.0f / (float)sg.nk;
+            s_seg[bi][si] = c;
+        }
+    }
+    unsigned char* wt = smem + a.sm_wt;
+    for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tslot;
-    unsigned char* wt = smem + a.sm_wt;
     float* a_s = reinterpret_cast<float*>(smem + a.sm_a);
     unsigned char* am_s = smem + a.sm_am;
     float* red = reinterpret_cast<float*>(smem + a.sm_a);       // Jacobian reduction scratch: the coefficients are dead by then
-    float (*s_eacc)[128][EP] = reinterpret_cast<float (*)[128][EP]>(wt);   // block end: bond partial sums (Wt is dead by then)
-    uint32_t ph_mma = 0u, ph_cp[2] = {0u, 0u};
+    uint32_t ph_mma = 0u, ph_img = 0u, ph_cp[2] = {0u, 0u};
     // power-of-two scale: |alpha * chi * g| / scale <= 2^10 (g sums at most 4 gradient entries)
     float scale, rscale;
     {
@@ -202,147 +293,109 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     }
     float gmax_local = 0.f;
     const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / 32-column part of this warp
-
-    for (int blk = 0; blk < a.tb.nb; ++blk) {
-        __syncthreads();
-        // ---- block set-up ----
-        tb_copy16(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2 * (int64_t)a.img_one);
-        for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
-        const int nseg = a.tb.nseg[blk];
-        const int rows = a.tb.rows[blk];
-        if (tid < nseg) {
-            const TileSeg sg = a.tb.seg[blk][tid];
-            const int L = a.L[sg.d - 1];
-            const PackedLayout pl(sg.d, L, a.Fp);
-            const float* pk = a.packed[sg.d - 1];
-            BSeg c;
-            c.alpha = pk[pl.w + 0] / pk[pl.w + 3] / (float)sg.d;
-            c.beta = pk[pl.w + 1] / pk[pl.w + 3];
-            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L; c.abase = 0;
-            c.rnk = 1.0f / (float)sg.nk;
-            s_seg[tid] = c;
+    bool img_pending = false;                             // an image copy is in flight (uniform across the CTA)
+    if ((int)blockIdx.x < a.n_tiles) {
+        if (tid == 0) {
+            tb_issue_copy(a, smem, smem + a.sm_buf, blockIdx.x, &bar_cp[0]);
+            tb_issue_img(a, smem, a.blist[0], &bar_img);
         }
-        // this thread's kernel row for the bond-gradient accumulation: row = tid & 127, node quarter = tid >> 7
-        int er_seg = -1, er_slot = 0, er_kl = 0;
-        {
-            const int row = tid & 127;
-            for (int si = 0; si < nseg; ++si) {
-                const TileSeg sg = a.tb.seg[blk][si];
-                const int r = row - sg.rowbase;
-                if (r >= 0 && r < sg.nk * sg.d) { er_seg = si; er_slot = r / sg.nk; er_kl = r % sg.nk; }
-            }
-        }
-        float eacc[EP];
-#pragma unroll
-        for (int c = 0; c < EP; ++c) eacc[c] = 0.f;
-        tc::fence_async_smem();
-        __syncthreads();
-        bool first = true;
-        int cur = 0;
-        if (tid == 0 && (int)blockIdx.x < a.n_tiles) tb_issue_copy(a, smem, smem + a.sm_buf, blockIdx.x, &bar_cp[0]);
+        img_pending = true;
+    }
+    int cur = 0;
+    bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
 
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            unsigned char* buf = smem + a.sm_buf + cur * a.buf_bytes;
-            const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
-            const float* ehat = reinterpret_cast<const float*>(buf + sizeof(TileMetaG));
-            tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
-            ph_cp[cur] ^= 1u;
-            const int t0 = m.t0, nn = m.nn;
-            // segment offsets into the coefficient arrays
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        unsigned char* buf = smem + a.sm_buf + cur * a.buf_bytes;
+        const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
+        tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
+        ph_cp[cur] ^= 1u;
+        const int t0 = m.t0, nn = m.nn;
+        const int tnext = tile + gridDim.x;
+        for (int bi = 0; bi < a.nbl; ++bi) {
+            const int blk = a.blist[bi];
+            const int nseg = a.tb.nseg[blk];
             int abase[TILE_MAXSEG];
             {
                 int run = 0;
-                for (int si = 0; si < nseg; ++si) { abase[si] = run; run += m.cnt[s_seg[si].d - 1] * s_seg[si].nk; }
+                for (int si = 0; si < nseg; ++si) { abase[si] = run; run += m.cnt[s_seg[bi][si].d - 1] * s_seg[bi][si].nk; }
             }
-            // ---- (A) coefficients a = chi * g / scale, one thread per (node, kernel) pair; centre entries of Wt ----
+            // ---- rank 0: one thread per (node, kernel) pair -- coefficient, centre entry, collision-free support entries ----
             for (int si = 0; si < nseg; ++si) {
-                const BSeg sg = s_seg[si];
+                const BSeg sg = s_seg[bi][si];
                 const int np = m.cnt[sg.d - 1] * sg.nk;
                 for (int p = tid; p < np; p += TB_THREADS) {
                     const int ni = (int)(((float)p + 0.5f) * sg.rnk);
                     const int kl = p - ni * sg.nk;
                     const int nl_ = m.list[sg.d - 1][ni];
-                    const int k = sg.k0 + kl;
-                    const size_t cidx = (size_t)a.scoff[sg.d - 1] + (size_t)m.posl[nl_] * sg.L + k;
-                    const float av = a.coef[cidx] * rscale;
-                    const uint8_t am = a.argmax[cidx];
+                    const size_t cidx = (size_t)a.scoff[sg.d - 1] + (size_t)m.posl[nl_] * sg.L + sg.k0 + kl;
+                    const float av = __ldg(a.coef + cidx) * rscale;
+                    const int am = a.argmax[cidx] & 0x7f;
                     a_s[abase[si] + p] = av;
-                    am_s[abase[si] + p] = am & 0x7f;
-                    __half hi, lo;
-                    tb_split(av * sg.beta, hi, lo);
-                    const uint32_t off = tc::il_off(sg.rowbase + sg.d * sg.nk + kl, nl_, 128);
-                    *reinterpret_cast<__half*>(wt + off) = hi;
-                    *reinterpret_cast<__half*>(wt + WT_ONE + off) = lo;
+                    am_s[abase[si] + p] = (unsigned char)am;
+                    const uint32_t code = s_lut[sg.d - 1][am];
+                    const uint32_t nw = m.nl[nl_];
+                    const uint32_t cr = m.cr[nl_];
+                    wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
+                    const float as = av * sg.alpha;
+                    for (int j = 0; j < sg.d; ++j) {
+                        if (((cr >> (2 * j)) & 3u) == 0u)
+                            wt_store(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), as);
+                    }
                 }
             }
-            __syncthreads();
-            // ---- (B) support entries of Wt: one thread per (neighbour slot, kernel), groups of rising collision rank ----
-            for (int r = 0; r < 4; ++r) {
-                bool any = false;
+            // ---- ranks 1..3: one thread per (neighbour slot, kernel), read-modify-write after a barrier ----
+            for (int r = 1; r < 4; ++r) {
+                bool more = false;
                 for (int si = 0; si < nseg; ++si) {
-                    const BSeg sg = s_seg[si];
+                    const int d = s_seg[bi][si].d;
+                    if (m.eoffs[d - 1][4] > m.eoffs[d - 1][r]) more = true;
+                }
+                if (!more) break;
+                __syncthreads();
+                for (int si = 0; si < nseg; ++si) {
+                    const BSeg sg = s_seg[bi][si];
                     const int e0 = m.eoffs[sg.d - 1][r], e1 = m.eoffs[sg.d - 1][r + 1];
                     const int ni_ = (e1 - e0) * sg.nk;
-                    if (ni_ > 0) any = true;
                     for (int p = tid; p < ni_; p += TB_THREADS) {
                         const int ei = (int)(((float)p + 0.5f) * sg.rnk);
                         const int kl = p - ei * sg.nk;
                         const int ent = m.elist[e0 + ei];
                         const int nl_ = ent >> 2, j = ent & 3;
                         const int pi = abase[si] + m.lidx[nl_] * sg.nk + kl;
-                        const float av = a_s[pi] * sg.alpha;
-                        const int s = (tb_perm_code(sg.d, am_s[pi]) >> (2 * j)) & 3;
-                        const int colv = (m.nl[nl_] >> (8 * j)) & 0xff;
-                        const uint32_t off = tc::il_off(sg.rowbase + s * sg.nk + kl, colv, 128);
-                        __half* ph = reinterpret_cast<__half*>(wt + off);
-                        __half* pl_ = reinterpret_cast<__half*>(wt + WT_ONE + off);
-                        float v = av;
-                        if (r > 0) v += __half2float(*ph) + __half2float(*pl_);
-                        __half hi, lo;
-                        tb_split(v, hi, lo);
-                        *ph = hi;
-                        *pl_ = lo;
+                        const int s = (s_lut[sg.d - 1][am_s[pi]] >> (2 * j)) & 3;
+                        wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), a_s[pi] * sg.alpha);
                     }
-                }
-                if (r < 3) {
-                    bool more = false;
-                    for (int si = 0; si < nseg; ++si) {
-                        const int d = s_seg[si].d;
-                        if (m.eoffs[d - 1][4] > m.eoffs[d - 1][r + 1]) more = true;
-                    }
-                    if (!more) break;
-                    __syncthreads();
-                }
-                (void)any;
-            }
-            // ---- (C) bond-attribute gradients: thread (kernel row, node quarter), fixed node order ----
-            if (er_seg >= 0) {
-                const BSeg sg = s_seg[er_seg];
-                const int cnt = m.cnt[sg.d - 1];
-                const int qtr = tid >> 7;
-                for (int ni = qtr; ni < cnt; ni += 4) {
-                    const int nl_ = m.list[sg.d - 1][ni];
-                    const int pi = abase[er_seg] + ni * sg.nk + er_kl;
-                    const float av = a_s[pi];
-                    const int j = (tb_perm_inv_code(sg.d, am_s[pi]) >> (2 * er_slot)) & 3;
-                    const float* e = ehat + (size_t)(m.eslot[nl_] + j) * EP;
-                    const float4 e0v = *reinterpret_cast<const float4*>(e), e1v = *reinterpret_cast<const float4*>(e + 4);
-                    eacc[0] = fmaf(av, e0v.x, eacc[0]); eacc[1] = fmaf(av, e0v.y, eacc[1]);
-                    eacc[2] = fmaf(av, e0v.z, eacc[2]); eacc[3] = fmaf(av, e0v.w, eacc[3]);
-                    eacc[4] = fmaf(av, e1v.x, eacc[4]); eacc[5] = fmaf(av, e1v.y, eacc[5]);
-                    eacc[6] = fmaf(av, e1v.z, eacc[6]); eacc[7] = fmaf(av, e1v.w, eacc[7]);
                 }
             }
             tc::fence_async_smem();
             __syncthreads();
-            // ---- (D) tensor cores ----
+            // ---- tensor cores ----
             if (tid == 0) {
+                if (img_pending) {                            // this block's images were requested after the previous MMAs
+                    tc::mbar_wait(&bar_img, ph_img);
+                    ph_img ^= 1u;
+                }
                 tc::fence_after_sync();
-                tb_issue_mma(a, smem, nn, rows, first, tmem, &bar_mma);
+                tb_issue_mma(a, smem, nn, a.tb.rows[blk], bi, fresh, tmem, &bar_mma);
             }
-            first = false;
-            // ---- (E) dxh epilogue: lane = node, 32 columns per warp.  Loads that do not depend on the tensor cores go first ----
-            const bool lastb = blk + 1 == a.tb.nb;
+            img_pending = false;
+            tc::mbar_wait(&bar_mma, ph_mma);
+            ph_mma ^= 1u;
+            tc::fence_after_sync();
+            // the tensor cores are done with Wt and the images: clear Wt, fetch the next block's images
+            for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
+            {
+                const int nblk = bi + 1 < a.nbl ? a.blist[bi + 1] : (tnext < a.n_tiles ? a.blist[0] : blk);
+                if (nblk != blk) {
+                    if (tid == 0) tb_issue_img(a, smem, nblk, &bar_img);
+                    img_pending = true;
+                }
+            }
+            if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
+        }
+        fresh = false;
+        // ---- dxh epilogue: lane = node, 32 columns per warp ----
+        {
             const int v = q * 32 + lane;
             const int f0 = cpart * 32;
             const bool colok = f0 < a.Fk;
@@ -352,7 +405,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
 #pragma unroll
             for (int i = 0; i < 32; ++i) dv[i] = 0.f;
             float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
-            if (blk > 0 && rowok && colok) {              // partial sums of the previous kernel blocks
+            if (!a.first && rowok && colok) {             // partial dxh of the first launch
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     if (i < nf) {
@@ -362,18 +415,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 }
             }
             float nrm = 1.f;
-            if (lastb && rowok) nrm = a.xnorm[t0 + v];
-            tc::mbar_wait(&bar_mma, ph_mma);
-            ph_mma ^= 1u;
-            tc::fence_after_sync();
-            // the tensor cores are done with Wt: clear it for the next tile (ordered by the barrier that ends this tile)
-            for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
-            const int tnext = tile + gridDim.x;
-            if (!lastb && tid == 0 && tnext < a.n_tiles)
-                tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
+            if (a.last && rowok) nrm = a.xnorm[t0 + v];
             if (colok) {
                 uint32_t u[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 128u + (uint32_t)f0;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)f0;
                 tc::tmem_ld16(taddr, u);
                 if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
                 else {
@@ -384,7 +429,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = fmaf(__uint_as_float(u[i]), scale, dv[i]); }
             }
-            if (!lastb) {
+            if (!a.last) {
+                if (tid == 0 && tnext < a.n_tiles)
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
                 if (rowok && colok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -444,73 +491,54 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     }
                 }
             }
-            tc::fence_before_sync();
-            __syncthreads();                 // Wt, coefficient arrays, TMEM dxh and this tile's buffer are free again
-            cur ^= 1;
         }
-        // ---- block end: kernel-parameter partial sums of this CTA ----
-        {
-            // bond part: sum the four node quarters in fixed order
+        tc::fence_before_sync();
+        __syncthreads();                 // coefficient arrays / Jacobian scratch, TMEM dxh and this tile's buffer are free again
+        cur ^= 1;
+    }
+    // ---- kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks ----
+    for (int bi = 0; bi < a.nbl; ++bi) {
+        const int blk = a.blist[bi];
+        const int row = q * 32 + lane;
+        int d = 0, slot = 0, kk = 0, L = 0;
+        for (int si = 0; si < a.tb.nseg[blk]; ++si) {
+            const TileSeg sg = a.tb.seg[blk][si];
+            const int r = row - sg.rowbase;
+            if (r >= 0 && r < sg.nk * (sg.d + 1)) { d = sg.d; slot = r / sg.nk; kk = sg.k0 + r % sg.nk; L = a.L[sg.d - 1]; }
+        }
+        const int f0 = cpart * 32;
+        if (f0 < a.Fk) {
+            uint32_t u[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * 128 + f0);
+            tc::tmem_ld16(taddr, u);
+            if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
+            else {
 #pragma unroll
-            for (int c = 0; c < EP; ++c) s_eacc[tid >> 7][tid & 127][c] = eacc[c];
-            __syncthreads();
-            const int row = q * 32 + lane;
-            int d = 0, slot = 0, kk = 0, L = 0;
-            for (int si = 0; si < nseg; ++si) {
-                const TileSeg sg = a.tb.seg[blk][si];
-                const int r = row - sg.rowbase;
-                if (r >= 0 && r < sg.nk * (sg.d + 1)) { d = sg.d; slot = r / sg.nk; kk = sg.k0 + r % sg.nk; L = a.L[sg.d - 1]; }
+                for (int i = 16; i < 32; ++i) u[i] = 0u;
             }
-            const int f0 = cpart * 32;
-            if (f0 < a.Fk) {
-                uint32_t u[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)f0;
-                tc::tmem_ld16(taddr, u);
-                if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
-                else {
+            tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 16; i < 32; ++i) u[i] = 0u;
-                }
-                tc::tmem_ld_wait();
+            for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(u[i]));
+            if (d > 0) {
+                const int rows_x = (d + 1) * L;
+                float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(u[i]));
-                if (d > 0) {
-                    const int rows_x = (d + 1) * L;
-                    float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
-                    const bool has_tiles = (int)blockIdx.x < a.n_tiles;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        if (f0 + i + 4 <= a.Fp) {
-                            float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (has_tiles)
-                                o = make_float4(__uint_as_float(u[i]) * scale, __uint_as_float(u[i + 1]) * scale,
-                                                __uint_as_float(u[i + 2]) * scale, __uint_as_float(u[i + 3]) * scale);
-                            st4(part + f0 + i, o);
-                        }
-                    }
-                    if (cpart == 0) {
-                        float e[EP];
-#pragma unroll
-                        for (int c = 0; c < EP; ++c) {
-                            e[c] = 0.f;
-                            if (slot < d) e[c] = ((s_eacc[0][row][c] + s_eacc[1][row][c]) + (s_eacc[2][row][c] + s_eacc[3][row][c])) * scale;
-                        }
-                        st4(part + a.Fp, make_float4(e[0], e[1], e[2], e[3]));
-                        st4(part + a.Fp + 4, make_float4(e[4], e[5], e[6], e[7]));
-                    }
+                for (int i = 0; i < 32; i += 4) {
+                    if (f0 + i + 4 <= a.Fp)
+                        st4(part + f0 + i, make_float4(__uint_as_float(u[i]) * scale, __uint_as_float(u[i + 1]) * scale,
+                                                       __uint_as_float(u[i + 2]) * scale, __uint_as_float(u[i + 3]) * scale));
                 }
             }
-            tc::fence_before_sync();
         }
     }
-    if (a.gx_absmax) {
+    if (a.gx_absmax && a.last) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) gmax_local = fmaxf(gmax_local, __shfl_xor_sync(0xffffffffu, gmax_local, o));
         if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(a.gx_absmax), __float_as_uint(gmax_local));
     }
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // max |x| of a buffer into a device scalar (the caller zeroes it): the scale of the fp16 coefficient operand
@@ -538,7 +566,11 @@ int tile_bwd_grid(const molkgnn_plan_t* plan) {
 }
 
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
-    return tile_plan_ok_b(plan) && layer->tile_img && tile_layer_ok(layer);
+    if (!tile_plan_ok_b(plan) || !layer->tile_img || !tile_layer_ok(layer)) return false;
+    TileBlocks tb;
+    if (!tb.build(layer->L) || tb.nb > 4) return false;                 // at most two launches of two blocks
+    for (int d = 0; d < 4; ++d) if (layer->L[d] * (d + 1) > CB_MAXR * CB_THREADS) return false;
+    return true;
 }
 
 // returns 1 if launched, 0 if not eligible, <0 on error.  part_off / ncta describe the partial copies for k_param_finalize.
@@ -547,7 +579,8 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* coef,
                          float* partials, float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4],
                          int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st) {
-    if (!ximg || !grad_absmax || !tile_bwd_ok(plan, layer)) return 0;
+    (void)x; (void)ldx;
+    if (!ximg || !grad_absmax || !coef || !tile_bwd_ok(plan, layer)) return 0;
     static int s_budget = 0;
     if (!s_budget) {
         s_budget = device_max_smem_optin();
@@ -555,18 +588,18 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     }
     BwdTileArgs a;
     if (!a.tb.build(layer->L)) return 0;
-    MK_REQUIRE(a.tb.nb == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than one kernel block");
-    a.x = x; a.xnorm = xnorm; a.ldx = ldx;
+    const int nlaunch = a.tb.nb > 2 ? 2 : 1;
+    MK_REQUIRE(nlaunch == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than two kernel blocks");
+    a.xnorm = xnorm;
     a.F = layer->F; a.Fp = layer->Fp; a.Fk = tile_fk(layer->Fp);
     a.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
-    a.ehat_node = plan->ehat_node;
     a.ximg = reinterpret_cast<const unsigned char*>(ximg);
     a.n_tiles = plan->n_tiles;
     const int grid = tile_bwd_grid(plan);
     a.FW = layer->Fp + EP;
     int64_t po = 0;
     for (int d = 0; d < 4; ++d) {
-        a.L[d] = layer->L[d]; a.koff[d] = layer->koff[d];
+        a.L[d] = layer->L[d];
         a.packed[d] = layer->packed[d];
         a.scoff[d] = scoff[d];
         a.part_off[d] = part_off[d] = po;
@@ -583,17 +616,15 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.partials = partials;
     a.scratch = scratch;
     a.gx = grad_x; a.ldgx = ldgx; a.gx_absmax = gx_absmax;
-    // capacities from the plan: bond slots and (node, kernel) pairs of the fullest tile
-    int ne_cap = 0, a_cap = 0;
-    for (int d = 0; d < 4; ++d) ne_cap += plan->tile_max_deg[d] * (d + 1);
-    ne_cap = std::min(ne_cap, TILE_ESLOTS);
+    // capacity from the plan: (node, kernel) pairs of the fullest tile of any block
+    int a_cap = 0;
     for (int b = 0; b < a.tb.nb; ++b) {
         int c = 0;
         for (int si = 0; si < a.tb.nseg[b]; ++si) c += plan->tile_max_deg[a.tb.seg[b][si].d - 1] * a.tb.seg[b][si].nk;
         a_cap = std::max(a_cap, c);
     }
-    a.ne_cap = ne_cap; a.a_cap = a_cap;
-    a.buf_bytes = (int)((sizeof(TileMetaG) + (size_t)ne_cap * EP * 4 + 127) / 128 * 128);
+    a.a_cap = a_cap;
+    a.buf_bytes = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
     int64_t off = 0;
     a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
     a.sm_x = (int)off; off += 2 * (int64_t)a.x_one;
@@ -601,36 +632,48 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.sm_buf = (int)off; off += 2 * (int64_t)a.buf_bytes;
     a.sm_a = (int)off; off += (std::max<int64_t>((int64_t)a_cap * 4, 4 * 128 * 4) + 127) / 128 * 128;
     a.sm_am = (int)off; off += ((int64_t)a_cap + 127) / 128 * 128;
-    a.sm_red = a.sm_a;
     if (off > s_budget - 2048) return 0;
+    int Lmax = 1;
+    for (int d = 0; d < 4; ++d) Lmax = std::max(Lmax, layer->L[d]);
+    const int64_t smem_c = (int64_t)CB_TN * Lmax * 5;
+    if (smem_c > s_budget - 2048) return 0;
     if (!do_launch) return 1;
-    static int64_t s_attr = 0;
+    static int64_t s_attr = 0, s_attr_c = 0;
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;
     }
+    if (smem_c > s_attr_c) {
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_bond, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        s_attr_c = smem_c;
+    }
     if (gx_absmax) MK_CHECK_CUDA(cudaMemsetAsync(gx_absmax, 0, sizeof(float), st));
     {
         CoefArgs c;
-        c.sel = plan->sel; c.nei = plan->nei;
-        long long tot = 0;
+        c.sel = plan->sel; c.nei = plan->nei; c.ehat = plan->ehat;
         for (int d = 0; d < 4; ++d) {
             c.n[d] = plan->n[d]; c.boff[d] = plan->boff[d]; c.eoff[d] = plan->eoff[d];
             c.L[d] = layer->L[d]; c.koff[d] = layer->koff[d]; c.scoff[d] = scoff[d];
-            tot = std::max<long long>(tot, scoff[d] + (long long)plan->n[d] * layer->L[d]);
+            c.part_off[d] = part_off[d];
         }
-        c.tot = tot;
         c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode;
         c.argmax = argmax; c.coef = coef;
-        if (tot > 0) {
-            count_launches(1);
-            k_coef<<<(int)((tot + 255) / 256), 256, 0, st>>>(c);
-            MK_CHECK_CUDA(cudaGetLastError());
-        }
+        c.partials = partials; c.FW = a.FW; c.Fp = layer->Fp;
+        c.G = grid;
+        count_launches(1);
+        k_coef_bond<<<4 * grid, CB_THREADS, smem_c, st>>>(c);
+        MK_CHECK_CUDA(cudaGetLastError());
     }
-    count_launches(1);
-    k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
-    MK_CHECK_CUDA(cudaGetLastError());
+    for (int l = 0; l < nlaunch; ++l) {
+        // blocks {0, 3} and {1, 2}: the scatter work of the two launches is about equal for the base model
+        if (a.tb.nb <= 2) { a.nbl = a.tb.nb; a.blist[0] = 0; a.blist[1] = a.tb.nb > 1 ? 1 : 0; }
+        else if (a.tb.nb == 3) { a.nbl = l == 0 ? 2 : 1; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 2; }
+        else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 1; a.blist[1] = l == 0 ? 3 : 2; }
+        a.first = l == 0; a.last = l == nlaunch - 1;
+        count_launches(1);
+        k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
+        MK_CHECK_CUDA(cudaGetLastError());
+    }
     return 1;
 }
 

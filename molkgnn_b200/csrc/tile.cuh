@@ -76,6 +76,7 @@ struct __align__(16) TileMetaG {
     unsigned char inj[TNODES][4];     // position of this node in that source's neighbour list
     unsigned char incnt[TNODES];
     unsigned char lidx[TNODES];       // index of the node inside list[deg - 1]
+    unsigned char cr[TNODES];         // collision rank of the node's neighbour slots, 2 bits per j (see elist)
     // neighbour slots (node << 2 | j) grouped by (degree d of the node, rank r): r = number of earlier in-edges of the
     // same target whose source also has degree d.  Two slots of one group never share a target, so the backward scatter
     // into (kernel row, target column) is collision free inside a group; groups of higher rank accumulate.
