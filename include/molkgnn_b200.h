@@ -62,6 +62,7 @@ typedef struct molkgnn_plan {
     void*    tile_meta;        /* [N/32 + 4] records of molkgnn_tile_meta_bytes() bytes: per-tile node lists, local neighbour
                                   ids, bucket rows, in-lists (csrc/tile.cuh TileMetaG) */
     float*   ehat_node;        /* [E,8] the rows of ehat in node order (tile-contiguous) */
+    int32_t* node_tile;        /* [N]   tile << 8 | row of the node inside its tile */
 } molkgnn_plan_t;
 
 /* One KernelSetConv layer (kernels.py:754-781): raw parameters of the four KernelConv modules + packed workspace. */
@@ -165,9 +166,11 @@ int molkgnn_set_fwd_path(int path);
 
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
 /* h[i, koff_d + k] = sum over in-edges (j -> i) in edge order of sc_{deg j}[pos j, k]; columns K..ldh-1 zeroed;
- * hnorm[i] = ||h_i|| (nullable). */
+ * hnorm[i] = ||h_i|| (nullable).  ximg (nullable; needs a tiled plan and ldh <= 112): additionally writes the normalised
+ * fp16 (hi, lo) images of h in tile order, i.e. what molkgnn_tile_ximg_build() would produce for the next layer
+ * (node_attr_dim = K, Fp = ldh), so that the next layer's activations are never re-read for the conversion. */
 int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* sc,
-                          const int64_t scoff[4], float* h, int32_t ldh, float* hnorm, void* stream);
+                          const int64_t scoff[4], float* h, int32_t ldh, float* hnorm, void* ximg, void* stream);
 
 /* ---- backward (the reference uses autograd over kernels.py:353-425 and KernelLayer.py:119) ---- */
 int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
@@ -179,18 +182,15 @@ int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgn
  * phases: bit 0 = k_bwd_w (coef + per-CTA partial sums), bit 1 = parameter finalize, bit 2 = k_bwd_x (grad_x);
  * 7 runs everything; the split exists so that a profiler can time the three kernels separately.
  *
- * Molecule-tile tensor-core path (default when eligible): runs when ximg (molkgnn_tile_ximg_build of this layer's x) and
- * grad_absmax (device scalar = max |grad|, e.g. from molkgnn_absmax or the gx_absmax of the layer above) are given, the
- * plan carries tiles, the layer is eligible and ldgx == Fp.  scratch: N * roundup(Fp,16) floats (partial input gradients
- * between kernel blocks).  gx_absmax (nullable, device scalar) receives max |grad_x|.  Then phase bit 0 runs the whole
- * backward kernel (coefficients, parameter partial sums AND grad_x), bit 2 is a no-op and coef is unused. */
+ * Molecule-tile tensor-core path (default when eligible): runs when ximg (molkgnn_tile_ximg_build of this layer's x, or
+ * the images molkgnn_propagate_fwd wrote) is given, the plan carries tiles, the layer is eligible and ldgx == Fp.
+ * scratch: N * roundup(Fp,16) floats (partial input gradients handed between the two launches of a 4-block layer).
+ * Then phase bit 0 runs the whole backward (coefficients + bond gradients, parameter partial sums AND grad_x), bit 2 is
+ * a no-op. */
 int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
                      const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
-                     const molkgnn_layer_grads_t* grads, int32_t phases, const void* ximg, const float* grad_absmax,
-                     float* scratch, float* gx_absmax, void* stream);
-/* out[0] = max |x[i]|, i < n (x 16-byte aligned): the scale of the fp16 coefficient operand of the tile backward */
-int molkgnn_absmax(const float* x, int64_t n, float* out, void* stream);
+                     const molkgnn_layer_grads_t* grads, int32_t phases, const void* ximg, float* scratch, void* stream);
 /* 1 = molecule-tile tensor-core backward when eligible (default), 0 = bucket-order SIMT kernels; returns the old value */
 int molkgnn_set_bwd_path(int path);
 /* how often each path ran so far: forward tile / forward other / backward tile / backward other */

@@ -14,7 +14,7 @@ class Plan(C.Structure):
                 ("deg", vp), ("pos", vp), ("sel", vp), ("nei", vp), ("nei_eid", vp), ("ehat", vp), ("tsign", vp),
                 ("in_cnt", vp), ("in_src", vp), ("in_j", vp),
                 ("tile_start", vp), ("n_tiles", i32), ("tile_max_nodes", i32), ("tile_max_deg", i32 * 4),
-                ("tile_meta", vp), ("ehat_node", vp)]
+                ("tile_meta", vp), ("ehat_node", vp), ("node_tile", vp)]
 
 
 class Layer(C.Structure):
@@ -48,13 +48,12 @@ EXPORTS = {
     "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
                                    vp, vp, vp, vp]),
-    "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp]),
+    "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp, vp]),
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),
     "molkgnn_tc_selftest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
-                                   vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp, vp, vp]),
-    "molkgnn_absmax": (C.c_int, [vp, i64, vp, vp]),
+                                   vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp]),
     "molkgnn_set_bwd_path": (C.c_int, [C.c_int]),
     "molkgnn_path_counts": (None, [i64 * 4]),
 }

@@ -75,17 +75,24 @@ __global__ void k_node_prepare(int N, const int* __restrict__ out_cnt, int* out_
     }
 }
 
-// totals[0..3] = n_d, totals[4] = bad nodes, totals[5..8] = boff, totals[9..12] = eoff
-__global__ void k_scan_blocks(int nblk, const int* __restrict__ blk_counts, int* blk_off, int* totals) {
-    int c = threadIdx.x;
-    if (c < 5) {
-        int run = 0;
-        for (int b = 0; b < nblk; ++b) {
-            blk_off[b * 5 + c] = run;
-            run += blk_counts[b * 5 + c];
+// totals[0..3] = n_d, totals[4] = bad nodes, totals[5..8] = boff, totals[9..12] = eoff.  One warp per class scans the
+// block histograms 32 blocks at a time.
+__global__ void __launch_bounds__(160) k_scan_blocks(int nblk, const int* __restrict__ blk_counts, int* blk_off, int* totals) {
+    const int c = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int run = 0;
+    for (int b0 = 0; b0 < nblk; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = b < nblk ? blk_counts[b * 5 + c] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        totals[c] = run;
+        if (b < nblk) blk_off[b * 5 + c] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (lane == 0) totals[c] = run;
     __syncthreads();
     if (threadIdx.x == 0) {
         int bo = 0, eo = 0;
@@ -208,33 +215,46 @@ __global__ void __launch_bounds__(256) k_cut_gaps(int N, const int* __restrict__
 }
 
 // tile i starts at the last valid cut <= i * S with S = TILE_CAP + 1 - (largest molecule): every tile then holds whole
-// molecules and at most TILE_CAP nodes
+// molecules and at most TILE_CAP nodes.  One warp per tile.
 __global__ void __launch_bounds__(128) k_tile_starts(int N, int cap, const int* __restrict__ cutpos,
                                                      const int* __restrict__ deg, int* tile_start, int* tinfo) {
-    const int i = blockIdx.x * 128 + threadIdx.x;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int gap = tinfo[0];
     const int S = TILE_CAP + 1 - gap;
     if (S < TILE_MIN_STRIDE || (tinfo[1] & 1)) {
-        if (i == 0) tinfo[2] = 0;
+        if (i == 0 && lane == 0) tinfo[2] = 0;
         return;
     }
     const int T = (N + S - 1) / S;
-    if (i == 0) tinfo[2] = T;
+    if (i == 0 && lane == 0) tinfo[2] = T;
     if (i > T || i >= cap) return;
-    int a = (int)min((long long)i * S, (long long)N);
-    while (a > 0 && cutpos[a] < 0) --a;
-    tile_start[i] = a;
-    if (i == T) return;
-    int b = (int)min((long long)(i + 1) * S, (long long)N);
-    while (b > 0 && cutpos[b] < 0) --b;
-    int cnt[4] = {0, 0, 0, 0};
-    for (int v = a; v < b; ++v) {
-        const int d = deg[v];
-        if (d >= 1 && d <= 4) ++cnt[d - 1];
+    int a = 0, b = 0;
+    if (lane == 0) {
+        a = (int)min((long long)i * S, (long long)N);
+        while (a > 0 && cutpos[a] < 0) --a;
+        tile_start[i] = a;
+    } else if (lane == 1 && i < T) {
+        b = (int)min((long long)(i + 1) * S, (long long)N);
+        while (b > 0 && cutpos[b] < 0) --b;
     }
-    atomicMax(&tinfo[3], b - a);
+    a = __shfl_sync(0xffffffffu, a, 0);
+    b = __shfl_sync(0xffffffffu, b, 1);
+    if (i == T) return;
+    int cnt[4] = {0, 0, 0, 0};
+    for (int v = a + lane; v < b; v += 32) {
+        const int d = deg[v];
 #pragma unroll
-    for (int d = 0; d < 4; ++d) atomicMax(&tinfo[4 + d], cnt[d]);
+        for (int c = 0; c < 4; ++c) cnt[c] += (d == c + 1);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt[c] += __shfl_xor_sync(0xffffffffu, cnt[c], o);
+    if (lane == 0) {
+        atomicMax(&tinfo[3], b - a);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) atomicMax(&tinfo[4 + d], cnt[d]);
+    }
 }
 
 // per-tile metadata record + bond rows in node order (one block of 128 threads per tile, thread = local node)
@@ -243,7 +263,8 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
                                                       const float* __restrict__ ehat, const int8_t* __restrict__ tsign,
                                                       const int* __restrict__ in_cnt, const int* __restrict__ in_src,
                                                       const int* __restrict__ in_j, const int* __restrict__ blk_off,
-                                                      const int* __restrict__ totals, TileMetaG* meta, float* ehat_node) {
+                                                      const int* __restrict__ totals, TileMetaG* meta, float* ehat_node,
+                                                      int* node_tile) {
     __shared__ int wsum[4][6];
     __shared__ int s_e0;
     __shared__ int s_gcnt[16], s_goff[17], s_gfill[16];
@@ -328,6 +349,7 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
             ij[t] = (unsigned char)in_j[4 * (size_t)(t0 + tid) + t];
         }
     }
+    if (tid < nn && node_tile) node_tile[t0 + tid] = (tile << 8) | tid;
     m->nl[tid] = w_nl;
     m->posl[tid] = R;
     m->eslot[tid] = (unsigned short)soff;
@@ -491,11 +513,11 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     if (E > 0)
         k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, far, err);
     k_node_prepare<<<nblk, BT, 0, st>>>(N, out_cnt, out_eid, plan->in_cnt, in_eid, plan->deg, blk_counts, err);
-    k_scan_blocks<<<1, 32, 0, st>>>(nblk, blk_counts, blk_off, totals);
+    k_scan_blocks<<<1, 160, 0, st>>>(nblk, blk_counts, blk_off, totals);
     if (tiles) {
         k_valid_cuts<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, far, cutpos, tinfo);
         k_cut_gaps<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, cutpos, tinfo);
-        k_tile_starts<<<(tile_cap + 127) / 128, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
+        k_tile_starts<<<(tile_cap + 3) / 4, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
     }
     int host[32];
     MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
@@ -518,7 +540,8 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
         count_launches(1);
         k_tile_meta<<<plan->n_tiles, TNODES, 0, st>>>(N, plan->tile_start, plan->deg, plan->pos, plan->nei, plan->ehat,
                                                     plan->tsign, plan->in_cnt, plan->in_src, plan->in_j, blk_off, totals,
-                                                    reinterpret_cast<TileMetaG*>(plan->tile_meta), plan->ehat_node);
+                                                    reinterpret_cast<TileMetaG*>(plan->tile_meta), plan->ehat_node,
+                                                    plan->node_tile);
     } else {
         plan->n_tiles = 0;
     }

@@ -19,9 +19,9 @@ int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, c
                           cudaStream_t st);
 int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
-                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* coef,
-                         float* partials, float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4],
-                         int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st);
+                         const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials, float* scratch,
+                         float* grad_x, int32_t ldgx, int64_t part_off[4], int ncta[4], int64_t* part_total, bool do_launch,
+                         cudaStream_t st);
 int tile_bwd_grid(const molkgnn_plan_t* plan);
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 long long g_path_counts[4] = {0, 0, 0, 0};   // forward tile / other, backward tile / other
@@ -518,19 +518,17 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                                 const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode,
                                 const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials,
                                 float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, int32_t phases,
-                                const void* ximg, const float* grad_absmax, float* scratch, float* gx_absmax,
-                                void* stream_) {
+                                const void* ximg, float* scratch, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (init_dev()) return -1;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_bwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE(!grad_x || (ldgx % 4 == 0 && ldgx >= layer->Fp), "conv_bwd: ldgx=%d must be a multiple of 4 >= Fp", ldgx);
     // ---------------- molecule-tile tensor-core path ----------------
-    if (ximg && grad_absmax && g_bwd_path != 0 && (!grad_x || ldgx == layer->Fp)) {
+    if (ximg && g_bwd_path != 0 && (!grad_x || ldgx == layer->Fp)) {
         int64_t t_off[4], t_total = 0;
         int t_ncta[4];
-        const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, grad_absmax, argmax, scoff,
-                                            coef, partials, scratch, grad_x, ldgx, gx_absmax, t_off, t_ncta, &t_total,
-                                            (phases & 1) != 0, st);
+        const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, argmax, scoff, coef,
+                                            partials, scratch, grad_x, ldgx, t_off, t_ncta, &t_total, (phases & 1) != 0, st);
         if (rc < 0) return rc;
         if (rc == 1) {
             if (phases & 1) ++g_path_counts[2];
@@ -630,10 +628,6 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                 else if (FQ <= 128) rc = launch_bwd_x<32, 4>(b, grid, smem, st);
                 else { MK_REQUIRE(false, "conv_bwd: node_attr_dim %d > 512 not supported", layer->F); }
             }
-            if (rc) return rc;
-        }
-        if (gx_absmax) {
-            const int rc = molkgnn_absmax(grad_x, (int64_t)plan->N * ldgx, gx_absmax, stream_);
             if (rc) return rc;
         }
     }

@@ -52,10 +52,11 @@ struct CoefArgs {
     float* coef;
     float* partials; long long part_off[4]; int FW, Fp;
     int G;                                     // CTAs (= partial copies) per degree
+    float* amax;                               // device scalar (zeroed by the launcher): max |coef|
 };
 
 template <int D>
-__device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, unsigned char* invS, int c) {
+__device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, unsigned char* invS, float4* ehS, int c) {
     const int L = a.L[D - 1], n = a.n[D - 1];
     const int tid = threadIdx.x;
     const int eoff = a.eoff[D - 1], koff = a.koff[D - 1];
@@ -65,33 +66,57 @@ __device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, 
     for (int r = 0; r < CB_MAXR; ++r)
 #pragma unroll
         for (int e = 0; e < EP; ++e) acc[r][e] = 0.f;
+    float amax = 0.f;
     const int ntiles = (n + CB_TN - 1) / CB_TN;
     for (int t = c; t < ntiles; t += a.G) {
         const int R0 = t * CB_TN;
         const int nv = min(CB_TN, n - R0);
         __syncthreads();
-        for (int i = tid; i < nv * L; i += CB_THREADS) {
-            const int nl = i / L, k = i - nl * L;
-            const int col = koff + k;
-            const int R = R0 + nl;
-            float g;
-            if (a.grad_mode == 0) {
-                g = a.grad[(size_t)a.sel[a.boff[D - 1] + R] * a.ldg + col];
-            } else {
-                const int* nb = a.nei + (size_t)eoff + (size_t)R * D;
-                g = a.grad[(size_t)nb[0] * a.ldg + col];
+        // bond rows of the node tile: contiguous in the plan, staged once
+        {
+            const float4* src = reinterpret_cast<const float4*>(a.ehat + ((size_t)eoff + (size_t)R0 * D) * EP);
+            for (int i = tid; i < nv * D * 2; i += CB_THREADS) ehS[i] = __ldg(src + i);
+        }
+        // coefficients: 4 pairs per thread in flight
+        constexpr int U = 4;
+        const int npair = nv * L;
+        for (int i0 = tid; i0 < npair; i0 += CB_THREADS * U) {
+            float g[U];
+            uint8_t am[U];
 #pragma unroll
-                for (int j = 1; j < D; ++j) g += a.grad[(size_t)nb[j] * a.ldg + col];
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * CB_THREADS;
+                g[u] = 0.f; am[u] = 0;
+                if (i < npair) {
+                    const int nl = i / L, k = i - nl * L;
+                    const int col = koff + k;
+                    const int R = R0 + nl;
+                    if (a.grad_mode == 0) {
+                        g[u] = a.grad[(size_t)a.sel[a.boff[D - 1] + R] * a.ldg + col];
+                    } else {
+                        const int* nb = a.nei + (size_t)eoff + (size_t)R * D;
+                        float s = a.grad[(size_t)nb[0] * a.ldg + col];
+#pragma unroll
+                        for (int j = 1; j < D; ++j) s += a.grad[(size_t)nb[j] * a.ldg + col];
+                        g[u] = s;
+                    }
+                    am[u] = a.argmax[(size_t)a.scoff[D - 1] + (size_t)R0 * L + i];
+                }
             }
-            const size_t cidx = (size_t)a.scoff[D - 1] + (size_t)R * L + k;
-            const uint8_t am = a.argmax[cidx];
-            const float av = (am & 0x80) ? -g : g;
-            a.coef[cidx] = av;
-            coefS[i] = av;
-            uint32_t inv = 0;
 #pragma unroll
-            for (int p = 0; p < Perm<D>::P; ++p) if (p == (am & 0x7f)) inv = perm_inv_code<D>(p);
-            invS[i] = (unsigned char)inv;
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * CB_THREADS;
+                if (i < npair) {
+                    const float av = (am[u] & 0x80) ? -g[u] : g[u];
+                    amax = fmaxf(amax, fabsf(av));
+                    a.coef[(size_t)a.scoff[D - 1] + (size_t)R0 * L + i] = av;
+                    coefS[i] = av;
+                    uint32_t inv = 0;
+#pragma unroll
+                    for (int p = 0; p < Perm<D>::P; ++p) if (p == (am[u] & 0x7f)) inv = perm_inv_code<D>(p);
+                    invS[i] = (unsigned char)inv;
+                }
+            }
         }
         __syncthreads();
         // bond-attribute support gradients: thread owns rows (s, k), sums over the nodes in fixed order
@@ -100,11 +125,11 @@ __device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, 
             const int row = tid + r * CB_THREADS;
             if (row < nrows) {
                 const int s = row / L, k = row - s * L;
+#pragma unroll 4
                 for (int nl = 0; nl < nv; ++nl) {
                     const float av = coefS[nl * L + k];
                     const int j = (invS[nl * L + k] >> (2 * s)) & 3;
-                    const float* e = a.ehat + ((size_t)eoff + (size_t)(R0 + nl) * D + j) * EP;
-                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(e)), e1 = __ldg(reinterpret_cast<const float4*>(e + 4));
+                    const float4 e0 = ehS[(nl * D + j) * 2], e1 = ehS[(nl * D + j) * 2 + 1];
                     acc[r][0] = fmaf(av, e0.x, acc[r][0]); acc[r][1] = fmaf(av, e0.y, acc[r][1]);
                     acc[r][2] = fmaf(av, e0.z, acc[r][2]); acc[r][3] = fmaf(av, e0.w, acc[r][3]);
                     acc[r][4] = fmaf(av, e1.x, acc[r][4]); acc[r][5] = fmaf(av, e1.y, acc[r][5]);
@@ -113,6 +138,9 @@ __device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, 
             }
         }
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.amax), __float_as_uint(amax));
     const int rows_x = (D + 1) * L;
     float* part = a.partials + a.part_off[D - 1] + (size_t)c * rows_x * a.FW + a.Fp;
 #pragma unroll
@@ -134,13 +162,14 @@ __global__ void __launch_bounds__(CB_THREADS) k_coef_bond(const __grid_constant_
     const int d = blockIdx.x / a.G + 1, c = blockIdx.x % a.G;
     const int L = a.L[d - 1];
     if (L == 0) return;
-    float* coefS = reinterpret_cast<float*>(smem_c);
-    unsigned char* invS = smem_c + (size_t)CB_TN * L * 4;
+    float4* ehS = reinterpret_cast<float4*>(smem_c);                     // [CB_TN * 4 slots][2]
+    float* coefS = reinterpret_cast<float*>(smem_c + CB_TN * 4 * 32);
+    unsigned char* invS = smem_c + CB_TN * 4 * 32 + (size_t)CB_TN * L * 4;
     switch (d) {
-        case 1: coef_bond_body<1>(a, coefS, invS, c); break;
-        case 2: coef_bond_body<2>(a, coefS, invS, c); break;
-        case 3: coef_bond_body<3>(a, coefS, invS, c); break;
-        default: coef_bond_body<4>(a, coefS, invS, c); break;
+        case 1: coef_bond_body<1>(a, coefS, invS, ehS, c); break;
+        case 2: coef_bond_body<2>(a, coefS, invS, ehS, c); break;
+        case 3: coef_bond_body<3>(a, coefS, invS, ehS, c); break;
+        default: coef_bond_body<4>(a, coefS, invS, ehS, c); break;
     }
 }
 
@@ -158,11 +187,10 @@ struct BwdTileArgs {
     int img_one, x_one;
     const float* coef;                 // chi * g per (node, kernel) pair, compact bucket order (k_coef_bond)
     const uint8_t* argmax; long long scoff[4];
-    const float* grad_absmax;          // device scalar: max |grad|
+    const float* amax;                 // device scalar: max |coef| (k_coef_bond)
     float* partials; long long part_off[4]; int FW;
     float* scratch;                    // [N, Fk] partial dxh handed from the first launch to the second
     float* gx; int ldgx;
-    float* gx_absmax;                  // device scalar (nullable): max |grad_x|, for the next layer down
     int nbl, blist[2];                 // kernel blocks of this launch
     int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
     int a_cap, buf_bytes;
@@ -282,16 +310,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     unsigned char* am_s = smem + a.sm_am;
     float* red = reinterpret_cast<float*>(smem + a.sm_a);       // Jacobian reduction scratch: the coefficients are dead by then
     uint32_t ph_mma = 0u, ph_img = 0u, ph_cp[2] = {0u, 0u};
-    // power-of-two scale: |alpha * chi * g| / scale <= 2^10 (g sums at most 4 gradient entries)
+    // power-of-two scale: |alpha * chi * g| / scale <= 2^10
     float scale, rscale;
     {
-        const float gm = fmaxf(*a.grad_absmax, 1e-30f) * 4.0f;
+        const float gm = fmaxf(*a.amax, 1e-30f);
         int e;
         frexpf(gm, &e);                                   // gm < 2^e
         scale = ldexpf(1.0f, e - 10);
         rscale = ldexpf(1.0f, 10 - e);
     }
-    float gmax_local = 0.f;
     const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / 32-column part of this warp
     bool img_pending = false;                             // an image copy is in flight (uniform across the CTA)
     if ((int)blockIdx.x < a.n_tiles) {
@@ -484,7 +511,6 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                             for (int c = 0; c < 4; ++c) {
                                 o[c] = clamped ? dv[i + c] * rden : (dv[i + c] - dot * xh[i + c]) * rden;
                                 if (f0 + i + c >= a.F) o[c] = 0.f;
-                                gmax_local = fmaxf(gmax_local, fabsf(o[c]));
                             }
                             st4(out + i, make_float4(o[0], o[1], o[2], o[3]));
                         }
@@ -531,28 +557,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             }
         }
     }
-    if (a.gx_absmax && a.last) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) gmax_local = fmaxf(gmax_local, __shfl_xor_sync(0xffffffffu, gmax_local, o));
-        if (lane == 0) atomicMax(reinterpret_cast<unsigned int*>(a.gx_absmax), __float_as_uint(gmax_local));
-    }
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
-}
-
-// max |x| of a buffer into a device scalar (the caller zeroes it): the scale of the fp16 coefficient operand
-__global__ void __launch_bounds__(256) k_absmax(const float* __restrict__ x, long long n4, long long n, float* out) {
-    float m = 0.f;
-    const long long stride = (long long)gridDim.x * 256;
-    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += stride) {
-        const float4 v = reinterpret_cast<const float4*>(x)[i];
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
-    }
-    for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) m = fmaxf(m, fabsf(x[i]));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -576,11 +583,11 @@ bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
 // returns 1 if launched, 0 if not eligible, <0 on error.  part_off / ncta describe the partial copies for k_param_finalize.
 int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
-                         const float* grad_absmax, const uint8_t* argmax, const int64_t scoff[4], float* coef,
-                         float* partials, float* scratch, float* grad_x, int32_t ldgx, float* gx_absmax, int64_t part_off[4],
-                         int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st) {
+                         const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials, float* scratch,
+                         float* grad_x, int32_t ldgx, int64_t part_off[4], int ncta[4], int64_t* part_total, bool do_launch,
+                         cudaStream_t st) {
     (void)x; (void)ldx;
-    if (!ximg || !grad_absmax || !coef || !tile_bwd_ok(plan, layer)) return 0;
+    if (!ximg || !coef || !tile_bwd_ok(plan, layer)) return 0;
     static int s_budget = 0;
     if (!s_budget) {
         s_budget = device_max_smem_optin();
@@ -597,7 +604,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.n_tiles = plan->n_tiles;
     const int grid = tile_bwd_grid(plan);
     a.FW = layer->Fp + EP;
-    int64_t po = 0;
+    int64_t po = 0, rows_all = 0;
     for (int d = 0; d < 4; ++d) {
         a.L[d] = layer->L[d];
         a.packed[d] = layer->packed[d];
@@ -605,17 +612,19 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         a.part_off[d] = part_off[d] = po;
         ncta[d] = layer->L[d] > 0 ? grid : 0;
         po += (int64_t)ncta[d] * (d + 2) * layer->L[d] * a.FW;
+        rows_all += (int64_t)(d + 2) * layer->L[d];
     }
     *part_total = po;
+    float* amax = partials + po + 2 * rows_all + 8;   // spare floats behind k_param_finalize's Q scratch
     a.img = reinterpret_cast<const unsigned char*>(layer->tile_img);
     a.img_one = tile_img_one(a.Fk);
     a.x_one = tile_img_one(a.Fk);
     a.coef = coef;
     a.argmax = argmax;
-    a.grad_absmax = grad_absmax;
+    a.amax = amax;
     a.partials = partials;
     a.scratch = scratch;
-    a.gx = grad_x; a.ldgx = ldgx; a.gx_absmax = gx_absmax;
+    a.gx = grad_x; a.ldgx = ldgx;
     // capacity from the plan: (node, kernel) pairs of the fullest tile of any block
     int a_cap = 0;
     for (int b = 0; b < a.tb.nb; ++b) {
@@ -635,7 +644,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     if (off > s_budget - 2048) return 0;
     int Lmax = 1;
     for (int d = 0; d < 4; ++d) Lmax = std::max(Lmax, layer->L[d]);
-    const int64_t smem_c = (int64_t)CB_TN * Lmax * 5;
+    const int64_t smem_c = (int64_t)CB_TN * 4 * 32 + (int64_t)CB_TN * Lmax * 5;
     if (smem_c > s_budget - 2048) return 0;
     if (!do_launch) return 1;
     static int64_t s_attr = 0, s_attr_c = 0;
@@ -647,7 +656,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_bond, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         s_attr_c = smem_c;
     }
-    if (gx_absmax) MK_CHECK_CUDA(cudaMemsetAsync(gx_absmax, 0, sizeof(float), st));
+    MK_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
     {
         CoefArgs c;
         c.sel = plan->sel; c.nei = plan->nei; c.ehat = plan->ehat;
@@ -660,6 +669,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         c.argmax = argmax; c.coef = coef;
         c.partials = partials; c.FW = a.FW; c.Fp = layer->Fp;
         c.G = grid;
+        c.amax = amax;
         count_launches(1);
         k_coef_bond<<<4 * grid, CB_THREADS, smem_c, st>>>(c);
         MK_CHECK_CUDA(cudaGetLastError());
@@ -679,16 +689,3 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 
 }  // namespace mk
 
-using namespace mk;
-
-extern "C" int molkgnn_absmax(const float* x, int64_t n, float* out, void* stream_) {
-    cudaStream_t st = (cudaStream_t)stream_;
-    MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "absmax: x must be 16-byte aligned");
-    MK_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), st));
-    if (n <= 0) return 0;
-    const int grid = (int)std::min<int64_t>(148 * 8, (n / 4 + 255) / 256 + 1);
-    count_launches(1);
-    k_absmax<<<grid, 256, 0, st>>>(x, n / 4, n, out);
-    MK_CHECK_CUDA(cudaGetLastError());
-    return 0;
-}

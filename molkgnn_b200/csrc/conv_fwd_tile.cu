@@ -177,10 +177,13 @@ template <int D> __device__ __forceinline__ uint32_t perm_code_rt(int p) {
     return c;
 }
 
-// one (node, kernel) pair: the reference arithmetic on its d x d similarity tile
-template <int D>
-__device__ __forceinline__ void tf_pair(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
-                                        const unsigned char* dupf, const SegConst& sg, int nl_, int kl) {
+// one (node, kernel) pair: the reference arithmetic on its d x d similarity tile.  Results are returned, the caller
+// stores them: two pairs per thread are evaluated back to back so that their dependency chains interleave.
+struct PairOut { float sc; size_t cidx, oidx; uint8_t am, free; };
+
+template <int D, bool FORCED>
+__device__ __forceinline__ PairOut tf_pair(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
+                                           const unsigned char* dupf, const SegConst& sg, int nl_, int kl) {
     constexpr int P = Perm<D>::P;
     const TileMetaG& m = tb->m;
     const uint32_t nw = m.nl[nl_];
@@ -196,8 +199,9 @@ __device__ __forceinline__ void tf_pair(const FwdTileArgs& a, const TileBuf* tb,
         for (int s = 0; s < D; ++s) T[j][s] = c[s * sg.nk];
     }
     const float cdot = col0[nl_ * 128 + D * sg.nk];
-    const size_t cidx = (size_t)a.scoff[D - 1] + (size_t)R * sg.L + k;
-    const int forced = a.argmax_in ? (a.argmax_in[cidx] & 0x7f) : -1;
+    PairOut o;
+    o.cidx = (size_t)a.scoff[D - 1] + (size_t)R * sg.L + k;
+    const int forced = FORCED && a.argmax_in ? (a.argmax_in[o.cidx] & 0x7f) : -1;
     // mean over j for every permutation: sequential sum, then true division (kernels.py:194)
     float best = 0.f, used = 0.f;
     int bi = 0;
@@ -208,10 +212,10 @@ __device__ __forceinline__ void tf_pair(const FwdTileArgs& a, const TileBuf* tb,
         for (int j = 1; j < D; ++j) s += T[j][Perm<D>::at(p, j)];
         s = div_deg<D>(s);
         if (p == 0 || s > best) { best = s; bi = p; }   // first maximum wins (torch.max, kernels.py:373)
-        if (p == forced) used = s;
+        if (FORCED && p == forced) used = s;
     }
-    if (a.argmax_free) a.argmax_free[cidx] = (uint8_t)bi;
-    if (forced >= 0 && forced < P) { bi = forced; best = used; }
+    o.free = (uint8_t)bi;
+    if (FORCED && forced >= 0 && forced < P) { bi = forced; best = used; }
     // bond-attribute cosine at the chosen permutation (kernels.py:382-390)
     const uint32_t code = perm_code_rt<D>(bi);
     float esum = 0.f;
@@ -236,30 +240,49 @@ __device__ __forceinline__ void tf_pair(const FwdTileArgs& a, const TileBuf* tb,
         if (!dupf[nl_]) chi = (m.tsg[nl_] == sg.supsign[k * 12 + bi]) ? 1 : -1;
         if (chi < 0) { sc = -sc; am |= 0x80; }
     }
-    a.argmax[cidx] = am;
-    const size_t oidx = a.sc_mode == 0 ? cidx : (size_t)(m.t0 + nl_) * a.ld_sc + a.koff[D - 1] + k;
-    a.sc[oidx] = sc;
+    o.sc = sc; o.am = am;
+    o.oidx = a.sc_mode == 0 ? o.cidx : (size_t)(m.t0 + nl_) * a.ld_sc + a.koff[D - 1] + k;
+    return o;
 }
 
-// the block's pairs (segment-major, then node, then kernel), strided over the CTA; part 0 / 1 = first / second half
+template <int D, bool FORCED>
+__device__ __forceinline__ void tf_pairs_of_thread(const FwdTileArgs& a, const TileBuf* tb, const float* dump,
+                                                   const float4* estab, const unsigned char* dupf, const SegConst& sg,
+                                                   int np) {
+    // the segment's pairs (node-major, then kernel), two per thread and iteration
+    for (int p = (int)threadIdx.x; p < np; p += 2 * TF_THREADS) {
+        const int p2 = p + TF_THREADS;
+        const int ni = (int)(((float)p + 0.5f) * sg.rnk);
+        const PairOut o1 = tf_pair<D, FORCED>(a, tb, dump, estab, dupf, sg, tb->m.list[D - 1][ni], p - ni * sg.nk);
+        PairOut o2;
+        const bool has2 = p2 < np;
+        if (has2) {
+            const int ni2 = (int)(((float)p2 + 0.5f) * sg.rnk);
+            o2 = tf_pair<D, FORCED>(a, tb, dump, estab, dupf, sg, tb->m.list[D - 1][ni2], p2 - ni2 * sg.nk);
+        }
+        if (FORCED && a.argmax_free) a.argmax_free[o1.cidx] = o1.free;
+        a.argmax[o1.cidx] = o1.am;
+        a.sc[o1.oidx] = o1.sc;
+        if (has2) {
+            if (FORCED && a.argmax_free) a.argmax_free[o2.cidx] = o2.free;
+            a.argmax[o2.cidx] = o2.am;
+            a.sc[o2.oidx] = o2.sc;
+        }
+    }
+}
+
+// the block's pairs, segment by segment
+template <bool FORCED>
 __device__ __forceinline__ void tf_epilogue(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
-                                            const unsigned char* dupf, const SegConst* segs, int nseg, int part) {
+                                            const unsigned char* dupf, const SegConst* segs, int nseg) {
     for (int si = 0; si < nseg; ++si) {
         const SegConst sg = segs[si];
-        const int cnt = tb->m.cnt[sg.d - 1];
-        const int np = cnt * sg.nk;
-        const int half = min(np, ((np / 2 + TF_THREADS - 1) / TF_THREADS) * TF_THREADS);   // whole CTA strides first
-        const int p0 = part == 0 ? 0 : half, p1 = part == 0 ? half : np;
-        for (int p = p0 + (int)threadIdx.x; p < p1; p += TF_THREADS) {
-            const int ni = (int)(((float)p + 0.5f) * sg.rnk);
-            const int kl = p - ni * sg.nk;
-            const int nl_ = tb->m.list[sg.d - 1][ni];
-            switch (sg.d) {
-                case 1: tf_pair<1>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
-                case 2: tf_pair<2>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
-                case 3: tf_pair<3>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
-                default: tf_pair<4>(a, tb, dump, estab, dupf, sg, nl_, kl); break;
-            }
+        const int np = tb->m.cnt[sg.d - 1] * sg.nk;
+        switch (sg.d) {
+            case 1: tf_pairs_of_thread<1, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
+            case 2: tf_pairs_of_thread<2, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
+            case 3: tf_pairs_of_thread<3, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
+            default: tf_pairs_of_thread<4, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
         }
     }
 }
@@ -289,18 +312,23 @@ __device__ __forceinline__ void tf_dup_flags(const FwdTileArgs& a, const TileBuf
     }
 }
 
-__global__ void __launch_bounds__(TF_THREADS, 1) k_conv_fwd_tile(const __grid_constant__ FwdTileArgs a) {
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TF_THREADS) : "memory"); }
+
+// 16 consumer warps (dump + epilogue) and one producer warp (tile queue, bulk copies, UMMA issue): the producer runs one
+// tile ahead, bounded only by the single node-image buffer (free when the previous tile's MMAs are done), the two TMEM
+// accumulators and the two metadata buffers.
+template <bool FORCED>
+__global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __grid_constant__ FwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma[2], bar_cp[2];
+    __shared__ uint64_t bar_mma[2], bar_cp[2], bar_tfree[2], bar_bfree[2];
     __shared__ uint32_t tslot;
     __shared__ int s_tile[2];
     __shared__ SegConst s_seg[TILE_MAXSEG];
     const int tid = threadIdx.x, warp = tid >> 5;
-    if (tid == 0) {
-        tc::mbar_init(&bar_mma[0], 1); tc::mbar_init(&bar_mma[1], 1);
-        tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
-        tc::fence_mbar_init();
-    }
+    const bool producer = warp == TF_WARPS;
     if (warp == 0) tc::tmem_alloc(&tslot, 256);
     tc::fence_before_sync();
     __syncthreads();
@@ -310,15 +338,21 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_conv_fwd_tile(const __grid_co
     float* dump = reinterpret_cast<float*>(smem + a.sm_dump);
     float4* estab = reinterpret_cast<float4*>(smem + a.sm_es);
     unsigned char* dupf = smem + a.sm_dup;
-    uint32_t ph_mma[2] = {0u, 0u}, ph_cp[2] = {0u, 0u};
 
     for (int blk = 0; blk < a.tb.nb; ++blk) {
         __syncthreads();                       // previous block completely finished
-        // ---- block set-up: images, segment constants, bond-support table [slot][half][kernel] ----
-        tf_copy16(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2 * (int64_t)a.img_one);
+        // ---- block set-up: barriers, images, segment constants, bond-support table [slot][half][kernel] ----
+        if (tid == 0) {
+            for (int i = 0; i < 2; ++i) {
+                tc::mbar_init(&bar_mma[i], 1); tc::mbar_init(&bar_cp[i], 1);
+                tc::mbar_init(&bar_tfree[i], 1); tc::mbar_init(&bar_bfree[i], 1);
+            }
+            tc::fence_mbar_init();
+        }
         const int nseg = a.tb.nseg[blk];
         bool has4 = false;
-        {
+        if (!producer) {
+            tf_copy16(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2 * (int64_t)a.img_one);
             int es_off = 0;
             for (int si = 0; si < nseg; ++si) {
                 const TileSeg sg = a.tb.seg[blk][si];
@@ -342,43 +376,45 @@ __global__ void __launch_bounds__(TF_THREADS, 1) k_conv_fwd_tile(const __grid_co
                 }
                 es_off += sg.d * 2 * sg.nk;
             }
+            tc::fence_async_smem();            // images were written through the generic proxy, the MMAs read them
         }
-        if (tid == 0) s_tile[0] = atomicAdd(a.counter + blk, 1);
-        tc::fence_async_smem();                // images were written through the generic proxy, the MMAs read them
         __syncthreads();
-        int t = s_tile[0];
-        int cur = 0;
-        if (t < a.n_tiles && tid == 0) {
-            tf_issue_copy(a, smem, &bufs[0], t, &bar_cp[0]);
-            tc::mbar_wait(&bar_cp[0], ph_cp[0]);
-            tc::fence_after_sync();
-            tf_issue_mma(a, smem, bufs[0].m.nn, tmem, 0, &bar_mma[0]);
-        }
-        while (t < a.n_tiles) {
-            const TileBuf* tb = &bufs[cur];
-            if (tid == 0) s_tile[1] = atomicAdd(a.counter + blk, 1);
-            tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);      // metadata of this tile visible to every thread
-            ph_cp[cur] ^= 1u;
-            tc::mbar_wait(&bar_mma[cur], ph_mma[cur]);    // accumulator ready, x image buffer free
-            ph_mma[cur] ^= 1u;
-            tc::fence_after_sync();
-            __syncthreads();                              // next tile id published
-            const int tn = s_tile[1];
-            if (tn < a.n_tiles && tid == 0) tf_issue_copy(a, smem, &bufs[cur ^ 1], tn, &bar_cp[cur ^ 1]);
-            tf_dump(dump, tmem, cur, tb->m.nn);
-            if (has4 && a.is_last) tf_dup_flags(a, tb, dupf);
-            tc::fence_before_sync();
-            __syncthreads();                              // dump complete
-            tf_epilogue(a, tb, dump, estab, dupf, s_seg, nseg, 0);
-            if (tn < a.n_tiles && tid == 0) {
-                tc::mbar_wait(&bar_cp[cur ^ 1], ph_cp[cur ^ 1]);
-                tc::fence_after_sync();
-                tf_issue_mma(a, smem, bufs[cur ^ 1].m.nn, tmem, cur ^ 1, &bar_mma[cur ^ 1]);
+
+        if (producer) {
+            if ((tid & 31) == 0) {
+                for (int seq = 0;; ++seq) {
+                    const int b = seq & 1;
+                    const uint32_t par = (uint32_t)(seq >> 1) & 1u;
+                    const int tile = atomicAdd(a.counter + blk, 1);
+                    tc::mbar_wait(&bar_bfree[b], par ^ 1u);            // metadata buffer released by the consumers
+                    s_tile[b] = tile < a.n_tiles ? tile : -1;
+                    if (tile >= a.n_tiles) { mbar_arrive(&bar_cp[b]); break; }
+                    if (seq > 0) tc::mbar_wait(&bar_mma[b ^ 1], (uint32_t)((seq - 1) >> 1) & 1u);   // node-image buffer free
+                    tf_issue_copy(a, smem, &bufs[b], tile, &bar_cp[b]);
+                    tc::mbar_wait(&bar_cp[b], par);
+                    tc::mbar_wait(&bar_tfree[b], par ^ 1u);            // accumulator drained by the consumers
+                    tc::fence_after_sync();
+                    tf_issue_mma(a, smem, bufs[b].m.nn, tmem, b, &bar_mma[b]);
+                }
             }
-            tf_epilogue(a, tb, dump, estab, dupf, s_seg, nseg, 1);
-            __syncthreads();                              // dump and this tile's buffer are free again
-            t = tn;
-            cur ^= 1;
+        } else {
+            for (int seq = 0;; ++seq) {
+                const int b = seq & 1;
+                const uint32_t par = (uint32_t)(seq >> 1) & 1u;
+                const TileBuf* tb = &bufs[b];
+                tc::mbar_wait(&bar_cp[b], par);                        // metadata (or the end marker) visible
+                if (s_tile[b] < 0) break;
+                tc::mbar_wait(&bar_mma[b], par);                       // accumulator ready
+                tc::fence_after_sync();
+                tf_dump(dump, tmem, b, tb->m.nn);
+                if (has4 && a.is_last) tf_dup_flags(a, tb, dupf);
+                tc::fence_before_sync();
+                consumer_sync();                                       // dump complete, accumulator drained
+                if (tid == 0) mbar_arrive(&bar_tfree[b]);
+                tf_epilogue<FORCED>(a, tb, dump, estab, dupf, s_seg, nseg);
+                consumer_sync();                                       // dump and this tile's buffer are free again
+                if (tid == 0) mbar_arrive(&bar_bfree[b]);
+            }
         }
     }
     tc::fence_before_sync();
@@ -448,12 +484,14 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, TILE_MAXB * sizeof(int), st));
     static int64_t s_attr = 0;
     if (off > s_attr) {
-        MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;
     }
     const int grid = std::min(plan->n_tiles, s_sms);
     count_launches(1);
-    k_conv_fwd_tile<<<grid, TF_THREADS, off, st>>>(a);
+    if (argmax_in || argmax_free) k_conv_fwd_tile<true><<<grid, TF_THREADS + 32, off, st>>>(a);     // parity harness / replay
+    else k_conv_fwd_tile<false><<<grid, TF_THREADS + 32, off, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
     return 1;
 }

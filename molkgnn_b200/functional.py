@@ -181,22 +181,21 @@ def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=Fal
     return sc, argmax, free
 
 
-def propagate_forward(plan: BucketPlan, pack: LayerPack, sc):
+def propagate_forward(plan: BucketPlan, pack: LayerPack, sc, next_pack=None):
+    """-> (h [N,Kp], ||h_i||, fp16 images of h for ``next_pack`` or None)"""
+    L = _lib.lib()
     scoff, _ = plan.scoff(pack.L)
     h = torch.empty(plan.N, pack.Kp, dtype=torch.float32, device=sc.device)
     hnorm = torch.empty(plan.N, dtype=torch.float32, device=sc.device)
+    ximg = None
+    if next_pack is not None and next_pack.tile_img is not None and pack.Kp <= 112 and next_pack.Fp == pack.Kp:
+        one = int(L.molkgnn_tile_ximg_bytes(C.byref(plan.c), C.byref(next_pack.c)))
+        if one > 0:
+            ximg = torch.empty(plan.n_tiles * one, dtype=torch.uint8, device=sc.device)
     with _timed("propagate_fwd"):
-        check(_lib.lib().molkgnn_propagate_fwd(C.byref(plan.c), C.byref(pack.c), ptr(sc), _i64x4(scoff), ptr(h),
-                                               pack.Kp, ptr(hnorm), stream_ptr()))
-    return h, hnorm
-
-
-def absmax(t):
-    """device scalar max |t| (scale of the tile backward's fp16 coefficient operand)"""
-    out = torch.empty(1, dtype=torch.float32, device=t.device)
-    with _timed("absmax"):
-        check(_lib.lib().molkgnn_absmax(ptr(t), t.numel(), ptr(out), stream_ptr()))
-    return out
+        check(L.molkgnn_propagate_fwd(C.byref(plan.c), C.byref(pack.c), ptr(sc), _i64x4(scoff), ptr(h), pack.Kp,
+                                      ptr(hnorm), ptr(ximg), stream_ptr()))
+    return h, hnorm, ximg
 
 
 def path_counts():
@@ -206,8 +205,8 @@ def path_counts():
 
 
 def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, argmax, need_gx, need_gparams,
-                  ximg=None, grad_absmax=None):
-    """-> (gx [N,Fp] or None, list of 4 dicts of parameter grads or None, device scalar max|gx| or None)."""
+                  ximg=None):
+    """-> (gx [N,Fp] or None, list of 4 dicts of parameter grads or None)."""
     L = _lib.lib()
     dev = x.device
     scoff, tot = plan.scoff(pack.L)
@@ -237,20 +236,17 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
             grads.append(g)
     if grad.stride(1) != 1 or grad.data_ptr() % 16:
         grad = grad.contiguous()
-    scratch = gmax = None
+    scratch = None
     if ximg is not None:
-        if grad_absmax is None:
-            grad_absmax = absmax(grad) if grad.is_contiguous() else absmax(grad.contiguous())
         scratch = torch.empty(plan.N * ((pack.Fp + 15) // 16 * 16), dtype=torch.float32, device=dev)
-        gmax = torch.empty(1, dtype=torch.float32, device=dev) if need_gx else None
     # one C call runs all three kernels; under the profiler they are issued separately so each can be timed
     for name, ph in ((("conv_bwd", 7),) if _PROF is None else (("bwd_w", 1), ("param_finalize", 2), ("bwd_x", 4))):
         with _timed(name):
             check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
                                      grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials),
                                      ptr(gx), pack.Fp if need_gx else 0, C.byref(gc) if gc is not None else None, ph,
-                                     ptr(ximg), ptr(grad_absmax), ptr(scratch), ptr(gmax), stream_ptr()))
-    return gx, grads, gmax
+                                     ptr(ximg), ptr(scratch), stream_ptr()))
+    return gx, grads
 
 
 def _flatten_param_grads(grads, pack, needs):
@@ -289,8 +285,8 @@ class KernelSetConvFn(torch.autograd.Function):
         xp, xnorm, argmax = ctx.saved_tensors
         pack = ctx.pack
         need_gp = any(ctx.needs_input_grad[7:])
-        gx, grads, _ = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float(), 0, argmax, ctx.need_gx, need_gp,
-                                     ximg=ctx.ximg)
+        gx, grads = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float(), 0, argmax, ctx.need_gx, need_gp,
+                                  ximg=ctx.ximg)
         flat = _flatten_param_grads(grads, pack, ctx.needs_input_grad[7:])
         return (gx[:, :ctx.F] if gx is not None else None, None, None, None, None, None, None, *flat)
 
@@ -304,12 +300,15 @@ class MolGCNFn(torch.autograd.Function):
         nl = len(layer_params)
         F = x.shape[1]
         packs, saved, ximgs = [], [], []
-        h, hnorm = None, None
-        for i, params in enumerate(layer_params):
-            pack = LayerPack(params, F, Fe, dev).pack()
+        for params in layer_params:
+            packs.append(LayerPack(params, F, Fe, dev).pack())
+            F = packs[-1].K
+        h, hnorm, ximg = None, None, None
+        for i, pack in enumerate(packs):
             if i == 0:
                 h, hnorm = pad_norm(x.detach(), pack.Fp)
-            ximg = x_images(plan, pack, h, hnorm)
+            if ximg is None:
+                ximg = x_images(plan, pack, h, hnorm)
             sc, argmax, free = conv_forward(plan, pack, h, hnorm, i == nl - 1, dense=False,
                                             argmax_in=None if argmax_in is None else argmax_in[i],
                                             want_free=aux is not None, ximg=ximg)
@@ -319,9 +318,7 @@ class MolGCNFn(torch.autograd.Function):
                 aux.setdefault("sc", []).append(sc)
             saved += [h, hnorm, argmax]
             ximgs.append(ximg)
-            h, hnorm = propagate_forward(plan, pack, sc)
-            packs.append(pack)
-            F = pack.K
+            h, hnorm, ximg = propagate_forward(plan, pack, sc, packs[i + 1] if i + 1 < nl else None)
         ctx.plan, ctx.packs, ctx.ximgs = plan, packs, ximgs
         ctx.save_for_backward(*saved)
         ctx.need_gx = x.requires_grad
@@ -335,14 +332,12 @@ class MolGCNFn(torch.autograd.Function):
         nl = len(packs)
         needs = ctx.needs_input_grad[6:]
         g = grad_h.float()
-        gmax = None
         flat_all = [None] * (nl * 28)
         for i in range(nl - 1, -1, -1):
             xp, xnorm, argmax = saved[3 * i:3 * i + 3]
             need_gp = any(needs[28 * i:28 * (i + 1)])
             need_gx = ctx.need_gx if i == 0 else True
-            gx, grads, gmax = conv_backward(ctx.plan, packs[i], xp, xnorm, g, 1, argmax, need_gx, need_gp,
-                                            ximg=ctx.ximgs[i], grad_absmax=gmax)
+            gx, grads = conv_backward(ctx.plan, packs[i], xp, xnorm, g, 1, argmax, need_gx, need_gp, ximg=ctx.ximgs[i])
             flat_all[28 * i:28 * (i + 1)] = _flatten_param_grads(grads, packs[i], None)
             g = gx
         return (g[:, :ctx.F0] if g is not None else None, None, None, None, None, None, *flat_all)

@@ -43,10 +43,11 @@ class BucketPlan(object):
         self.tile_meta = torch.empty((self.N // 32 + 4) * int(_lib.lib().molkgnn_tile_meta_bytes()), dtype=torch.uint8,
                                      device=device)
         self.ehat_node = torch.empty(max(self.E, 1), EDGE_PAD, dtype=torch.float32, device=device)
+        self.node_tile = torch.empty(max(self.N, 1), **i32)
         c = _lib.Plan()
         c.N, c.E = self.N, self.E
         for name in ("deg", "pos", "sel", "nei", "nei_eid", "ehat", "tsign", "in_cnt", "in_src", "in_j", "tile_start", "tile_meta",
-                     "ehat_node"):
+                     "ehat_node", "node_tile"):
             setattr(c, name, getattr(self, name).data_ptr())
         self.c = c
         self.n = [0, 0, 0, 0]
