@@ -196,7 +196,55 @@ int molkgnn_set_bwd_path(int path);
 /* how often each path ran so far: forward tile / forward other / backward tile / backward other */
 void molkgnn_path_counts(int64_t out[4]);
 
+/* ---- the whole conv stack in one call: MolGCN.forward / its autograd backward (KernelLayer.py:107-120) ----
+ * The per-layer entry points above stay the public building blocks; these two issue the same launches for every layer
+ * from native code (one host call per pass instead of ~15 per layer) out of ONE caller-owned workspace. */
+#define MOLKGNN_MAX_LAYERS 16
+#define MOLKGNN_STACK_KEEP_SC 1      /* flags: keep every layer's compact scores (else one buffer is reused) */
+#define MOLKGNN_STACK_WANT_FREE 2    /* flags: also record the free-running arg-max of every layer */
+typedef struct molkgnn_stack_layout {
+    int64_t fwd_bytes;                          /* forward workspace: lives from stack_fwd to stack_bwd */
+    int64_t bwd_bytes;                          /* backward scratch: only during stack_bwd */
+    int64_t grad_floats;                        /* flat parameter-gradient buffer, floats */
+    /* byte offsets into the forward workspace (128-byte aligned); -1 = absent */
+    int64_t h[MOLKGNN_MAX_LAYERS];              /* input activations of layer i, [N, Fp_i] fp32 (layer 0: padded x) */
+    int64_t hnorm[MOLKGNN_MAX_LAYERS + 1];      /* their row norms [N]; [nl] = norms of the output */
+    int64_t ximg[MOLKGNN_MAX_LAYERS];           /* fp16 (hi, lo) tile images of layer i's input */
+    int64_t sc[MOLKGNN_MAX_LAYERS];             /* compact scores of layer i */
+    int64_t argmax[MOLKGNN_MAX_LAYERS];         /* uint8 per (node, kernel) pair, compact */
+    int64_t argmax_free[MOLKGNN_MAX_LAYERS];
+    int64_t counter;
+    int64_t sc_elems[MOLKGNN_MAX_LAYERS];       /* sum_d n_d * L_d of layer i */
+    int64_t scoff[MOLKGNN_MAX_LAYERS][4];       /* element offsets of the per-degree blocks inside sc / argmax */
+    /* byte offsets into the backward scratch */
+    int64_t coef, partials, scratch, gx[2];
+    /* float offsets into the flat gradient buffer, per layer and degree (d-1); g_w = 3 floats: support, centre, edge */
+    int64_t g_x_center[MOLKGNN_MAX_LAYERS][4], g_x_support[MOLKGNN_MAX_LAYERS][4],
+            g_edge_attr_support[MOLKGNN_MAX_LAYERS][4], g_w[MOLKGNN_MAX_LAYERS][4];
+} molkgnn_stack_layout_t;
+
+/* Sizes and offsets for a built plan (plan->n / n_tiles valid) and nl layers (layers[i].F must chain: F_{i+1} = K_i). */
+int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl, int32_t flags,
+                         molkgnn_stack_layout_t* out);
+/* Forward of the stack: parameter packing of every layer, pad + norm of x [N, ldx] (F = layers[0].F columns), then per
+ * layer conv (all four buckets) and propagate.  h_out [N, ldh] (ldh = roundup4(K_last)) receives the output of the last
+ * propagate.  argmax_in: nullable array of nl nullable pointers (forced permutations, parity harness). */
+int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
+                      const molkgnn_stack_layout_t* lay, int32_t flags, const float* x, int32_t ldx, void* workspace,
+                      float* h_out, int32_t ldh, const uint8_t* const* argmax_in, void* stream);
+/* Backward of the stack from grad_h [N, ldg] (gradient w.r.t. h_out).  grad_x (nullable) [N, Fp_0].  grad_flat
+ * (nullable): flat parameter-gradient buffer laid out by molkgnn_stack_layout (g_* offsets). */
+int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
+                      const molkgnn_stack_layout_t* lay, void* workspace, void* bwd_scratch, const float* grad_h,
+                      int32_t ldg, float* grad_x, float* grad_flat, void* stream);
+
 /* ---- diagnostics ---- */
+/* CUDA-event profiler of the library's own launches (bench.py: live per-kernel durations on the launching stream).
+ * enable(1) clears and starts recording one (start, end) event pair per launch group; read() synchronises the device,
+ * writes one line "name launches total_ms" per group name into buf and clears the records.  Returns the previous state /
+ * the text length (<0 on error).  Not thread safe; off by default. */
+int molkgnn_profile_enable(int on);
+int molkgnn_profile_read(char* buf, int cap);
 /* Known-answer test of the tcgen05 (UMMA) plumbing: D[128,N] (fp32) = A * B^T on the tensor cores, one CTA.
  * A, B: fp16.  a_mn = 0: A is [128,K] row-major (K-major operand); a_mn = 1: A is [K,128] row-major (MN-major
  * operand); same for B with N.  swap = 1 exchanges the two stride fields of the descriptors (diagnostic only). */

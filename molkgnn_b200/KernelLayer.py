@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 from torch.nn import Module, ModuleList
 
-from .functional import MolGCNFn, flat_params
+from .functional import MolGCNFn, StackPack, flat_params
 from .kernels import KernelSetConv
 from .plan import BucketPlan
 
@@ -69,8 +69,13 @@ class MolGCN(Module):
         flat = []
         for lp in layer_params:
             flat += flat_params(lp)
-        h = MolGCNFn.apply(x, plan, layer_params, self.edge_attr_dim, kwargv.get('argmax_in', None),
-                           kwargv.get('aux', None), *flat)
+        # native descriptors of the layers: rebuilt only when a parameter tensor moved (new storage, device, dtype)
+        key = StackPack.make_key(layer_params, x.shape[1], self.edge_attr_dim, x.device)
+        stack = getattr(self, '_stack', None)
+        if stack is None or stack.key != key:
+            stack = StackPack(layer_params, x.shape[1], self.edge_attr_dim, x.device)
+            object.__setattr__(self, '_stack', stack)
+        h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), kwargv.get('aux', None), *flat)
         if save_score:
             raise NotImplementedError('save_score=True: call the last KernelSetConv layer directly to obtain sim_sc')
         return h

@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmolkgnn_b200.so")
+# MOLKGNN_B200_LIB: alternative build of the same library (the -DMK_PHASE_CLOCKS profiling variant), never a fallback
+LIB_PATH = os.environ.get("MOLKGNN_B200_LIB") or os.path.join(HERE, "libmolkgnn_b200.so")
 
 i32, i64, vp, fp = C.c_int32, C.c_int64, C.c_void_p, C.c_void_p
 
@@ -27,6 +28,19 @@ class Layer(C.Structure):
 class LayerGrads(C.Structure):
     _fields_ = [("x_center", vp * 4), ("x_support", vp * 4), ("edge_attr_support", vp * 4),
                 ("w_support", vp * 4), ("w_center", vp * 4), ("w_edge", vp * 4)]
+
+
+MAX_LAYERS = 16
+
+
+class StackLayout(C.Structure):
+    _fields_ = [("fwd_bytes", i64), ("bwd_bytes", i64), ("grad_floats", i64),
+                ("h", i64 * MAX_LAYERS), ("hnorm", i64 * (MAX_LAYERS + 1)), ("ximg", i64 * MAX_LAYERS),
+                ("sc", i64 * MAX_LAYERS), ("argmax", i64 * MAX_LAYERS), ("argmax_free", i64 * MAX_LAYERS),
+                ("counter", i64), ("sc_elems", i64 * MAX_LAYERS), ("scoff", (i64 * 4) * MAX_LAYERS),
+                ("coef", i64), ("partials", i64), ("scratch", i64), ("gx", i64 * 2),
+                ("g_x_center", (i64 * 4) * MAX_LAYERS), ("g_x_support", (i64 * 4) * MAX_LAYERS),
+                ("g_edge_attr_support", (i64 * 4) * MAX_LAYERS), ("g_w", (i64 * 4) * MAX_LAYERS)]
 
 
 EXPORTS = {
@@ -56,6 +70,13 @@ EXPORTS = {
                                    vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp]),
     "molkgnn_set_bwd_path": (C.c_int, [C.c_int]),
     "molkgnn_path_counts": (None, [i64 * 4]),
+    "molkgnn_stack_layout": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, i32, C.POINTER(StackLayout)]),
+    "molkgnn_stack_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), i32, vp, i32, vp, vp,
+                                    i32, C.POINTER(vp), vp]),
+    "molkgnn_stack_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), vp, vp, vp, i32, vp,
+                                    vp, vp]),
+    "molkgnn_profile_enable": (C.c_int, [C.c_int]),
+    "molkgnn_profile_read": (C.c_int, [C.c_char_p, C.c_int]),
 }
 
 _lib = None

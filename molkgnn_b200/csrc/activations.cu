@@ -146,6 +146,7 @@ extern "C" int molkgnn_pad_norm(const float* x, int32_t N, int32_t F, int32_t ld
     MK_REQUIRE(ldo >= F, "pad_norm: ldo=%d < F=%d", ldo, F);
     if (N == 0) return 0;
     count_launches(1);
+    ProfScope prof("pad_norm", (cudaStream_t)stream_);
     k_pad_norm<<<(N + 7) / 8, 256, 0, (cudaStream_t)stream_>>>(x, N, F, ldx, out, ldo, norm);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -164,6 +165,7 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
     cudaStream_t st = (cudaStream_t)stream_;
     const int grid = (a.N + 7) / 8;
     count_launches(1);
+    ProfScope prof("propagate_fwd", st);
     if (ximg) {
         MK_REQUIRE(plan->n_tiles > 0 && plan->node_tile && plan->tile_start && ldh % 4 == 0 && ldh <= 112 && hnorm,
                    "propagate_fwd: fused images need a tiled plan, hnorm and ldh %% 4 == 0, ldh <= 112 (got %d)", ldh);

@@ -505,6 +505,7 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     int* cutpos = s;
     const bool tiles = plan->tile_start != nullptr;
     const int tile_cap = N / TILE_MIN_STRIDE + 4;
+    ProfScope* prof = new ProfScope("bucket_count", st);
     MK_CHECK_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 32, st));
@@ -521,6 +522,7 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     }
     int host[32];
     MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
+    delete prof;
     MK_CHECK_CUDA(cudaStreamSynchronize(st));
     plan->n_tiles = 0; plan->tile_max_nodes = 0;
     for (int d = 0; d < 4; ++d) plan->tile_max_deg[d] = 0;
@@ -533,6 +535,7 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
                "bucket_build: unsupported graph (flags=0x%x: 1=node id out of range, 2=out-degree>4, 4=in-degree>4, "
                "8=node with out-degree 0 or >4; %d offending nodes)", host[16], host[4]);
     for (int d = 0; d < 4; ++d) { plan->n[d] = host[d]; plan->boff[d] = host[5 + d]; plan->eoff[d] = host[9 + d]; }
+    ProfScope prof2("bucket_assign", st);
     k_assign<<<nblk, BT, 0, st>>>(N, E, edge_index, plan->deg, out_eid, plan->in_cnt, in_eid, blk_off, totals, p, p_dim,
                                   edge_attr, Fe, plan->pos, plan->sel, plan->nei, plan->nei_eid, plan->ehat,
                                   plan->tsign, plan->in_src, plan->in_j);

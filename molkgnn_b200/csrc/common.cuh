@@ -129,6 +129,44 @@ template <int D> __device__ __forceinline__ float div_deg(float x) {
 inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 void count_launches(int n);
+// named CUDA-event scope on the launching stream (no-op unless molkgnn_profile_enable(1)); params.cu
+class ProfScope {
+public:
+    ProfScope(const char* name, cudaStream_t st);
+    ~ProfScope();
+private:
+    int rec_;
+    cudaStream_t st_;
+};
+
+// ---- optional in-kernel phase clocks (profiling build only: -DMK_PHASE_CLOCKS, tools/phase_clocks.py) ----
+// One designated thread accumulates clock64() deltas per phase; barriers make its view the CTA's critical path.
+#ifdef MK_PHASE_CLOCKS
+#define MK_PH_DECL(on_)                                                     \
+    const bool ph_on_ = (on_);                                              \
+    unsigned long long ph_last_ = clock64();                                \
+    unsigned long long ph_acc_[16];                                         \
+    _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_) ph_acc_[i_] = 0ull;
+#define MK_PH(i_)                                                           \
+    do {                                                                    \
+        if (ph_on_) {                                                       \
+            const unsigned long long t_ = clock64();                        \
+            ph_acc_[i_] += t_ - ph_last_;                                   \
+            ph_last_ = t_;                                                  \
+        }                                                                   \
+    } while (0)
+#define MK_PH_FLUSH(arr_)                                                   \
+    do {                                                                    \
+        if (ph_on_) {                                                       \
+            _Pragma("unroll") for (int i_ = 0; i_ < 16; ++i_)               \
+                if (ph_acc_[i_]) atomicAdd(&(arr_)[i_], ph_acc_[i_]);       \
+        }                                                                   \
+    } while (0)
+#else
+#define MK_PH_DECL(on_)
+#define MK_PH(i_)
+#define MK_PH_FLUSH(arr_)
+#endif
 int device_num_sms();
 int device_max_smem_optin();
 

@@ -472,6 +472,7 @@ static int launch_bwd_x(const BwdXArgs& a, int grid, int64_t smem, cudaStream_t 
         s_attr = smem;
     }
     count_launches(1);
+    ProfScope prof("bwd_x", st);
     k_bwd_x<LPN, NACC><<<grid, BX_THREADS, smem, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -565,6 +566,7 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
             s_attr = smem_w;
         }
         count_launches(1);
+        ProfScope prof("bwd_w", st);
         k_bwd_w<<<cb, BW_THREADS, smem_w, st>>>(w);
         MK_CHECK_CUDA(cudaGetLastError());
     }

@@ -264,6 +264,10 @@ __device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char
     tc::umma_commit(bar);
 }
 
+#ifdef MK_PHASE_CLOCKS
+__device__ unsigned long long g_ph_bwd[16];
+#endif
+
 __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_constant__ BwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_mma, bar_img, bar_cp[2];
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     __shared__ BSeg s_seg[2][TILE_MAXSEG];
     __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    MK_PH_DECL(tid == 0)
     if (tid == 0) {
         tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_img, 1);
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
@@ -328,6 +333,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         }
         img_pending = true;
     }
+    MK_PH(0);                                             // prologue
     int cur = 0;
     bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
 
@@ -336,6 +342,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
         tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
         ph_cp[cur] ^= 1u;
+        MK_PH(1);                                         // wait for the tile's metadata + node images
         const int t0 = m.t0, nn = m.nn;
         const int tnext = tile + gridDim.x;
         for (int bi = 0; bi < a.nbl; ++bi) {
@@ -370,6 +377,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     }
                 }
             }
+            MK_PH(2);                                     // rank-0 scatter (thread 0's own share)
             // ---- ranks 1..3: one thread per (neighbour slot, kernel), read-modify-write after a barrier ----
             for (int r = 1; r < 4; ++r) {
                 bool more = false;
@@ -394,8 +402,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     }
                 }
             }
+            MK_PH(3);                                     // ranks 1..3 (incl. waiting for the slowest rank-0 thread)
             tc::fence_async_smem();
             __syncthreads();
+            MK_PH(4);                                     // barrier before the MMAs
             // ---- tensor cores ----
             if (tid == 0) {
                 if (img_pending) {                            // this block's images were requested after the previous MMAs
@@ -406,9 +416,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 tb_issue_mma(a, smem, nn, a.tb.rows[blk], bi, fresh, tmem, &bar_mma);
             }
             img_pending = false;
+            MK_PH(5);                                     // image wait + MMA issue
             tc::mbar_wait(&bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc::fence_after_sync();
+            MK_PH(6);                                     // MMA completion
             // the tensor cores are done with Wt and the images: clear Wt, fetch the next block's images
             for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
             {
@@ -419,6 +431,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 }
             }
             if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
+            MK_PH(7);                                     // Wt clear
         }
         fresh = false;
         // ---- dxh epilogue: lane = node, 32 columns per warp ----
@@ -520,6 +533,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         }
         tc::fence_before_sync();
         __syncthreads();                 // coefficient arrays / Jacobian scratch, TMEM dxh and this tile's buffer are free again
+        MK_PH(8);                                         // dxh epilogue
         cur ^= 1;
     }
     // ---- kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks ----
@@ -559,6 +573,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     }
     tc::fence_before_sync();
     __syncthreads();
+    MK_PH(9);                                             // G partial sums -> global
+    MK_PH_FLUSH(g_ph_bwd);
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -671,6 +687,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         c.G = grid;
         c.amax = amax;
         count_launches(1);
+        ProfScope prof("coef_bond", st);
         k_coef_bond<<<4 * grid, CB_THREADS, smem_c, st>>>(c);
         MK_CHECK_CUDA(cudaGetLastError());
     }
@@ -681,6 +698,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 1; a.blist[1] = l == 0 ? 3 : 2; }
         a.first = l == 0; a.last = l == nlaunch - 1;
         count_launches(1);
+        ProfScope prof("conv_bwd_tile", st);
         k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
         MK_CHECK_CUDA(cudaGetLastError());
     }
@@ -689,3 +707,13 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 
 }  // namespace mk
 
+
+#ifdef MK_PHASE_CLOCKS
+// profiling build only: read (and clear) the accumulated phase clocks of k_conv_bwd_tile
+extern "C" int molkgnn_debug_phase_clocks_bwd(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, mk::g_ph_bwd, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(mk::g_ph_bwd, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -440,6 +440,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         s_sms = device_num_sms();
         MK_REQUIRE(s_budget > 0 && s_sms > 0, "conv_fwd: no CUDA device");
     }
+    ProfScope prof("conv_fwd", st);
     if (g_fwd_path < 0) {
         const char* e = getenv("MOLKGNN_FWD");
         g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)

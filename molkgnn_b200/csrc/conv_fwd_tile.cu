@@ -320,6 +320,10 @@ __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;"
 // 16 consumer warps (dump + epilogue) and one producer warp (tile queue, bulk copies, UMMA issue): the producer runs one
 // tile ahead, bounded only by the single node-image buffer (free when the previous tile's MMAs are done), the two TMEM
 // accumulators and the two metadata buffers.
+#ifdef MK_PHASE_CLOCKS
+__device__ unsigned long long g_ph_fwd[32];      // [0..15] consumer thread 0, [16..31] producer lane
+#endif
+
 template <bool FORCED>
 __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __grid_constant__ FwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -329,6 +333,7 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
     __shared__ SegConst s_seg[TILE_MAXSEG];
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool producer = warp == TF_WARPS;
+    MK_PH_DECL(tid == 0 || tid == TF_THREADS)
     if (warp == 0) tc::tmem_alloc(&tslot, 256);
     tc::fence_before_sync();
     __syncthreads();
@@ -379,6 +384,7 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
             tc::fence_async_smem();            // images were written through the generic proxy, the MMAs read them
         }
         __syncthreads();
+        MK_PH(0);                                                          // block set-up (images, tables)
 
         if (producer) {
             if ((tid & 31) == 0) {
@@ -387,14 +393,19 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
                     const uint32_t par = (uint32_t)(seq >> 1) & 1u;
                     const int tile = atomicAdd(a.counter + blk, 1);
                     tc::mbar_wait(&bar_bfree[b], par ^ 1u);            // metadata buffer released by the consumers
+                    MK_PH(1);
                     s_tile[b] = tile < a.n_tiles ? tile : -1;
                     if (tile >= a.n_tiles) { mbar_arrive(&bar_cp[b]); break; }
                     if (seq > 0) tc::mbar_wait(&bar_mma[b ^ 1], (uint32_t)((seq - 1) >> 1) & 1u);   // node-image buffer free
+                    MK_PH(2);
                     tf_issue_copy(a, smem, &bufs[b], tile, &bar_cp[b]);
                     tc::mbar_wait(&bar_cp[b], par);
+                    MK_PH(3);
                     tc::mbar_wait(&bar_tfree[b], par ^ 1u);            // accumulator drained by the consumers
                     tc::fence_after_sync();
+                    MK_PH(4);
                     tf_issue_mma(a, smem, bufs[b].m.nn, tmem, b, &bar_mma[b]);
+                    MK_PH(5);
                 }
             }
         } else {
@@ -403,22 +414,32 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
                 const uint32_t par = (uint32_t)(seq >> 1) & 1u;
                 const TileBuf* tb = &bufs[b];
                 tc::mbar_wait(&bar_cp[b], par);                        // metadata (or the end marker) visible
+                MK_PH(1);
                 if (s_tile[b] < 0) break;
                 tc::mbar_wait(&bar_mma[b], par);                       // accumulator ready
                 tc::fence_after_sync();
+                MK_PH(2);
                 tf_dump(dump, tmem, b, tb->m.nn);
+                MK_PH(3);
                 if (has4 && a.is_last) tf_dup_flags(a, tb, dupf);
                 tc::fence_before_sync();
                 consumer_sync();                                       // dump complete, accumulator drained
+                MK_PH(4);
                 if (tid == 0) mbar_arrive(&bar_tfree[b]);
                 tf_epilogue<FORCED>(a, tb, dump, estab, dupf, s_seg, nseg);
+                MK_PH(5);
                 consumer_sync();                                       // dump and this tile's buffer are free again
+                MK_PH(6);
                 if (tid == 0) mbar_arrive(&bar_bfree[b]);
             }
         }
     }
     tc::fence_before_sync();
     __syncthreads();
+    MK_PH(7);
+#ifdef MK_PHASE_CLOCKS
+    MK_PH_FLUSH(g_ph_fwd + (tid == 0 ? 0 : 16));
+#endif
     if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
@@ -436,6 +457,7 @@ int launch_x_images(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, co
     a.ximg = reinterpret_cast<unsigned char*>(ximg);
     a.x_one = tile_img_one(a.Fk);
     count_launches(1);
+    ProfScope prof("x_images", st);
     k_x_images<<<plan->n_tiles, 512, 0, st>>>(a);
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -513,3 +535,13 @@ extern "C" int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn
                "tile_ximg_build: x must be 16-byte and ximg 128-byte aligned");
     return launch_x_images(plan, layer, x, ldx, xnorm, ximg, (cudaStream_t)stream_);
 }
+
+#ifdef MK_PHASE_CLOCKS
+// profiling build only: read (and clear) the accumulated phase clocks of k_conv_fwd_tile
+extern "C" int molkgnn_debug_phase_clocks_fwd(unsigned long long* out32) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out32, mk::g_ph_fwd, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    unsigned long long z[32] = {0};
+    return cudaMemcpyToSymbol(mk::g_ph_fwd, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -24,6 +24,35 @@ static long long g_launches = 0;
 void count_launches(int n) { __atomic_fetch_add(&g_launches, (long long)n, __ATOMIC_RELAXED); }
 long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 
+// ---- optional CUDA-event profiler: named scopes around the launches of the host entry points --------------------------
+// Off by default (one relaxed load per scope).  bench.py switches it on around its timed region to get the live
+// per-kernel launch durations on the launching stream (molkgnn_profile_enable / molkgnn_profile_read).
+struct ProfRec { const char* name; cudaEvent_t e0, e1; };
+static int g_prof_on = 0;
+static ProfRec g_prof[4096];
+static int g_prof_n = 0;
+static cudaEvent_t g_prof_pool[8192];
+static int g_prof_pool_n = 0, g_prof_pool_used = 0;
+static cudaEvent_t prof_event() {
+    if (g_prof_pool_used == g_prof_pool_n) {
+        if (g_prof_pool_n == 8192) return nullptr;
+        if (cudaEventCreate(&g_prof_pool[g_prof_pool_n]) != cudaSuccess) return nullptr;
+        ++g_prof_pool_n;
+    }
+    return g_prof_pool[g_prof_pool_used++];
+}
+ProfScope::ProfScope(const char* name, cudaStream_t st) : rec_(-1), st_(st) {
+    if (!__atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) || g_prof_n >= 4096) return;
+    cudaEvent_t a = prof_event(), b = prof_event();
+    if (!a || !b) return;
+    rec_ = g_prof_n++;
+    g_prof[rec_] = ProfRec{name, a, b};
+    cudaEventRecord(a, st_);
+}
+ProfScope::~ProfScope() {
+    if (rec_ >= 0) cudaEventRecord(g_prof[rec_].e1, st_);
+}
+
 int device_num_sms() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;
@@ -380,6 +409,7 @@ int launch_param_finalize(const molkgnn_layer_t* layer, const float* partials, c
     ta.q = q_scratch;
     ta.Fp = layer->Fp;
     if (rb == 0) return 0;
+    ProfScope prof("param_finalize", st);
     k_param_finalize<<<rb, 128, 0, st>>>(fa);
     k_theta<<<4, 128, 0, st>>>(ta);
     count_launches(2);
@@ -396,6 +426,31 @@ extern "C" int molkgnn_version(void) { return 100; }
 extern "C" int molkgnn_num_sms(void) { return device_num_sms(); }
 namespace mk { long long launches(); }
 extern "C" int64_t molkgnn_launch_count(void) { return mk::launches(); }
+
+extern "C" int molkgnn_profile_enable(int on) {
+    const int old = mk::g_prof_on;
+    if (on) { mk::g_prof_n = 0; mk::g_prof_pool_used = 0; }
+    __atomic_store_n(&mk::g_prof_on, on ? 1 : 0, __ATOMIC_RELAXED);
+    return old;
+}
+// "name launches total_ms\n" per scope name, in first-seen order; synchronises the device.  Returns the text length.
+extern "C" int molkgnn_profile_read(char* buf, int cap) {
+    if (cudaDeviceSynchronize() != cudaSuccess) { mk::set_error("profile_read: device error"); return -2; }
+    const char* names[64]; int cnt[64]; double ms[64]; int nn = 0;
+    for (int i = 0; i < mk::g_prof_n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, mk::g_prof[i].e0, mk::g_prof[i].e1) != cudaSuccess) continue;
+        int j = 0;
+        while (j < nn && strcmp(names[j], mk::g_prof[i].name)) ++j;
+        if (j == nn) { if (nn == 64) continue; names[nn] = mk::g_prof[i].name; cnt[nn] = 0; ms[nn] = 0.0; ++nn; }
+        ++cnt[j]; ms[j] += t;
+    }
+    int len = 0;
+    for (int j = 0; j < nn && len < cap - 96; ++j) len += snprintf(buf + len, cap - len, "%s %d %.6f\n", names[j], cnt[j], ms[j]);
+    if (cap > 0) buf[len < cap ? len : cap - 1] = 0;
+    mk::g_prof_n = 0; mk::g_prof_pool_used = 0;
+    return len;
+}
 
 extern "C" int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp) {
     if (d < 1 || d > 4 || L < 0 || Fp < 4 || Fp % 4) return -1;
@@ -437,6 +492,7 @@ extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
         a.packed[d] = layer->packed[d];
     }
     a.row_begin[4] = rb;
+    ProfScope prof("param_pack", (cudaStream_t)stream_);
     k_param_pack<<<rb + 4, 128, 0, (cudaStream_t)stream_>>>(a);
     count_launches(1);
     MK_CHECK_CUDA(cudaGetLastError());

@@ -1,0 +1,169 @@
+// The whole conv stack behind two host calls: MolGCN.forward (reference KernelLayer.py:107-120: per layer
+// `sim_sc = layer(...)`, `h = propagate(edge_index, sim_sc)`) and the backward autograd derives from it.  Pure host code:
+// carves ONE caller-owned workspace and issues the launches of the per-layer entry points (conv_fwd.cu, activations.cu,
+// conv_bwd.cu, params.cu) back to back, so that a training step costs three host calls (bucket pass, forward, backward)
+// instead of ~45 calls and ~60 allocations driven from Python.
+#include <algorithm>
+#include <cstring>
+#include "common.cuh"
+#include "tile.cuh"
+
+using namespace mk;
+
+namespace {
+inline int64_t al128(int64_t v) { return (v + 127) / 128 * 128; }
+inline int rup4(int v) { return (v + 3) / 4 * 4; }
+}  // namespace
+
+extern "C" int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl, int32_t flags,
+                                    molkgnn_stack_layout_t* out) {
+    MK_REQUIRE(nl >= 1 && nl <= MOLKGNN_MAX_LAYERS, "stack_layout: %d layers (1..%d)", nl, MOLKGNN_MAX_LAYERS);
+    memset(out, 0, sizeof(*out));
+    const int64_t N = plan->N;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { const int64_t o = off; off += al128(std::max<int64_t>(bytes, 16)); return o; };
+    int64_t sc_max = 0;
+    for (int i = 0; i < nl; ++i) {
+        const molkgnn_layer_t& ly = layers[i];
+        MK_REQUIRE(ly.Fp == rup4(ly.F) && ly.K > 0, "stack_layout: layer %d: Fp=%d must be roundup4(F=%d), K=%d > 0", i,
+                   ly.Fp, ly.F, ly.K);
+        MK_REQUIRE(i == 0 || ly.F == layers[i - 1].K, "stack_layout: layer %d: node_attr_dim %d != kernels of layer %d (%d)",
+                   i, ly.F, i - 1, layers[i - 1].K);
+        int64_t tot = 0;
+        for (int d = 0; d < 4; ++d) { out->scoff[i][d] = tot; tot += (int64_t)plan->n[d] * ly.L[d]; }
+        out->sc_elems[i] = tot;
+        sc_max = std::max(sc_max, tot);
+    }
+    for (int i = 0; i < nl; ++i) {
+        const molkgnn_layer_t& ly = layers[i];
+        out->h[i] = take(N * ly.Fp * 4);
+        out->hnorm[i] = take(N * 4);
+        const int64_t one = molkgnn_tile_ximg_bytes(plan, &ly);
+        out->ximg[i] = (one > 0 && ly.tile_img) ? take((int64_t)plan->n_tiles * one) : -1;
+        out->argmax[i] = take(out->sc_elems[i]);
+        out->argmax_free[i] = (flags & MOLKGNN_STACK_WANT_FREE) ? take(out->sc_elems[i]) : -1;
+        if (flags & MOLKGNN_STACK_KEEP_SC) out->sc[i] = take(out->sc_elems[i] * 4);
+    }
+    out->hnorm[nl] = take(N * 4);
+    if (!(flags & MOLKGNN_STACK_KEEP_SC)) {
+        const int64_t o = take(sc_max * 4);
+        for (int i = 0; i < nl; ++i) out->sc[i] = o;
+    }
+    out->counter = take(MOLKGNN_MAX_LAYERS * 8 * 4);
+    out->fwd_bytes = off;
+    // backward scratch
+    off = 0;
+    int64_t part_max = 0, scr_max = 0, gx_max = 0;
+    for (int i = 0; i < nl; ++i) {
+        const int64_t pf = molkgnn_conv_bwd_partial_floats(plan, &layers[i]);
+        MK_REQUIRE(pf >= 0, "stack_layout: conv_bwd_partial_floats failed");
+        part_max = std::max(part_max, pf);
+        scr_max = std::max(scr_max, N * (int64_t)tile_fk(layers[i].Fp));
+        if (i > 0) gx_max = std::max(gx_max, N * (int64_t)layers[i].Fp);
+    }
+    out->coef = take(sc_max * 4);
+    out->partials = take(part_max * 4);
+    out->scratch = take(scr_max * 4);
+    out->gx[0] = take(gx_max * 4);
+    out->gx[1] = take(gx_max * 4);
+    out->bwd_bytes = off;
+    // flat parameter gradients: reference layouts, degree by degree
+    int64_t g = 0;
+    for (int i = 0; i < nl; ++i) {
+        const molkgnn_layer_t& ly = layers[i];
+        for (int d = 0; d < 4; ++d) {
+            const int64_t L = ly.L[d];
+            out->g_x_center[i][d] = g; g += L * ly.F;
+            out->g_x_support[i][d] = g; g += L * (d + 1) * ly.F;
+            out->g_edge_attr_support[i][d] = g; g += L * (d + 1) * ly.Fe;
+            out->g_w[i][d] = g; g += L > 0 ? 4 : 0;
+            g = (g + 3) / 4 * 4;
+        }
+    }
+    out->grad_floats = g;
+    return 0;
+}
+
+extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
+                                 const molkgnn_stack_layout_t* lay, int32_t flags, const float* x, int32_t ldx,
+                                 void* workspace, float* h_out, int32_t ldh, const uint8_t* const* argmax_in,
+                                 void* stream) {
+    MK_REQUIRE(nl >= 1 && nl <= MOLKGNN_MAX_LAYERS && workspace && h_out && x, "stack_fwd: bad arguments");
+    MK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "stack_fwd: workspace must be 128-byte aligned");
+    MK_REQUIRE(ldh % 4 == 0 && ldh >= layers[nl - 1].K && (reinterpret_cast<uintptr_t>(h_out) & 15) == 0,
+               "stack_fwd: h_out must be 16-byte aligned with ldh %% 4 == 0 and ldh >= K (ldh=%d)", ldh);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    const int N = plan->N;
+    int rc;
+    for (int i = 0; i < nl; ++i)
+        if ((rc = molkgnn_param_pack(&layers[i], stream))) return rc;
+    float* h = reinterpret_cast<float*>(ws + lay->h[0]);
+    float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);
+    if ((rc = molkgnn_pad_norm(x, N, layers[0].F, ldx, h, layers[0].Fp, hn, stream))) return rc;
+    if (lay->ximg[0] >= 0 && (rc = molkgnn_tile_ximg_build(plan, &layers[0], h, layers[0].Fp, hn, ws + lay->ximg[0], stream)))
+        return rc;
+    for (int i = 0; i < nl; ++i) {
+        const molkgnn_layer_t& ly = layers[i];
+        const bool last = i == nl - 1;
+        float* sc = reinterpret_cast<float*>(ws + lay->sc[i]);
+        if ((rc = molkgnn_conv_fwd(plan, &ly, h, ly.Fp, hn, last ? 1 : 0, sc, 0, 0, lay->scoff[i], ws + lay->argmax[i],
+                                   lay->argmax_free[i] >= 0 ? ws + lay->argmax_free[i] : nullptr,
+                                   argmax_in ? argmax_in[i] : nullptr,
+                                   reinterpret_cast<int32_t*>(ws + lay->counter) + 8 * i,
+                                   lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr, stream)))
+            return rc;
+        float* hnext = last ? h_out : reinterpret_cast<float*>(ws + lay->h[i + 1]);
+        const int ldn = last ? ldh : layers[i + 1].Fp;
+        float* hnn = reinterpret_cast<float*>(ws + lay->hnorm[i + 1]);
+        // the propagate kernel writes the next layer's tile images on the way out when the shapes allow it
+        const bool fuse_img = !last && lay->ximg[i + 1] >= 0 && ldn <= 112 && ldn == rup4(ly.K);
+        if ((rc = molkgnn_propagate_fwd(plan, &ly, sc, lay->scoff[i], hnext, ldn, hnn, fuse_img ? ws + lay->ximg[i + 1] : nullptr,
+                                        stream)))
+            return rc;
+        if (!last && lay->ximg[i + 1] >= 0 && !fuse_img &&
+            (rc = molkgnn_tile_ximg_build(plan, &layers[i + 1], hnext, ldn, hnn, ws + lay->ximg[i + 1], stream)))
+            return rc;
+        h = hnext; hn = hnn;
+    }
+    (void)flags;
+    return 0;
+}
+
+extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
+                                 const molkgnn_stack_layout_t* lay, void* workspace, void* bwd_scratch, const float* grad_h,
+                                 int32_t ldg, float* grad_x, float* grad_flat, void* stream) {
+    MK_REQUIRE(nl >= 1 && nl <= MOLKGNN_MAX_LAYERS && workspace && bwd_scratch && grad_h, "stack_bwd: bad arguments");
+    MK_REQUIRE((reinterpret_cast<uintptr_t>(bwd_scratch) & 127) == 0 && (reinterpret_cast<uintptr_t>(grad_h) & 15) == 0 &&
+               ldg >= layers[nl - 1].K, "stack_bwd: scratch must be 128-byte, grad_h 16-byte aligned, ldg >= K (ldg=%d)", ldg);
+    unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+    unsigned char* bs = reinterpret_cast<unsigned char*>(bwd_scratch);
+    const float* g = grad_h;
+    int ld = ldg;
+    for (int i = nl - 1; i >= 0; --i) {
+        const molkgnn_layer_t& ly = layers[i];
+        float* gx = i == 0 ? grad_x : reinterpret_cast<float*>(bs + lay->gx[i & 1]);
+        molkgnn_layer_grads_t gr;
+        memset(&gr, 0, sizeof(gr));
+        if (grad_flat) {
+            for (int d = 0; d < 4; ++d) {
+                if (ly.L[d] <= 0) continue;
+                gr.x_center[d] = grad_flat + lay->g_x_center[i][d];
+                gr.x_support[d] = grad_flat + lay->g_x_support[i][d];
+                gr.edge_attr_support[d] = grad_flat + lay->g_edge_attr_support[i][d];
+                gr.w_support[d] = grad_flat + lay->g_w[i][d];
+                gr.w_center[d] = grad_flat + lay->g_w[i][d] + 1;
+                gr.w_edge[d] = grad_flat + lay->g_w[i][d] + 2;
+            }
+        }
+        if (!gx && !grad_flat) break;          // nothing below this layer needs a gradient
+        const int rc = molkgnn_conv_bwd(plan, &ly, reinterpret_cast<const float*>(ws + lay->h[i]), ly.Fp,
+                                        reinterpret_cast<const float*>(ws + lay->hnorm[i]), g, ld, 1, ws + lay->argmax[i],
+                                        lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef),
+                                        reinterpret_cast<float*>(bs + lay->partials), gx, gx ? ly.Fp : 0,
+                                        grad_flat ? &gr : nullptr, 7, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
+                                        reinterpret_cast<float*>(bs + lay->scratch), stream);
+        if (rc) return rc;
+        g = gx; ld = ly.Fp;
+    }
+    return 0;
+}

@@ -29,6 +29,12 @@ def shard_bounds(num_nodes_per_molecule, world):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+def _native_flat_of(module):
+    flats = [m._stack.last_grad_flat for m in module.modules()
+             if getattr(m, "_stack", None) is not None and getattr(m._stack, "last_grad_flat", None) is not None]
+    return flats[0] if len(flats) == 1 else None
+
+
 class GradBucket(object):
     """Flat all-reduce bucket over the gradients of the kernel parameters of a module."""
 
@@ -40,12 +46,35 @@ class GradBucket(object):
         self.average = average
         self.group = group
         self.flat = None
+        self.module = module
+
+    def _native_flat(self, ps):
+        flat = _native_flat_of(self.module)
+        if flat is None or len(ps) != len(self.params):
+            return None
+        lo = flat.data_ptr()
+        hi = lo + flat.numel() * flat.element_size()
+        for p in ps:
+            a = p.grad.data_ptr()
+            if p.grad.device != flat.device or a < lo or a + p.grad.numel() * 4 > hi or not p.grad.is_contiguous():
+                return None
+        return flat
 
     def allreduce(self):
         """sum (or mean) the gradients over ranks; afterwards every p.grad is a view into the reduced flat bucket"""
         ps = [p for p in self.params if p.grad is not None]
         if not ps:
             return None
+        # fast path: the native backward wrote every kernel-parameter gradient of the stack into ONE flat buffer and the
+        # p.grad tensors are views of it (functional.MolGCNFn.backward) -> reduce that buffer in place, no gather/scatter
+        flat = self._native_flat(ps)
+        if flat is not None:
+            if self.world > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                if self.average:
+                    flat.div_(self.world)
+            self.flat = flat
+            return flat
         flat = torch.cat([p.grad.reshape(-1) for p in ps])
         if self.world > 1:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)

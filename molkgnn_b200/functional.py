@@ -19,8 +19,11 @@ _PROF_NAMES = None
 
 
 def profile_start(names=None):
+    """Starts the library's CUDA-event profiler (one event pair per launch group, recorded on the launching stream by the
+    native code, include/molkgnn_b200.h molkgnn_profile_enable) and the Python-side scopes of the per-layer API."""
     global _PROF, _PROF_NAMES
     _PROF, _PROF_NAMES = {}, (None if names is None else set(names))
+    _lib.lib().molkgnn_profile_enable(1)
 
 
 def profile_stop():
@@ -29,12 +32,25 @@ def profile_stop():
     torch.cuda.synchronize()
     out = {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in (_PROF or {}).items()}
     _PROF = None
+    buf = C.create_string_buffer(8192)
+    n = _lib.lib().molkgnn_profile_read(buf, 8192)
+    _lib.lib().molkgnn_profile_enable(0)
+    if n < 0:
+        raise _lib.MolKGNNError(_lib.lib().molkgnn_last_error().decode())
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split()
+        if name not in out:                      # the native scopes are the finer ones; Python scopes win on a clash
+            out[name] = (int(cnt), float(ms))
     return out
 
 
 class _timed(object):
+    """Python-side scope; only used for names the native profiler does not record itself."""
+    NATIVE = {"param_pack", "pad_norm", "x_images", "conv_fwd", "propagate_fwd", "bwd_w", "bwd_x", "param_finalize",
+              "conv_bwd", "bucket_build"}
+
     def __init__(self, name):
-        self.on = _PROF is not None and (_PROF_NAMES is None or name in _PROF_NAMES)
+        self.on = _PROF is not None and name not in self.NATIVE and (_PROF_NAMES is None or name in _PROF_NAMES)
         self.name = name
 
     def __enter__(self):
@@ -62,13 +78,14 @@ class LayerPack(object):
     ``params``: list of 4 (degree 1..4) dicts/objects with the KernelConv parameter tensors, or None for a degree
     without kernels."""
 
-    def __init__(self, params, F, Fe, device):
+    def __init__(self, params, F, Fe, device, c=None):
         L = _lib.lib()
         self.F, self.Fp, self.Fe = int(F), _rup4(F), int(Fe)
         if not (1 <= self.Fe <= 8):
             raise _lib.MolKGNNError(f"edge_attr_dim {Fe} not supported (1..8)")
         self.L = []
-        c = _lib.Layer()
+        if c is None:
+            c = _lib.Layer()
         c.F, c.Fp, c.Fe = self.F, self.Fp, self.Fe
         self._keep = []
         koff = 0
@@ -240,7 +257,7 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
     if ximg is not None:
         scratch = torch.empty(plan.N * ((pack.Fp + 15) // 16 * 16), dtype=torch.float32, device=dev)
     # one C call runs all three kernels; under the profiler they are issued separately so each can be timed
-    for name, ph in ((("conv_bwd", 7),) if _PROF is None else (("bwd_w", 1), ("param_finalize", 2), ("bwd_x", 4))):
+    for name, ph in (("conv_bwd", 7),):
         with _timed(name):
             check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
                                      grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials),
@@ -291,56 +308,126 @@ class KernelSetConvFn(torch.autograd.Function):
         return (gx[:, :ctx.F] if gx is not None else None, None, None, None, None, None, None, *flat)
 
 
-class MolGCNFn(torch.autograd.Function):
-    """The whole conv stack: for every layer conv -> propagate (MolGCN.forward, KernelLayer.py:107-120)."""
+class StackPack(object):
+    """The layers of one MolGCN as a contiguous ``molkgnn_layer_t[nl]`` + their packed workspaces.  Built once per module
+    and reused while the parameter storages stay in place (in-place optimizer updates keep them)."""
+
+    def __init__(self, layer_params, F0, Fe, device):
+        self.nl = len(layer_params)
+        if not (1 <= self.nl <= _lib.MAX_LAYERS):
+            raise _lib.MolKGNNError(f"{self.nl} layers not supported (1..{_lib.MAX_LAYERS})")
+        self.arr = (_lib.Layer * self.nl)()
+        self.packs = []
+        F = F0
+        for i, params in enumerate(layer_params):
+            self.packs.append(LayerPack(params, F, Fe, device, c=self.arr[i]))
+            F = self.packs[-1].K
+        self.F0, self.Fe, self.device = F0, Fe, device
+        self.key = self.make_key(layer_params, F0, Fe, device)
+        # flat parameter-gradient views, in flat_params() order; offsets come from the native layout (plan independent)
+        self.last_grad_flat = None
 
     @staticmethod
-    def forward(ctx, x, plan, layer_params, Fe, argmax_in, aux, *flat):
-        dev = x.device
-        nl = len(layer_params)
-        F = x.shape[1]
-        packs, saved, ximgs = [], [], []
+    def make_key(layer_params, F0, Fe, device):
+        k = [F0, Fe, str(device)]
         for params in layer_params:
-            packs.append(LayerPack(params, F, Fe, dev).pack())
-            F = packs[-1].K
-        h, hnorm, ximg = None, None, None
-        for i, pack in enumerate(packs):
-            if i == 0:
-                h, hnorm = pad_norm(x.detach(), pack.Fp)
-            if ximg is None:
-                ximg = x_images(plan, pack, h, hnorm)
-            sc, argmax, free = conv_forward(plan, pack, h, hnorm, i == nl - 1, dense=False,
-                                            argmax_in=None if argmax_in is None else argmax_in[i],
-                                            want_free=aux is not None, ximg=ximg)
-            if aux is not None:
-                aux.setdefault("argmax", []).append(argmax)
-                aux.setdefault("argmax_free", []).append(free)
-                aux.setdefault("sc", []).append(sc)
-            saved += [h, hnorm, argmax]
-            ximgs.append(ximg)
-            h, hnorm, ximg = propagate_forward(plan, pack, sc, packs[i + 1] if i + 1 < nl else None)
-        ctx.plan, ctx.packs, ctx.ximgs = plan, packs, ximgs
-        ctx.save_for_backward(*saved)
+            for prm in params:
+                if prm is None:
+                    k.append(0)
+                else:
+                    k += [prm[n].data_ptr() if prm[n].is_contiguous() else object() for n in PARAMS_PER_DEGREE]
+        return tuple(k)
+
+    def layout(self, plan: BucketPlan, flags):
+        lay = _lib.StackLayout()
+        check(_lib.lib().molkgnn_stack_layout(C.byref(plan.c), self.arr, self.nl, flags, C.byref(lay)))
+        return lay
+
+    def grad_views(self, lay, flat):
+        """Views of the flat gradient buffer in flat_params() order (None for parameters without a gradient)."""
+        out = []
+        for i, pk in enumerate(self.packs):
+            for d in range(4):
+                Ld = pk.L[d]
+                if not Ld:
+                    out += [None] * 7
+                    continue
+                oc, os_, oe, ow = lay.g_x_center[i][d], lay.g_x_support[i][d], lay.g_edge_attr_support[i][d], lay.g_w[i][d]
+                out += [flat[oc:oc + Ld * pk.F].view(Ld, pk.F),
+                        flat[os_:os_ + Ld * (d + 1) * pk.F].view(Ld, d + 1, pk.F),
+                        flat[oe:oe + Ld * (d + 1) * pk.Fe].view(Ld, d + 1, pk.Fe),
+                        None, flat[ow], flat[ow + 1], flat[ow + 2]]
+        return out
+
+
+FLAG_KEEP_SC, FLAG_WANT_FREE = 1, 2
+
+
+class MolGCNFn(torch.autograd.Function):
+    """The whole conv stack: for every layer conv -> propagate (MolGCN.forward, KernelLayer.py:107-120); one native call
+    for the forward and one for the backward (csrc/stack.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, plan, stack, argmax_in, aux, *flat):
+        L = _lib.lib()
+        dev = x.device
+        nl = stack.nl
+        flags = (FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0
+        lay = stack.layout(plan, flags)
+        xc = x.detach()
+        if xc.dtype != torch.float32:
+            xc = xc.float()
+        if xc.stride(1) != 1:
+            xc = xc.contiguous()
+        ws = torch.empty(lay.fwd_bytes, dtype=torch.uint8, device=dev)
+        Kl, Kpl = stack.packs[-1].K, stack.packs[-1].Kp
+        h = torch.empty(plan.N, Kpl, dtype=torch.float32, device=dev)
+        forced, keep = None, []
+        if argmax_in is not None:
+            forced = (C.c_void_p * nl)()
+            for i in range(nl):
+                if argmax_in[i] is None:
+                    continue
+                t = argmax_in[i].to(device=dev, dtype=torch.uint8).contiguous()
+                if t.numel() != max(lay.sc_elems[i], 1) and t.numel() != lay.sc_elems[i]:
+                    raise _lib.MolKGNNError("argmax_in has the wrong size")
+                keep.append(t)
+                forced[i] = t.data_ptr()
+        check(L.molkgnn_stack_fwd(C.byref(plan.c), stack.arr, nl, C.byref(lay), flags, ptr(xc), xc.stride(0), ptr(ws),
+                                  ptr(h), Kpl, forced, stream_ptr()))
+        if aux is not None:
+            for i in range(nl):
+                n = lay.sc_elems[i]
+                aux.setdefault("argmax", []).append(ws[lay.argmax[i]:lay.argmax[i] + max(n, 1)])
+                aux.setdefault("argmax_free", []).append(ws[lay.argmax_free[i]:lay.argmax_free[i] + max(n, 1)])
+                aux.setdefault("sc", []).append(ws[lay.sc[i]:lay.sc[i] + 4 * max(n, 1)].view(torch.float32))
+        ctx.plan, ctx.stack, ctx.lay = plan, stack, lay
+        ctx.save_for_backward(ws)
         ctx.need_gx = x.requires_grad
         ctx.F0 = x.shape[1]
-        return h[:, :packs[-1].K]
+        return h[:, :Kl]
 
     @staticmethod
     def backward(ctx, grad_h):
-        saved = ctx.saved_tensors
-        packs = ctx.packs
-        nl = len(packs)
-        needs = ctx.needs_input_grad[6:]
-        g = grad_h.float()
-        flat_all = [None] * (nl * 28)
-        for i in range(nl - 1, -1, -1):
-            xp, xnorm, argmax = saved[3 * i:3 * i + 3]
-            need_gp = any(needs[28 * i:28 * (i + 1)])
-            need_gx = ctx.need_gx if i == 0 else True
-            gx, grads = conv_backward(ctx.plan, packs[i], xp, xnorm, g, 1, argmax, need_gx, need_gp, ximg=ctx.ximgs[i])
-            flat_all[28 * i:28 * (i + 1)] = _flatten_param_grads(grads, packs[i], None)
-            g = gx
-        return (g[:, :ctx.F0] if g is not None else None, None, None, None, None, None, *flat_all)
+        L = _lib.lib()
+        (ws,) = ctx.saved_tensors
+        plan, stack, lay = ctx.plan, ctx.stack, ctx.lay
+        dev = ws.device
+        g = grad_h
+        if g.dtype != torch.float32:
+            g = g.float()
+        if g.stride(1) != 1 or g.data_ptr() % 16:
+            g = g.contiguous()
+        need_gp = any(ctx.needs_input_grad[5:])
+        bs = torch.empty(lay.bwd_bytes, dtype=torch.uint8, device=dev)
+        gflat = torch.empty(lay.grad_floats, dtype=torch.float32, device=dev) if need_gp else None
+        Fp0 = stack.packs[0].Fp
+        gx = torch.empty(plan.N, Fp0, dtype=torch.float32, device=dev) if ctx.need_gx else None
+        check(L.molkgnn_stack_bwd(C.byref(plan.c), stack.arr, stack.nl, C.byref(lay), ptr(ws), ptr(bs), ptr(g), g.stride(0),
+                                  ptr(gx), ptr(gflat), stream_ptr()))
+        flat_all = stack.grad_views(lay, gflat) if need_gp else [None] * (stack.nl * 28)
+        stack.last_grad_flat = gflat                # dp.GradBucket all-reduces this buffer in place
+        return (gx[:, :ctx.F0] if gx is not None else None, None, None, None, None, *flat_all)
 
 
 def flat_params(params):

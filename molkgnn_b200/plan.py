@@ -26,32 +26,60 @@ def _require_cuda(t, name):
 class BucketPlan(object):
     """Owns the device arrays of ``molkgnn_plan_t``; ``self.c`` is the ctypes struct handed to the kernels."""
 
-    def __init__(self, N, E, device):
+    # device arrays of molkgnn_plan_t: (name, dtype, elements as a function of N, E)
+    _ARRAYS = (("deg", torch.int32, lambda N, E: N), ("pos", torch.int32, lambda N, E: N),
+               ("sel", torch.int32, lambda N, E: N), ("nei", torch.int32, lambda N, E: max(E, 1)),
+               ("nei_eid", torch.int32, lambda N, E: max(E, 1)), ("ehat", torch.float32, lambda N, E: max(E, 1) * EDGE_PAD),
+               ("tsign", torch.int8, lambda N, E: max(N, 1)), ("in_cnt", torch.int32, lambda N, E: N),
+               ("in_src", torch.int32, lambda N, E: 4 * N), ("in_j", torch.int32, lambda N, E: 4 * N),
+               ("tile_start", torch.int32, lambda N, E: N // 32 + 4), ("tile_meta", torch.uint8, None),
+               ("ehat_node", torch.float32, lambda N, E: max(E, 1) * EDGE_PAD),
+               ("node_tile", torch.int32, lambda N, E: max(N, 1)))
+    _SHAPES = {"ehat": (-1, EDGE_PAD), "ehat_node": (-1, EDGE_PAD), "in_src": (-1, 4), "in_j": (-1, 4)}
+    _layout_cache = {}
+
+    def __init__(self, N, E, device, scratch_bytes=0, zero_tsign=True):
+        """One allocation holds every device array of the plan (+ the scratch of the bucket pass behind them)."""
         self.N, self.E, self.device = int(N), int(E), device
-        i32 = dict(dtype=torch.int32, device=device)
-        self.deg = torch.empty(self.N, **i32)
-        self.pos = torch.empty(self.N, **i32)
-        self.sel = torch.empty(self.N, **i32)
-        self.nei = torch.empty(max(self.E, 1), **i32)
-        self.nei_eid = torch.empty(max(self.E, 1), **i32)
-        self.ehat = torch.empty(max(self.E, 1), EDGE_PAD, dtype=torch.float32, device=device)
-        self.tsign = torch.zeros(max(self.N, 1), dtype=torch.int8, device=device)
-        self.in_cnt = torch.empty(self.N, **i32)
-        self.in_src = torch.empty(self.N, 4, **i32)
-        self.in_j = torch.empty(self.N, 4, **i32)
-        self.tile_start = torch.empty(self.N // 32 + 4, **i32)      # molecule tiles (filled by molkgnn_bucket_build)
-        self.tile_meta = torch.empty((self.N // 32 + 4) * int(_lib.lib().molkgnn_tile_meta_bytes()), dtype=torch.uint8,
-                                     device=device)
-        self.ehat_node = torch.empty(max(self.E, 1), EDGE_PAD, dtype=torch.float32, device=device)
-        self.node_tile = torch.empty(max(self.N, 1), **i32)
+        key = (self.N, self.E)
+        lay = BucketPlan._layout_cache.get(key)
+        if lay is None:
+            meta = (self.N // 32 + 4) * int(_lib.lib().molkgnn_tile_meta_bytes())
+            off, lay = 0, {}
+            for name, dt, fn in self._ARRAYS:
+                nbytes = meta if fn is None else fn(self.N, self.E) * torch.empty(0, dtype=dt).element_size()
+                lay[name] = (off, nbytes, dt)
+                off += (nbytes + 127) // 128 * 128
+            lay["_total"] = off
+            if len(BucketPlan._layout_cache) > 64:
+                BucketPlan._layout_cache.clear()
+            BucketPlan._layout_cache[key] = lay
+        self._lay = lay
+        self._buf = torch.empty(lay["_total"] + int(scratch_bytes), dtype=torch.uint8, device=device)
+        base = self._buf.data_ptr()
         c = _lib.Plan()
         c.N, c.E = self.N, self.E
-        for name in ("deg", "pos", "sel", "nei", "nei_eid", "ehat", "tsign", "in_cnt", "in_src", "in_j", "tile_start", "tile_meta",
-                     "ehat_node", "node_tile"):
-            setattr(c, name, getattr(self, name).data_ptr())
+        for name, _, _ in self._ARRAYS:
+            setattr(c, name, base + lay[name][0])
+        if zero_tsign:      # plans built from reference tensors with p_dim != 3 never write the chirality signs
+            o, nb, _ = lay["tsign"]
+            self._buf[o:o + nb].zero_()
         self.c = c
         self.n = [0, 0, 0, 0]
         self.n_tiles = 0
+
+    def __getattr__(self, name):
+        # tensor views of the device arrays, created on demand (tests, export)
+        lay = self.__dict__.get("_lay")
+        if lay is not None and name in lay and not name.startswith("_"):
+            o, nb, dt = lay[name]
+            t = self._buf[o:o + nb].view(dt)
+            return t.view(*self._SHAPES[name]) if name in self._SHAPES else t
+        raise AttributeError(name)
+
+    @property
+    def scratch_ptr(self):
+        return C.c_void_p(self._buf.data_ptr() + self._lay["_total"])
 
     # ---- constructors -------------------------------------------------------------------------------------
     @classmethod
@@ -65,13 +93,11 @@ class BucketPlan(object):
         p = p.contiguous().float()
         edge_attr = edge_attr.contiguous().float()
         E = edge_index.shape[1]
-        self = cls(num_nodes, E, edge_index.device)
         L = _lib.lib()
-        scratch = torch.empty(int(L.molkgnn_bucket_scratch_bytes(self.N, E)), dtype=torch.uint8, device=self.device)
-        from .functional import _timed
-        with _timed("bucket_build"):
-            check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
-                                         edge_attr.shape[1], ptr(scratch), stream_ptr()))
+        self = cls(num_nodes, E, edge_index.device, scratch_bytes=int(L.molkgnn_bucket_scratch_bytes(int(num_nodes), E)),
+                   zero_tsign=False)
+        check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
+                                     edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
         self.n = list(self.c.n)
         self.n_tiles = int(self.c.n_tiles)          # 0: no molecule tiling (bucket-order kernels are used)
         self._keep = (edge_index, p, edge_attr)

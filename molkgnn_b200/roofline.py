@@ -66,7 +66,11 @@ def kernel_bytes_per_step(kernel, N, E, n, x_dim, L1, LN, num_layers, Fe=7):
             tot += 4 * N * K + 4 * N * F + am + 4 * E * Fe + topo
         elif kernel == "bwd_x":
             tot += 4 * N * F
-        elif kernel == "bucket_build":
+        elif kernel == "coef_bond":          # tile backward, pre-pass: grad_h gather, arg-max, bond rows
+            tot += 4 * N * K + am + 4 * E * Fe + topo
+        elif kernel == "conv_bwd_tile":      # tile backward, main kernel: x (as fp16 images) in, grad_x out
+            tot += 8 * N * F + topo
+        elif kernel in ("bucket_build", "bucket_assign"):
             tot += (16 * E + 12 * N + 4 * E * Fe) if i == 0 else 0
         else:
             tot += 0
