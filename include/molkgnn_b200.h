@@ -174,9 +174,12 @@ int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* lay
 
 /* ---- backward (the reference uses autograd over kernels.py:353-425 and KernelLayer.py:119) ---- */
 int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+/* floats of the `coef` scratch: sum_d n_d*L_d for the bucket-order kernels, the tile-ordered coefficient + arg-max arrays
+ * (n_tiles slots of the fullest tile's size) for the molecule-tile path */
+int64_t molkgnn_conv_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 /* grad_mode 0: g[n,k] = grad[n*ldg + koff_d + k]                 (grad w.r.t. the dense score matrix)
  * grad_mode 1: g[n,k] = sum_{i in nei(n)} grad[i*ldg + koff_d + k] (grad w.r.t. the propagated h: fuses propagate^T)
- * coef: scratch, sum_d n_d*L_d floats (compact, offsets scoff).  partials: scratch of
+ * coef: scratch of molkgnn_conv_bwd_coef_floats() floats, 16-byte aligned.  partials: scratch of
  * molkgnn_conv_bwd_partial_floats() floats.  grad_x (nullable) [N,ldgx] receives dL/dx including the cosine
  * normalisation Jacobian; columns F..ldgx-1 zeroed.  grads (nullable members skipped) receives dL/dparam.
  * phases: bit 0 = k_bwd_w (coef + per-CTA partial sums), bit 1 = parameter finalize, bit 2 = k_bwd_x (grad_x);

@@ -64,6 +64,7 @@ EXPORTS = {
                                    vp, vp, vp, vp]),
     "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp, vp]),
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
+    "molkgnn_conv_bwd_coef_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),
     "molkgnn_tc_selftest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,

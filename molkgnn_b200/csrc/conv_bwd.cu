@@ -501,6 +501,14 @@ static int init_dev() {
     return 0;
 }
 
+namespace mk { int64_t tile_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer); }
+
+extern "C" int64_t molkgnn_conv_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    int64_t tot = 0;
+    for (int d = 0; d < 4; ++d) tot += (int64_t)plan->n[d] * layer->L[d];
+    return std::max<int64_t>(std::max(tot, mk::tile_bwd_coef_floats(plan, layer)), 4);
+}
+
 extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     if (init_dev()) return -1;
     int ncta[4];

@@ -36,141 +36,223 @@ bool tile_layer_ok(const molkgnn_layer_t* layer);
 
 constexpr int TB_THREADS = 512;
 constexpr int WT_ONE = 16 * 16 * 128;          // one fp16 image of the 128 x 128 coefficient block
-constexpr int CB_TN = 64;                      // nodes per step of k_coef_bond
-constexpr int CB_THREADS = 256;
-constexpr int CB_MAXR = 4;                     // support rows per thread of k_coef_bond (L * d <= 1024)
 
 // =============================================================================================================
-// k_coef_bond
+// k_coef_tile
 // =============================================================================================================
-struct CoefArgs {
-    const int* sel; const int* nei; const float* ehat;
-    int n[4], boff[4], eoff[4], L[4], koff[4];
+// Tile-ordered pre-pass.  Per tile the incoming gradient rows of its nodes are ONE contiguous range of grad (tiles hold
+// whole molecules), staged in shared memory by cp.async one tile ahead; g[n,k] = sum over the node's neighbours (all inside
+// the tile) is then shared-memory arithmetic.  Outputs per tile, in the order the tile kernel consumes them (one bulk copy):
+//   coefT[tile * stride + off_d + i * L_d + k] = chi * g   for the i-th degree-d node of the tile (list[d-1][i]),
+//   amT  [tile * stride_am + same index]       = saved arg-max permutation,
+// off_d = sum_{d' < d} cnt_d' * L_d'.  Bond-attribute support gradients: thread owns support rows, sums over the tile's
+// nodes in fixed order, one partial copy per CTA (k_param_finalize reduces them).
+constexpr int CT_THREADS = 512;
+constexpr int CT_MAXR = 4;                     // support rows per thread (sum_d d * L_d <= 2048)
+
+struct CoefTileArgs {
+    const TileMetaG* meta; const float* ehat_node; int n_tiles;
+    int L[4], koff[4];
     long long scoff[4];
-    const float* grad; int ldg; int grad_mode;
+    const float* grad; int ldg; int grad_mode; int vec;     // vec: floats per cp.async of the gradient rows (1, 2 or 4)
     const uint8_t* argmax;
-    float* coef;
+    float* coefT; uint8_t* amT; int stride, stride_am;
     float* partials; long long part_off[4]; int FW, Fp;
-    int G;                                     // CTAs (= partial copies) per degree
     float* amax;                               // device scalar (zeroed by the launcher): max |coef|
+    int buf_bytes, sm_grad, sm_eh, sm_coef, sm_inv;   // per-buffer size / offsets inside a buffer / offsets of the pair arrays
 };
 
-template <int D>
-__device__ __forceinline__ void coef_bond_body(const CoefArgs& a, float* coefS, unsigned char* invS, float4* ehS, int c) {
-    const int L = a.L[D - 1], n = a.n[D - 1];
+__device__ __forceinline__ void cp_async_n(void* dst, const void* src, int bytes) {
+    const uint32_t d = tc::smem_u32(dst);
+    if (bytes == 16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else if (bytes == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// all threads: metadata record, gradient rows and bond rows of `tile` -> buffer
+__device__ __forceinline__ void ct_issue(const CoefTileArgs& a, unsigned char* buf, int tile) {
+    const TileMetaG* g = a.meta + tile;
+    const int4 hdr = __ldg(reinterpret_cast<const int4*>(g));          // t0, nn, e0, ne
     const int tid = threadIdx.x;
-    const int eoff = a.eoff[D - 1], koff = a.koff[D - 1];
-    const int nrows = L * D;
-    float acc[CB_MAXR][EP];
-#pragma unroll
-    for (int r = 0; r < CB_MAXR; ++r)
-#pragma unroll
-        for (int e = 0; e < EP; ++e) acc[r][e] = 0.f;
-    float amax = 0.f;
-    const int ntiles = (n + CB_TN - 1) / CB_TN;
-    for (int t = c; t < ntiles; t += a.G) {
-        const int R0 = t * CB_TN;
-        const int nv = min(CB_TN, n - R0);
-        __syncthreads();
-        // bond rows of the node tile: contiguous in the plan, staged once
-        {
-            const float4* src = reinterpret_cast<const float4*>(a.ehat + ((size_t)eoff + (size_t)R0 * D) * EP);
-            for (int i = tid; i < nv * D * 2; i += CB_THREADS) ehS[i] = __ldg(src + i);
-        }
-        // coefficients: 4 pairs per thread in flight
-        constexpr int U = 4;
-        const int npair = nv * L;
-        for (int i0 = tid; i0 < npair; i0 += CB_THREADS * U) {
-            float g[U];
-            uint8_t am[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * CB_THREADS;
-                g[u] = 0.f; am[u] = 0;
-                if (i < npair) {
-                    const int nl = i / L, k = i - nl * L;
-                    const int col = koff + k;
-                    const int R = R0 + nl;
-                    if (a.grad_mode == 0) {
-                        g[u] = a.grad[(size_t)a.sel[a.boff[D - 1] + R] * a.ldg + col];
-                    } else {
-                        const int* nb = a.nei + (size_t)eoff + (size_t)R * D;
-                        float s = a.grad[(size_t)nb[0] * a.ldg + col];
-#pragma unroll
-                        for (int j = 1; j < D; ++j) s += a.grad[(size_t)nb[j] * a.ldg + col];
-                        g[u] = s;
-                    }
-                    am[u] = a.argmax[(size_t)a.scoff[D - 1] + (size_t)R0 * L + i];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * CB_THREADS;
-                if (i < npair) {
-                    const float av = (am[u] & 0x80) ? -g[u] : g[u];
-                    amax = fmaxf(amax, fabsf(av));
-                    a.coef[(size_t)a.scoff[D - 1] + (size_t)R0 * L + i] = av;
-                    coefS[i] = av;
-                    uint32_t inv = 0;
-#pragma unroll
-                    for (int p = 0; p < Perm<D>::P; ++p) if (p == (am[u] & 0x7f)) inv = perm_inv_code<D>(p);
-                    invS[i] = (unsigned char)inv;
-                }
-            }
-        }
-        __syncthreads();
-        // bond-attribute support gradients: thread owns rows (s, k), sums over the nodes in fixed order
-#pragma unroll
-        for (int r = 0; r < CB_MAXR; ++r) {
-            const int row = tid + r * CB_THREADS;
-            if (row < nrows) {
-                const int s = row / L, k = row - s * L;
-#pragma unroll 4
-                for (int nl = 0; nl < nv; ++nl) {
-                    const float av = coefS[nl * L + k];
-                    const int j = (invS[nl * L + k] >> (2 * s)) & 3;
-                    const float4 e0 = ehS[(nl * D + j) * 2], e1 = ehS[(nl * D + j) * 2 + 1];
-                    acc[r][0] = fmaf(av, e0.x, acc[r][0]); acc[r][1] = fmaf(av, e0.y, acc[r][1]);
-                    acc[r][2] = fmaf(av, e0.z, acc[r][2]); acc[r][3] = fmaf(av, e0.w, acc[r][3]);
-                    acc[r][4] = fmaf(av, e1.x, acc[r][4]); acc[r][5] = fmaf(av, e1.y, acc[r][5]);
-                    acc[r][6] = fmaf(av, e1.z, acc[r][6]); acc[r][7] = fmaf(av, e1.w, acc[r][7]);
-                }
-            }
-        }
+    for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += CT_THREADS)
+        cp_async_n(buf + i * 16, reinterpret_cast<const unsigned char*>(g) + i * 16, 16);
+    {
+        // rows t0 .. t0+nn-1 of grad are contiguous: nn * ldg floats; the staged copy starts at the vec-aligned float below
+        const long long first = (long long)hdr.x * a.ldg;
+        const long long f0 = first - (first % a.vec);
+        const int nfl = (int)(first - f0) + hdr.y * a.ldg;
+        const int nv = (nfl + a.vec - 1) / a.vec;
+        float* dst = reinterpret_cast<float*>(buf + a.sm_grad);
+        const float* src = a.grad + f0;
+        const int bytes = a.vec * 4;
+        for (int i = tid; i < nv; i += CT_THREADS) cp_async_n(dst + i * a.vec, src + (size_t)i * a.vec, bytes);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.amax), __float_as_uint(amax));
-    const int rows_x = (D + 1) * L;
-    float* part = a.partials + a.part_off[D - 1] + (size_t)c * rows_x * a.FW + a.Fp;
-#pragma unroll
-    for (int r = 0; r < CB_MAXR; ++r) {
-        const int row = tid + r * CB_THREADS;
-        if (row < nrows) {
-            st4(part + (size_t)row * a.FW, make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]));
-            st4(part + (size_t)row * a.FW + 4, make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]));
-        }
-    }
-    for (int row = nrows + tid; row < rows_x; row += CB_THREADS) {   // centre rows carry no bond part
-        st4(part + (size_t)row * a.FW, make_float4(0.f, 0.f, 0.f, 0.f));
-        st4(part + (size_t)row * a.FW + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    {
+        const float* src = a.ehat_node + (size_t)hdr.z * EP;
+        float* dst = reinterpret_cast<float*>(buf + a.sm_eh);
+        for (int i = tid; i < hdr.w * 2; i += CT_THREADS) cp_async_n(dst + i * 4, src + (size_t)i * 4, 16);
     }
 }
 
-__global__ void __launch_bounds__(CB_THREADS) k_coef_bond(const __grid_constant__ CoefArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_c[];
-    const int d = blockIdx.x / a.G + 1, c = blockIdx.x % a.G;
-    const int L = a.L[d - 1];
-    if (L == 0) return;
-    float4* ehS = reinterpret_cast<float4*>(smem_c);                     // [CB_TN * 4 slots][2]
-    float* coefS = reinterpret_cast<float*>(smem_c + CB_TN * 4 * 32);
-    unsigned char* invS = smem_c + CB_TN * 4 * 32 + (size_t)CB_TN * L * 4;
-    switch (d) {
-        case 1: coef_bond_body<1>(a, coefS, invS, ehS, c); break;
-        case 2: coef_bond_body<2>(a, coefS, invS, ehS, c); break;
-        case 3: coef_bond_body<3>(a, coefS, invS, ehS, c); break;
-        default: coef_bond_body<4>(a, coefS, invS, ehS, c); break;
+#ifdef MK_PHASE_CLOCKS
+__device__ unsigned long long g_ph_coef[16];
+#endif
+
+__global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_constant__ CoefTileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_c[];
+    __shared__ unsigned char s_inv[4][12];               // inverse permutation codes per degree
+    const int tid = threadIdx.x;
+    MK_PH_DECL(tid == 0)
+    if (tid < 48) {
+        const int d = tid / 12 + 1, p = tid % 12;
+        uint32_t code = 0;
+        if (d == 2) code = p < 2 ? perm_inv_code<2>(p) : 0;
+        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_inv_code<3>(q); }
+        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_inv_code<4>(q); }
+        s_inv[d - 1][p] = (unsigned char)code;
     }
+    float* coefS = reinterpret_cast<float*>(smem_c + a.sm_coef);
+    unsigned char* invS = smem_c + a.sm_inv;
+    // support rows owned by this thread: row r = tid + q * CT_THREADS over the concatenation of the degrees' (s, k) rows
+    int rd[CT_MAXR], rs[CT_MAXR], rk[CT_MAXR];
+    float acc[CT_MAXR][EP];
+#pragma unroll
+    for (int q = 0; q < CT_MAXR; ++q) {
+        int r = tid + q * CT_THREADS;
+        rd[q] = 0; rs[q] = 0; rk[q] = 0;
+#pragma unroll
+        for (int d = 1; d <= 4; ++d) {
+            const int rows = d * a.L[d - 1];
+            if (rd[q] == 0 && r >= 0) {
+                if (r < rows) { rd[q] = d; rs[q] = r / a.L[d - 1]; rk[q] = r - rs[q] * a.L[d - 1]; }
+                else r -= rows;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < EP; ++e) acc[q][e] = 0.f;
+    }
+    float amax = 0.f;
+    int cur = 0;
+    if ((int)blockIdx.x < a.n_tiles) ct_issue(a, smem_c, blockIdx.x);
+    cp_async_commit();
+    MK_PH(0);
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        unsigned char* buf = smem_c + (size_t)cur * a.buf_bytes;
+        const int tnext = tile + gridDim.x;
+        __syncthreads();                                 // the previous tile's readers are done with the other buffer
+        if (tnext < a.n_tiles) ct_issue(a, smem_c + (size_t)(cur ^ 1) * a.buf_bytes, tnext);
+        cp_async_commit();
+        MK_PH(1);                                        // barrier + issue of the next tile's copies
+        cp_async_wait<1>();
+        __syncthreads();                                 // this tile's buffer is complete; coefS / invS are free
+        MK_PH(2);                                        // wait for this tile's data
+        const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
+        const float* gS = reinterpret_cast<const float*>(buf + a.sm_grad) + (int)(((long long)m.t0 * a.ldg) % a.vec);
+        const float4* ehS = reinterpret_cast<const float4*>(buf + a.sm_eh);
+        int off[5];
+        off[0] = 0;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) off[d + 1] = off[d] + m.cnt[d] * a.L[d];
+        float* cT = a.coefT + (size_t)tile * a.stride;
+        uint8_t* aT = a.amT + (size_t)tile * a.stride_am;
+        // ---- coefficients: one thread per (node, kernel) pair over all degrees, U pairs in flight per thread (the saved
+        // arg-max is the only global read: its loads are issued for all U pairs before any is consumed) ----
+        {
+            constexpr int U = 5;
+            const int total = off[4];
+            for (int p0 = tid; p0 < total; p0 += CT_THREADS * U) {
+                int dd[U], pl_[U], nl_[U], kk[U];
+                uint8_t am[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int p = p0 + u * CT_THREADS;
+                    dd[u] = 0; am[u] = 0; pl_[u] = 0; nl_[u] = 0; kk[u] = 0;
+                    if (p < total) {
+                        const int d = 1 + (p >= off[1]) + (p >= off[2]) + (p >= off[3]);
+                        const int L = a.L[d - 1];
+                        const int qd = p - off[d - 1];
+                        const int i = (int)(((float)qd + 0.5f) / (float)L);
+                        const int k = qd - i * L;
+                        const int n_ = m.list[d - 1][i];
+                        am[u] = a.argmax[(size_t)a.scoff[d - 1] + (size_t)m.posl[n_] * L + k];
+                        dd[u] = d; pl_[u] = p; nl_[u] = n_; kk[u] = a.koff[d - 1] + k;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int d = dd[u];
+                    if (d == 0) continue;
+                    float g;
+                    if (a.grad_mode == 0) {
+                        g = gS[nl_[u] * a.ldg + kk[u]];
+                    } else {
+                        const uint32_t nw = m.nl[nl_[u]];
+                        g = gS[(int)(nw & 0xffu) * a.ldg + kk[u]];
+                        for (int j = 1; j < d; ++j) g += gS[(int)((nw >> (8 * j)) & 0xffu) * a.ldg + kk[u]];
+                    }
+                    const float av = (am[u] & 0x80) ? -g : g;
+                    amax = fmaxf(amax, fabsf(av));
+                    cT[pl_[u]] = av;
+                    aT[pl_[u]] = am[u] & 0x7f;
+                    coefS[pl_[u]] = av;
+                    invS[pl_[u]] = s_inv[d - 1][am[u] & 0x7f];
+                }
+            }
+        }
+        MK_PH(3);                                        // pairs (thread 0's share)
+        __syncthreads();
+        MK_PH(4);                                        // waiting for the slowest pair thread
+        // ---- bond-attribute support gradients ----
+#pragma unroll
+        for (int q = 0; q < CT_MAXR; ++q) {
+            const int d = rd[q];
+            if (d == 0) continue;
+            const int L = a.L[d - 1], cnt = m.cnt[d - 1];
+            const float* cs = coefS + off[d - 1] + rk[q];
+            const unsigned char* is = invS + off[d - 1] + rk[q];
+            const unsigned char* lst = m.list[d - 1];
+            const int sh = 2 * rs[q];
+#pragma unroll 4
+            for (int i = 0; i < cnt; ++i) {
+                const float av = cs[i * L];
+                const int j = (is[i * L] >> sh) & 3;
+                const int e = m.eslot[lst[i]] + j;
+                const float4 e0 = ehS[2 * e], e1 = ehS[2 * e + 1];
+                acc[q][0] = fmaf(av, e0.x, acc[q][0]); acc[q][1] = fmaf(av, e0.y, acc[q][1]);
+                acc[q][2] = fmaf(av, e0.z, acc[q][2]); acc[q][3] = fmaf(av, e0.w, acc[q][3]);
+                acc[q][4] = fmaf(av, e1.x, acc[q][4]); acc[q][5] = fmaf(av, e1.y, acc[q][5]);
+                acc[q][6] = fmaf(av, e1.z, acc[q][6]); acc[q][7] = fmaf(av, e1.w, acc[q][7]);
+            }
+        }
+        MK_PH(5);                                        // bond sums (thread 0's rows)
+        cur ^= 1;
+    }
+    cp_async_wait<0>();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.amax), __float_as_uint(amax));
+    // one partial copy per CTA: bond columns of the support rows; the centre rows carry no bond part
+#pragma unroll
+    for (int q = 0; q < CT_MAXR; ++q) {
+        const int d = rd[q];
+        if (d == 0) continue;
+        const int L = a.L[d - 1];
+        float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * (d + 1) * L + (size_t)rs[q] * L + rk[q]) * a.FW + a.Fp;
+        st4(part, make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
+        st4(part + 4, make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]));
+    }
+    for (int d = 1; d <= 4; ++d) {
+        const int L = a.L[d - 1];
+        for (int k = tid; k < L; k += CT_THREADS) {
+            float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * (d + 1) * L + (size_t)d * L + k) * a.FW + a.Fp;
+            st4(part, make_float4(0.f, 0.f, 0.f, 0.f));
+            st4(part + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+    MK_PH(6);
+    MK_PH_FLUSH(g_ph_coef);
 }
 
 // =============================================================================================================
@@ -185,16 +267,18 @@ struct BwdTileArgs {
     const unsigned char* img;
     TileBlocks tb;
     int img_one, x_one;
-    const float* coef;                 // chi * g per (node, kernel) pair, compact bucket order (k_coef_bond)
-    const uint8_t* argmax; long long scoff[4];
-    const float* amax;                 // device scalar: max |coef| (k_coef_bond)
+    const float* coefT;                // chi * g per (node, kernel) pair, tile order (k_coef_tile)
+    const uint8_t* amT; int stride, stride_am;
+    const float* amax;                 // device scalar: max |coef| (k_coef_tile)
     float* partials; long long part_off[4]; int FW;
     float* scratch;                    // [N, Fk] partial dxh handed from the first launch to the second
     float* gx; int ldgx;
-    int nbl, blist[2];                 // kernel blocks of this launch
+    int nbl, blist[4];                 // kernel blocks of this launch
+    int gstride, dxcol;                // TMEM columns: G of block bi at bi * gstride, dxh at dxcol
+    int nimg;                          // kernel-block image buffers in shared memory (1..4)
     int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
-    int a_cap, buf_bytes;
-    int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am;
+    int buf_bytes;
+    int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
 };
 
 struct BSeg {
@@ -220,30 +304,38 @@ __device__ __forceinline__ void wt_add(unsigned char* wt, int row, int col, floa
     *pl = __float2half_rn(v - __half2float(hi));
 }
 
-// thread 0: metadata record and node images of `tile`
-__device__ __forceinline__ void tb_issue_copy(const BwdTileArgs& a, unsigned char* smem, unsigned char* buf, int tile,
+// thread 0: metadata record, node images and the tile-ordered coefficients / arg-max codes of `tile` (np pairs).  The
+// coefficient arrays and the image buffer are single: the caller issues this only after the previous tile's last use of them.
+__device__ __forceinline__ void tb_issue_copy(const BwdTileArgs& a, unsigned char* smem, unsigned char* buf, int tile, int np,
                                               uint64_t* bar) {
-    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + 2u * (uint32_t)a.x_one);
+    const uint32_t cb = (uint32_t)((np * 4 + 15) & ~15), ab = (uint32_t)((np + 15) & ~15);
+    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + 2u * (uint32_t)a.x_one + cb + ab);
     bulk_g2s(buf, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
     bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
+    if (np > 0) {
+        bulk_g2s(smem + a.sm_a, a.coefT + (size_t)tile * a.stride, cb, bar);
+        bulk_g2s(smem + a.sm_am, a.amT + (size_t)tile * a.stride_am, ab, bar);
+    }
 }
-// thread 0: images of kernel block `blk`
-__device__ __forceinline__ void tb_issue_img(const BwdTileArgs& a, unsigned char* smem, int blk, uint64_t* bar) {
+__device__ __forceinline__ int tb_tile_pairs(const BwdTileArgs& a, int tile) {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(&a.meta[tile].cnt[0]));
+    return c.x * a.L[0] + c.y * a.L[1] + c.z * a.L[2] + c.w * a.L[3];
+}
+// thread 0: images of kernel block `blk` -> image buffer `ib`
+__device__ __forceinline__ void tb_issue_img(const BwdTileArgs& a, unsigned char* smem, int blk, int ib, uint64_t* bar) {
     mbar_expect_tx(bar, 2u * (uint32_t)a.img_one);
-    bulk_g2s(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2u * (uint32_t)a.img_one, bar);
+    bulk_g2s(smem + a.sm_img + (size_t)ib * 2 * a.img_one, a.img + (size_t)blk * 2 * a.img_one, 2u * (uint32_t)a.img_one, bar);
 }
 
-// thread 0: G_bi (TMEM columns bi*128 ..) += Wt . xhat ;  dxh (TMEM columns 256 ..) (+)= Wt^T . khat
-__device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char* smem, int nn, int rows, int bi,
-                                             bool g_fresh, uint32_t tmem, uint64_t* bar) {
+// thread 0: G_bi (TMEM columns bi * gstride ..) += Wt . xhat
+__device__ __forceinline__ void tb_issue_mma_g(const BwdTileArgs& a, unsigned char* smem, int nn, int bi, bool g_fresh,
+                                               uint32_t tmem) {
     const uint32_t whi = tc::smem_u32(smem + a.sm_wt), wlo = whi + WT_ONE;
     const uint32_t xhi = tc::smem_u32(smem + a.sm_x), xlo = xhi + (uint32_t)a.x_one;
-    const uint32_t ihi = tc::smem_u32(smem + a.sm_img), ilo = ihi + (uint32_t)a.img_one;
     const uint32_t fgrp = (uint32_t)(a.Fk >> 3) * 128u;      // bytes of one 8-row group of an [R x Fk] image
     const uint32_t idesc_g = tc::idesc_f16(128, a.Fk, 0, 1);  // A = Wt K-major (K = node), B = xhat MN-major (N = feature)
-    const uint32_t idesc_x = tc::idesc_f16(128, a.Fk, 1, 1);  // A = Wt MN-major (M = node, K = row), B = khat MN-major
-    const uint32_t dG = tmem + (uint32_t)bi * 128u, dX = tmem + 256u;
-    // G: K = nodes, 16 per step.  Wt K-major: +256 B per step (two 8-column chunks); xhat MN-major: +2 row groups per step
+    const uint32_t dG = tmem + (uint32_t)(bi * a.gstride);
+    // K = nodes, 16 per step.  Wt K-major: +256 B per step (two 8-column chunks); xhat MN-major: +2 row groups per step
     const int nkg = (max(16, (nn + 15) & ~15)) >> 4;
     for (int ks = 0; ks < nkg; ++ks) {
         const uint64_t dAh = tc::smem_desc(whi + ks * 256u, 128u, 2048u), dAl = tc::smem_desc(wlo + ks * 256u, 128u, 2048u);
@@ -252,12 +344,21 @@ __device__ __forceinline__ void tb_issue_mma(const BwdTileArgs& a, unsigned char
         tc::umma_f16(dG, dAl, dBh, idesc_g, 1u);
         tc::umma_f16(dG, dAh, dBl, idesc_g, 1u);
     }
-    // dxh: K = kernel rows, 16 per step.  Wt MN-major: +2 row groups (2 * 2048 B) per step; khat MN-major likewise
+}
+// thread 0: dxh (TMEM columns dxcol ..) (+)= Wt^T . khat (image buffer ib), then commit everything issued so far
+__device__ __forceinline__ void tb_issue_mma_x(const BwdTileArgs& a, unsigned char* smem, int rows, bool x_fresh, int ib,
+                                               uint32_t tmem, uint64_t* bar) {
+    const uint32_t whi = tc::smem_u32(smem + a.sm_wt), wlo = whi + WT_ONE;
+    const uint32_t ihi = tc::smem_u32(smem + a.sm_img + (size_t)ib * 2 * a.img_one), ilo = ihi + (uint32_t)a.img_one;
+    const uint32_t fgrp = (uint32_t)(a.Fk >> 3) * 128u;
+    const uint32_t idesc_x = tc::idesc_f16(128, a.Fk, 1, 1);  // A = Wt MN-major (M = node, K = row), B = khat MN-major
+    const uint32_t dX = tmem + (uint32_t)a.dxcol;
+    // K = kernel rows, 16 per step.  Wt MN-major: +2 row groups (2 * 2048 B) per step; khat MN-major likewise
     const int nkx = (max(16, (rows + 15) & ~15)) >> 4;
     for (int ks = 0; ks < nkx; ++ks) {
         const uint64_t dAh = tc::smem_desc(whi + ks * 4096u, 2048u, 128u), dAl = tc::smem_desc(wlo + ks * 4096u, 2048u, 128u);
         const uint64_t dBh = tc::smem_desc(ihi + ks * 2u * fgrp, fgrp, 128u), dBl = tc::smem_desc(ilo + ks * 2u * fgrp, fgrp, 128u);
-        tc::umma_f16(dX, dAh, dBh, idesc_x, (bi == 0 && ks == 0) ? 0u : 1u);
+        tc::umma_f16(dX, dAh, dBh, idesc_x, (x_fresh && ks == 0) ? 0u : 1u);
         tc::umma_f16(dX, dAl, dBh, idesc_x, 1u);
         tc::umma_f16(dX, dAh, dBl, idesc_x, 1u);
     }
@@ -270,14 +371,15 @@ __device__ unsigned long long g_ph_bwd[16];
 
 __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_constant__ BwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma, bar_img, bar_cp[2];
+    __shared__ uint64_t bar_mma, bar_img[4], bar_cp[2];
     __shared__ uint32_t tslot;
-    __shared__ BSeg s_seg[2][TILE_MAXSEG];
+    __shared__ BSeg s_seg[4][TILE_MAXSEG];
     __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MK_PH_DECL(tid == 0)
     if (tid == 0) {
-        tc::mbar_init(&bar_mma, 1); tc::mbar_init(&bar_img, 1);
+        tc::mbar_init(&bar_mma, 1);
+        for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_img[i], 1);
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
         tc::fence_mbar_init();
     }
@@ -290,7 +392,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
         s_lut[d - 1][p] = (unsigned char)code;
     }
-    if (tid >= 64 && tid < 64 + 2 * TILE_MAXSEG) {
+    if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
         const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
         if (bi < a.nbl && si < a.tb.nseg[a.blist[bi]]) {
             const TileSeg sg = a.tb.seg[a.blist[bi]][si];
@@ -311,10 +413,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tslot;
-    float* a_s = reinterpret_cast<float*>(smem + a.sm_a);
-    unsigned char* am_s = smem + a.sm_am;
-    float* red = reinterpret_cast<float*>(smem + a.sm_a);       // Jacobian reduction scratch: the coefficients are dead by then
-    uint32_t ph_mma = 0u, ph_img = 0u, ph_cp[2] = {0u, 0u};
+    const float* a_s = reinterpret_cast<const float*>(smem + a.sm_a);
+    const unsigned char* am_s = smem + a.sm_am;
+    float* red = reinterpret_cast<float*>(smem + a.sm_red);     // Jacobian reduction scratch
+    uint32_t ph_mma = 0u, ph_cp[2] = {0u, 0u};
     // power-of-two scale: |alpha * chi * g| / scale <= 2^10
     float scale, rscale;
     {
@@ -325,35 +427,39 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         rscale = ldexpf(1.0f, 10 - e);
     }
     const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / 32-column part of this warp
-    bool img_pending = false;                             // an image copy is in flight (uniform across the CTA)
-    if ((int)blockIdx.x < a.n_tiles) {
-        if (tid == 0) {
-            tb_issue_copy(a, smem, smem + a.sm_buf, blockIdx.x, &bar_cp[0]);
-            tb_issue_img(a, smem, a.blist[0], &bar_img);
-        }
-        img_pending = true;
+    // image uses u = 0, 1, ...: block blist[u % nbl] in buffer u % nimg.  With nbl <= nimg the images stay resident.
+    const int my_tiles = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_uses = my_tiles * a.nbl;
+    const bool resident = a.nbl <= a.nimg;
+    int np_next = 0;
+    if (tid == 0 && my_tiles > 0) {
+        tb_issue_copy(a, smem, smem + a.sm_buf, blockIdx.x, tb_tile_pairs(a, blockIdx.x), &bar_cp[0]);
+        const int n0 = resident ? a.nbl : min(a.nimg, total_uses);
+        for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, a.blist[u % a.nbl], u % a.nimg, &bar_img[u % a.nimg]);
     }
     MK_PH(0);                                             // prologue
-    int cur = 0;
+    int cur = 0, use = 0;
     bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         unsigned char* buf = smem + a.sm_buf + cur * a.buf_bytes;
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
+        const int tnext = tile + gridDim.x;
+        if (tid == 0 && tnext < a.n_tiles) np_next = tb_tile_pairs(a, tnext);   // latency hidden behind this tile's work
         tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
         ph_cp[cur] ^= 1u;
-        MK_PH(1);                                         // wait for the tile's metadata + node images
+        MK_PH(1);                                         // wait for the tile's metadata, node images, coefficients
         const int t0 = m.t0, nn = m.nn;
-        const int tnext = tile + gridDim.x;
+        int doff[4];                                      // first pair of degree d in the tile-ordered arrays
+        doff[0] = 0;
+#pragma unroll
+        for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * a.L[d - 1];
         for (int bi = 0; bi < a.nbl; ++bi) {
             const int blk = a.blist[bi];
             const int nseg = a.tb.nseg[blk];
             int abase[TILE_MAXSEG];
-            {
-                int run = 0;
-                for (int si = 0; si < nseg; ++si) { abase[si] = run; run += m.cnt[s_seg[bi][si].d - 1] * s_seg[bi][si].nk; }
-            }
-            // ---- rank 0: one thread per (node, kernel) pair -- coefficient, centre entry, collision-free support entries ----
+            for (int si = 0; si < nseg; ++si) abase[si] = doff[s_seg[bi][si].d - 1] + s_seg[bi][si].k0;
+            // ---- rank 0: one thread per (node, kernel) pair -- centre entry, collision-free support entries ----
             for (int si = 0; si < nseg; ++si) {
                 const BSeg sg = s_seg[bi][si];
                 const int np = m.cnt[sg.d - 1] * sg.nk;
@@ -361,12 +467,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     const int ni = (int)(((float)p + 0.5f) * sg.rnk);
                     const int kl = p - ni * sg.nk;
                     const int nl_ = m.list[sg.d - 1][ni];
-                    const size_t cidx = (size_t)a.scoff[sg.d - 1] + (size_t)m.posl[nl_] * sg.L + sg.k0 + kl;
-                    const float av = __ldg(a.coef + cidx) * rscale;
-                    const int am = a.argmax[cidx] & 0x7f;
-                    a_s[abase[si] + p] = av;
-                    am_s[abase[si] + p] = (unsigned char)am;
-                    const uint32_t code = s_lut[sg.d - 1][am];
+                    const int pi = abase[si] + ni * sg.L + kl;
+                    const float av = a_s[pi] * rscale;
+                    const uint32_t code = s_lut[sg.d - 1][am_s[pi]];
                     const uint32_t nw = m.nl[nl_];
                     const uint32_t cr = m.cr[nl_];
                     wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
@@ -396,9 +499,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                         const int kl = p - ei * sg.nk;
                         const int ent = m.elist[e0 + ei];
                         const int nl_ = ent >> 2, j = ent & 3;
-                        const int pi = abase[si] + m.lidx[nl_] * sg.nk + kl;
+                        const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
                         const int s = (s_lut[sg.d - 1][am_s[pi]] >> (2 * j)) & 3;
-                        wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), a_s[pi] * sg.alpha);
+                        wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
                     }
                 }
             }
@@ -408,28 +511,23 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             MK_PH(4);                                     // barrier before the MMAs
             // ---- tensor cores ----
             if (tid == 0) {
-                if (img_pending) {                            // this block's images were requested after the previous MMAs
-                    tc::mbar_wait(&bar_img, ph_img);
-                    ph_img ^= 1u;
-                }
                 tc::fence_after_sync();
-                tb_issue_mma(a, smem, nn, a.tb.rows[blk], bi, fresh, tmem, &bar_mma);
+                tb_issue_mma_g(a, smem, nn, bi, fresh, tmem);
+                const int ib = resident ? use % a.nbl : use % a.nimg;
+                if (!resident) tc::mbar_wait(&bar_img[ib], (uint32_t)(use / a.nimg) & 1u);
+                else if (use < a.nbl) tc::mbar_wait(&bar_img[ib], 0u);
+                tb_issue_mma_x(a, smem, a.tb.rows[blk], bi == 0, ib, tmem, &bar_mma);
             }
-            img_pending = false;
+            ++use;
             MK_PH(5);                                     // image wait + MMA issue
             tc::mbar_wait(&bar_mma, ph_mma);
             ph_mma ^= 1u;
             tc::fence_after_sync();
             MK_PH(6);                                     // MMA completion
-            // the tensor cores are done with Wt and the images: clear Wt, fetch the next block's images
+            // the tensor cores are done with Wt and this block's images: fetch the images of a later use, clear Wt
             for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
-            {
-                const int nblk = bi + 1 < a.nbl ? a.blist[bi + 1] : (tnext < a.n_tiles ? a.blist[0] : blk);
-                if (nblk != blk) {
-                    if (tid == 0) tb_issue_img(a, smem, nblk, &bar_img);
-                    img_pending = true;
-                }
-            }
+            if (tid == 0 && !resident && use - 1 + a.nimg < total_uses)
+                tb_issue_img(a, smem, a.blist[(use - 1 + a.nimg) % a.nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
             if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
             MK_PH(7);                                     // Wt clear
         }
@@ -458,7 +556,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             if (a.last && rowok) nrm = a.xnorm[t0 + v];
             if (colok) {
                 uint32_t u[32];
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + 256u + (uint32_t)f0;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a.dxcol + f0);
                 tc::tmem_ld16(taddr, u);
                 if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
                 else {
@@ -471,7 +569,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             }
             if (!a.last) {
                 if (tid == 0 && tnext < a.n_tiles)
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1]);
                 if (rowok && colok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -509,7 +607,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 red[cpart * 128 + v] = dot;
                 __syncthreads();
                 if (tid == 0 && tnext < a.n_tiles)      // every thread has read its xhat: the image buffer may be refilled
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, &bar_cp[cur ^ 1]);
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1]);
                 dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
                 const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
                 const float rden = 1.0f / den;
@@ -532,7 +630,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             }
         }
         tc::fence_before_sync();
-        __syncthreads();                 // coefficient arrays / Jacobian scratch, TMEM dxh and this tile's buffer are free again
+        __syncthreads();                 // Jacobian scratch, TMEM dxh and this tile's buffer are free again
         MK_PH(8);                                         // dxh epilogue
         cur ^= 1;
     }
@@ -549,7 +647,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         const int f0 = cpart * 32;
         if (f0 < a.Fk) {
             uint32_t u[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * 128 + f0);
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * a.gstride + f0);
             tc::tmem_ld16(taddr, u);
             if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
             else {
@@ -564,9 +662,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    if (f0 + i + 4 <= a.Fp)
-                        st4(part + f0 + i, make_float4(__uint_as_float(u[i]) * scale, __uint_as_float(u[i + 1]) * scale,
-                                                       __uint_as_float(u[i + 2]) * scale, __uint_as_float(u[i + 3]) * scale));
+                    if (f0 + i + 4 <= a.Fp) {
+                        // a CTA that saw no tile never ran an MMA: its accumulators are undefined, its partial sums zero
+                        const float sc2 = my_tiles > 0 ? scale : 0.f;
+                        st4(part + f0 + i, my_tiles > 0 ? make_float4(__uint_as_float(u[i]) * sc2, __uint_as_float(u[i + 1]) * sc2,
+                                                                      __uint_as_float(u[i + 2]) * sc2, __uint_as_float(u[i + 3]) * sc2)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f));
+                    }
                 }
             }
         }
@@ -588,12 +690,29 @@ int tile_bwd_grid(const molkgnn_plan_t* plan) {
     return std::max(1, std::min(plan->n_tiles, sms));
 }
 
+// tile-ordered coefficient layout: floats per tile / bytes per tile of the arg-max codes
+static void coef_strides(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, int* stride, int* stride_am) {
+    int64_t st = 0;
+    for (int d = 0; d < 4; ++d) st += (int64_t)plan->tile_max_deg[d] * layer->L[d];
+    *stride = (int)((st + 3) / 4 * 4);
+    *stride_am = (*stride + 15) / 16 * 16;
+}
+
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     if (!tile_plan_ok_b(plan) || !layer->tile_img || !tile_layer_ok(layer)) return false;
     TileBlocks tb;
     if (!tb.build(layer->L) || tb.nb > 4) return false;                 // at most two launches of two blocks
-    for (int d = 0; d < 4; ++d) if (layer->L[d] * (d + 1) > CB_MAXR * CB_THREADS) return false;
-    return true;
+    int rows = 0;
+    for (int d = 0; d < 4; ++d) rows += layer->L[d] * (d + 1);
+    return rows <= CT_MAXR * CT_THREADS;
+}
+
+// floats of the `coef` scratch the tile path needs (tile-ordered coefficients + arg-max codes behind them); 0 = not eligible
+int64_t tile_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    if (!tile_bwd_ok(plan, layer)) return 0;
+    int stride, stride_am;
+    coef_strides(plan, layer, &stride, &stride_am);
+    return (int64_t)plan->n_tiles * stride + ((int64_t)plan->n_tiles * stride_am + 3) / 4 + 4;
 }
 
 // returns 1 if launched, 0 if not eligible, <0 on error.  part_off / ncta describe the partial copies for k_param_finalize.
@@ -611,8 +730,6 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     }
     BwdTileArgs a;
     if (!a.tb.build(layer->L)) return 0;
-    const int nlaunch = a.tb.nb > 2 ? 2 : 1;
-    MK_REQUIRE(nlaunch == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than two kernel blocks");
     a.xnorm = xnorm;
     a.F = layer->F; a.Fp = layer->Fp; a.Fk = tile_fk(layer->Fp);
     a.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
@@ -624,7 +741,6 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     for (int d = 0; d < 4; ++d) {
         a.L[d] = layer->L[d];
         a.packed[d] = layer->packed[d];
-        a.scoff[d] = scoff[d];
         a.part_off[d] = part_off[d] = po;
         ncta[d] = layer->L[d] > 0 ? grid : 0;
         po += (int64_t)ncta[d] * (d + 2) * layer->L[d] * a.FW;
@@ -635,67 +751,89 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.img = reinterpret_cast<const unsigned char*>(layer->tile_img);
     a.img_one = tile_img_one(a.Fk);
     a.x_one = tile_img_one(a.Fk);
-    a.coef = coef;
-    a.argmax = argmax;
     a.amax = amax;
     a.partials = partials;
     a.scratch = scratch;
     a.gx = grad_x; a.ldgx = ldgx;
-    // capacity from the plan: (node, kernel) pairs of the fullest tile of any block
-    int a_cap = 0;
-    for (int b = 0; b < a.tb.nb; ++b) {
-        int c = 0;
-        for (int si = 0; si < a.tb.nseg[b]; ++si) c += plan->tile_max_deg[a.tb.seg[b][si].d - 1] * a.tb.seg[b][si].nk;
-        a_cap = std::max(a_cap, c);
-    }
-    a.a_cap = a_cap;
+    int stride, stride_am;
+    coef_strides(plan, layer, &stride, &stride_am);
+    a.coefT = coef;
+    a.amT = reinterpret_cast<const uint8_t*>(coef + (size_t)plan->n_tiles * stride);
+    a.stride = stride; a.stride_am = stride_am;
     a.buf_bytes = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
+    // TMEM: G of block bi at bi * gstride, dxh behind them.  A layer whose feature width lets (blocks + 1) accumulators fit
+    // the 512 columns runs ONE launch over all blocks; else two launches of two blocks, the first handing its partial dxh
+    // to the second through `scratch`.
+    static int s_merge = -1;
+    if (s_merge < 0) { const char* e = getenv("MOLKGNN_BWD_MERGE"); s_merge = (e && e[0] == '0') ? 0 : 1; }
+    const bool one_launch = a.tb.nb <= 2 || (s_merge && (a.tb.nb + 1) * a.Fk <= 512);
+    const int nlaunch = one_launch ? 1 : 2;
+    const int nbl_max = one_launch ? a.tb.nb : 2;
     int64_t off = 0;
-    a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
     a.sm_x = (int)off; off += 2 * (int64_t)a.x_one;
     a.sm_wt = (int)off; off += 2 * (int64_t)WT_ONE;
     a.sm_buf = (int)off; off += 2 * (int64_t)a.buf_bytes;
-    a.sm_a = (int)off; off += (std::max<int64_t>((int64_t)a_cap * 4, 4 * 128 * 4) + 127) / 128 * 128;
-    a.sm_am = (int)off; off += ((int64_t)a_cap + 127) / 128 * 128;
+    a.sm_a = (int)off; off += ((int64_t)stride * 4 + 127) / 128 * 128;
+    a.sm_am = (int)off; off += ((int64_t)stride_am + 127) / 128 * 128;
+    a.sm_red = (int)off; off += 4 * 128 * 4;
+    a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
     if (off > s_budget - 2048) return 0;
-    int Lmax = 1;
-    for (int d = 0; d < 4; ++d) Lmax = std::max(Lmax, layer->L[d]);
-    const int64_t smem_c = (int64_t)CB_TN * 4 * 32 + (int64_t)CB_TN * Lmax * 5;
+    a.nimg = 1;                      // as many image buffers as fit (all blocks resident if possible)
+    while (a.nimg < nbl_max && off + 2 * (int64_t)a.img_one <= s_budget - 2048) { ++a.nimg; off += 2 * (int64_t)a.img_one; }
+    // k_coef_tile: two tile buffers (metadata + gradient rows + bond rows) and the pair arrays of the current tile
+    CoefTileArgs c;
+    c.vec = ((int64_t)plan->N * ldg) % 4 == 0 ? 4 : ((int64_t)plan->N * ldg) % 2 == 0 ? 2 : 1;
+    {
+        int64_t o = (sizeof(TileMetaG) + 127) / 128 * 128;
+        c.sm_grad = (int)o; o += (((int64_t)TNODES * ldg + 4) * 4 + 127) / 128 * 128;
+        c.sm_eh = (int)o; o += (int64_t)TILE_ESLOTS * EP * 4;
+        c.buf_bytes = (int)o;
+        c.sm_coef = (int)(2 * o);
+        c.sm_inv = c.sm_coef + (int)(((int64_t)stride * 4 + 127) / 128 * 128);
+    }
+    const int64_t smem_c = c.sm_inv + ((int64_t)stride + 127) / 128 * 128;
     if (smem_c > s_budget - 2048) return 0;
     if (!do_launch) return 1;
+    MK_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(coef) & 15) == 0,
+               "conv_bwd_tile: grad and coef must be 16-byte aligned");
     static int64_t s_attr = 0, s_attr_c = 0;
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;
     }
     if (smem_c > s_attr_c) {
-        MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_bond, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         s_attr_c = smem_c;
     }
     MK_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
     {
-        CoefArgs c;
-        c.sel = plan->sel; c.nei = plan->nei; c.ehat = plan->ehat;
+        c.meta = a.meta; c.ehat_node = plan->ehat_node; c.n_tiles = plan->n_tiles;
         for (int d = 0; d < 4; ++d) {
-            c.n[d] = plan->n[d]; c.boff[d] = plan->boff[d]; c.eoff[d] = plan->eoff[d];
             c.L[d] = layer->L[d]; c.koff[d] = layer->koff[d]; c.scoff[d] = scoff[d];
             c.part_off[d] = part_off[d];
         }
         c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode;
-        c.argmax = argmax; c.coef = coef;
+        c.argmax = argmax;
+        c.coefT = coef; c.amT = const_cast<uint8_t*>(a.amT); c.stride = stride; c.stride_am = stride_am;
         c.partials = partials; c.FW = a.FW; c.Fp = layer->Fp;
-        c.G = grid;
         c.amax = amax;
         count_launches(1);
-        ProfScope prof("coef_bond", st);
-        k_coef_bond<<<4 * grid, CB_THREADS, smem_c, st>>>(c);
+        ProfScope prof("coef_tile", st);
+        k_coef_tile<<<grid, CT_THREADS, smem_c, st>>>(c);
         MK_CHECK_CUDA(cudaGetLastError());
     }
+    MK_REQUIRE(nlaunch == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than two kernel blocks");
     for (int l = 0; l < nlaunch; ++l) {
         // blocks {0, 3} and {1, 2}: the scatter work of the two launches is about equal for the base model
-        if (a.tb.nb <= 2) { a.nbl = a.tb.nb; a.blist[0] = 0; a.blist[1] = a.tb.nb > 1 ? 1 : 0; }
-        else if (a.tb.nb == 3) { a.nbl = l == 0 ? 2 : 1; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 2; }
+        for (int i = 0; i < 4; ++i) a.blist[i] = 0;
+        if (one_launch) {
+            a.nbl = a.tb.nb;
+            for (int i = 0; i < a.tb.nb; ++i) a.blist[i] = i;
+            a.gstride = a.tb.nb <= 2 ? 128 : a.Fk;
+            a.dxcol = a.tb.nb <= 2 ? 256 : a.tb.nb * a.Fk;
+        } else if (a.tb.nb == 3) { a.nbl = l == 0 ? 2 : 1; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 2; }
         else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 1; a.blist[1] = l == 0 ? 3 : 2; }
+        if (!one_launch) { a.gstride = 128; a.dxcol = 256; }
         a.first = l == 0; a.last = l == nlaunch - 1;
         count_launches(1);
         ProfScope prof("conv_bwd_tile", st);
@@ -709,6 +847,12 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 
 
 #ifdef MK_PHASE_CLOCKS
+extern "C" int molkgnn_debug_phase_clocks_coef(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, mk::g_ph_coef, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(mk::g_ph_coef, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
 // profiling build only: read (and clear) the accumulated phase clocks of k_conv_bwd_tile
 extern "C" int molkgnn_debug_phase_clocks_bwd(unsigned long long* out16) {
     cudaDeviceSynchronize();

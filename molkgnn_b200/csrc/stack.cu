@@ -53,15 +53,16 @@ extern "C" int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_la
     out->fwd_bytes = off;
     // backward scratch
     off = 0;
-    int64_t part_max = 0, scr_max = 0, gx_max = 0;
+    int64_t part_max = 0, scr_max = 0, gx_max = 0, coef_max = 0;
     for (int i = 0; i < nl; ++i) {
         const int64_t pf = molkgnn_conv_bwd_partial_floats(plan, &layers[i]);
         MK_REQUIRE(pf >= 0, "stack_layout: conv_bwd_partial_floats failed");
         part_max = std::max(part_max, pf);
+        coef_max = std::max(coef_max, molkgnn_conv_bwd_coef_floats(plan, &layers[i]));
         scr_max = std::max(scr_max, N * (int64_t)tile_fk(layers[i].Fp));
         if (i > 0) gx_max = std::max(gx_max, N * (int64_t)layers[i].Fp);
     }
-    out->coef = take(sc_max * 4);
+    out->coef = take(coef_max * 4);
     out->partials = take(part_max * 4);
     out->scratch = take(scr_max * 4);
     out->gx[0] = take(gx_max * 4);

@@ -227,7 +227,7 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
     L = _lib.lib()
     dev = x.device
     scoff, tot = plan.scoff(pack.L)
-    coef = torch.empty(max(tot, 1), dtype=torch.float32, device=dev)
+    coef = torch.empty(int(L.molkgnn_conv_bwd_coef_floats(C.byref(plan.c), C.byref(pack.c))), dtype=torch.float32, device=dev)
     partials = torch.empty(int(L.molkgnn_conv_bwd_partial_floats(C.byref(plan.c), C.byref(pack.c))),
                            dtype=torch.float32, device=dev)
     gx = torch.empty(plan.N, pack.Fp, dtype=torch.float32, device=dev) if need_gx else None

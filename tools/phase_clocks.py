@@ -48,6 +48,7 @@ torch.cuda.synchronize()
 if has_clk:
     read("molkgnn_debug_phase_clocks_bwd", 16)
     read("molkgnn_debug_phase_clocks_fwd", 32)
+    read("molkgnn_debug_phase_clocks_coef", 16)
 out = {}
 # (1) full step, plan rebuilt every step (one stream sync inside the bucket pass)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -61,7 +62,10 @@ out["ms_per_step_plan_rebuilt"] = e0.elapsed_time(e1) / steps
 if has_clk:
     bw = read("molkgnn_debug_phase_clocks_bwd", 16)
     fw = read("molkgnn_debug_phase_clocks_fwd", 32)
+    cf = read("molkgnn_debug_phase_clocks_coef", 16)
+    names_c = ["prologue", "barrier + issue next", "wait data", "pairs", "pairs barrier", "bond sums", "final"]
     ncta = 148
+    out["coef_tile_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_c, cf)}
     names_b = ["prologue", "wait tile copy", "rank-0 scatter", "ranks 1-3", "barrier before MMA", "img wait + MMA issue",
                "MMA wait", "Wt clear", "dxh epilogue", "G store"]
     names_fc = ["block set-up", "wait copy", "wait MMA", "dump", "dupflags+sync", "epilogue", "sync", "teardown"]
