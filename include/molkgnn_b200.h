@@ -112,6 +112,13 @@ int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E);
  * out-degree outside 1..4 or in-degree > 4 (the reference silently mis-shapes its output, kernels.py:743-747). */
 int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                          const float* edge_attr, int32_t Fe, void* scratch, void* stream);
+/* The same pass in two halves, so that the host can queue other work (parameter packing, its own bookkeeping) behind the
+ * counting kernels before it blocks: _begin enqueues the counting kernels and returns; _finish (same arguments) brings the
+ * bucket sizes to the host (the one stream synchronisation), validates them and enqueues the assignment kernels. */
+int molkgnn_bucket_build_begin(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                               const float* edge_attr, int32_t Fe, void* scratch, void* stream);
+int molkgnn_bucket_build_finish(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                const float* edge_attr, int32_t Fe, void* scratch, void* stream);
 /* Writes the reference-format attributes of degree d (int64 indices, raw fp32 gathers), bit-exact with
  * wrapper.py:595-635 after PyG collation: selected_index[n_d], nei_index[n_d*d], p_focal[n_d,p_dim],
  * nei_p[n_d,d,p_dim], nei_edge_attr[n_d,d,Fe].  Any output pointer may be NULL. */
@@ -205,6 +212,7 @@ void molkgnn_path_counts(int64_t out[4]);
 #define MOLKGNN_MAX_LAYERS 16
 #define MOLKGNN_STACK_KEEP_SC 1      /* flags: keep every layer's compact scores (else one buffer is reused) */
 #define MOLKGNN_STACK_WANT_FREE 2    /* flags: also record the free-running arg-max of every layer */
+#define MOLKGNN_STACK_PACKED 4       /* flags: molkgnn_param_pack() already ran for every layer on this stream */
 typedef struct molkgnn_stack_layout {
     int64_t fwd_bytes;                          /* forward workspace: lives from stack_fwd to stack_bwd */
     int64_t bwd_bytes;                          /* backward scratch: only during stack_bwd */

@@ -64,7 +64,10 @@ class MolGCN(Module):
         raw_edge_attr = kwargv.get('raw_edge_attr', None)
         plan = kwargv.get('plan', None)
         if plan is None:
-            plan = self.build_plan(edge_index, p, edge_attr if raw_edge_attr is None else raw_edge_attr, x.shape[0])
+            # first half of the GPU bucket pass: counting kernels queued; the host round trip for the bucket sizes happens
+            # inside MolGCNFn.forward, after the host-side preparation below and the parameter packing were queued
+            plan = BucketPlan.begin_from_edge_index(edge_index, p, edge_attr if raw_edge_attr is None else raw_edge_attr,
+                                                    x.shape[0])
         layer_params = [layer._degree_params() for layer in self.layers]
         flat = []
         for lp in layer_params:
@@ -75,6 +78,7 @@ class MolGCN(Module):
         if stack is None or stack.key != key:
             stack = StackPack(layer_params, x.shape[1], self.edge_attr_dim, x.device)
             object.__setattr__(self, '_stack', stack)
+        stack.prepack()
         h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), kwargv.get('aux', None), *flat)
         if save_score:
             raise NotImplementedError('save_score=True: call the last KernelSetConv layer directly to obtain sim_sc')

@@ -53,6 +53,8 @@ EXPORTS = {
     "molkgnn_tile_ximg_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_tile_ximg_build": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp]),
     "molkgnn_bucket_build": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
+    "molkgnn_bucket_build_begin": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
+    "molkgnn_bucket_build_finish": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
     "molkgnn_bucket_export": (C.c_int, [C.POINTER(Plan), i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     "molkgnn_plan_from_buckets": (C.c_int, [C.POINTER(Plan), vp * 4, vp * 4, vp * 4, vp * 4, i32, vp * 4, i32, vp]),
     "molkgnn_pad_norm": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, vp]),

@@ -484,8 +484,9 @@ extern "C" int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E) {
     return (int64_t)sizeof(int) * ((int64_t)N * 11 + nblk * 10 + 64);
 }
 
-extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
-                                    const float* edge_attr, int32_t Fe, void* scratch, void* stream_) {
+// phases: bit 0 = counting kernels (asynchronous), bit 1 = host round trip of the bucket sizes + assignment kernels
+static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                               const float* edge_attr, int32_t Fe, void* scratch, void* stream_, int phases) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int N = plan->N, E = plan->E;
     MK_REQUIRE(N > 0 && E >= 0, "bucket_build: empty batch (N=%d E=%d)", N, E);
@@ -505,7 +506,8 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     int* cutpos = s;
     const bool tiles = plan->tile_start != nullptr;
     const int tile_cap = N / TILE_MIN_STRIDE + 4;
-    ProfScope* prof = new ProfScope("bucket_count", st);
+    if (phases & 1) {
+    ProfScope prof("bucket_count", st);
     MK_CHECK_CUDA(cudaMemsetAsync(out_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));
     MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 32, st));
@@ -520,9 +522,11 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
         k_cut_gaps<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, cutpos, tinfo);
         k_tile_starts<<<(tile_cap + 3) / 4, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
     }
+    MK_CHECK_CUDA(cudaGetLastError());
+    }
+    if (!(phases & 2)) return 0;
     int host[32];
     MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
-    delete prof;
     MK_CHECK_CUDA(cudaStreamSynchronize(st));
     plan->n_tiles = 0; plan->tile_max_nodes = 0;
     for (int d = 0; d < 4; ++d) plan->tile_max_deg[d] = 0;
@@ -550,6 +554,19 @@ extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_in
     }
     MK_CHECK_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                    const float* edge_attr, int32_t Fe, void* scratch, void* stream) {
+    return bucket_build_phases(plan, edge_index, p, p_dim, edge_attr, Fe, scratch, stream, 3);
+}
+extern "C" int molkgnn_bucket_build_begin(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                          const float* edge_attr, int32_t Fe, void* scratch, void* stream) {
+    return bucket_build_phases(plan, edge_index, p, p_dim, edge_attr, Fe, scratch, stream, 1);
+}
+extern "C" int molkgnn_bucket_build_finish(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                           const float* edge_attr, int32_t Fe, void* scratch, void* stream) {
+    return bucket_build_phases(plan, edge_index, p, p_dim, edge_attr, Fe, scratch, stream, 2);
 }
 
 extern "C" int64_t molkgnn_tile_meta_bytes(void) { return (int64_t)sizeof(TileMetaG); }

@@ -96,8 +96,9 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     const int N = plan->N;
     int rc;
-    for (int i = 0; i < nl; ++i)
-        if ((rc = molkgnn_param_pack(&layers[i], stream))) return rc;
+    if (!(flags & MOLKGNN_STACK_PACKED))
+        for (int i = 0; i < nl; ++i)
+            if ((rc = molkgnn_param_pack(&layers[i], stream))) return rc;
     float* h = reinterpret_cast<float*>(ws + lay->h[0]);
     float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);
     if ((rc = molkgnn_pad_norm(x, N, layers[0].F, ldx, h, layers[0].Fp, hn, stream))) return rc;
@@ -126,7 +127,6 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
             return rc;
         h = hnext; hn = hnn;
     }
-    (void)flags;
     return 0;
 }
 

@@ -338,6 +338,12 @@ class StackPack(object):
                     k += [prm[n].data_ptr() if prm[n].is_contiguous() else object() for n in PARAMS_PER_DEGREE]
         return tuple(k)
 
+    def prepack(self):
+        """Queues the parameter packing of every layer (normalised kernel rows, tensor-core images) on the current stream."""
+        L = _lib.lib()
+        for i in range(self.nl):
+            check(L.molkgnn_param_pack(C.byref(self.arr[i]), stream_ptr()))
+
     def layout(self, plan: BucketPlan, flags):
         lay = _lib.StackLayout()
         check(_lib.lib().molkgnn_stack_layout(C.byref(plan.c), self.arr, self.nl, flags, C.byref(lay)))
@@ -360,7 +366,7 @@ class StackPack(object):
         return out
 
 
-FLAG_KEEP_SC, FLAG_WANT_FREE = 1, 2
+FLAG_KEEP_SC, FLAG_WANT_FREE, FLAG_PACKED = 1, 2, 4
 
 
 class MolGCNFn(torch.autograd.Function):
@@ -372,7 +378,8 @@ class MolGCNFn(torch.autograd.Function):
         L = _lib.lib()
         dev = x.device
         nl = stack.nl
-        flags = (FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0
+        flags = ((FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0) | FLAG_PACKED
+        plan.finish()                                # bucket sizes to the host (the packing queued by the caller runs meanwhile)
         lay = stack.layout(plan, flags)
         xc = x.detach()
         if xc.dtype != torch.float32:

@@ -85,6 +85,13 @@ class BucketPlan(object):
     @classmethod
     def from_edge_index(cls, edge_index, p, edge_attr, num_nodes):
         """One GPU CSR->degree-bucket pass over the collated ``edge_index`` (replaces wrapper.py:637-672)."""
+        return cls.begin_from_edge_index(edge_index, p, edge_attr, num_nodes).finish()
+
+    @classmethod
+    def begin_from_edge_index(cls, edge_index, p, edge_attr, num_nodes):
+        """First half of the pass: the counting kernels are queued, nothing is waited for.  ``finish()`` (called by
+        ``from_edge_index`` / by the MolGCN forward) does the one host round trip for the bucket sizes; whatever the caller
+        queues or computes in between overlaps with the counting kernels."""
         for t, nme in ((edge_index, "edge_index"), (p, "p"), (edge_attr, "edge_attr")):
             _require_cuda(t, nme)
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -96,11 +103,20 @@ class BucketPlan(object):
         L = _lib.lib()
         self = cls(num_nodes, E, edge_index.device, scratch_bytes=int(L.molkgnn_bucket_scratch_bytes(int(num_nodes), E)),
                    zero_tsign=False)
-        check(L.molkgnn_bucket_build(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
-                                     edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
-        self.n = list(self.c.n)
-        self.n_tiles = int(self.c.n_tiles)          # 0: no molecule tiling (bucket-order kernels are used)
+        check(L.molkgnn_bucket_build_begin(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
+                                           edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
         self._keep = (edge_index, p, edge_attr)
+        self._pending = True
+        return self
+
+    def finish(self):
+        if self.__dict__.get("_pending"):
+            edge_index, p, edge_attr = self._keep
+            self._pending = False
+            check(_lib.lib().molkgnn_bucket_build_finish(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1],
+                                                         ptr(edge_attr), edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
+            self.n = list(self.c.n)
+            self.n_tiles = int(self.c.n_tiles)      # 0: no molecule tiling (bucket-order kernels are used)
         return self
 
     @classmethod
