@@ -255,6 +255,8 @@ int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers,
  * writes one line "name launches total_ms" per group name into buf and clears the records.  Returns the previous state /
  * the text length (<0 on error).  Not thread safe; off by default. */
 int molkgnn_profile_enable(int on);
+/* restrict recording to the launch groups of one name (NULL = all): keeps the event overhead out of a timed region */
+int molkgnn_profile_only(const char* name);
 int molkgnn_profile_read(char* buf, int cap);
 /* Known-answer test of the tcgen05 (UMMA) plumbing: D[128,N] (fp32) = A * B^T on the tensor cores, one CTA.
  * A, B: fp16.  a_mn = 0: A is [128,K] row-major (K-major operand); a_mn = 1: A is [K,128] row-major (MN-major

@@ -79,6 +79,7 @@ EXPORTS = {
     "molkgnn_stack_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), vp, vp, vp, i32, vp,
                                     vp, vp]),
     "molkgnn_profile_enable": (C.c_int, [C.c_int]),
+    "molkgnn_profile_only": (C.c_int, [C.c_char_p]),
     "molkgnn_profile_read": (C.c_int, [C.c_char_p, C.c_int]),
 }
 

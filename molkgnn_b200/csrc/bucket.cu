@@ -257,6 +257,82 @@ __global__ void __launch_bounds__(128) k_tile_starts(int N, int cap, const int* 
     }
 }
 
+// Greedy tiling: every tile starts where the previous one ended and takes as many whole molecules as fit TILE_CAP nodes
+// (the stride scheme above leaves a quarter of every tile empty).  The walk is sequential, so ONE CTA does it on a bitmap
+// of the valid cuts held in shared memory (N + 1 bits): warp 0 hops tile by tile (the last set bit of a 128-bit window),
+// then all warps gather the per-tile maxima.  Used whenever the bitmap fits shared memory.
+__global__ void __launch_bounds__(1024) k_tile_starts_greedy(int N, int cap, const int* __restrict__ cutpos,
+                                                             int* tile_start, int* tinfo) {
+    extern __shared__ uint32_t bits[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwords = (N + 32) / 32;
+    constexpr int U = 8;                                  // words per warp in flight
+    for (int w0 = warp * U; w0 < nwords; w0 += 32 * U) {
+        int v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = 32 * (w0 + u) + lane;
+            v[u] = (w0 + u < nwords && c <= N) ? cutpos[c] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t word = __ballot_sync(0xffffffffu, v[u] >= 0);
+            if (lane == 0 && w0 + u < nwords) bits[w0 + u] = word;
+        }
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const int gap = tinfo[0];
+    if ((TILE_CAP + 1 - gap < TILE_MIN_STRIDE) || (tinfo[1] & 1)) { tinfo[2] = 0; return; }
+    int c = 0, t = 0;
+    while (c < N && t < cap - 1) {
+        tile_start[t] = c;
+        const int hi = min(c + TILE_CAP, N);
+        // last valid cut in (c, hi]: scan the words downwards from hi's word (molecules are short: usually the first one)
+        int w = hi >> 5;
+        uint32_t word = bits[w];
+        if ((hi & 31) != 31) word &= (2u << (hi & 31)) - 1u;
+        int best = -1;
+        const int wlo = (c + 1) >> 5;
+        while (true) {
+            if (w == wlo) word &= ~((1u << ((c + 1) & 31)) - 1u);
+            if (word) { best = 32 * w + 31 - __clz(word); break; }
+            if (w == wlo) break;
+            word = bits[--w];
+        }
+        if (best <= c) { t = 0; c = N; break; }           // cannot happen when gap <= TILE_CAP; disables tiling if it does
+        c = best;
+        ++t;
+    }
+    if (c < N) t = 0;                                     // ran out of tile slots
+    if (t > 0) tile_start[t] = N;
+    tinfo[2] = t;
+}
+
+// largest tile and largest per-degree node count of a tile (one warp per tile)
+__global__ void __launch_bounds__(128) k_tile_stats(int cap, const int* __restrict__ tile_start, const int* __restrict__ deg,
+                                                    int* tinfo) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int T = tinfo[2];
+    if (i >= T || i >= cap) return;
+    const int a = tile_start[i], b = tile_start[i + 1];
+    int cnt[4] = {0, 0, 0, 0};
+    for (int v = a + lane; v < b; v += 32) {
+        const int d = deg[v];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cnt[c] += (d == c + 1);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt[c] += __shfl_xor_sync(0xffffffffu, cnt[c], o);
+    if (lane == 0) {
+        atomicMax(&tinfo[3], b - a);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) atomicMax(&tinfo[4 + d], cnt[d]);
+    }
+}
+
 // per-tile metadata record + bond rows in node order (one block of 128 threads per tile, thread = local node)
 __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restrict__ tile_start, const int* __restrict__ deg,
                                                       const int* __restrict__ pos, const int* __restrict__ nei,
@@ -484,6 +560,26 @@ extern "C" int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E) {
     return (int64_t)sizeof(int) * ((int64_t)N * 11 + nblk * 10 + 64);
 }
 
+// Side stream of the tile-cut chain (valid cuts -> greedy walk -> per-tile maxima).  The walk is a single-CTA sequential
+// kernel; on its own stream it runs beside the counting kernels and whatever the caller queues before _finish (parameter
+// packing), instead of holding up the launching stream.  One set per device, created on first use; the library is driven
+// by one host thread per process (SURVEY 8(b) threading).
+struct SideStream { cudaStream_t st; cudaEvent_t far_ready, deg_ready, done; bool ok; };
+static SideStream* side_stream() {
+    static SideStream s_side[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    SideStream& s = s_side[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&s.far_ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.deg_ready, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
+
 // phases: bit 0 = counting kernels (asynchronous), bit 1 = host round trip of the bucket sizes + assignment kernels
 static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                                const float* edge_attr, int32_t Fe, void* scratch, void* stream_, int phases) {
@@ -513,18 +609,47 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
     MK_CHECK_CUDA(cudaMemsetAsync(totals, 0, sizeof(int) * 32, st));
     MK_CHECK_CUDA(cudaMemsetAsync(far, 0, sizeof(int) * (size_t)N, st));
     count_launches((E > 0 ? 4 : 3) + (tiles ? 3 : 0));
+    SideStream* side = tiles ? side_stream() : nullptr;
+    MK_REQUIRE(!tiles || side, "bucket_build: cannot create the side stream");
     if (E > 0)
         k_edge_slots<<<(E + 255) / 256, 256, 0, st>>>(edge_index, E, N, out_cnt, out_eid, plan->in_cnt, in_eid, far, err);
+    if (tiles) MK_CHECK_CUDA(cudaEventRecord(side->far_ready, st));
     k_node_prepare<<<nblk, BT, 0, st>>>(N, out_cnt, out_eid, plan->in_cnt, in_eid, plan->deg, blk_counts, err);
+    if (tiles) MK_CHECK_CUDA(cudaEventRecord(side->deg_ready, st));
     k_scan_blocks<<<1, 160, 0, st>>>(nblk, blk_counts, blk_off, totals);
     if (tiles) {
+        cudaStream_t main_st = st;
+        cudaStream_t st = side->st;                       // the cut chain runs on the side stream from here on
+        MK_CHECK_CUDA(cudaStreamWaitEvent(st, side->far_ready, 0));
         k_valid_cuts<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, far, cutpos, tinfo);
         k_cut_gaps<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, cutpos, tinfo);
-        k_tile_starts<<<(tile_cap + 3) / 4, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
+        MK_CHECK_CUDA(cudaStreamWaitEvent(st, side->deg_ready, 0));
+        (void)main_st;
+        const int64_t bitmap = (int64_t)((N + 32) / 32) * 4;
+        static int s_budget = 0;
+        if (!s_budget) s_budget = device_max_smem_optin();
+        if (bitmap <= s_budget - 4096) {
+            static int64_t s_attr = 0;
+            if (bitmap > s_attr) {
+                MK_CHECK_CUDA(cudaFuncSetAttribute(k_tile_starts_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap));
+                s_attr = bitmap;
+            }
+            k_tile_starts_greedy<<<1, 1024, bitmap, st>>>(N, tile_cap, cutpos, plan->tile_start, tinfo);
+            k_tile_stats<<<(tile_cap + 3) / 4, 128, 0, st>>>(tile_cap, plan->tile_start, plan->deg, tinfo);
+            count_launches(1);
+        } else {
+            k_tile_starts<<<(tile_cap + 3) / 4, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
+        }
+        MK_CHECK_CUDA(cudaEventRecord(side->done, st));
     }
     MK_CHECK_CUDA(cudaGetLastError());
     }
     if (!(phases & 2)) return 0;
+    if (tiles) {                                           // the launching stream picks the cut chain's results up here
+        SideStream* side = side_stream();
+        MK_REQUIRE(side, "bucket_build: cannot create the side stream");
+        MK_CHECK_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+    }
     int host[32];
     MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
     MK_CHECK_CUDA(cudaStreamSynchronize(st));

@@ -29,6 +29,7 @@ long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 // per-kernel launch durations on the launching stream (molkgnn_profile_enable / molkgnn_profile_read).
 struct ProfRec { const char* name; cudaEvent_t e0, e1; };
 static int g_prof_on = 0;
+static char g_prof_only[64] = "";        // record only scopes of this name ("" = all)
 static ProfRec g_prof[4096];
 static int g_prof_n = 0;
 static cudaEvent_t g_prof_pool[8192];
@@ -43,6 +44,7 @@ static cudaEvent_t prof_event() {
 }
 ProfScope::ProfScope(const char* name, cudaStream_t st) : rec_(-1), st_(st) {
     if (!__atomic_load_n(&g_prof_on, __ATOMIC_RELAXED) || g_prof_n >= 4096) return;
+    if (g_prof_only[0] && strcmp(g_prof_only, name)) return;
     cudaEvent_t a = prof_event(), b = prof_event();
     if (!a || !b) return;
     rec_ = g_prof_n++;
@@ -427,6 +429,12 @@ extern "C" int molkgnn_num_sms(void) { return device_num_sms(); }
 namespace mk { long long launches(); }
 extern "C" int64_t molkgnn_launch_count(void) { return mk::launches(); }
 
+extern "C" int molkgnn_profile_only(const char* name) {
+    if (!name) { mk::g_prof_only[0] = 0; return 0; }
+    strncpy(mk::g_prof_only, name, sizeof(mk::g_prof_only) - 1);
+    mk::g_prof_only[sizeof(mk::g_prof_only) - 1] = 0;
+    return 0;
+}
 extern "C" int molkgnn_profile_enable(int on) {
     const int old = mk::g_prof_on;
     if (on) { mk::g_prof_n = 0; mk::g_prof_pool_used = 0; }

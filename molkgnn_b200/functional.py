@@ -23,6 +23,8 @@ def profile_start(names=None):
     native code, include/molkgnn_b200.h molkgnn_profile_enable) and the Python-side scopes of the per-layer API."""
     global _PROF, _PROF_NAMES
     _PROF, _PROF_NAMES = {}, (None if names is None else set(names))
+    # the native profiler filters on ONE name (what bench.py needs inside its timed region) or records everything
+    _lib.lib().molkgnn_profile_only(list(names)[0].encode() if names is not None and len(names) == 1 else None)
     _lib.lib().molkgnn_profile_enable(1)
 
 
