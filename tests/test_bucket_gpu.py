@@ -146,6 +146,13 @@ def test_molecule_tiles(n_mol, seed):
     for d in range(1, 5):
         cnt = np.bincount(tile_of[deg == d], minlength=T)
         assert plan.c.tile_max_deg[d - 1] == cnt.max()
-    # packing efficiency: tiles hold whole molecules of <= 32 atoms, so they are at least 128 - 31 - 31 nodes wide on average
+    # greedy packing: a tile ends only where the next molecule would not fit any more (batch['batch'] = molecule of a node)
+    mol = b["batch"]
+    first = np.flatnonzero(np.diff(np.concatenate([[-1], mol])))           # first node of every molecule
+    sizes = np.diff(np.concatenate([first, [N]]))
+    for t in range(T - 1):
+        m = mol[ts[t + 1]]                                                 # molecule that opens the next tile
+        assert ts[t + 1] == first[m]
+        assert ts[t + 1] - ts[t] + sizes[m] > 128
     if n_mol >= 300:
-        assert np.diff(ts).mean() > 90
+        assert np.diff(ts).mean() > 105
