@@ -290,8 +290,16 @@ def main():
     launches_per_step = cnt / args.steps
     achieved = (kbytes / max(launches_per_step, 1e-9)) / (per_launch_ms * 1e-3) / 1e9 if cnt else 0.0
     step_gbs = (fwd_b + bwd_b) * args.steps / (ms * 1e-3) / 1e9
+    # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json), or null
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if top in tj and B == 4096:
+            traffic, traffic_src = tj[top]["bytes_per_launch"], tj[top]["source"]
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel_ms_per_launch": per_launch_ms,
             "kernel_share_of_step": kms / ms if ms else None,
             "algorithmic_bytes_per_launch": kbytes / max(launches_per_step, 1e-9),
             "step_algorithmic_bytes": fwd_b + bwd_b, "step_achieved_gbs": step_gbs, "step_frac": step_gbs / peak,

@@ -288,17 +288,24 @@ __global__ void __launch_bounds__(1024) k_tile_starts_greedy(int N, int cap, con
     while (c < N && t < cap - 1) {
         tile_start[t] = c;
         const int hi = min(c + TILE_CAP, N);
-        // last valid cut in (c, hi]: scan the words downwards from hi's word (molecules are short: usually the first one)
-        int w = hi >> 5;
-        uint32_t word = bits[w];
-        if ((hi & 31) != 31) word &= (2u << (hi & 31)) - 1u;
+        // last valid cut in (c, hi].  Fast path: a 64-bit window ending at hi (bit 63 <-> position hi) holds at least the 32
+        // positions below hi, enough whenever the last molecule before hi has <= 32 atoms; both words load independently.
+        const int w1 = hi >> 5, sh = 31 - (hi & 31);
+        const unsigned long long win = (((unsigned long long)bits[w1] << 32) | (w1 > 0 ? bits[w1 - 1] : 0u)) << sh;
         int best = -1;
-        const int wlo = (c + 1) >> 5;
-        while (true) {
-            if (w == wlo) word &= ~((1u << ((c + 1) & 31)) - 1u);
-            if (word) { best = 32 * w + 31 - __clz(word); break; }
-            if (w == wlo) break;
-            word = bits[--w];
+        if (win != 0ull && hi - __clzll(win) > c) {
+            best = hi - __clzll(win);
+        } else {                                           // long molecule: scan the words downwards from hi's word
+            int w = w1;
+            uint32_t word = bits[w];
+            if ((hi & 31) != 31) word &= (2u << (hi & 31)) - 1u;
+            const int wlo = (c + 1) >> 5;
+            while (true) {
+                if (w == wlo) word &= ~((1u << ((c + 1) & 31)) - 1u);
+                if (word) { best = 32 * w + 31 - __clz(word); break; }
+                if (w == wlo) break;
+                word = bits[--w];
+            }
         }
         if (best <= c) { t = 0; c = N; break; }           // cannot happen when gap <= TILE_CAP; disables tiling if it does
         c = best;
