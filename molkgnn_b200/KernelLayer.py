@@ -9,7 +9,7 @@ from __future__ import annotations
 import torch
 from torch.nn import Module, ModuleList
 
-from .functional import MolGCNFn, StackPack, flat_params
+from .functional import MolGCNFn, StackPack, PARAMS_PER_DEGREE
 from .kernels import KernelSetConv
 from .plan import BucketPlan
 
@@ -44,6 +44,14 @@ class MolGCN(Module):
     def num_kernels(self, layer):
         return self.num_kernels_list[layer]
 
+    def __getstate__(self):
+        # the native layer descriptors (ctypes) are a cache: never pickled / deep-copied with the module
+        st = super(MolGCN, self).__getstate__() if hasattr(super(MolGCN, self), '__getstate__') else self.__dict__.copy()
+        st = dict(st)
+        st.pop('_stack', None)
+        st.pop('_param_slots', None)
+        return st
+
     def build_plan(self, edge_index, p, edge_attr, num_nodes):
         """GPU degree-bucket pass for one collated batch (replaces the offline pre-transform, wrapper.py:559-672)."""
         return BucketPlan.from_edge_index(edge_index, p, edge_attr, num_nodes)
@@ -68,16 +76,28 @@ class MolGCN(Module):
             # inside MolGCNFn.forward, after the host-side preparation below and the parameter packing were queued
             plan = BucketPlan.begin_from_edge_index(edge_index, p, edge_attr if raw_edge_attr is None else raw_edge_attr,
                                                     x.shape[0])
-        layer_params = [layer._degree_params() for layer in self.layers]
-        flat = []
-        for lp in layer_params:
-            flat += flat_params(lp)
-        # native descriptors of the layers: rebuilt only when a parameter tensor moved (new storage, device, dtype)
-        key = StackPack.make_key(layer_params, x.shape[1], self.edge_attr_dim, x.device)
-        stack = getattr(self, '_stack', None)
+        # Host-side fast path: the 84 parameter tensors are fetched straight from the modules' _parameters dicts (the
+        # slots are collected once; nn.Module.__getattr__ per parameter and step is what made a step host bound), and the
+        # native layer descriptors are rebuilt only when a parameter tensor moved (new storage, device, dtype).
+        slots = self.__dict__.get('_param_slots')
+        if slots is None:
+            slots = []
+            for layer in self.layers:
+                for prm_owner in layer._degree_owners():
+                    for k in PARAMS_PER_DEGREE:
+                        slots.append(None if prm_owner is None else (prm_owner._parameters, k))
+            self.__dict__['_param_slots'] = slots
+        flat = [None if sl is None else sl[0][sl[1]] for sl in slots]
+        key = (x.shape[1], x.device) + tuple(0 if t is None else t.data_ptr() for t in flat)
+        stack = self.__dict__.get('_stack')
         if stack is None or stack.key != key:
+            layer_params = [layer._degree_params() for layer in self.layers]
+            for t in flat:
+                if t is not None and not t.is_contiguous():
+                    raise Exception('MolGCN: kernel parameters must be contiguous tensors')
             stack = StackPack(layer_params, x.shape[1], self.edge_attr_dim, x.device)
-            object.__setattr__(self, '_stack', stack)
+            stack.key = key
+            self.__dict__['_stack'] = stack
         stack.prepack()
         h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), kwargv.get('aux', None), *flat)
         if save_score:

@@ -261,9 +261,40 @@ __global__ void __launch_bounds__(128) k_tile_starts(int N, int cap, const int* 
 // (the stride scheme above leaves a quarter of every tile empty).  The walk is sequential, so ONE CTA does it on a bitmap
 // of the valid cuts held in shared memory (N + 1 bits): warp 0 hops tile by tile (the last set bit of a 128-bit window),
 // then all warps gather the per-tile maxima.  Used whenever the bitmap fits shared memory.
+// one greedy hop on the cut bitmap: the last valid cut in (c, min(c + TILE_CAP, N)], or -1
+__device__ __forceinline__ int greedy_hop(const uint32_t* bits, int c, int N) {
+    const int hi = min(c + TILE_CAP, N);
+    // Fast path: a 64-bit window ending at hi (bit 63 <-> position hi) holds at least the 32 positions below hi, enough
+    // whenever the last molecule before hi has <= 32 atoms; both words load independently.
+    const int w1 = hi >> 5, sh = 31 - (hi & 31);
+    const unsigned long long win = (((unsigned long long)bits[w1] << 32) | (w1 > 0 ? bits[w1 - 1] : 0u)) << sh;
+    if (win != 0ull) {
+        const int b = hi - __clzll(win);
+        if (b > c) return b;
+    }
+    int w = w1;                                            // long molecule: scan the words downwards from hi's word
+    uint32_t word = bits[w];
+    if ((hi & 31) != 31) word &= (2u << (hi & 31)) - 1u;
+    const int wlo = (c + 1) >> 5;
+    while (true) {
+        if (w == wlo) word &= ~((1u << ((c + 1) & 31)) - 1u);
+        if (word) return 32 * w + 31 - __clz(word);
+        if (w == wlo) return -1;
+        word = bits[--w];
+    }
+}
+
+// The walk is a chain of dependent hops (~160 cycles each), so it is cut into up to 32 node segments walked by one warp
+// each.  The chain enters segment p at its first tile start >= p*S, one of the valid cuts in [p*S, p*S + TILE_CAP): every
+// lane of warp p walks from one of those candidates to the segment's end and notes where it leaves and how many tiles it
+// made; one thread then threads the true entry through the segments (32 table look-ups), and the warps re-walk from their
+// true entries writing tile_start at their prefix offsets.  Exact: the result is the sequential greedy tiling.
+constexpr int GW = 32;                                     // segments = warps
 __global__ void __launch_bounds__(1024) k_tile_starts_greedy(int N, int cap, const int* __restrict__ cutpos,
                                                              int* tile_start, int* tinfo) {
     extern __shared__ uint32_t bits[];
+    __shared__ int s_cand[GW][32], s_exit[GW][32], s_cnt[GW][32], s_ncand[GW];
+    __shared__ int s_entry[GW + 1], s_off[GW + 1], s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (N + 32) / 32;
     constexpr int U = 8;                                  // words per warp in flight
@@ -280,40 +311,90 @@ __global__ void __launch_bounds__(1024) k_tile_starts_greedy(int N, int cap, con
             if (lane == 0 && w0 + u < nwords) bits[w0 + u] = word;
         }
     }
+    if (tid == 0) s_fail = 0;
     __syncthreads();
-    if (tid != 0) return;
     const int gap = tinfo[0];
-    if ((TILE_CAP + 1 - gap < TILE_MIN_STRIDE) || (tinfo[1] & 1)) { tinfo[2] = 0; return; }
-    int c = 0, t = 0;
-    while (c < N && t < cap - 1) {
-        tile_start[t] = c;
-        const int hi = min(c + TILE_CAP, N);
-        // last valid cut in (c, hi].  Fast path: a 64-bit window ending at hi (bit 63 <-> position hi) holds at least the 32
-        // positions below hi, enough whenever the last molecule before hi has <= 32 atoms; both words load independently.
-        const int w1 = hi >> 5, sh = 31 - (hi & 31);
-        const unsigned long long win = (((unsigned long long)bits[w1] << 32) | (w1 > 0 ? bits[w1 - 1] : 0u)) << sh;
-        int best = -1;
-        if (win != 0ull && hi - __clzll(win) > c) {
-            best = hi - __clzll(win);
-        } else {                                           // long molecule: scan the words downwards from hi's word
-            int w = w1;
-            uint32_t word = bits[w];
-            if ((hi & 31) != 31) word &= (2u << (hi & 31)) - 1u;
-            const int wlo = (c + 1) >> 5;
-            while (true) {
-                if (w == wlo) word &= ~((1u << ((c + 1) & 31)) - 1u);
-                if (word) { best = 32 * w + 31 - __clz(word); break; }
-                if (w == wlo) break;
-                word = bits[--w];
+    if ((TILE_CAP + 1 - gap < TILE_MIN_STRIDE) || (tinfo[1] & 1)) { if (tid == 0) tinfo[2] = 0; return; }
+    const int P = max(1, min(GW, N / 2048));              // segments of >= 2048 nodes
+    const int S = (N + P - 1) / P;
+    const int seg_lo = warp * S, seg_hi = min(N, (warp + 1) * S);
+    // ---- candidates of this segment and their (exit, tiles) ----
+    if (warp < P) {
+        int cand = -1;
+        if (warp == 0) {
+            if (lane == 0) cand = 0;
+        } else {
+            // the valid cuts in [seg_lo, seg_lo + TILE_CAP), in order, one per lane
+            int found = 0;
+            for (int q0 = 0; q0 < TILE_CAP; q0 += 32) {
+                const int q = seg_lo + q0 + lane;
+                const bool ok = q <= N && ((bits[q >> 5] >> (q & 31)) & 1u);
+                const uint32_t m = __ballot_sync(0xffffffffu, ok);
+                const int rank = found + __popc(m & ((1u << lane) - 1u));
+                if (ok && rank < 32) s_cand[warp][rank] = q;
+                found += __popc(m);
+            }
+            __syncwarp();
+            if (lane < min(found, 32)) cand = s_cand[warp][lane];
+            __syncwarp();
+            if (found > 32 && lane == 0) s_fail = 1;       // more candidates than lanes (tiny molecules): sequential fallback
+            if (lane == 0) s_ncand[warp] = min(found, 32);
+        }
+        if (warp == 0 && lane == 0) s_ncand[0] = 1;
+        int c = cand, n = 0;
+        if (c >= 0) {
+            while (c < seg_hi) {
+                const int b = greedy_hop(bits, c, N);
+                if (b < 0) { s_fail = 1; break; }
+                c = b;
+                ++n;
             }
         }
-        if (best <= c) { t = 0; c = N; break; }           // cannot happen when gap <= TILE_CAP; disables tiling if it does
-        c = best;
-        ++t;
+        s_cand[warp][lane] = cand; s_exit[warp][lane] = c; s_cnt[warp][lane] = n;
     }
-    if (c < N) t = 0;                                     // ran out of tile slots
-    if (t > 0) tile_start[t] = N;
-    tinfo[2] = t;
+    __syncthreads();
+    // ---- thread the true entry through the segments ----
+    if (tid == 0) {
+        int e = 0, off = 0;
+        bool ok = !s_fail;
+        for (int p = 0; p < P && ok; ++p) {
+            s_entry[p] = e; s_off[p] = off;
+            if (e >= min(N, (p + 1) * S)) continue;        // the chain jumps over this segment's start window entirely
+            int l = -1;
+            for (int i = 0; i < s_ncand[p]; ++i) if (s_cand[p][i] == e) l = i;
+            if (l < 0) { ok = false; break; }
+            off += s_cnt[p][l];
+            e = s_exit[p][l];
+        }
+        if (ok && (e != N || off > cap - 1)) ok = false;
+        s_entry[P] = N; s_off[P] = off;
+        if (!ok) s_fail = 1;
+    }
+    __syncthreads();
+    if (s_fail) {                                          // exact sequential walk
+        if (tid != 0) return;
+        int c = 0, t = 0;
+        while (c < N && t < cap - 1) {
+            tile_start[t] = c;
+            const int b = greedy_hop(bits, c, N);
+            if (b <= c) { t = 0; c = N; break; }           // cannot happen when gap <= TILE_CAP; disables tiling if it does
+            c = b;
+            ++t;
+        }
+        if (c < N) t = 0;                                  // ran out of tile slots
+        if (t > 0) tile_start[t] = N;
+        tinfo[2] = t;
+        return;
+    }
+    // ---- write the tile starts: warp p re-walks its part of the chain ----
+    if (warp < P && lane == 0) {
+        int c = s_entry[warp], t = s_off[warp];
+        while (c < seg_hi) {
+            tile_start[t++] = c;
+            c = greedy_hop(bits, c, N);
+        }
+    }
+    if (tid == 0) { tile_start[s_off[P]] = N; tinfo[2] = s_off[P]; }
 }
 
 // largest tile and largest per-degree node count of a tile (one warp per tile)
@@ -635,7 +716,7 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
         const int64_t bitmap = (int64_t)((N + 32) / 32) * 4;
         static int s_budget = 0;
         if (!s_budget) s_budget = device_max_smem_optin();
-        if (bitmap <= s_budget - 4096) {
+        if (bitmap <= s_budget - 16384) {                  // + the kernel's static tables
             static int64_t s_attr = 0;
             if (bitmap > s_attr) {
                 MK_CHECK_CUDA(cudaFuncSetAttribute(k_tile_starts_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap));

@@ -127,6 +127,17 @@ class BaseKernelSetConv(Module):
             headers += ['std_kernel'] * self.num_trainable_kernel_list[i]
         pd.DataFrame(sc_np, columns=headers).transpose().to_csv('scores.csv')
 
+    def _degree_owners(self):
+        """Per degree: the KernelConv module that owns the parameters (None for a degree without kernels)."""
+        out = []
+        for d in range(4):
+            f, t = self.fixed_kernelconv_set[d], self.trainable_kernelconv_set[d]
+            if f is not None and t is not None:
+                raise NotImplementedError('mixed fixed+trainable kernel sets for one degree are not supported yet '
+                                          '(SURVEY.md 8(f) N4)')
+            out.append(t if f is None else f)
+        return out
+
     def _degree_params(self):
         """Per degree: concatenation [fixed ; trainable] kernels (kernels.py:702-715) as one parameter dict."""
         out = []
