@@ -137,6 +137,99 @@ __global__ void __launch_bounds__(256) k_propagate_img(const __grid_constant__ P
     }
 }
 
+// Tile-ordered neighbour sum (plans with molecule tiles, K <= 112): one CTA per tile.  The compact score rows of the tile's
+// nodes are expanded once into a dense [node][column] block in shared memory (coalesced reads, one thread per
+// (node, kernel) pair); every in-neighbour of a tile node is a tile node (TileMetaG::inl), so h[v] is then a sum of <= 4
+// shared-memory rows in edge order -- same arithmetic and lane <-> column mapping as k_propagate_img (bitwise equal
+// results), an eighth of its instructions.  Writes h, ||h|| and (optionally) the next layer's fp16 (hi, lo) tile images.
+struct PropTileArgs {
+    const TileMetaG* meta;
+    int K, ldh;
+    int L[4], koff[4];
+    long long scoff[4];
+    const float* sc;
+    float* h; float* hnorm;
+    unsigned char* ximg; int Fk, x_one;
+};
+
+__global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ PropTileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_p[];
+    TileMetaG& m = *reinterpret_cast<TileMetaG*>(smem_p);
+    float* scS = reinterpret_cast<float*>(smem_p + (sizeof(TileMetaG) + 15) / 16 * 16);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    {
+        const uint4* src = reinterpret_cast<const uint4*>(a.meta + tile);
+        uint4* dst = reinterpret_cast<uint4*>(smem_p);
+        for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += 256) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int nn = m.nn, t0 = m.t0, ld = a.ldh;
+    for (int i = tid; i < nn * (ld >> 2); i += 256) reinterpret_cast<float4*>(scS)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+#pragma unroll
+    for (int d = 1; d <= 4; ++d) {
+        const int L = a.L[d - 1];
+        if (L == 0) continue;
+        const int np = m.cnt[d - 1] * L;
+        const float rL = 1.0f / (float)L;
+        const float* base = a.sc + a.scoff[d - 1];
+        const int ko = a.koff[d - 1];
+#pragma unroll 4
+        for (int p = tid; p < np; p += 256) {
+            const int i = (int)(((float)p + 0.5f) * rL);
+            const int k = p - i * L;
+            const int nl_ = m.list[d - 1][i];
+            scS[nl_ * ld + ko + k] = __ldg(base + (size_t)m.posl[nl_] * L + k);
+        }
+    }
+    __syncthreads();
+    const int c0 = 4 * lane;
+    unsigned char* Xhi = a.ximg ? a.ximg + (size_t)tile * 2 * a.x_one : nullptr;
+    unsigned char* Xlo = a.ximg ? Xhi + a.x_one : nullptr;
+    for (int v = warp; v < nn; v += 8) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int cnt = min((int)m.incnt[v], 4);
+        const uint32_t w = m.inl[v];
+        if (c0 < ld) {
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {        // edge order
+                if (t < cnt) {
+                    const float4 s4 = *reinterpret_cast<const float4*>(scS + (int)((w >> (8 * t)) & 0xffu) * ld + c0);
+                    acc[0] += s4.x; acc[1] += s4.y; acc[2] += s4.z; acc[3] += s4.w;
+                }
+            }
+        }
+        float ss = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { if (c0 + u >= a.K) acc[u] = 0.f; ss += acc[u] * acc[u]; }
+        ss = warp_sum(ss);
+        const float nrm = sqrtf(ss);
+        const int i = t0 + v;
+        if (c0 < ld) st4(a.h + (size_t)i * ld + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        if (lane == 0 && a.hnorm) a.hnorm[i] = nrm;
+        if (Xhi && c0 < a.Fk) {
+            const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
+            __align__(8) __half2 hi[2];
+            __align__(8) __half2 lo[2];
+            tc::split_u2(acc[0] * rinv, acc[1] * rinv, hi[0], lo[0]);
+            tc::split_u2(acc[2] * rinv, acc[3] * rinv, hi[1], lo[1]);
+            const uint32_t off = tc::il_off(v, c0, a.Fk);
+            *reinterpret_cast<uint2*>(Xhi + off) = *reinterpret_cast<const uint2*>(hi);
+            *reinterpret_cast<uint2*>(Xlo + off) = *reinterpret_cast<const uint2*>(lo);
+        }
+    }
+    // pad rows up to the next multiple of 16: the extent the tile kernels' MMAs read
+    if (Xhi && c0 < a.Fk) {
+        const int rend = min(TNODES, (nn + 15) & ~15);
+        for (int rr = nn + warp; rr < rend; rr += 8) {
+            const uint32_t off = tc::il_off(rr, c0, a.Fk);
+            *reinterpret_cast<uint2*>(Xhi + off) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(Xlo + off) = make_uint2(0u, 0u);
+        }
+    }
+}
+
 }  // namespace mk
 
 using namespace mk;
@@ -166,6 +259,26 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
     const int grid = (a.N + 7) / 8;
     count_launches(1);
     ProfScope prof("propagate_fwd", st);
+    // tile-ordered kernel: tiled plan, K <= 112, 16-byte rows (always the case on the molecule-tile path)
+    if (plan->n_tiles > 0 && plan->tile_meta && plan->tile_max_nodes <= TNODES && ldh % 4 == 0 && ldh <= 112 &&
+        (reinterpret_cast<uintptr_t>(h) & 15) == 0 && (!ximg || (hnorm && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0))) {
+        PropTileArgs t;
+        t.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
+        t.K = layer->K; t.ldh = ldh;
+        for (int d = 0; d < 4; ++d) { t.L[d] = layer->L[d]; t.koff[d] = layer->koff[d]; t.scoff[d] = scoff[d]; }
+        t.sc = sc; t.h = h; t.hnorm = hnorm;
+        t.ximg = reinterpret_cast<unsigned char*>(ximg);
+        t.Fk = tile_fk(ldh); t.x_one = tile_img_one(t.Fk);
+        const int smem = (int)((sizeof(TileMetaG) + 15) / 16 * 16) + TNODES * ldh * 4;
+        static int s_attr = 0;
+        if (smem > s_attr) {
+            MK_CHECK_CUDA(cudaFuncSetAttribute(k_propagate_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            s_attr = smem;
+        }
+        k_propagate_tile<<<plan->n_tiles, 256, smem, st>>>(t);
+        MK_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (ximg) {
         MK_REQUIRE(plan->n_tiles > 0 && plan->node_tile && plan->tile_start && ldh % 4 == 0 && ldh <= 112 && hnorm,
                    "propagate_fwd: fused images need a tiled plan, hnorm and ldh %% 4 == 0, ldh <= 112 (got %d)", ldh);
