@@ -157,6 +157,7 @@ int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
 /* sc_mode 0: compact per-degree blocks at sc + scoff[d-1] (n_d*L_d floats each, scoff in floats);
  * sc_mode 1: dense sc[node*ld_sc + koff_d + k] (only the L_d entries of the node's own block are written).
  * argmax (compact, byte offsets = scoff) always receives the permutation actually used + chirality bit;
+ * argmax_tile (nullable, molkgnn_tile_argmax_bytes() bytes): tile-ordered copy for the backward (tile kernel only);
  * argmax_free (nullable) receives the free-running arg-max; argmax_in (nullable) forces the permutation
  * (parity harness / replay).  counter: 8 int32 of scratch per call.  ximg (nullable): the activations' fp16 images
  * from molkgnn_tile_ximg_build(); with them, a plan that carries molecule tiles and an eligible layer the molecule-tile
@@ -164,7 +165,11 @@ int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
 int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                      const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
-                     int32_t* counter, const void* ximg, void* stream);
+                     int32_t* counter, const void* ximg, uint8_t* argmax_tile, void* stream);
+/* bytes of the optional tile-ordered copy of the arg-max (argmax_tile above / below): n_tiles slots of the fullest tile's
+ * (node, kernel) pair count; the molecule-tile forward writes it, the molecule-tile backward fetches a tile's slot with one
+ * bulk copy instead of per-pair reads of the bucket-order array.  0 if the plan / layer is not eligible. */
+int64_t molkgnn_tile_argmax_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 
 /* Selects the forward kernel: 2 = molecule-tile tcgen05 kernel (default; needs ximg, a tiled plan and an eligible layer,
  * else falls back to 1), 1 = bucket-order tcgen05 kernel (falls back to 0 for layers whose kernel set does not fit shared
@@ -200,7 +205,8 @@ int64_t molkgnn_conv_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_l
 int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                      const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
                      const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx,
-                     const molkgnn_layer_grads_t* grads, int32_t phases, const void* ximg, float* scratch, void* stream);
+                     const molkgnn_layer_grads_t* grads, int32_t phases, const void* ximg, float* scratch,
+                     const uint8_t* argmax_tile, void* stream);
 /* 1 = molecule-tile tensor-core backward when eligible (default), 0 = bucket-order SIMT kernels; returns the old value */
 int molkgnn_set_bwd_path(int path);
 /* how often each path ran so far: forward tile / forward other / backward tile / backward other */
@@ -224,6 +230,7 @@ typedef struct molkgnn_stack_layout {
     int64_t sc[MOLKGNN_MAX_LAYERS];             /* compact scores of layer i */
     int64_t argmax[MOLKGNN_MAX_LAYERS];         /* uint8 per (node, kernel) pair, compact */
     int64_t argmax_free[MOLKGNN_MAX_LAYERS];
+    int64_t argmax_tile[MOLKGNN_MAX_LAYERS];    /* tile-ordered copy of the arg-max (molecule-tile path), -1 = absent */
     int64_t counter;
     int64_t sc_elems[MOLKGNN_MAX_LAYERS];       /* sum_d n_d * L_d of layer i */
     int64_t scoff[MOLKGNN_MAX_LAYERS][4];       /* element offsets of the per-degree blocks inside sc / argmax */
@@ -239,15 +246,17 @@ int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          molkgnn_stack_layout_t* out);
 /* Forward of the stack: parameter packing of every layer, pad + norm of x [N, ldx] (F = layers[0].F columns), then per
  * layer conv (all four buckets) and propagate.  h_out [N, ldh] (ldh = roundup4(K_last)) receives the output of the last
- * propagate.  argmax_in: nullable array of nl nullable pointers (forced permutations, parity harness). */
+ * propagate.  argmax_in: nullable array of nl nullable pointers (forced permutations, parity harness).  tile_fwd (HOST,
+ * nullable, nl ints): receives per layer whether the molecule-tile forward ran, i.e. whether the tile-ordered arg-max copy
+ * in the workspace is valid; hand it to molkgnn_stack_bwd. */
 int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
                       const molkgnn_stack_layout_t* lay, int32_t flags, const float* x, int32_t ldx, void* workspace,
-                      float* h_out, int32_t ldh, const uint8_t* const* argmax_in, void* stream);
+                      float* h_out, int32_t ldh, const uint8_t* const* argmax_in, int32_t* tile_fwd, void* stream);
 /* Backward of the stack from grad_h [N, ldg] (gradient w.r.t. h_out).  grad_x (nullable) [N, Fp_0].  grad_flat
  * (nullable): flat parameter-gradient buffer laid out by molkgnn_stack_layout (g_* offsets). */
 int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
                       const molkgnn_stack_layout_t* lay, void* workspace, void* bwd_scratch, const float* grad_h,
-                      int32_t ldg, float* grad_x, float* grad_flat, void* stream);
+                      int32_t ldg, float* grad_x, float* grad_flat, const int32_t* tile_fwd, void* stream);
 
 /* ---- diagnostics ---- */
 /* CUDA-event profiler of the library's own launches (bench.py: live per-kernel durations on the launching stream).

@@ -37,6 +37,7 @@ class StackLayout(C.Structure):
     _fields_ = [("fwd_bytes", i64), ("bwd_bytes", i64), ("grad_floats", i64),
                 ("h", i64 * MAX_LAYERS), ("hnorm", i64 * (MAX_LAYERS + 1)), ("ximg", i64 * MAX_LAYERS),
                 ("sc", i64 * MAX_LAYERS), ("argmax", i64 * MAX_LAYERS), ("argmax_free", i64 * MAX_LAYERS),
+                ("argmax_tile", i64 * MAX_LAYERS),
                 ("counter", i64), ("sc_elems", i64 * MAX_LAYERS), ("scoff", (i64 * 4) * MAX_LAYERS),
                 ("coef", i64), ("partials", i64), ("scratch", i64), ("gx", i64 * 2),
                 ("g_x_center", (i64 * 4) * MAX_LAYERS), ("g_x_support", (i64 * 4) * MAX_LAYERS),
@@ -63,21 +64,22 @@ EXPORTS = {
     "molkgnn_tile_img_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
-                                   vp, vp, vp, vp]),
+                                   vp, vp, vp, vp, vp]),
+    "molkgnn_tile_argmax_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_propagate_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i64 * 4, vp, i32, vp, vp, vp]),
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_conv_bwd_coef_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),
     "molkgnn_tc_selftest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
-                                   vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp]),
+                                   vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp, vp]),
     "molkgnn_set_bwd_path": (C.c_int, [C.c_int]),
     "molkgnn_path_counts": (None, [i64 * 4]),
     "molkgnn_stack_layout": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, i32, C.POINTER(StackLayout)]),
     "molkgnn_stack_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), i32, vp, i32, vp, vp,
-                                    i32, C.POINTER(vp), vp]),
+                                    i32, C.POINTER(vp), C.POINTER(i32), vp]),
     "molkgnn_stack_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), vp, vp, vp, i32, vp,
-                                    vp, vp]),
+                                    vp, C.POINTER(i32), vp]),
     "molkgnn_profile_enable": (C.c_int, [C.c_int]),
     "molkgnn_profile_only": (C.c_int, [C.c_char_p]),
     "molkgnn_profile_read": (C.c_int, [C.c_char_p, C.c_int]),

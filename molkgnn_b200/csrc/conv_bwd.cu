@@ -21,7 +21,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
                          const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials, float* scratch,
                          float* grad_x, int32_t ldgx, int64_t part_off[4], int ncta[4], int64_t* part_total, bool do_launch,
-                         cudaStream_t st);
+                         const uint8_t* argmax_tile, cudaStream_t st);
 int tile_bwd_grid(const molkgnn_plan_t* plan);
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 long long g_path_counts[4] = {0, 0, 0, 0};   // forward tile / other, backward tile / other
@@ -503,6 +503,12 @@ static int init_dev() {
 
 namespace mk { int64_t tile_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer); }
 
+namespace mk { int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer); }
+extern "C" int64_t molkgnn_tile_argmax_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    if (!tile_bwd_ok(plan, layer)) return 0;
+    return (int64_t)plan->n_tiles * mk::tile_argmax_stride(plan, layer) + 16;
+}
+
 extern "C" int64_t molkgnn_conv_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     int64_t tot = 0;
     for (int d = 0; d < 4; ++d) tot += (int64_t)plan->n[d] * layer->L[d];
@@ -527,7 +533,7 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                                 const float* xnorm, const float* grad, int32_t ldg, int32_t grad_mode,
                                 const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials,
                                 float* grad_x, int32_t ldgx, const molkgnn_layer_grads_t* grads, int32_t phases,
-                                const void* ximg, float* scratch, void* stream_) {
+                                const void* ximg, float* scratch, const uint8_t* argmax_tile, void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     if (init_dev()) return -1;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_bwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
@@ -537,7 +543,8 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         int64_t t_off[4], t_total = 0;
         int t_ncta[4];
         const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, argmax, scoff, coef,
-                                            partials, scratch, grad_x, ldgx, t_off, t_ncta, &t_total, (phases & 1) != 0, st);
+                                            partials, scratch, grad_x, ldgx, t_off, t_ncta, &t_total, (phases & 1) != 0,
+                                            argmax_tile, st);
         if (rc < 0) return rc;
         if (rc == 1) {
             if (phases & 1) ++g_path_counts[2];

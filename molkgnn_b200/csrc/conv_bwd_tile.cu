@@ -48,7 +48,8 @@ constexpr int WT_ONE = 16 * 16 * 128;          // one fp16 image of the 128 x 12
 // off_d = sum_{d' < d} cnt_d' * L_d'.  Bond-attribute support gradients: thread owns support rows, sums over the tile's
 // nodes in fixed order, one partial copy per CTA (k_param_finalize reduces them).
 constexpr int CT_THREADS = 512;
-constexpr int CT_MAXR = 4;                     // support rows per thread (sum_d d * L_d <= 2048)
+constexpr int CT_MAXR = 4;                     // bond-gradient items per thread (sum_d d * L_d * nch_d <= 2048)
+constexpr int CT_CHUNK = 12;                   // nodes per item and tile
 
 struct CoefTileArgs {
     const TileMetaG* meta; const float* ehat_node; int n_tiles;
@@ -57,9 +58,11 @@ struct CoefTileArgs {
     const float* grad; int ldg; int grad_mode; int vec;     // vec: floats per cp.async of the gradient rows (1, 2 or 4)
     const uint8_t* argmax;
     float* coefT; uint8_t* amT; int stride, stride_am;
+    int nch[4];                                // node chunks per degree for the bond gradients
+    const uint8_t* amT_in;                     // tile-ordered arg-max written by the forward (nullable: read `argmax`, write amT)
     float* partials; long long part_off[4]; int FW, Fp;
     float* amax;                               // device scalar (zeroed by the launcher): max |coef|
-    int buf_bytes, sm_grad, sm_eh, sm_coef, sm_inv;   // per-buffer size / offsets inside a buffer / offsets of the pair arrays
+    int buf_bytes, sm_grad, sm_eh, sm_am, sm_coef, sm_inv;   // per-buffer size / offsets inside a buffer / pair arrays
 };
 
 __device__ __forceinline__ void cp_async_n(void* dst, const void* src, int bytes) {
@@ -94,6 +97,46 @@ __device__ __forceinline__ void ct_issue(const CoefTileArgs& a, unsigned char* b
         float* dst = reinterpret_cast<float*>(buf + a.sm_eh);
         for (int i = tid; i < hdr.w * 2; i += CT_THREADS) cp_async_n(dst + i * 4, src + (size_t)i * 4, 16);
     }
+    if (a.amT_in) {
+        const int4 c = __ldg(reinterpret_cast<const int4*>(&g->cnt[0]));
+        const int np = c.x * a.L[0] + c.y * a.L[1] + c.z * a.L[2] + c.w * a.L[3];
+        const unsigned char* src = a.amT_in + (size_t)tile * a.stride_am;
+        for (int i = tid; i < (np + 15) / 16; i += CT_THREADS) cp_async_n(buf + a.sm_am + i * 16, src + (size_t)i * 16, 16);
+    }
+}
+
+// (node, kernel) pairs of degree D of one tile: chi * g from the staged gradient rows, tile-ordered outputs
+template <int D>
+__device__ __forceinline__ void ct_pairs(const CoefTileArgs& a, const TileMetaG& m, const float* gS, const unsigned char* amS,
+                                         const unsigned char* inv_lut, int off, float* cT, uint8_t* aT, float* coefS,
+                                         unsigned char* invS, float& amax) {
+    const int L = a.L[D - 1];
+    if (L == 0) return;
+    const int np = m.cnt[D - 1] * L;
+    const float rL = 1.0f / (float)L;
+    const int koff = a.koff[D - 1];
+#pragma unroll 2
+    for (int p = threadIdx.x; p < np; p += CT_THREADS) {
+        const int i = (int)(((float)p + 0.5f) * rL);
+        const int k = p - i * L;
+        const int nl_ = m.list[D - 1][i];
+        const uint8_t am = amS ? amS[off + p] : a.argmax[(size_t)a.scoff[D - 1] + (size_t)m.posl[nl_] * L + k];
+        float g;
+        if (a.grad_mode == 0) {
+            g = gS[nl_ * a.ldg + koff + k];
+        } else {
+            const uint32_t nw = m.nl[nl_];
+            g = gS[(int)(nw & 0xffu) * a.ldg + koff + k];
+#pragma unroll
+            for (int j = 1; j < D; ++j) g += gS[(int)((nw >> (8 * j)) & 0xffu) * a.ldg + koff + k];
+        }
+        const float av = (am & 0x80) ? -g : g;
+        amax = fmaxf(amax, fabsf(av));
+        cT[off + p] = av;
+        if (aT) aT[off + p] = am & 0x7f;
+        coefS[off + p] = av;
+        invS[off + p] = inv_lut[am & 0x7f];
+    }
 }
 
 #ifdef MK_PHASE_CLOCKS
@@ -115,19 +158,26 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
     }
     float* coefS = reinterpret_cast<float*>(smem_c + a.sm_coef);
     unsigned char* invS = smem_c + a.sm_inv;
-    // support rows owned by this thread: row r = tid + q * CT_THREADS over the concatenation of the degrees' (s, k) rows
-    int rd[CT_MAXR], rs[CT_MAXR], rk[CT_MAXR];
+    // Bond-gradient work items owned by this thread: item r = tid + q * CT_THREADS over the concatenation, degree by degree,
+    // of (node chunk c, support row (s, k)).  A long degree bucket is cut into nch[d] chunks of CT_CHUNK nodes so that no
+    // thread walks more than a few nodes per tile (a thread per whole row left two warps walking ~50 nodes while the rest
+    // idled); the chunks' sums are combined in chunk order at the end.
+    int rd[CT_MAXR], rs[CT_MAXR], rk[CT_MAXR], rc[CT_MAXR];
     float acc[CT_MAXR][EP];
 #pragma unroll
     for (int q = 0; q < CT_MAXR; ++q) {
         int r = tid + q * CT_THREADS;
-        rd[q] = 0; rs[q] = 0; rk[q] = 0;
+        rd[q] = 0; rs[q] = 0; rk[q] = 0; rc[q] = 0;
 #pragma unroll
         for (int d = 1; d <= 4; ++d) {
             const int rows = d * a.L[d - 1];
+            const int items = rows * a.nch[d - 1];
             if (rd[q] == 0 && r >= 0) {
-                if (r < rows) { rd[q] = d; rs[q] = r / a.L[d - 1]; rk[q] = r - rs[q] * a.L[d - 1]; }
-                else r -= rows;
+                if (r < items) {
+                    rd[q] = d; rc[q] = r / rows;
+                    const int rr = r - rc[q] * rows;
+                    rs[q] = rr / a.L[d - 1]; rk[q] = rr - rs[q] * a.L[d - 1];
+                } else r -= items;
             }
         }
 #pragma unroll
@@ -156,51 +206,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
 #pragma unroll
         for (int d = 0; d < 4; ++d) off[d + 1] = off[d] + m.cnt[d] * a.L[d];
         float* cT = a.coefT + (size_t)tile * a.stride;
-        uint8_t* aT = a.amT + (size_t)tile * a.stride_am;
-        // ---- coefficients: one thread per (node, kernel) pair over all degrees, U pairs in flight per thread (the saved
-        // arg-max is the only global read: its loads are issued for all U pairs before any is consumed) ----
-        {
-            constexpr int U = 5;
-            const int total = off[4];
-            for (int p0 = tid; p0 < total; p0 += CT_THREADS * U) {
-                int dd[U], pl_[U], nl_[U], kk[U];
-                uint8_t am[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int p = p0 + u * CT_THREADS;
-                    dd[u] = 0; am[u] = 0; pl_[u] = 0; nl_[u] = 0; kk[u] = 0;
-                    if (p < total) {
-                        const int d = 1 + (p >= off[1]) + (p >= off[2]) + (p >= off[3]);
-                        const int L = a.L[d - 1];
-                        const int qd = p - off[d - 1];
-                        const int i = (int)(((float)qd + 0.5f) / (float)L);
-                        const int k = qd - i * L;
-                        const int n_ = m.list[d - 1][i];
-                        am[u] = a.argmax[(size_t)a.scoff[d - 1] + (size_t)m.posl[n_] * L + k];
-                        dd[u] = d; pl_[u] = p; nl_[u] = n_; kk[u] = a.koff[d - 1] + k;
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int d = dd[u];
-                    if (d == 0) continue;
-                    float g;
-                    if (a.grad_mode == 0) {
-                        g = gS[nl_[u] * a.ldg + kk[u]];
-                    } else {
-                        const uint32_t nw = m.nl[nl_[u]];
-                        g = gS[(int)(nw & 0xffu) * a.ldg + kk[u]];
-                        for (int j = 1; j < d; ++j) g += gS[(int)((nw >> (8 * j)) & 0xffu) * a.ldg + kk[u]];
-                    }
-                    const float av = (am[u] & 0x80) ? -g : g;
-                    amax = fmaxf(amax, fabsf(av));
-                    cT[pl_[u]] = av;
-                    aT[pl_[u]] = am[u] & 0x7f;
-                    coefS[pl_[u]] = av;
-                    invS[pl_[u]] = s_inv[d - 1][am[u] & 0x7f];
-                }
-            }
-        }
+        uint8_t* aT = a.amT ? a.amT + (size_t)tile * a.stride_am : nullptr;
+        const unsigned char* amS = a.amT_in ? buf + a.sm_am : nullptr;
+        // ---- coefficients: one thread per (node, kernel) pair, degree by degree ----
+        ct_pairs<1>(a, m, gS, amS, s_inv[0], off[0], cT, aT, coefS, invS, amax);
+        ct_pairs<2>(a, m, gS, amS, s_inv[1], off[1], cT, aT, coefS, invS, amax);
+        ct_pairs<3>(a, m, gS, amS, s_inv[2], off[2], cT, aT, coefS, invS, amax);
+        ct_pairs<4>(a, m, gS, amS, s_inv[3], off[3], cT, aT, coefS, invS, amax);
         MK_PH(3);                                        // pairs (thread 0's share)
         __syncthreads();
         MK_PH(4);                                        // waiting for the slowest pair thread
@@ -214,8 +226,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
             const unsigned char* is = invS + off[d - 1] + rk[q];
             const unsigned char* lst = m.list[d - 1];
             const int sh = 2 * rs[q];
+            const int i0 = rc[q] * CT_CHUNK;
+            const int i1 = rc[q] == a.nch[d - 1] - 1 ? cnt : min(cnt, i0 + CT_CHUNK);   // the last chunk takes the rest
 #pragma unroll 4
-            for (int i = 0; i < cnt; ++i) {
+            for (int i = i0; i < i1; ++i) {
                 const float av = cs[i * L];
                 const int j = (is[i * L] >> sh) & 3;
                 const int e = m.eslot[lst[i]] + j;
@@ -233,15 +247,33 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.amax), __float_as_uint(amax));
-    // one partial copy per CTA: bond columns of the support rows; the centre rows carry no bond part
+    // one partial copy per CTA: bond columns of the support rows (chunks combined in chunk order through shared memory,
+    // the tile buffers are free now); the centre rows carry no bond part
+    __syncthreads();
+    float4* stage = reinterpret_cast<float4*>(smem_c);
+#pragma unroll
+    for (int q = 0; q < CT_MAXR; ++q) {
+        if (rd[q] == 0) continue;
+        const int r = tid + q * CT_THREADS;
+        stage[2 * r] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        stage[2 * r + 1] = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+    }
+    __syncthreads();
 #pragma unroll
     for (int q = 0; q < CT_MAXR; ++q) {
         const int d = rd[q];
-        if (d == 0) continue;
-        const int L = a.L[d - 1];
+        if (d == 0 || rc[q] != 0) continue;                  // the chunk-0 owner of a row writes it
+        const int L = a.L[d - 1], rows = d * L;
+        const int r = tid + q * CT_THREADS;
+        float4 s0 = stage[2 * r], s1 = stage[2 * r + 1];
+        for (int c = 1; c < a.nch[d - 1]; ++c) {
+            const float4 t0 = stage[2 * (r + c * rows)], t1 = stage[2 * (r + c * rows) + 1];
+            s0.x += t0.x; s0.y += t0.y; s0.z += t0.z; s0.w += t0.w;
+            s1.x += t1.x; s1.y += t1.y; s1.z += t1.z; s1.w += t1.w;
+        }
         float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * (d + 1) * L + (size_t)rs[q] * L + rk[q]) * a.FW + a.Fp;
-        st4(part, make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]));
-        st4(part + 4, make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]));
+        st4(part, s0);
+        st4(part + 4, s1);
     }
     for (int d = 1; d <= 4; ++d) {
         const int L = a.L[d - 1];
@@ -469,7 +501,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     const int nl_ = m.list[sg.d - 1][ni];
                     const int pi = abase[si] + ni * sg.L + kl;
                     const float av = a_s[pi] * rscale;
-                    const uint32_t code = s_lut[sg.d - 1][am_s[pi]];
+                    const uint32_t code = s_lut[sg.d - 1][am_s[pi] & 0x7f];
                     const uint32_t nw = m.nl[nl_];
                     const uint32_t cr = m.cr[nl_];
                     wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                         const int ent = m.elist[e0 + ei];
                         const int nl_ = ent >> 2, j = ent & 3;
                         const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
-                        const int s = (s_lut[sg.d - 1][am_s[pi]] >> (2 * j)) & 3;
+                        const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
                         wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
                     }
                 }
@@ -707,6 +739,12 @@ bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     return rows <= CT_MAXR * CT_THREADS;
 }
 
+int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    int stride, stride_am;
+    coef_strides(plan, layer, &stride, &stride_am);
+    return stride_am;
+}
+
 // floats of the `coef` scratch the tile path needs (tile-ordered coefficients + arg-max codes behind them); 0 = not eligible
 int64_t tile_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     if (!tile_bwd_ok(plan, layer)) return 0;
@@ -720,7 +758,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
                          const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials, float* scratch,
                          float* grad_x, int32_t ldgx, int64_t part_off[4], int ncta[4], int64_t* part_total, bool do_launch,
-                         cudaStream_t st) {
+                         const uint8_t* argmax_tile, cudaStream_t st) {
     (void)x; (void)ldx;
     if (!ximg || !coef || !tile_bwd_ok(plan, layer)) return 0;
     static int s_budget = 0;
@@ -758,7 +796,8 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     int stride, stride_am;
     coef_strides(plan, layer, &stride, &stride_am);
     a.coefT = coef;
-    a.amT = reinterpret_cast<const uint8_t*>(coef + (size_t)plan->n_tiles * stride);
+    // arg-max bytes in tile order: the forward's copy if the caller kept one, else k_coef_tile writes its own behind coefT
+    a.amT = argmax_tile ? argmax_tile : reinterpret_cast<const uint8_t*>(coef + (size_t)plan->n_tiles * stride);
     a.stride = stride; a.stride_am = stride_am;
     a.buf_bytes = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
     // TMEM: G of block bi at bi * gstride, dxh behind them.  A layer whose feature width lets (blocks + 1) accumulators fit
@@ -787,6 +826,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         int64_t o = (sizeof(TileMetaG) + 127) / 128 * 128;
         c.sm_grad = (int)o; o += (((int64_t)TNODES * ldg + 4) * 4 + 127) / 128 * 128;
         c.sm_eh = (int)o; o += (int64_t)TILE_ESLOTS * EP * 4;
+        c.sm_am = (int)o; o += ((int64_t)stride_am + 127) / 128 * 128;
         c.buf_bytes = (int)o;
         c.sm_coef = (int)(2 * o);
         c.sm_inv = c.sm_coef + (int)(((int64_t)stride * 4 + 127) / 128 * 128);
@@ -814,9 +854,19 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         }
         c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode;
         c.argmax = argmax;
-        c.coefT = coef; c.amT = const_cast<uint8_t*>(a.amT); c.stride = stride; c.stride_am = stride_am;
+        c.coefT = coef; c.stride = stride; c.stride_am = stride_am;
+        c.amT_in = argmax_tile; c.amT = argmax_tile ? nullptr : const_cast<uint8_t*>(a.amT);
         c.partials = partials; c.FW = a.FW; c.Fp = layer->Fp;
         c.amax = amax;
+        // node chunks per degree: as many as the fullest tile needs, fewer if the items would exceed the threads' capacity
+        for (int div = 1;; ++div) {
+            int items = 0;
+            for (int d = 0; d < 4; ++d) {
+                c.nch[d] = std::max(1, std::min(8, ((plan->tile_max_deg[d] + CT_CHUNK - 1) / CT_CHUNK + div - 1) / div));
+                items += (d + 1) * layer->L[d] * c.nch[d];
+            }
+            if (items <= CT_MAXR * CT_THREADS || div >= 8) break;
+        }
         count_launches(1);
         ProfScope prof("coef_tile", st);
         k_coef_tile<<<grid, CT_THREADS, smem_c, st>>>(c);

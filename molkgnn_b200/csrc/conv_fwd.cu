@@ -403,7 +403,7 @@ int launch_conv_fwd_tc(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer,
 int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const void* ximg, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
-                         int32_t* counter, cudaStream_t st);
+                         uint8_t* argmax_tile, int32_t* counter, cudaStream_t st);
 
 extern long long g_path_counts[4];
 
@@ -430,7 +430,8 @@ extern "C" int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer) {
 extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                                 const float* xnorm, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                                 const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free,
-                                const uint8_t* argmax_in, int32_t* counter, const void* ximg, void* stream_) {
+                                const uint8_t* argmax_in, int32_t* counter, const void* ximg, uint8_t* argmax_tile,
+                                void* stream_) {
     cudaStream_t st = (cudaStream_t)stream_;
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "conv_fwd: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "conv_fwd: x must be 16-byte aligned");
@@ -447,7 +448,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     }
     if (g_fwd_path == 2) {
         const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
-                                            argmax_free, argmax_in, counter, st);
+                                            argmax_free, argmax_in, argmax_tile, counter, st);
         if (rc > 0) ++g_path_counts[0];
         if (rc != 0) return rc < 0 ? rc : 0;
     }

@@ -26,6 +26,7 @@
 namespace mk {
 
 bool tile_layer_ok(const molkgnn_layer_t* layer);
+int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 
 constexpr int TF_THREADS = 512;
 constexpr int TF_WARPS = TF_THREADS / 32;
@@ -103,6 +104,7 @@ struct FwdTileArgs {
     int is_last;
     float* sc; int sc_mode; int ld_sc; long long scoff[4];
     uint8_t* argmax; uint8_t* argmax_free; const uint8_t* argmax_in;
+    uint8_t* amT; int stride_am;      // nullable: the arg-max bytes once more in tile order (the backward's bulk-copy operand)
     int* counter;                     // [TILE_MAXB] tile queues
     int sm_img, sm_x, sm_dump, sm_buf, sm_es, sm_dup;   // byte offsets into dynamic shared memory
 };
@@ -179,7 +181,7 @@ template <int D> __device__ __forceinline__ uint32_t perm_code_rt(int p) {
 
 // one (node, kernel) pair: the reference arithmetic on its d x d similarity tile.  Results are returned, the caller
 // stores them: two pairs per thread are evaluated back to back so that their dependency chains interleave.
-struct PairOut { float sc; size_t cidx, oidx; uint8_t am, free; };
+struct PairOut { float sc; size_t cidx, oidx; int tidx; uint8_t am, free; };
 
 template <int D, bool FORCED>
 __device__ __forceinline__ PairOut tf_pair(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
@@ -201,6 +203,12 @@ __device__ __forceinline__ PairOut tf_pair(const FwdTileArgs& a, const TileBuf* 
     const float cdot = col0[nl_ * 128 + D * sg.nk];
     PairOut o;
     o.cidx = (size_t)a.scoff[D - 1] + (size_t)R * sg.L + k;
+    {
+        int t = m.lidx[nl_] * sg.L + k;              // tile order: degree blocks, node-of-degree major, kernel minor
+#pragma unroll
+        for (int dd = 1; dd < D; ++dd) t += m.cnt[dd - 1] * a.L[dd - 1];
+        o.tidx = t;
+    }
     const int forced = FORCED && a.argmax_in ? (a.argmax_in[o.cidx] & 0x7f) : -1;
     // mean over j for every permutation: sequential sum, then true division (kernels.py:194)
     float best = 0.f, used = 0.f;
@@ -248,7 +256,7 @@ __device__ __forceinline__ PairOut tf_pair(const FwdTileArgs& a, const TileBuf* 
 template <int D, bool FORCED>
 __device__ __forceinline__ void tf_pairs_of_thread(const FwdTileArgs& a, const TileBuf* tb, const float* dump,
                                                    const float4* estab, const unsigned char* dupf, const SegConst& sg,
-                                                   int np) {
+                                                   int np, int tile) {
     // the segment's pairs (node-major, then kernel), two per thread and iteration
     for (int p = (int)threadIdx.x; p < np; p += 2 * TF_THREADS) {
         const int p2 = p + TF_THREADS;
@@ -262,10 +270,12 @@ __device__ __forceinline__ void tf_pairs_of_thread(const FwdTileArgs& a, const T
         }
         if (FORCED && a.argmax_free) a.argmax_free[o1.cidx] = o1.free;
         a.argmax[o1.cidx] = o1.am;
+        if (a.amT) a.amT[(size_t)tile * a.stride_am + o1.tidx] = o1.am;
         a.sc[o1.oidx] = o1.sc;
         if (has2) {
             if (FORCED && a.argmax_free) a.argmax_free[o2.cidx] = o2.free;
             a.argmax[o2.cidx] = o2.am;
+            if (a.amT) a.amT[(size_t)tile * a.stride_am + o2.tidx] = o2.am;
             a.sc[o2.oidx] = o2.sc;
         }
     }
@@ -274,15 +284,15 @@ __device__ __forceinline__ void tf_pairs_of_thread(const FwdTileArgs& a, const T
 // the block's pairs, segment by segment
 template <bool FORCED>
 __device__ __forceinline__ void tf_epilogue(const FwdTileArgs& a, const TileBuf* tb, const float* dump, const float4* estab,
-                                            const unsigned char* dupf, const SegConst* segs, int nseg) {
+                                            const unsigned char* dupf, const SegConst* segs, int nseg, int tile) {
     for (int si = 0; si < nseg; ++si) {
         const SegConst sg = segs[si];
         const int np = tb->m.cnt[sg.d - 1] * sg.nk;
         switch (sg.d) {
-            case 1: tf_pairs_of_thread<1, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
-            case 2: tf_pairs_of_thread<2, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
-            case 3: tf_pairs_of_thread<3, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
-            default: tf_pairs_of_thread<4, FORCED>(a, tb, dump, estab, dupf, sg, np); break;
+            case 1: tf_pairs_of_thread<1, FORCED>(a, tb, dump, estab, dupf, sg, np, tile); break;
+            case 2: tf_pairs_of_thread<2, FORCED>(a, tb, dump, estab, dupf, sg, np, tile); break;
+            case 3: tf_pairs_of_thread<3, FORCED>(a, tb, dump, estab, dupf, sg, np, tile); break;
+            default: tf_pairs_of_thread<4, FORCED>(a, tb, dump, estab, dupf, sg, np, tile); break;
         }
     }
 }
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
                 consumer_sync();                                       // dump complete, accumulator drained
                 MK_PH(4);
                 if (tid == 0) mbar_arrive(&bar_tfree[b]);
-                tf_epilogue<FORCED>(a, tb, dump, estab, dupf, s_seg, nseg);
+                tf_epilogue<FORCED>(a, tb, dump, estab, dupf, s_seg, nseg, s_tile[b]);
                 MK_PH(5);
                 consumer_sync();                                       // dump and this tile's buffer are free again
                 MK_PH(6);
@@ -467,7 +477,7 @@ int launch_x_images(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, co
 int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const void* ximg, int32_t is_last_layer, float* sc, int32_t sc_mode, int32_t ld_sc,
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
-                         int32_t* counter, cudaStream_t st) {
+                         uint8_t* argmax_tile, int32_t* counter, cudaStream_t st) {
     if (!ximg || !tile_plan_ok(plan) || !layer->tile_img || !tile_layer_ok(layer)) return 0;
     static int s_budget = 0, s_sms = 0;
     if (!s_budget) {
@@ -494,6 +504,7 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.is_last = is_last_layer;
     a.sc = sc; a.sc_mode = sc_mode; a.ld_sc = ld_sc;
     a.argmax = argmax; a.argmax_free = argmax_free; a.argmax_in = argmax_in;
+    a.amT = argmax_tile; a.stride_am = tile_argmax_stride(plan, layer);
     a.counter = counter;
     int64_t off = 0;
     a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;

@@ -42,6 +42,8 @@ extern "C" int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_la
         out->ximg[i] = (one > 0 && ly.tile_img) ? take((int64_t)plan->n_tiles * one) : -1;
         out->argmax[i] = take(out->sc_elems[i]);
         out->argmax_free[i] = (flags & MOLKGNN_STACK_WANT_FREE) ? take(out->sc_elems[i]) : -1;
+        const int64_t amt = out->ximg[i] >= 0 ? molkgnn_tile_argmax_bytes(plan, &ly) : 0;
+        out->argmax_tile[i] = amt > 0 ? take(amt) : -1;
         if (flags & MOLKGNN_STACK_KEEP_SC) out->sc[i] = take(out->sc_elems[i] * 4);
     }
     out->hnorm[nl] = take(N * 4);
@@ -88,7 +90,7 @@ extern "C" int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_la
 extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
                                  const molkgnn_stack_layout_t* lay, int32_t flags, const float* x, int32_t ldx,
                                  void* workspace, float* h_out, int32_t ldh, const uint8_t* const* argmax_in,
-                                 void* stream) {
+                                 int32_t* tile_fwd, void* stream) {
     MK_REQUIRE(nl >= 1 && nl <= MOLKGNN_MAX_LAYERS && workspace && h_out && x, "stack_fwd: bad arguments");
     MK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 127) == 0, "stack_fwd: workspace must be 128-byte aligned");
     MK_REQUIRE(ldh % 4 == 0 && ldh >= layers[nl - 1].K && (reinterpret_cast<uintptr_t>(h_out) & 15) == 0,
@@ -108,12 +110,17 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
         const molkgnn_layer_t& ly = layers[i];
         const bool last = i == nl - 1;
         float* sc = reinterpret_cast<float*>(ws + lay->sc[i]);
+        int64_t pc0[4], pc1[4];
+        molkgnn_path_counts(pc0);
         if ((rc = molkgnn_conv_fwd(plan, &ly, h, ly.Fp, hn, last ? 1 : 0, sc, 0, 0, lay->scoff[i], ws + lay->argmax[i],
                                    lay->argmax_free[i] >= 0 ? ws + lay->argmax_free[i] : nullptr,
                                    argmax_in ? argmax_in[i] : nullptr,
                                    reinterpret_cast<int32_t*>(ws + lay->counter) + 8 * i,
-                                   lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr, stream)))
+                                   lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
+                                   lay->argmax_tile[i] >= 0 ? ws + lay->argmax_tile[i] : nullptr, stream)))
             return rc;
+        molkgnn_path_counts(pc1);
+        if (tile_fwd) tile_fwd[i] = pc1[0] > pc0[0] ? 1 : 0;      // the molecule-tile forward ran: argmax_tile[i] is valid
         float* hnext = last ? h_out : reinterpret_cast<float*>(ws + lay->h[i + 1]);
         const int ldn = last ? ldh : layers[i + 1].Fp;
         float* hnn = reinterpret_cast<float*>(ws + lay->hnorm[i + 1]);
@@ -132,7 +139,7 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
 
 extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
                                  const molkgnn_stack_layout_t* lay, void* workspace, void* bwd_scratch, const float* grad_h,
-                                 int32_t ldg, float* grad_x, float* grad_flat, void* stream) {
+                                 int32_t ldg, float* grad_x, float* grad_flat, const int32_t* tile_fwd, void* stream) {
     MK_REQUIRE(nl >= 1 && nl <= MOLKGNN_MAX_LAYERS && workspace && bwd_scratch && grad_h, "stack_bwd: bad arguments");
     MK_REQUIRE((reinterpret_cast<uintptr_t>(bwd_scratch) & 127) == 0 && (reinterpret_cast<uintptr_t>(grad_h) & 15) == 0 &&
                ldg >= layers[nl - 1].K, "stack_bwd: scratch must be 128-byte, grad_h 16-byte aligned, ldg >= K (ldg=%d)", ldg);
@@ -162,7 +169,9 @@ extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer
                                         lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef),
                                         reinterpret_cast<float*>(bs + lay->partials), gx, gx ? ly.Fp : 0,
                                         grad_flat ? &gr : nullptr, 7, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
-                                        reinterpret_cast<float*>(bs + lay->scratch), stream);
+                                        reinterpret_cast<float*>(bs + lay->scratch),
+                                        (lay->argmax_tile[i] >= 0 && tile_fwd && tile_fwd[i]) ? ws + lay->argmax_tile[i] : nullptr,
+                                        stream);
         if (rc) return rc;
         g = gx; ld = ly.Fp;
     }

@@ -195,7 +195,7 @@ def conv_forward(plan: BucketPlan, pack: LayerPack, x, xnorm, is_last, dense=Fal
     with _timed("conv_fwd"):
         check(_lib.lib().molkgnn_conv_fwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm),
                                           1 if is_last else 0, ptr(sc), 1 if dense else 0, ld, _i64x4(scoff),
-                                          ptr(argmax), ptr(free), ptr(argmax_in), ptr(counter), ptr(ximg),
+                                          ptr(argmax), ptr(free), ptr(argmax_in), ptr(counter), ptr(ximg), None,
                                           stream_ptr()))
     return sc, argmax, free
 
@@ -264,7 +264,7 @@ def conv_backward(plan: BucketPlan, pack: LayerPack, x, xnorm, grad, grad_mode, 
             check(L.molkgnn_conv_bwd(C.byref(plan.c), C.byref(pack.c), ptr(x), x.stride(0), ptr(xnorm), ptr(grad),
                                      grad.stride(0), grad_mode, ptr(argmax), _i64x4(scoff), ptr(coef), ptr(partials),
                                      ptr(gx), pack.Fp if need_gx else 0, C.byref(gc) if gc is not None else None, ph,
-                                     ptr(ximg), ptr(scratch), stream_ptr()))
+                                     ptr(ximg), ptr(scratch), None, stream_ptr()))
     return gx, grads
 
 
@@ -402,8 +402,10 @@ class MolGCNFn(torch.autograd.Function):
                     raise _lib.MolKGNNError("argmax_in has the wrong size")
                 keep.append(t)
                 forced[i] = t.data_ptr()
+        tile_fwd = (C.c_int32 * nl)()
         check(L.molkgnn_stack_fwd(C.byref(plan.c), stack.arr, nl, C.byref(lay), flags, ptr(xc), xc.stride(0), ptr(ws),
-                                  ptr(h), Kpl, forced, stream_ptr()))
+                                  ptr(h), Kpl, forced, tile_fwd, stream_ptr()))
+        ctx.tile_fwd = tile_fwd
         if aux is not None:
             for i in range(nl):
                 n = lay.sc_elems[i]
@@ -433,7 +435,7 @@ class MolGCNFn(torch.autograd.Function):
         Fp0 = stack.packs[0].Fp
         gx = torch.empty(plan.N, Fp0, dtype=torch.float32, device=dev) if ctx.need_gx else None
         check(L.molkgnn_stack_bwd(C.byref(plan.c), stack.arr, stack.nl, C.byref(lay), ptr(ws), ptr(bs), ptr(g), g.stride(0),
-                                  ptr(gx), ptr(gflat), stream_ptr()))
+                                  ptr(gx), ptr(gflat), ctx.tile_fwd, stream_ptr()))
         flat_all = stack.grad_views(lay, gflat) if need_gp else [None] * (stack.nl * 28)
         stack.last_grad_flat = gflat                # dp.GradBucket all-reduces this buffer in place
         return (gx[:, :ctx.F0] if gx is not None else None, None, None, None, None, *flat_all)
