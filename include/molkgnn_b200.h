@@ -143,6 +143,10 @@ int64_t molkgnn_packed_floats(int32_t d, int32_t L, int32_t Fp);
  * kernel side), evaluates the softmax mixing weights (kernels.py:402-412) and the support chirality signs
  * (kernels.py:338-341) for every permutation. */
 int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream);
+/* The same for nl layers in three launches (one per pack kernel, blockIdx.y = layer).  what: bit 0 = normalised rows,
+ * weights, signs; bit 1 = operand images of the bucket-order tensor-core forward; bit 2 = kernel-block images of the
+ * molecule-tile kernels.  molkgnn_param_pack(layer) == molkgnn_param_pack_layers(layer, 1, 7). */
+int molkgnn_param_pack_layers(const molkgnn_layer_t* layers, int32_t nl, int32_t what, void* stream);
 /* bytes of the fp16 (hi, lo) tensor-core operand images of the whole kernel set used by the tile kernels;
  * 0 if the layer is not eligible (too many kernels per degree for two 128-row blocks per role, or F > 240) */
 int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer);
@@ -151,6 +155,10 @@ int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer);
 int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                             const float* xnorm, void* ximg, void* stream);
+/* molkgnn_pad_norm + molkgnn_tile_ximg_build of the raw layer-0 input in one pass over x (node_attr_dim <= 64): x [N, ldx]
+ * with F valid columns, out [N, Fp] zero padded, norm [N] (bitwise what molkgnn_pad_norm writes), ximg as above. */
+int molkgnn_tile_ximg_build_raw(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                                float* out, float* norm, void* ximg, void* stream);
 
 /* ---- forward: KernelConv.calculate_total_score for the four buckets (kernels.py:353-425, 610-751) ---- */
 int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer);
@@ -175,6 +183,8 @@ int64_t molkgnn_tile_argmax_bytes(const molkgnn_plan_t* plan, const molkgnn_laye
  * else falls back to 1), 1 = bucket-order tcgen05 kernel (falls back to 0 for layers whose kernel set does not fit shared
  * memory), 0 = fp32 SIMT kernel.  Returns the previous setting (-1 = not yet chosen). */
 int molkgnn_set_fwd_path(int path);
+/* the forward kernel currently selected (0, 1 or 2; resolves the MOLKGNN_FWD environment override on first use) */
+int molkgnn_get_fwd_path(void);
 
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
 /* h[i, koff_d + k] = sum over in-edges (j -> i) in edge order of sc_{deg j}[pos j, k]; columns K..ldh-1 zeroed;

@@ -53,6 +53,7 @@ EXPORTS = {
     "molkgnn_tile_meta_bytes": (i64, []),
     "molkgnn_tile_ximg_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_tile_ximg_build": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp]),
+    "molkgnn_tile_ximg_build_raw": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp, vp]),
     "molkgnn_bucket_build": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
     "molkgnn_bucket_build_begin": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
     "molkgnn_bucket_build_finish": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp, i32, vp, vp]),
@@ -61,6 +62,7 @@ EXPORTS = {
     "molkgnn_pad_norm": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "molkgnn_packed_floats": (i64, [i32, i32, i32]),
     "molkgnn_param_pack": (C.c_int, [C.POINTER(Layer), vp]),
+    "molkgnn_param_pack_layers": (C.c_int, [C.POINTER(Layer), i32, i32, vp]),
     "molkgnn_tile_img_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd_smem_bytes": (i64, [C.POINTER(Layer)]),
     "molkgnn_conv_fwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, i32, vp, i32, i32, i64 * 4, vp, vp,
@@ -70,6 +72,7 @@ EXPORTS = {
     "molkgnn_conv_bwd_partial_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_conv_bwd_coef_floats": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_set_fwd_path": (C.c_int, [C.c_int]),
+    "molkgnn_get_fwd_path": (C.c_int, []),
     "molkgnn_tc_selftest": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "molkgnn_conv_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, i32, i32, vp, i64 * 4, vp, vp,
                                    vp, i32, C.POINTER(LayerGrads), i32, vp, vp, vp, vp]),

@@ -420,6 +420,17 @@ extern "C" int molkgnn_set_fwd_path(int path) {
     return old;
 }
 
+static void resolve_fwd_path() {
+    if (g_fwd_path < 0) {
+        const char* e = getenv("MOLKGNN_FWD");
+        g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)
+    }
+}
+extern "C" int molkgnn_get_fwd_path(void) {
+    resolve_fwd_path();
+    return g_fwd_path;
+}
+
 extern "C" int64_t molkgnn_conv_fwd_smem_bytes(const molkgnn_layer_t* layer) {
     FwdArgs a;
     int budget = device_max_smem_optin();
@@ -442,10 +453,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         MK_REQUIRE(s_budget > 0 && s_sms > 0, "conv_fwd: no CUDA device");
     }
     ProfScope prof("conv_fwd", st);
-    if (g_fwd_path < 0) {
-        const char* e = getenv("MOLKGNN_FWD");
-        g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)
-    }
+    resolve_fwd_path();
     if (g_fwd_path == 2) {
         const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                             argmax_free, argmax_in, argmax_tile, counter, st);

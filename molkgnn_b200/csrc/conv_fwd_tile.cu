@@ -34,17 +34,62 @@ constexpr int TF_WARPS = TF_THREADS / 32;
 // ---- normalised fp16 images of the activations in tile order --------------------------------------------------------
 struct XImgArgs {
     const float* x; const float* xnorm; int ldx;
+    // fused pad + norm (layer 0): x is the raw input with F valid columns and any row stride; the kernel also writes the
+    // zero-padded copy out[N, Fp] and the row norms (what k_pad_norm would have produced) -- x is read once
+    int F; float* out; float* norm_out;
     int Fp, Fk;
     const int* tile_start;
     unsigned char* ximg;
     int x_one;
 };
 
+// fused variant for narrow inputs (Fp <= 64): a quarter-warp (8 lanes x 8 columns) owns a node row, computes the norm with
+// the summation order of k_pad_norm (lane-strided partial sums, butterfly) -- bitwise the same norms -- and emits the padded
+// row, the norm and the (hi, lo) images
+__device__ __forceinline__ void k_x_images_fused(const XImgArgs& a, int tile, int t0, int nn) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char* Xhi = a.ximg + (size_t)tile * 2 * a.x_one;
+    unsigned char* Xlo = Xhi + a.x_one;
+    const int rend = min(TNODES, (nn + 15) & ~15);
+    for (int r = warp; r < rend; r += 16) {
+        float v[2] = {0.f, 0.f};                  // columns lane, lane + 32
+        const bool ok = r < nn;
+        if (ok) {
+            const float* xr = a.x + (size_t)(t0 + r) * a.ldx;
+            if (lane < a.F) v[0] = xr[lane];
+            if (lane + 32 < a.F) v[1] = xr[lane + 32];
+        }
+        float ss = v[0] * v[0];
+        if (lane + 32 < a.Fp) ss += v[1] * v[1];
+        ss = warp_sum(ss);
+        const float nrm = sqrtf(ss);
+        const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
+        if (ok) {
+            if (lane < a.Fp) a.out[(size_t)(t0 + r) * a.Fp + lane] = v[0];
+            if (lane + 32 < a.Fp) a.out[(size_t)(t0 + r) * a.Fp + lane + 32] = v[1];
+            if (lane == 0) a.norm_out[t0 + r] = nrm;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int col = lane + 32 * h;
+            if (col < a.Fk) {
+                const float xv = v[h] * rinv;
+                const __half hi = __float2half_rn(xv);
+                const __half lo = __float2half_rn(xv - __half2float(hi));
+                const uint32_t off = tc::il_off(r, col, a.Fk);
+                *reinterpret_cast<__half*>(Xhi + off) = hi;
+                *reinterpret_cast<__half*>(Xlo + off) = lo;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(512) k_x_images(const XImgArgs a) {
     const int tile = blockIdx.x, tid = threadIdx.x;
     const int t0 = a.tile_start[tile], nn = a.tile_start[tile + 1] - t0;
     const int r = tid & (TNODES - 1), cg = tid >> 7;
     const bool ok = r < nn;
+    if (a.out) { k_x_images_fused(a, tile, t0, nn); return; }
     float rinv = 0.f;
     const float* xr = a.x;
     if (ok) {
@@ -459,9 +504,10 @@ static bool tile_plan_ok(const molkgnn_plan_t* plan) {
 }
 
 int launch_x_images(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
-                    const float* xnorm, void* ximg, cudaStream_t st) {
+                    const float* xnorm, void* ximg, float* pad_out, float* norm_out, cudaStream_t st) {
     XImgArgs a;
     a.x = x; a.xnorm = xnorm; a.ldx = ldx;
+    a.F = layer->F; a.out = pad_out; a.norm_out = norm_out;
     a.Fp = layer->Fp; a.Fk = tile_fk(layer->Fp);
     a.tile_start = plan->tile_start;
     a.ximg = reinterpret_cast<unsigned char*>(ximg);
@@ -544,7 +590,16 @@ extern "C" int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "tile_ximg_build: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0,
                "tile_ximg_build: x must be 16-byte and ximg 128-byte aligned");
-    return launch_x_images(plan, layer, x, ldx, xnorm, ximg, (cudaStream_t)stream_);
+    return launch_x_images(plan, layer, x, ldx, xnorm, ximg, nullptr, nullptr, (cudaStream_t)stream_);
+}
+
+// pad + norm + images of the raw layer-0 input in one pass (Fp <= 64): out [N, Fp] zero padded, norm [N], ximg as above
+extern "C" int molkgnn_tile_ximg_build_raw(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x,
+                                           int32_t ldx, float* out, float* norm, void* ximg, void* stream_) {
+    MK_REQUIRE(tile_plan_ok(plan) && tile_layer_ok(layer) && layer->Fp <= 64,
+               "tile_ximg_build_raw: needs a tiled plan, an eligible layer and Fp <= 64");
+    MK_REQUIRE(out && norm && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0, "tile_ximg_build_raw: bad arguments");
+    return launch_x_images(plan, layer, x, ldx, nullptr, ximg, out, norm, (cudaStream_t)stream_);
 }
 
 #ifdef MK_PHASE_CLOCKS

@@ -4,6 +4,7 @@
 //                     every permuted support (kernels.py:338-341) -> packed, smem-ready layout
 //   k_param_finalize  deterministic reduction of the per-CTA partial sums written by the backward kernel, chain
 //                     rule through the normalisation and the softmax weights, results in the reference's layouts
+#include <algorithm>
 #include <stdarg.h>
 #include <string.h>
 #include "common.cuh"
@@ -112,9 +113,15 @@ __device__ void sup_signs(const float* __restrict__ ps, int L, int8_t* out) {
     }
 }
 
-__global__ void __launch_bounds__(128) k_param_pack(PackArgs a) {
+// the pack kernels take up to PACK_NL layers per launch (blockIdx.y = layer): a step packs its whole stack in three launches
+constexpr int PACK_NL = 4;
+struct PackArgsN { PackArgs a[PACK_NL]; };
+
+__global__ void __launch_bounds__(128) k_param_pack(const __grid_constant__ PackArgsN an) {
     __shared__ float red[4];
+    const PackArgs& a = an.a[blockIdx.y];
     int b = blockIdx.x;
+    if (b >= a.row_begin[4] + 4) return;
     if (b >= a.row_begin[4]) {  // tail blocks: weights + support signs of degree d
         int d = b - a.row_begin[4] + 1;
         int L = a.L[d - 1];
@@ -174,7 +181,10 @@ struct PackTcArgs {
     float* packed[4];
 };
 
-__global__ void __launch_bounds__(256) k_param_pack_tc(PackTcArgs a) {
+struct PackTcArgsN { PackTcArgs a[PACK_NL]; };
+
+__global__ void __launch_bounds__(256) k_param_pack_tc(const __grid_constant__ PackTcArgsN an) {
+    const PackTcArgs& a = an.a[blockIdx.y];
     const int it = blockIdx.x * 256 + threadIdx.x;
     if (it >= a.item_begin[4]) return;
     int d = 1;
@@ -221,7 +231,11 @@ struct PackTileArgs {
     unsigned char* img;
 };
 
-__global__ void __launch_bounds__(256) k_param_pack_tile(const __grid_constant__ PackTileArgs a) {
+struct PackTileArgsN { PackTileArgs a[PACK_NL]; };
+
+__global__ void __launch_bounds__(256) k_param_pack_tile(const __grid_constant__ PackTileArgsN an) {
+    const PackTileArgs& a = an.a[blockIdx.y];
+    if (!a.img) return;
     const int nch = a.Fk / 8;
     const int it = blockIdx.x * 256 + threadIdx.x;
     if (it >= a.tb.nb * 128 * nch) return;
@@ -479,60 +493,85 @@ extern "C" int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer) {
     return (int64_t)tb.nb * 2 * tile_img_one(tile_fk(layer->Fp));
 }
 
-extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
-    PackArgs a;
-    MK_REQUIRE(layer->Fp % 4 == 0 && layer->Fp >= layer->F, "param_pack: Fp=%d must be a multiple of 4 >= F=%d",
-               layer->Fp, layer->F);
-    MK_REQUIRE(layer->Fe >= 1 && layer->Fe <= EP, "param_pack: edge_attr_dim %d not in 1..%d", layer->Fe, EP);
-    a.F = layer->F; a.Fp = layer->Fp; a.Fe = layer->Fe;
-    int rb = 0;
-    for (int d = 0; d < 4; ++d) {
-        a.L[d] = layer->L[d];
-        a.row_begin[d] = rb;
-        rb += (2 * (d + 1) + 1) * layer->L[d];
-        a.x_center[d] = layer->x_center[d];
-        a.x_support[d] = layer->x_support[d];
-        a.edge_attr_support[d] = layer->edge_attr_support[d];
-        a.p_support[d] = layer->p_support[d];
-        a.w_support[d] = layer->w_support[d];
-        a.w_center[d] = layer->w_center[d];
-        a.w_edge[d] = layer->w_edge[d];
-        a.packed[d] = layer->packed[d];
-    }
-    a.row_begin[4] = rb;
-    ProfScope prof("param_pack", (cudaStream_t)stream_);
-    k_param_pack<<<rb + 4, 128, 0, (cudaStream_t)stream_>>>(a);
-    count_launches(1);
-    MK_CHECK_CUDA(cudaGetLastError());
-    PackTcArgs t;
-    t.Fp = layer->Fp;
-    int ib = 0;
-    for (int d = 0; d < 4; ++d) {
-        t.L[d] = layer->L[d];
-        t.packed[d] = layer->packed[d];
-        t.item_begin[d] = ib;
-        if (layer->L[d] > 0) {
-            const PackedLayout pl(d + 1, layer->L[d], layer->Fp);
-            ib += (pl.KSpad + pl.Lpad) * (pl.Fk / 8);
+// what: bit 0 = normalised rows / weights / signs, bit 1 = bucket-order tensor-core images, bit 2 = tile images
+extern "C" int molkgnn_param_pack_layers(const molkgnn_layer_t* layers, int32_t nl, int32_t what, void* stream_) {
+    cudaStream_t st = (cudaStream_t)stream_;
+    MK_REQUIRE(nl >= 1 && layers, "param_pack: no layers");
+    for (int l0 = 0; l0 < nl; l0 += PACK_NL) {
+        const int n = std::min(PACK_NL, nl - l0);
+        PackArgsN pa;
+        PackTcArgsN pt;
+        PackTileArgsN pi;
+        memset(&pa, 0, sizeof(pa)); memset(&pt, 0, sizeof(pt)); memset(&pi, 0, sizeof(pi));
+        int rb_max = 0, ib_max = 0, items_max = 0;
+        for (int i = 0; i < n; ++i) {
+            const molkgnn_layer_t* layer = layers + l0 + i;
+            MK_REQUIRE(layer->Fp % 4 == 0 && layer->Fp >= layer->F, "param_pack: Fp=%d must be a multiple of 4 >= F=%d",
+                       layer->Fp, layer->F);
+            MK_REQUIRE(layer->Fe >= 1 && layer->Fe <= EP, "param_pack: edge_attr_dim %d not in 1..%d", layer->Fe, EP);
+            PackArgs& a = pa.a[i];
+            a.F = layer->F; a.Fp = layer->Fp; a.Fe = layer->Fe;
+            int rb = 0;
+            for (int d = 0; d < 4; ++d) {
+                a.L[d] = layer->L[d];
+                a.row_begin[d] = rb;
+                rb += (2 * (d + 1) + 1) * layer->L[d];
+                a.x_center[d] = layer->x_center[d];
+                a.x_support[d] = layer->x_support[d];
+                a.edge_attr_support[d] = layer->edge_attr_support[d];
+                a.p_support[d] = layer->p_support[d];
+                a.w_support[d] = layer->w_support[d];
+                a.w_center[d] = layer->w_center[d];
+                a.w_edge[d] = layer->w_edge[d];
+                a.packed[d] = layer->packed[d];
+            }
+            a.row_begin[4] = rb;
+            rb_max = std::max(rb_max, rb + 4);
+            PackTcArgs& t = pt.a[i];
+            t.Fp = layer->Fp;
+            int ib = 0;
+            for (int d = 0; d < 4; ++d) {
+                t.L[d] = layer->L[d];
+                t.packed[d] = layer->packed[d];
+                t.item_begin[d] = ib;
+                if (layer->L[d] > 0) {
+                    const PackedLayout pl(d + 1, layer->L[d], layer->Fp);
+                    ib += (pl.KSpad + pl.Lpad) * (pl.Fk / 8);
+                }
+            }
+            t.item_begin[4] = ib;
+            ib_max = std::max(ib_max, ib);
+            PackTileArgs& ta = pi.a[i];
+            ta.img = nullptr;
+            if (layer->tile_img && tile_layer_ok(layer)) {
+                MK_REQUIRE((reinterpret_cast<uintptr_t>(layer->tile_img) & 127) == 0, "param_pack: tile_img must be 128-byte aligned");
+                ta.Fp = layer->Fp; ta.Fk = tile_fk(layer->Fp);
+                for (int d = 0; d < 4; ++d) { ta.L[d] = layer->L[d]; ta.packed[d] = layer->packed[d]; }
+                ta.tb.build(layer->L);
+                ta.img = reinterpret_cast<unsigned char*>(layer->tile_img);
+                items_max = std::max(items_max, ta.tb.nb * 128 * (ta.Fk / 8));
+            }
+        }
+        ProfScope prof("param_pack", st);
+        if (what & 1) {
+            k_param_pack<<<dim3(rb_max, n), 128, 0, st>>>(pa);
+            count_launches(1);
+            MK_CHECK_CUDA(cudaGetLastError());
+        }
+        if ((what & 2) && ib_max > 0) {
+            k_param_pack_tc<<<dim3((ib_max + 255) / 256, n), 256, 0, st>>>(pt);
+            count_launches(1);
+            MK_CHECK_CUDA(cudaGetLastError());
+        }
+        if ((what & 4) && items_max > 0) {
+            k_param_pack_tile<<<dim3((items_max + 255) / 256, n), 256, 0, st>>>(pi);
+            count_launches(1);
+            MK_CHECK_CUDA(cudaGetLastError());
         }
     }
-    t.item_begin[4] = ib;
-    if (ib > 0) {
-        k_param_pack_tc<<<(ib + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(t);
-        count_launches(1);
-        MK_CHECK_CUDA(cudaGetLastError());
-    }
-    if (layer->tile_img && tile_layer_ok(layer)) {
-        MK_REQUIRE((reinterpret_cast<uintptr_t>(layer->tile_img) & 127) == 0, "param_pack: tile_img must be 128-byte aligned");
-        PackTileArgs ta;
-        ta.Fp = layer->Fp; ta.Fk = tile_fk(layer->Fp);
-        for (int d = 0; d < 4; ++d) { ta.L[d] = layer->L[d]; ta.packed[d] = layer->packed[d]; }
-        ta.tb.build(layer->L);
-        ta.img = reinterpret_cast<unsigned char*>(layer->tile_img);
-        const int items = ta.tb.nb * 128 * (ta.Fk / 8);
-        k_param_pack_tile<<<(items + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(ta);
-        count_launches(1);
-        MK_CHECK_CUDA(cudaGetLastError());
-    }
     return 0;
+}
+
+extern "C" int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream_) {
+    return molkgnn_param_pack_layers(layer, 1, 7, stream_);
 }

@@ -98,14 +98,17 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
     const int N = plan->N;
     int rc;
-    if (!(flags & MOLKGNN_STACK_PACKED))
-        for (int i = 0; i < nl; ++i)
-            if ((rc = molkgnn_param_pack(&layers[i], stream))) return rc;
+    if (!(flags & MOLKGNN_STACK_PACKED) && (rc = molkgnn_param_pack_layers(layers, nl, 7, stream))) return rc;
     float* h = reinterpret_cast<float*>(ws + lay->h[0]);
     float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);
-    if ((rc = molkgnn_pad_norm(x, N, layers[0].F, ldx, h, layers[0].Fp, hn, stream))) return rc;
-    if (lay->ximg[0] >= 0 && (rc = molkgnn_tile_ximg_build(plan, &layers[0], h, layers[0].Fp, hn, ws + lay->ximg[0], stream)))
-        return rc;
+    if (lay->ximg[0] >= 0 && layers[0].Fp <= 64) {      // one pass over x: padded copy, norms, tensor-core images
+        if ((rc = molkgnn_tile_ximg_build_raw(plan, &layers[0], x, ldx, h, hn, ws + lay->ximg[0], stream))) return rc;
+    } else {
+        if ((rc = molkgnn_pad_norm(x, N, layers[0].F, ldx, h, layers[0].Fp, hn, stream))) return rc;
+        if (lay->ximg[0] >= 0 &&
+            (rc = molkgnn_tile_ximg_build(plan, &layers[0], h, layers[0].Fp, hn, ws + lay->ximg[0], stream)))
+            return rc;
+    }
     for (int i = 0; i < nl; ++i) {
         const molkgnn_layer_t& ly = layers[i];
         const bool last = i == nl - 1;

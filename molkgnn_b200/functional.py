@@ -328,6 +328,7 @@ class StackPack(object):
         self.key = self.make_key(layer_params, F0, Fe, device)
         # flat parameter-gradient views, in flat_params() order; offsets come from the native layout (plan independent)
         self.last_grad_flat = None
+        self.packed_all = False
 
     @staticmethod
     def make_key(layer_params, F0, Fe, device):
@@ -342,9 +343,10 @@ class StackPack(object):
 
     def prepack(self):
         """Queues the parameter packing of every layer (normalised kernel rows, tensor-core images) on the current stream."""
-        L = _lib.lib()
-        for i in range(self.nl):
-            check(L.molkgnn_param_pack(C.byref(self.arr[i]), stream_ptr()))
+        # layers that run the molecule-tile kernels do not need the bucket-order tensor-core images (what = 1 | 4); should
+        # the plan turn out untiled, MolGCNFn.forward lets the native forward pack everything again
+        self.packed_all = any(pk.tile_img is None for pk in self.packs) or _lib.lib().molkgnn_get_fwd_path() != 2
+        check(_lib.lib().molkgnn_param_pack_layers(self.arr, self.nl, 7 if self.packed_all else 5, stream_ptr()))
 
     def layout(self, plan: BucketPlan, flags):
         lay = _lib.StackLayout()
@@ -380,8 +382,10 @@ class MolGCNFn(torch.autograd.Function):
         L = _lib.lib()
         dev = x.device
         nl = stack.nl
-        flags = ((FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0) | FLAG_PACKED
         plan.finish()                                # bucket sizes to the host (the packing queued by the caller runs meanwhile)
+        flags = (FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0
+        if stack.packed_all or plan.n_tiles > 0:
+            flags |= FLAG_PACKED
         lay = stack.layout(plan, flags)
         xc = x.detach()
         if xc.dtype != torch.float32:
