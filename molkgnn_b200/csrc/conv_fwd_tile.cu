@@ -169,33 +169,37 @@ __device__ __forceinline__ void tf_copy16(unsigned char* dst, const unsigned cha
 }
 
 // thread 0: metadata record, bond rows and node images of `tile` -> buffer, all completing on `bar`
-__device__ __forceinline__ void tf_issue_copy(const FwdTileArgs& a, unsigned char* smem, TileBuf* buf, int tile, uint64_t* bar) {
+__device__ __forceinline__ void tf_issue_copy(const FwdTileArgs& a, unsigned char* smem, TileBuf* buf, int xb, int tile,
+                                              int e0, int ne, uint64_t* bar) {
     const TileMetaG* g = a.meta + tile;
-    const int e0 = g->e0, ne = g->ne;          // two scalar loads ahead of the copies (L2 hits: the plan is small)
     const uint32_t eb = (uint32_t)ne * EP * 4u;
     mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + eb + 2u * (uint32_t)a.x_one);
     bulk_g2s(&buf->m, g, (uint32_t)sizeof(TileMetaG), bar);
     if (eb) bulk_g2s(&buf->ehat[0][0], a.ehat_node + (size_t)e0 * EP, eb, bar);
-    bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
+    bulk_g2s(smem + a.sm_x + (size_t)xb * 2 * a.x_one, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
 }
 
 // thread 0: (Fk/16) K steps x 3 UMMAs into accumulator `set`
+// The kernel block's images (the A operand) live in TENSOR MEMORY (TF_A_HI / TF_A_LO, written once per block by the
+// consumer warps): that frees 57 KB of shared memory for a second node-image buffer, so the copy of tile t+1 overlaps the
+// MMAs and the epilogue of tile t instead of waiting for the single buffer.
+constexpr uint32_t TF_A_HI = 256u, TF_A_LO = 320u;      // TMEM columns: accumulators 0..255, A hi 256.., A lo 320.. (Fk/2 <= 64 each)
+
 __device__ __forceinline__ void tf_issue_mma(const FwdTileArgs& a, unsigned char* smem, int nn, uint32_t tmem, int set,
                                              uint64_t* bar) {
     const uint32_t sbo = (uint32_t)(a.Fk >> 3) * 128u;
-    const uint32_t ihi = tc::smem_u32(smem + a.sm_img), ilo = ihi + (uint32_t)a.img_one;
-    const uint32_t xhi = tc::smem_u32(smem + a.sm_x), xlo = xhi + (uint32_t)a.x_one;
+    const uint32_t xhi = tc::smem_u32(smem + a.sm_x + (size_t)set * 2 * a.x_one), xlo = xhi + (uint32_t)a.x_one;
     const int N = max(16, (nn + 15) & ~15);
     const uint32_t idesc = tc::idesc_f16(128, N, 0, 0);
     const uint32_t d = tmem + (uint32_t)(set * TNODES);
     const int nks = a.Fk >> 4;
     for (int ks = 0; ks < nks; ++ks) {
         const uint32_t o = (uint32_t)ks * 256u;
-        const uint64_t dAh = tc::smem_desc(ihi + o, 128u, sbo), dAl = tc::smem_desc(ilo + o, 128u, sbo);
+        const uint32_t aH = tmem + TF_A_HI + (uint32_t)ks * 8u, aL = tmem + TF_A_LO + (uint32_t)ks * 8u;
         const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
-        tc::umma_f16(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
-        tc::umma_f16(d, dAl, dBh, idesc, 1u);
-        tc::umma_f16(d, dAh, dBl, idesc, 1u);
+        tc::umma_f16_ts(d, aH, dBh, idesc, ks > 0 ? 1u : 0u);
+        tc::umma_f16_ts(d, aL, dBh, idesc, 1u);
+        tc::umma_f16_ts(d, aH, dBl, idesc, 1u);
     }
     tc::umma_commit(bar);
 }
@@ -389,7 +393,7 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
     const int tid = threadIdx.x, warp = tid >> 5;
     const bool producer = warp == TF_WARPS;
     MK_PH_DECL(tid == 0 || tid == TF_THREADS)
-    if (warp == 0) tc::tmem_alloc(&tslot, 256);
+    if (warp == 0) tc::tmem_alloc(&tslot, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -412,7 +416,25 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
         const int nseg = a.tb.nseg[blk];
         bool has4 = false;
         if (!producer) {
-            tf_copy16(smem + a.sm_img, a.img + (size_t)blk * 2 * a.img_one, 2 * (int64_t)a.img_one);
+            // kernel-block images -> tensor memory: thread = kernel row (TMEM lane), 4 warps per lane quadrant share the
+            // Fk / 2 packed columns; the global image row is 16 B per 8-column chunk in the interleaved layout
+            {
+                const int row = (warp & 3) * 32 + (tid & 31);
+                const unsigned char* gh = a.img + (size_t)blk * 2 * a.img_one;
+                const unsigned char* gl = gh + a.img_one;
+                const int c_end = min(a.Fk >> 1, ((warp >> 2) + 1) * 16);
+                for (int c0 = (warp >> 2) * 16; c0 < c_end; c0 += 8) {       // 8 TMEM columns = 16 fp16 = two 16-byte chunks
+                    const uint32_t o0 = tc::il_off(row, 2 * c0, a.Fk), o1 = tc::il_off(row, 2 * c0 + 8, a.Fk);
+                    uint4 h0 = __ldg(reinterpret_cast<const uint4*>(gh + o0)), h1 = __ldg(reinterpret_cast<const uint4*>(gh + o1));
+                    uint4 l0 = __ldg(reinterpret_cast<const uint4*>(gl + o0)), l1 = __ldg(reinterpret_cast<const uint4*>(gl + o1));
+                    const uint32_t vh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+                    const uint32_t vl[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+                    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+                    tc::tmem_st8(lane_addr + TF_A_HI + (uint32_t)c0, vh);
+                    tc::tmem_st8(lane_addr + TF_A_LO + (uint32_t)c0, vl);
+                }
+                tc::tmem_st_wait();
+            }
             int es_off = 0;
             for (int si = 0; si < nseg; ++si) {
                 const TileSeg sg = a.tb.seg[blk][si];
@@ -436,31 +458,58 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
                 }
                 es_off += sg.d * 2 * sg.nk;
             }
-            tc::fence_async_smem();            // images were written through the generic proxy, the MMAs read them
         }
+        tc::fence_before_sync();               // the images were written with tcgen05.st, the producer's MMAs read them
         __syncthreads();
+        tc::fence_after_sync();
         MK_PH(0);                                                          // block set-up (images, tables)
 
         if (producer) {
             if ((tid & 31) == 0) {
-                for (int seq = 0;; ++seq) {
-                    const int b = seq & 1;
-                    const uint32_t par = (uint32_t)(seq >> 1) & 1u;
-                    const int tile = atomicAdd(a.counter + blk, 1);
-                    tc::mbar_wait(&bar_bfree[b], par ^ 1u);            // metadata buffer released by the consumers
-                    MK_PH(1);
-                    s_tile[b] = tile < a.n_tiles ? tile : -1;
-                    if (tile >= a.n_tiles) { mbar_arrive(&bar_cp[b]); break; }
-                    if (seq > 0) tc::mbar_wait(&bar_mma[b ^ 1], (uint32_t)((seq - 1) >> 1) & 1u);   // node-image buffer free
-                    MK_PH(2);
-                    tf_issue_copy(a, smem, &bufs[b], tile, &bar_cp[b]);
-                    tc::mbar_wait(&bar_cp[b], par);
-                    MK_PH(3);
-                    tc::mbar_wait(&bar_tfree[b], par ^ 1u);            // accumulator drained by the consumers
-                    tc::fence_after_sync();
-                    MK_PH(4);
-                    tf_issue_mma(a, smem, bufs[b].m.nn, tmem, b, &bar_mma[b]);
-                    MK_PH(5);
+                // Event loop over two independent duties, each for the oldest tile that still needs it:
+                //   copy  (tile seq_c): needs buffer set seq_c & 1 released by the consumers (tile seq_c - 2 finished)
+                //   MMA   (tile seq_m): needs its copies landed and accumulator seq_m & 1 drained (dump of seq_m - 2 done)
+                // so the copy of tile t+1 is in flight while the MMAs of tile t are issued and run.
+                int seq_c = 0, seq_m = 0;
+                bool last_copied = false;            // the end marker went out: no more tiles in this block's queue
+                // the next tile of the queue and its bond-slot range are fetched one tile ahead: the atomic and the header
+                // load (two L2 round trips) stay off the path between "buffer released" and "copy issued"
+                int nxt = atomicAdd(a.counter + blk, 1);
+                int2 nxt_e = nxt < a.n_tiles ? *reinterpret_cast<const int2*>(&a.meta[nxt].e0) : make_int2(0, 0);
+                uint32_t idle = 0;                   // bounded: a lost completion traps instead of hanging the device
+                while (true) {
+                    if (++idle > (1u << 26)) __trap();
+                    if (!last_copied && seq_c - seq_m < 2) {
+                        const int b = seq_c & 1;
+                        if (tc::mbar_try_wait(&bar_bfree[b], ((uint32_t)(seq_c >> 1) & 1u) ^ 1u)) {
+                            const int tile = nxt;
+                            s_tile[b] = tile < a.n_tiles ? tile : -1;
+                            if (tile >= a.n_tiles) { mbar_arrive(&bar_cp[b]); last_copied = true; }
+                            else {
+                                tf_issue_copy(a, smem, &bufs[b], b, tile, nxt_e.x, nxt_e.y, &bar_cp[b]);
+                                nxt = atomicAdd(a.counter + blk, 1);
+                                nxt_e = nxt < a.n_tiles ? *reinterpret_cast<const int2*>(&a.meta[nxt].e0) : make_int2(0, 0);
+                            }
+                            ++seq_c;
+                            idle = 0;
+                            MK_PH(2);
+                        }
+                    }
+                    const int pending = seq_c - seq_m - (last_copied ? 1 : 0);     // copied tiles whose MMAs are not issued yet
+                    if (pending > 0) {
+                        const int b = seq_m & 1;
+                        const uint32_t par = (uint32_t)(seq_m >> 1) & 1u;
+                        if (tc::mbar_try_wait(&bar_cp[b], par) && tc::mbar_try_wait(&bar_tfree[b], par ^ 1u)) {
+                            tc::fence_after_sync();
+                            MK_PH(4);
+                            tf_issue_mma(a, smem, bufs[b].m.nn, tmem, b, &bar_mma[b]);
+                            ++seq_m;
+                            idle = 0;
+                            MK_PH(5);
+                        }
+                    } else if (last_copied) {
+                        break;
+                    }
                 }
             }
         } else {
@@ -495,7 +544,7 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
 #ifdef MK_PHASE_CLOCKS
     MK_PH_FLUSH(g_ph_fwd + (tid == 0 ? 0 : 16));
 #endif
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
@@ -553,8 +602,8 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.amT = argmax_tile; a.stride_am = tile_argmax_stride(plan, layer);
     a.counter = counter;
     int64_t off = 0;
-    a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
-    a.sm_x = (int)off; off += 2 * (int64_t)a.x_one;
+    a.sm_img = 0;                                  // the kernel-block images live in tensor memory
+    a.sm_x = (int)off; off += 2 * 2 * (int64_t)a.x_one;   // two node-image buffers
     a.sm_dump = (int)off; off += (int64_t)TNODES * 128 * 4;
     a.sm_buf = (int)off; off += 2 * (int64_t)sizeof(TileBuf);
     a.sm_es = (int)off; off += 128 * 32;        // <= 128 support rows x 8 floats per block

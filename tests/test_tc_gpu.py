@@ -18,7 +18,7 @@ def run(N, K, a_mn, b_mn, swap=0, seed=0):
     A = (torch.randn(128, K, generator=g) * 0.5).half()
     B = (torch.randn(N, K, generator=g) * 0.5).half()
     ref = A.double() @ B.double().T
-    Ad = (A.T if a_mn else A).contiguous().to(dev)
+    Ad = (A.T if a_mn == 1 else A).contiguous().to(dev)
     Bd = (B.T if b_mn else B).contiguous().to(dev)
     D = torch.full((128, N), float("nan"), device=dev)
     _lib.check(_lib.lib().molkgnn_tc_selftest(_lib.ptr(Ad), _lib.ptr(Bd), _lib.ptr(D), N, K, a_mn, b_mn, swap,
@@ -35,3 +35,11 @@ def test_umma_known_answer(N, K, a_mn, b_mn):
     with open("gpurun_out/tc_selftest.jsonl", "a") as f:
         f.write(json.dumps(dict(N=N, K=K, a_mn=a_mn, b_mn=b_mn, err=err, mag=mag)) + "\n")
     assert err < 1e-3 * max(mag, 1.0), f"UMMA mismatch: max err {err} (|ref| max {mag})"
+
+
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("N,K", [(16, 16), (128, 112), (112, 128), (256, 64)])
+def test_umma_a_operand_in_tensor_memory(N, K, b_mn):
+    """A operand read from TMEM (a_mn = 2: lane = row, fp16 pairs packed per 32-bit column)."""
+    err, mag = run(N, K, 2, b_mn)
+    assert err < 1e-3 * max(mag, 1.0), f"UMMA (A in TMEM) mismatch: max err {err} (|ref| max {mag})"
