@@ -249,6 +249,8 @@ typedef struct molkgnn_stack_layout {
     /* float offsets into the flat gradient buffer, per layer and degree (d-1); g_w = 3 floats: support, centre, edge */
     int64_t g_x_center[MOLKGNN_MAX_LAYERS][4], g_x_support[MOLKGNN_MAX_LAYERS][4],
             g_edge_attr_support[MOLKGNN_MAX_LAYERS][4], g_w[MOLKGNN_MAX_LAYERS][4];
+    int64_t partials_alt;                       /* second partial-copy buffer (backward scratch): layers alternate, so that
+                                                   the parameter finalisation of layer i runs beside layer i-1's kernels */
 } molkgnn_stack_layout_t;
 
 /* Sizes and offsets for a built plan (plan->n / n_tiles valid) and nl layers (layers[i].F must chain: F_{i+1} = K_i). */

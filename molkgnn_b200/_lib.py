@@ -41,7 +41,8 @@ class StackLayout(C.Structure):
                 ("counter", i64), ("sc_elems", i64 * MAX_LAYERS), ("scoff", (i64 * 4) * MAX_LAYERS),
                 ("coef", i64), ("partials", i64), ("scratch", i64), ("gx", i64 * 2),
                 ("g_x_center", (i64 * 4) * MAX_LAYERS), ("g_x_support", (i64 * 4) * MAX_LAYERS),
-                ("g_edge_attr_support", (i64 * 4) * MAX_LAYERS), ("g_w", (i64 * 4) * MAX_LAYERS)]
+                ("g_edge_attr_support", (i64 * 4) * MAX_LAYERS), ("g_w", (i64 * 4) * MAX_LAYERS),
+                ("partials_alt", i64)]
 
 
 EXPORTS = {

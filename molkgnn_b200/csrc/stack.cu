@@ -4,6 +4,7 @@
 // conv_bwd.cu, params.cu) back to back, so that a training step costs three host calls (bucket pass, forward, backward)
 // instead of ~45 calls and ~60 allocations driven from Python.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include "common.cuh"
 #include "tile.cuh"
@@ -66,6 +67,7 @@ extern "C" int molkgnn_stack_layout(const molkgnn_plan_t* plan, const molkgnn_la
     }
     out->coef = take(coef_max * 4);
     out->partials = take(part_max * 4);
+    out->partials_alt = take(part_max * 4);
     out->scratch = take(scr_max * 4);
     out->gx[0] = take(gx_max * 4);
     out->gx[1] = take(gx_max * 4);
@@ -140,6 +142,27 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     return 0;
 }
 
+// Side stream of the parameter finalisation: k_param_finalize / k_theta of layer i only read layer i's partial copies, so
+// they run beside the coefficient pre-pass and the tile kernel of layer i-1 (whose CTAs leave registers and shared memory
+// for the small finalize CTAs) instead of between the layers.  Partial-copy buffers alternate between layers.
+namespace {
+struct FinSide { cudaStream_t st; cudaEvent_t ready[2], done[2]; bool ok; };
+FinSide* fin_side() {
+    static FinSide s_side[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    FinSide& s = s_side[dev];
+    if (!s.ok) {
+        if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 2; ++i)
+            if (cudaEventCreateWithFlags(&s.ready[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&s.done[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        s.ok = true;
+    }
+    return &s;
+}
+}  // namespace
+
 extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int32_t nl,
                                  const molkgnn_stack_layout_t* lay, void* workspace, void* bwd_scratch, const float* grad_h,
                                  int32_t ldg, float* grad_x, float* grad_flat, const int32_t* tile_fwd, void* stream) {
@@ -150,6 +173,12 @@ extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer
     unsigned char* bs = reinterpret_cast<unsigned char*>(bwd_scratch);
     const float* g = grad_h;
     int ld = ldg;
+    cudaStream_t main_st = (cudaStream_t)stream;
+    static int s_use_side = -1;
+    if (s_use_side < 0) { const char* e = getenv("MOLKGNN_FIN_SIDE"); s_use_side = (e && e[0] == '0') ? 0 : 1; }
+    FinSide* side = (grad_flat && s_use_side) ? fin_side() : nullptr;
+    MK_REQUIRE(!grad_flat || !s_use_side || side, "stack_bwd: cannot create the side stream");
+    bool used[2] = {false, false};
     for (int i = nl - 1; i >= 0; --i) {
         const molkgnn_layer_t& ly = layers[i];
         float* gx = i == 0 ? grad_x : reinterpret_cast<float*>(bs + lay->gx[i & 1]);
@@ -167,16 +196,40 @@ extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer
             }
         }
         if (!gx && !grad_flat) break;          // nothing below this layer needs a gradient
-        const int rc = molkgnn_conv_bwd(plan, &ly, reinterpret_cast<const float*>(ws + lay->h[i]), ly.Fp,
-                                        reinterpret_cast<const float*>(ws + lay->hnorm[i]), g, ld, 1, ws + lay->argmax[i],
-                                        lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef),
-                                        reinterpret_cast<float*>(bs + lay->partials), gx, gx ? ly.Fp : 0,
-                                        grad_flat ? &gr : nullptr, 7, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
-                                        reinterpret_cast<float*>(bs + lay->scratch),
-                                        (lay->argmax_tile[i] >= 0 && tile_fwd && tile_fwd[i]) ? ws + lay->argmax_tile[i] : nullptr,
-                                        stream);
+        const int pb = i & 1;
+        float* partials = reinterpret_cast<float*>(bs + (pb ? lay->partials_alt : lay->partials));
+        const uint8_t* amt = (lay->argmax_tile[i] >= 0 && tile_fwd && tile_fwd[i]) ? ws + lay->argmax_tile[i] : nullptr;
+        // this layer's kernels overwrite partial buffer pb: the finalisation that last read it (layer i + 2) must be done
+        if (side && used[pb]) MK_CHECK_CUDA(cudaStreamWaitEvent(main_st, side->done[pb], 0));
+        int rc = molkgnn_conv_bwd(plan, &ly, reinterpret_cast<const float*>(ws + lay->h[i]), ly.Fp,
+                                  reinterpret_cast<const float*>(ws + lay->hnorm[i]), g, ld, 1, ws + lay->argmax[i],
+                                  lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef), partials, gx, gx ? ly.Fp : 0,
+                                  grad_flat ? &gr : nullptr, 5, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
+                                  reinterpret_cast<float*>(bs + lay->scratch), amt, stream);
         if (rc) return rc;
+        if (!side && grad_flat) {                         // MOLKGNN_FIN_SIDE=0: finalisation in line on the launching stream
+            rc = molkgnn_conv_bwd(plan, &ly, reinterpret_cast<const float*>(ws + lay->h[i]), ly.Fp,
+                                  reinterpret_cast<const float*>(ws + lay->hnorm[i]), g, ld, 1, ws + lay->argmax[i],
+                                  lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef), partials, gx, gx ? ly.Fp : 0,
+                                  &gr, 2, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
+                                  reinterpret_cast<float*>(bs + lay->scratch), amt, stream);
+            if (rc) return rc;
+        }
+        if (side) {                                       // parameter finalisation on the side stream
+            MK_CHECK_CUDA(cudaEventRecord(side->ready[pb], main_st));
+            MK_CHECK_CUDA(cudaStreamWaitEvent(side->st, side->ready[pb], 0));
+            rc = molkgnn_conv_bwd(plan, &ly, reinterpret_cast<const float*>(ws + lay->h[i]), ly.Fp,
+                                  reinterpret_cast<const float*>(ws + lay->hnorm[i]), g, ld, 1, ws + lay->argmax[i],
+                                  lay->scoff[i], reinterpret_cast<float*>(bs + lay->coef), partials, gx, gx ? ly.Fp : 0,
+                                  &gr, 2, lay->ximg[i] >= 0 ? ws + lay->ximg[i] : nullptr,
+                                  reinterpret_cast<float*>(bs + lay->scratch), amt, side->st);
+            if (rc) return rc;
+            MK_CHECK_CUDA(cudaEventRecord(side->done[pb], side->st));
+            used[pb] = true;
+        }
         g = gx; ld = ly.Fp;
     }
+    for (int pb = 0; pb < 2; ++pb)                        // the launching stream owns the gradients again
+        if (side && used[pb]) MK_CHECK_CUDA(cudaStreamWaitEvent(main_st, side->done[pb], 0));
     return 0;
 }
