@@ -10,6 +10,6 @@ timeout 600 python bench.py --steps 30 --warmup 5 > gpurun_out/${TAG}_bench.json
 cat gpurun_out/${TAG}_bench.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv \
     python tools/prof_step.py 4096 2 > gpurun_out/${TAG}_ncu_launches.log 2>&1; echo "ncu launches exit $?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_conv|k_bwd|k_propagate|k_coef|k_x_images' -s 15 -c 15 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_conv|k_bwd|k_propagate|k_coef|k_x_images' -s 16 -c 16 \
     -f -o gpurun_out/${TAG}_prof python tools/prof_step.py 4096 2 > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full exit $?"
 ls -la gpurun_out
