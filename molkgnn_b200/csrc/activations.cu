@@ -69,79 +69,11 @@ __global__ void __launch_bounds__(256) k_propagate_fwd(const __grid_constant__ P
     if (lane == 0 && a.hnorm) a.hnorm[i] = sqrtf(ss);
 }
 
-// Same sum for K <= 128 with the next layer's tensor-core operand fused in: lane owns 4 consecutive columns, so the
-// normalised row goes straight into the tile-ordered fp16 (hi, lo) images (8-byte stores) and the activations are never
-// re-read for the conversion.  The warp of a tile's last node also clears the pad rows up to the next multiple of 16
-// (the extent the tile kernels' MMAs read).
-struct PropImgArgs {
-    PropArgs p;
-    const int* node_tile; const int* tile_start;
-    unsigned char* ximg; int Fk, x_one;
-};
-
-__global__ void __launch_bounds__(256) k_propagate_img(const __grid_constant__ PropImgArgs b) {
-    const PropArgs& a = b.p;
-    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (i >= a.N) return;
-    const int c0 = 4 * lane;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int cnt = min(a.in_cnt[i], 4);
-    int js[4], ds[4], ps[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) { js[t] = t < cnt ? a.in_src[4 * i + t] : -1; }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) { ds[t] = js[t] >= 0 ? a.deg[js[t]] : 1; ps[t] = js[t] >= 0 ? a.pos[js[t]] : 0; }
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {            // edge order
-        if (t < cnt) {
-            const int d = ds[t];
-            const int L = a.L[d - 1], ko = a.koff[d - 1];
-            const float* src = a.sc + a.scoff[d - 1] + (size_t)ps[t] * L - ko;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int col = c0 + u;
-                if (col >= ko && col < ko + L) acc[u] += src[col];
-            }
-        }
-    }
-    float ss = 0.f;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { if (c0 + u >= a.K) acc[u] = 0.f; ss += acc[u] * acc[u]; }
-    ss = warp_sum(ss);
-    const float nrm = sqrtf(ss);
-    if (c0 < a.ldh) st4(a.h + (size_t)i * a.ldh + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-    if (lane == 0 && a.hnorm) a.hnorm[i] = nrm;
-    const int nt = b.node_tile[i];
-    const int tile = nt >> 8, r = nt & 255;
-    unsigned char* Xhi = b.ximg + (size_t)tile * 2 * b.x_one;
-    unsigned char* Xlo = Xhi + b.x_one;
-    if (c0 < b.Fk) {
-        const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
-        __align__(8) __half2 hi[2];
-        __align__(8) __half2 lo[2];
-        tc::split_u2(acc[0] * rinv, acc[1] * rinv, hi[0], lo[0]);
-        tc::split_u2(acc[2] * rinv, acc[3] * rinv, hi[1], lo[1]);
-        const uint32_t off = tc::il_off(r, c0, b.Fk);
-        *reinterpret_cast<uint2*>(Xhi + off) = *reinterpret_cast<const uint2*>(hi);
-        *reinterpret_cast<uint2*>(Xlo + off) = *reinterpret_cast<const uint2*>(lo);
-    }
-    const int nn = b.tile_start[tile + 1] - b.tile_start[tile];
-    if (r == nn - 1 && c0 < b.Fk) {
-        const int rend = min(TNODES, (nn + 15) & ~15);
-        for (int rr = nn; rr < rend; ++rr) {
-            const uint32_t off = tc::il_off(rr, c0, b.Fk);
-            *reinterpret_cast<uint2*>(Xhi + off) = make_uint2(0u, 0u);
-            *reinterpret_cast<uint2*>(Xlo + off) = make_uint2(0u, 0u);
-        }
-    }
-}
-
 // Tile-ordered neighbour sum (plans with molecule tiles, K <= 112): one CTA per tile.  The compact score rows of the tile's
 // nodes are expanded once into a dense [node][column] block in shared memory (coalesced reads, one thread per
 // (node, kernel) pair); every in-neighbour of a tile node is a tile node (TileMetaG::inl), so h[v] is then a sum of <= 4
-// shared-memory rows in edge order -- same arithmetic and lane <-> column mapping as k_propagate_img (bitwise equal
-// results), an eighth of its instructions.  Writes h, ||h|| and (optionally) the next layer's fp16 (hi, lo) tile images.
+// shared-memory rows in edge order -- the same fp32 sums, element by element, as k_propagate_fwd (bitwise equal
+// results), an eighth of the instructions of a warp-per-node gather from global memory.  Writes h, ||h|| and (optionally) the next layer's fp16 (hi, lo) tile images.
 struct PropTileArgs {
     const TileMetaG* meta;
     int K, ldh;
@@ -279,20 +211,8 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
         MK_CHECK_CUDA(cudaGetLastError());
         return 0;
     }
-    if (ximg) {
-        MK_REQUIRE(plan->n_tiles > 0 && plan->node_tile && plan->tile_start && ldh % 4 == 0 && ldh <= 112 && hnorm,
-                   "propagate_fwd: fused images need a tiled plan, hnorm and ldh %% 4 == 0, ldh <= 112 (got %d)", ldh);
-        MK_REQUIRE((reinterpret_cast<uintptr_t>(h) & 15) == 0 && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0,
-                   "propagate_fwd: h must be 16-byte and ximg 128-byte aligned");
-        PropImgArgs b;
-        b.p = a;
-        b.node_tile = plan->node_tile; b.tile_start = plan->tile_start;
-        b.ximg = reinterpret_cast<unsigned char*>(ximg);
-        b.Fk = tile_fk(ldh); b.x_one = tile_img_one(b.Fk);
-        k_propagate_img<<<grid, 256, 0, st>>>(b);
-        MK_CHECK_CUDA(cudaGetLastError());
-        return 0;
-    }
+    MK_REQUIRE(!ximg, "propagate_fwd: fused images need a tiled plan, hnorm, 16-byte aligned h, 128-byte aligned ximg and "
+                      "ldh %% 4 == 0, ldh <= 112 (got ldh=%d)", ldh);
     if (ldh <= 32 * 1) k_propagate_fwd<1><<<grid, 256, 0, st>>>(a);
     else if (ldh <= 32 * 4) k_propagate_fwd<4><<<grid, 256, 0, st>>>(a);
     else if (ldh <= 32 * 8) k_propagate_fwd<8><<<grid, 256, 0, st>>>(a);
