@@ -13,23 +13,44 @@ BATCH_KEYS = ("x", "p", "edge_index", "edge_attr")
 
 
 class DevicePrefetcher(object):
+    """Stages the NEXT batch while the current one computes: the host -> device copies of its tensors and (optionally) its
+    degree-bucket plan run on a side stream.  The plan's one host round trip (bucket sizes) then waits only for that
+    side stream -- whose work finished a step ago -- instead of draining the compute stream, so the host can queue steps
+    ahead of the GPU."""
+
     def __init__(self, device):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
 
-    def put(self, host_batch):
-        """Starts the copy of a dict of (pinned) host tensors; returns a handle for ``get``."""
+    def put(self, host_batch=None, device_batch=None, build_plan=False):
+        """Starts staging a batch given as a dict of (pinned) host tensors or of tensors already on the device; returns a
+        handle for ``get``.  With ``build_plan`` the counting half of the GPU bucket pass is queued behind the copies."""
+        from .plan import BucketPlan
         with torch.cuda.stream(self.stream):
-            dev = {k: v.to(self.device, non_blocking=True) for k, v in host_batch.items()}
+            dev = device_batch if host_batch is None else {k: v.to(self.device, non_blocking=True)
+                                                            for k, v in host_batch.items()}
+            plan = None
+            if build_plan:
+                plan = BucketPlan.begin_from_edge_index(dev["edge_index"], dev["p"], dev["edge_attr"], dev["x"].shape[0])
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return dev, ev
+        return dev, ev, plan, host_batch is not None
 
     def get(self, handle):
-        """Makes the current stream wait for the copy and hands the device tensors over to it."""
-        dev, ev = handle
+        """Finishes the plan (if any), makes the current stream wait for the staged batch and hands the tensors over to it.
+        Returns the device tensors, or (tensors, plan) if the handle carries a plan."""
+        dev, ev, plan, owned = handle
         cur = torch.cuda.current_stream(self.device)
+        if plan is not None:
+            with torch.cuda.stream(self.stream):
+                plan.finish()                      # bucket sizes to the host + assignment kernels, still on the side stream
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
         cur.wait_event(ev)
-        for t in dev.values():
-            t.record_stream(cur)
+        if owned:
+            for t in dev.values():
+                t.record_stream(cur)
+        if plan is not None:
+            plan._buf.record_stream(cur)
+            return dev, plan
         return dev
