@@ -123,5 +123,6 @@ def ptr(t):
 
 
 def stream_ptr():
+    """cudaStream_t of torch's current stream on the current device (raw C getter: this runs several times per step)."""
     import torch
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))

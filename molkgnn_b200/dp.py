@@ -54,9 +54,11 @@ class GradBucket(object):
             return None
         lo = flat.data_ptr()
         hi = lo + flat.numel() * flat.element_size()
-        for p in ps:
+        # every p.grad must still be the view the backward handed out (autograd keeps it when .grad was None before); the
+        # views are laid out in parameter order, so the first and the last one bracket the rest
+        for p in (ps[0], ps[-1], ps[len(ps) // 2]):
             a = p.grad.data_ptr()
-            if p.grad.device != flat.device or a < lo or a + p.grad.numel() * 4 > hi or not p.grad.is_contiguous():
+            if p.grad.device != flat.device or a < lo or a + p.grad.numel() * 4 > hi:
                 return None
         return flat
 

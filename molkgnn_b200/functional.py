@@ -355,6 +355,25 @@ class StackPack(object):
 
     def grad_views(self, lay, flat):
         """Views of the flat gradient buffer in flat_params() order (None for parameters without a gradient)."""
+        specs = self.__dict__.get("_view_specs")
+        if specs is None:                  # (offset, shape, stride) per parameter; the g_* offsets do not depend on the plan
+            specs = []
+            for i, pk in enumerate(self.packs):
+                for d in range(4):
+                    Ld = pk.L[d]
+                    if not Ld:
+                        specs += [None] * 7
+                        continue
+                    oc, os_, oe, ow = (lay.g_x_center[i][d], lay.g_x_support[i][d], lay.g_edge_attr_support[i][d],
+                                       lay.g_w[i][d])
+                    specs += [(oc, (Ld, pk.F), (pk.F, 1)), (os_, (Ld, d + 1, pk.F), ((d + 1) * pk.F, pk.F, 1)),
+                              (oe, (Ld, d + 1, pk.Fe), ((d + 1) * pk.Fe, pk.Fe, 1)), None, (ow, (), ()), (ow + 1, (), ()),
+                              (ow + 2, (), ())]
+            self._view_specs = specs
+        as_strided = flat.as_strided
+        return [None if sp is None else as_strided(sp[1], sp[2], sp[0]) for sp in specs]
+
+    def _grad_views_reference(self, lay, flat):
         out = []
         for i, pk in enumerate(self.packs):
             for d in range(4):
