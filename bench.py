@@ -36,7 +36,7 @@ METRIC = "molecules/sec fwd+bwd MolKGNN conv (1/2/4/8 B200, % HBM roofline) vs h
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--molecules", type=int, default=4096, help="molecules per GPU per step")
@@ -122,7 +122,7 @@ class ClockSampler(object):
         self.rows, self.p = [], None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:

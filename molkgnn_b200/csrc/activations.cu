@@ -84,7 +84,9 @@ struct PropTileArgs {
     unsigned char* ximg; int Fk, x_one;
 };
 
-__global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ PropTileArgs a) {
+constexpr int PT_THREADS = 512;
+
+__global__ void __launch_bounds__(PT_THREADS) k_propagate_tile(const __grid_constant__ PropTileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_p[];
     TileMetaG& m = *reinterpret_cast<TileMetaG*>(smem_p);
     float* scS = reinterpret_cast<float*>(smem_p + (sizeof(TileMetaG) + 15) / 16 * 16);
@@ -93,11 +95,11 @@ __global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ 
     {
         const uint4* src = reinterpret_cast<const uint4*>(a.meta + tile);
         uint4* dst = reinterpret_cast<uint4*>(smem_p);
-        for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += 256) dst[i] = __ldg(src + i);
+        for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += PT_THREADS) dst[i] = __ldg(src + i);
     }
     __syncthreads();
     const int nn = m.nn, t0 = m.t0, ld = a.ldh;
-    for (int i = tid; i < nn * (ld >> 2); i += 256) reinterpret_cast<float4*>(scS)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < nn * (ld >> 2); i += PT_THREADS) reinterpret_cast<float4*>(scS)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
 #pragma unroll
     for (int d = 1; d <= 4; ++d) {
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ 
         const float* base = a.sc + a.scoff[d - 1];
         const int ko = a.koff[d - 1];
 #pragma unroll 4
-        for (int p = tid; p < np; p += 256) {
+        for (int p = tid; p < np; p += PT_THREADS) {
             const int i = (int)(((float)p + 0.5f) * rL);
             const int k = p - i * L;
             const int nl_ = m.list[d - 1][i];
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ 
     const int c0 = 4 * lane;
     unsigned char* Xhi = a.ximg ? a.ximg + (size_t)tile * 2 * a.x_one : nullptr;
     unsigned char* Xlo = a.ximg ? Xhi + a.x_one : nullptr;
-    for (int v = warp; v < nn; v += 8) {
+    for (int v = warp; v < nn; v += PT_THREADS / 32) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
         const int cnt = min((int)m.incnt[v], 4);
         const uint32_t w = m.inl[v];
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(256) k_propagate_tile(const __grid_constant__ 
     // pad rows up to the next multiple of 16: the extent the tile kernels' MMAs read
     if (Xhi && c0 < a.Fk) {
         const int rend = min(TNODES, (nn + 15) & ~15);
-        for (int rr = nn + warp; rr < rend; rr += 8) {
+        for (int rr = nn + warp; rr < rend; rr += PT_THREADS / 32) {
             const uint32_t off = tc::il_off(rr, c0, a.Fk);
             *reinterpret_cast<uint2*>(Xhi + off) = make_uint2(0u, 0u);
             *reinterpret_cast<uint2*>(Xlo + off) = make_uint2(0u, 0u);
@@ -207,7 +209,7 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
             MK_CHECK_CUDA(cudaFuncSetAttribute(k_propagate_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             s_attr = smem;
         }
-        k_propagate_tile<<<plan->n_tiles, 256, smem, st>>>(t);
+        k_propagate_tile<<<plan->n_tiles, PT_THREADS, smem, st>>>(t);
         MK_CHECK_CUDA(cudaGetLastError());
         return 0;
     }

@@ -26,6 +26,11 @@ class DevicePrefetcher(object):
         """Starts staging a batch given as a dict of (pinned) host tensors or of tensors already on the device; returns a
         handle for ``get``.  With ``build_plan`` the counting half of the GPU bucket pass is queued behind the copies."""
         from .plan import BucketPlan
+        # Memory protocol: everything staged here is allocated from the side stream's pool and later used on the compute
+        # stream WITHOUT record_stream (recorded blocks come back late, the pool keeps growing with synchronising
+        # cudaMallocs).  Instead the side stream first waits for everything queued on the compute stream so far: a block
+        # freed by the host (its last compute-stream use was queued before this point) is then safe to reuse here.
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             dev = device_batch if host_batch is None else {k: v.to(self.device, non_blocking=True)
                                                             for k, v in host_batch.items()}
@@ -47,10 +52,6 @@ class DevicePrefetcher(object):
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
         cur.wait_event(ev)
-        if owned:
-            for t in dev.values():
-                t.record_stream(cur)
         if plan is not None:
-            plan._buf.record_stream(cur)
             return dev, plan
         return dev
