@@ -29,6 +29,7 @@ bool tile_layer_ok(const molkgnn_layer_t* layer);
 int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 
 constexpr int TF_THREADS = 512;
+constexpr int TF_STEAL_MIN = 8;                // tiles left in another block's queue that justify a block set-up
 constexpr int TF_WARPS = TF_THREADS / 32;
 
 // ---- normalised fp16 images of the activations in tile order --------------------------------------------------------
@@ -151,6 +152,7 @@ struct FwdTileArgs {
     uint8_t* argmax; uint8_t* argmax_free; const uint8_t* argmax_in;
     uint8_t* amT; int stride_am;      // nullable: the arg-max bytes once more in tile order (the backward's bulk-copy operand)
     int* counter;                     // [TILE_MAXB] tile queues
+    int steal_min;                    // tiles left in another block's queue that justify a block set-up there
     int sm_img, sm_x, sm_dump, sm_buf, sm_es, sm_dup;   // byte offsets into dynamic shared memory
 };
 
@@ -403,8 +405,22 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
     float4* estab = reinterpret_cast<float4*>(smem + a.sm_es);
     unsigned char* dupf = smem + a.sm_dup;
 
-    for (int blk = 0; blk < a.tb.nb; ++blk) {
+    // Every CTA has a HOME block (blockIdx % nb) whose queue it drains first: with the CTAs spread over the blocks a CTA pays
+    // one block set-up + pipeline fill per launch instead of one per block.  Afterwards it helps with the other blocks'
+    // queues, but only where enough tiles are left to be worth a set-up; whatever it leaves is drained by that block's home
+    // CTAs, which never leave their queue before it is empty.
+    __shared__ int s_left;
+    const int nb = a.tb.nb;
+    for (int bi = 0; bi < nb; ++bi) {
+        const int blk = ((int)blockIdx.x + bi) % nb;
         __syncthreads();                       // previous block completely finished
+        if (tid == 0) s_left = a.n_tiles - min(a.n_tiles, *reinterpret_cast<volatile int*>(a.counter + blk));
+        __syncthreads();
+        {
+            const bool has_home = blk < (int)gridDim.x;                 // some CTA c < gridDim with c % nb == blk
+            const int need = (bi == 0 || !has_home) ? 1 : a.steal_min;
+            if (s_left < need) continue;
+        }
         // ---- block set-up: barriers, images, segment constants, bond-support table [slot][half][kernel] ----
         if (tid == 0) {
             for (int i = 0; i < 2; ++i) {
@@ -601,6 +617,9 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.argmax = argmax; a.argmax_free = argmax_free; a.argmax_in = argmax_in;
     a.amT = argmax_tile; a.stride_am = tile_argmax_stride(plan, layer);
     a.counter = counter;
+    static int s_steal = -1;
+    if (s_steal < 0) { const char* e = getenv("MOLKGNN_FWD_STEAL_MIN"); s_steal = e ? std::max(1, atoi(e)) : TF_STEAL_MIN; }
+    a.steal_min = s_steal;
     int64_t off = 0;
     a.sm_img = 0;                                  // the kernel-block images live in tensor memory
     a.sm_x = (int)off; off += 2 * 2 * (int64_t)a.x_one;   // two node-image buffers

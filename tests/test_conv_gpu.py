@@ -122,6 +122,8 @@ def _oracle_run(net, b, wout, force=None):
     (48, 3, (10, 20, 30, 50), (10, 20, 30, 50), 11),      # README shape, a few tiles per degree
     (300, 2, (3, 5, 7, 9), (4, 6, 8, 10), 12),            # odd kernel counts: partial kernel groups, K % 4 != 0
     (16, 2, (1, 1, 1, 1), (1, 2, 1, 2), 13),              # minimum kernel counts
+    (1, 3, (10, 20, 30, 50), (10, 20, 30, 50), 21),       # a single molecule: one tile, one CTA walks every kernel block
+    (3, 2, (10, 20, 30, 50), (10, 20, 30, 50), 22),       # fewer tiles than kernel blocks
 ])
 def test_molgcn_vs_oracle(n_mol, layers, L1, LN, seed):
     import molkgnn_b200 as mk
