@@ -19,6 +19,8 @@
 // (kernels.py:279-350), softmax mix (kernels.py:402-425).  The next tile's MMAs are issued between the two halves of the
 // epilogue and run on the second TMEM accumulator.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 #include "tc.cuh"
 #include "tile.cuh"
@@ -153,6 +155,7 @@ struct FwdTileArgs {
     uint8_t* amT; int stride_am;      // nullable: the arg-max bytes once more in tile order (the backward's bulk-copy operand)
     int* counter;                     // [TILE_MAXB] tile queues
     int steal_min;                    // tiles left in another block's queue that justify a block set-up there
+    int home_split[TILE_MAXB + 1];    // CTAs [home_split[b], home_split[b + 1]) have block b as their home
     int sm_img, sm_x, sm_dump, sm_buf, sm_es, sm_dup;   // byte offsets into dynamic shared memory
 };
 
@@ -411,13 +414,15 @@ __global__ void __launch_bounds__(TF_THREADS + 32, 1) k_conv_fwd_tile(const __gr
     // CTAs, which never leave their queue before it is empty.
     __shared__ int s_left;
     const int nb = a.tb.nb;
+    int home = 0;
+    while (home + 1 < nb && (int)blockIdx.x >= a.home_split[home + 1]) ++home;
     for (int bi = 0; bi < nb; ++bi) {
-        const int blk = ((int)blockIdx.x + bi) % nb;
+        const int blk = (home + bi) % nb;
         __syncthreads();                       // previous block completely finished
         if (tid == 0) s_left = a.n_tiles - min(a.n_tiles, *reinterpret_cast<volatile int*>(a.counter + blk));
         __syncthreads();
         {
-            const bool has_home = blk < (int)gridDim.x;                 // some CTA c < gridDim with c % nb == blk
+            const bool has_home = a.home_split[blk + 1] > a.home_split[blk];
             const int need = (bi == 0 || !has_home) ? 1 : a.steal_min;
             if (s_left < need) continue;
         }
@@ -620,6 +625,34 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     static int s_steal = -1;
     if (s_steal < 0) { const char* e = getenv("MOLKGNN_FWD_STEAL_MIN"); s_steal = e ? std::max(1, atoi(e)) : TF_STEAL_MIN; }
     a.steal_min = s_steal;
+    {
+        // home CTAs per block in proportion to the block's estimated cost per tile visit (fixed part + its share of the
+        // (node, kernel) pairs, weighted by the degree's permutation work); MOLKGNN_FWD_HOME="w0,w1,.." overrides
+        const int grid_ = std::min(plan->n_tiles, s_sms);
+        double w[TILE_MAXB], wsum = 0.0;
+        static const double pair_cost[4] = {0.35, 0.6, 1.0, 1.6};      // relative epilogue cost of a degree-d pair
+        for (int b = 0; b < a.tb.nb; ++b) {
+            double pairs = 0.0;
+            for (int si = 0; si < a.tb.nseg[b]; ++si) {
+                const TileSeg sg = a.tb.seg[b][si];
+                pairs += pair_cost[sg.d - 1] * sg.nk * (double)plan->n[sg.d - 1] / std::max(1, plan->n_tiles);
+            }
+            w[b] = 1400.0 + pairs;                                      // ~ cycles / 2: fixed visit cost + pair work
+            wsum += w[b];
+        }
+        if (const char* e = getenv("MOLKGNN_FWD_HOME")) {
+            wsum = 0.0;
+            for (int b = 0; b < a.tb.nb; ++b) { w[b] = std::max(0.0, atof(e)); wsum += w[b]; const char* c = strchr(e, ','); e = c ? c + 1 : e; }
+            if (wsum <= 0.0) { for (int b = 0; b < a.tb.nb; ++b) w[b] = 1.0; wsum = a.tb.nb; }
+        }
+        double acc = 0.0;
+        a.home_split[0] = 0;
+        for (int b = 0; b < a.tb.nb; ++b) {
+            acc += w[b];
+            a.home_split[b + 1] = b + 1 == a.tb.nb ? grid_ : (int)(grid_ * acc / wsum + 0.5);
+        }
+        for (int b = a.tb.nb + 1; b <= TILE_MAXB; ++b) a.home_split[b] = grid_;
+    }
     int64_t off = 0;
     a.sm_img = 0;                                  // the kernel-block images live in tensor memory
     a.sm_x = (int)off; off += 2 * 2 * (int64_t)a.x_one;   // two node-image buffers
