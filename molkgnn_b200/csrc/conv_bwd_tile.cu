@@ -557,18 +557,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             tc::fence_after_sync();
             MK_PH(6);                                     // MMA completion
             // the tensor cores are done with Wt and this block's images: fetch the images of a later use, clear Wt
-            // only the part this (tile, block) wrote: row groups below the block's rows (rounded to the MMA's K = 16
-            // extent), 8-column chunks below the tile's nodes (rounded likewise) -- the rest is still zero
-            {
-                const int ngr = (a.tb.rows[blk] + 15) >> 4 << 1, nch = (max(16, (nn + 15) & ~15)) >> 3;
-                const int per = nch * 8, tot = ngr * per;
-                for (int i = tid; i < tot; i += TB_THREADS) {
-                    const int g = i / per, r = i - g * per;
-                    const uint32_t off = (uint32_t)(g * 16 + (r >> 3)) * 128u + (uint32_t)(r & 7) * 16u;
-                    *reinterpret_cast<uint4*>(wt + off) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(wt + WT_ONE + off) = make_uint4(0, 0, 0, 0);
-                }
-            }
+            for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
             if (tid == 0 && !resident && use - 1 + a.nimg < total_uses)
                 tb_issue_img(a, smem, a.blist[(use - 1 + a.nimg) % a.nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
             if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
