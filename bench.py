@@ -199,7 +199,7 @@ def main():
         x = t["x"].detach().requires_grad_(True)
         h = net(x=x, edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False, plan=plan)
         h.backward(wout)                     # dL/dh handed in directly: no torch arithmetic inside the timed region
-        if bucket is not None:
+        if bucket is not None and not os.environ.get("MOLKGNN_BENCH_NO_ALLREDUCE"):   # (diagnostic switch)
             bucket.allreduce()
         return h
 

@@ -72,9 +72,13 @@ class GradBucket(object):
         flat = self._native_flat(ps)
         if flat is not None:
             if self.world > 1:
-                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
-                if self.average:
-                    flat.div_(self.world)
+                if self.average and flat.is_cuda:
+                    # NCCL averages inside the collective: no separate scaling kernel behind it
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
+                else:
+                    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+                    if self.average:
+                        flat.div_(self.world)
             self.flat = flat
             return flat
         flat = torch.cat([p.grad.reshape(-1) for p in ps])
