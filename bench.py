@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--molecules", type=int, default=4096, help="molecules per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=None, help="synthetic-batch seed (default 1000 * rank, SURVEY 8(d))")
     return ap.parse_args()
 
 
@@ -180,7 +181,7 @@ def main():
     from molkgnn_b200.dp import GradBucket
 
     B = args.molecules
-    batch = synth.make_batch(B, seed=1000 * rank)     # shard of this rank (seed = 1000*s)
+    batch = synth.make_batch(B, seed=1000 * rank if args.seed is None else args.seed)   # shard of this rank
     N, E = batch["x"].shape[0], batch["edge_index"].shape[1]
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("x", "p", "edge_index", "edge_attr")}
     devt = {k: v.to(dev) for k, v in host.items()}
