@@ -294,3 +294,53 @@ def test_wide_layer_chunked_paths():
     (h * wout.to(DEV)).sum().backward()
     assert rel_err(x.grad.cpu(), gx_ref) < TOL
     _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
+
+
+def test_wide_five_layer_stack():
+    """BASELINE configs[2] at a size the oracle finishes in seconds: kernels 40/80/120/200, FIVE layers (F = 28, then 440),
+    so the last-layer chirality, the propagate between wide layers and the layer loop of the wide stack are all covered."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    b = synth.make_batch(24, seed=43)
+    torch.manual_seed(43)
+    L = (40, 80, 120, 200)
+    net = mk.MolGCN(5, *L, *L, x_dim=28, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], 440)
+    h_ref, gx_ref, params_ref, auxs = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    x = d["x"].clone().requires_grad_(True)
+    forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+    h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, argmax_in=forced)
+    assert rel_err(h.detach().cpu(), h_ref) < TOL
+    (h * wout.to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), gx_ref) < TOL
+    _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
+
+
+def test_inference_sweep_forward_only():
+    """BASELINE configs[4] (virtual-screening sweep): the forward under torch.no_grad() is the same kernels as the training
+    forward -- bitwise the same h -- chunk after chunk through one module, and matches the oracle."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    torch.manual_seed(5)
+    net = mk.MolGCN(3, 10, 20, 30, 50, 10, 20, 30, 50, x_dim=28, p_dim=3, edge_attr_dim=7)
+    chunks = [synth.make_batch(n, seed=50 + n) for n in (40, 7, 64)]
+    refs = []
+    for b in chunks:
+        h_ref, _, _, auxs = _oracle_run(net, b, torch.zeros(b["x"].shape[0], 110))
+        refs.append((h_ref, auxs))
+    net = net.to(DEV)
+    for b, (h_ref, auxs) in zip(chunks, refs):
+        d = _to_dev(b)
+        with torch.no_grad():
+            h0 = net(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False)
+        assert not h0.requires_grad
+        x = d["x"].clone().requires_grad_(True)
+        h1 = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False)
+        assert torch.equal(h0, h1.detach())
+        forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+        with torch.no_grad():
+            hf = net(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False,
+                     argmax_in=forced)
+        assert rel_err(hf.cpu(), h_ref) < TOL
