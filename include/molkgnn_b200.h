@@ -63,6 +63,9 @@ typedef struct molkgnn_plan {
                                   ids, bucket rows, in-lists (csrc/tile.cuh TileMetaG) */
     float*   ehat_node;        /* [E,8] the rows of ehat in node order (tile-contiguous) */
     int32_t* node_tile;        /* [N]   tile << 8 | row of the node inside its tile */
+    int32_t* tile_order;       /* [N/32 + 4] balanced schedule of the tile-major backward kernels (nullable): the tiles of
+                                  persistent CTA b of a tile_grid-CTA launch, CTA after CTA (csrc/tile.cuh TileWalk) */
+    int32_t tile_grid;         /* CTAs the schedule was built for (0 = none: round robin) */
 } molkgnn_plan_t;
 
 /* One KernelSetConv layer (kernels.py:754-781): raw parameters of the four KernelConv modules + packed workspace. */
@@ -105,6 +108,10 @@ int molkgnn_num_sms(void);
 /* ---- degree bucketing: replaces ToXAndPAndEdgeAttrForDeg.__call__ (wrapper.py:559-672) + PyG collation ---- */
 /* size of one per-tile metadata record (plan->tile_meta) */
 int64_t molkgnn_tile_meta_bytes(void);
+/* Tile schedule of the tile-major backward kernels (plan->tile_order): 0 = round robin, 1 = balanced schedule for plans where
+ * a few persistent CTAs would walk one tile more than the rest (default; env MOLKGNN_TILE_ORDER), 2 = always.  Returns the
+ * previous mode.  Takes effect for plans built afterwards. */
+int molkgnn_set_tile_order(int mode);
 /* bytes of scratch needed by molkgnn_bucket_build */
 int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E);
 /* Builds the plan from a collated batch.  edge_index is the PyG [2,E] int64 tensor (row 0 = source).  SYNCHRONISES

@@ -15,7 +15,7 @@ class Plan(C.Structure):
                 ("deg", vp), ("pos", vp), ("sel", vp), ("nei", vp), ("nei_eid", vp), ("ehat", vp), ("tsign", vp),
                 ("in_cnt", vp), ("in_src", vp), ("in_j", vp),
                 ("tile_start", vp), ("n_tiles", i32), ("tile_max_nodes", i32), ("tile_max_deg", i32 * 4),
-                ("tile_meta", vp), ("ehat_node", vp), ("node_tile", vp)]
+                ("tile_meta", vp), ("ehat_node", vp), ("node_tile", vp), ("tile_order", vp), ("tile_grid", i32)]
 
 
 class Layer(C.Structure):
@@ -52,6 +52,7 @@ EXPORTS = {
     "molkgnn_launch_count": (i64, []),
     "molkgnn_bucket_scratch_bytes": (i64, [i32, i32]),
     "molkgnn_tile_meta_bytes": (i64, []),
+    "molkgnn_set_tile_order": (C.c_int, [C.c_int]),
     "molkgnn_tile_ximg_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_tile_ximg_build": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp]),
     "molkgnn_tile_ximg_build_raw": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp, vp]),

@@ -53,6 +53,7 @@ constexpr int CT_CHUNK = 12;                   // nodes per item and tile
 
 struct CoefTileArgs {
     const TileMetaG* meta; const float* ehat_node; int n_tiles;
+    const int* order; int order_grid;          // balanced tile schedule (tile.cuh TileWalk), nullable
     int L[4], koff[4];
     long long scoff[4];
     const float* grad; int ldg; int grad_mode; int vec;     // vec: floats per cp.async of the gradient rows (1, 2 or 4)
@@ -185,12 +186,14 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
     }
     float amax = 0.f;
     int cur = 0;
-    if ((int)blockIdx.x < a.n_tiles) ct_issue(a, smem_c, blockIdx.x);
+    const TileWalk walk(a.order, a.order_grid, a.n_tiles);
+    if (walk.cnt > 0) ct_issue(a, smem_c, walk.tile(0));
     cp_async_commit();
     MK_PH(0);
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int wk = 0; wk < walk.cnt; ++wk) {
+        const int tile = walk.tile(wk);
         unsigned char* buf = smem_c + (size_t)cur * a.buf_bytes;
-        const int tnext = tile + gridDim.x;
+        const int tnext = wk + 1 < walk.cnt ? walk.tile(wk + 1) : a.n_tiles;
         __syncthreads();                                 // the previous tile's readers are done with the other buffer
         if (tnext < a.n_tiles) ct_issue(a, smem_c + (size_t)(cur ^ 1) * a.buf_bytes, tnext);
         cp_async_commit();
@@ -294,6 +297,7 @@ struct BwdTileArgs {
     const float* xnorm;
     int F, Fp, Fk;
     const TileMetaG* meta; const unsigned char* ximg; int n_tiles;
+    const int* order; int order_grid;  // balanced tile schedule (tile.cuh TileWalk), nullable
     int L[4];
     const float* packed[4];
     const unsigned char* img;
@@ -460,12 +464,13 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     }
     const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / 32-column part of this warp
     // image uses u = 0, 1, ...: block blist[u % nbl] in buffer u % nimg.  With nbl <= nimg the images stay resident.
-    const int my_tiles = (int)blockIdx.x < a.n_tiles ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const TileWalk walk(a.order, a.order_grid, a.n_tiles);
+    const int my_tiles = walk.cnt;
     const int total_uses = my_tiles * a.nbl;
     const bool resident = a.nbl <= a.nimg;
     int np_next = 0;
     if (tid == 0 && my_tiles > 0) {
-        tb_issue_copy(a, smem, smem + a.sm_buf, blockIdx.x, tb_tile_pairs(a, blockIdx.x), &bar_cp[0]);
+        tb_issue_copy(a, smem, smem + a.sm_buf, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0]);
         const int n0 = resident ? a.nbl : min(a.nimg, total_uses);
         for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, a.blist[u % a.nbl], u % a.nimg, &bar_img[u % a.nimg]);
     }
@@ -473,10 +478,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     int cur = 0, use = 0;
     bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int wk = 0; wk < walk.cnt; ++wk) {
+        const int tile = walk.tile(wk);
         unsigned char* buf = smem + a.sm_buf + cur * a.buf_bytes;
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
-        const int tnext = tile + gridDim.x;
+        const int tnext = wk + 1 < walk.cnt ? walk.tile(wk + 1) : a.n_tiles;
         if (tid == 0 && tnext < a.n_tiles) np_next = tb_tile_pairs(a, tnext);   // latency hidden behind this tile's work
         tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
         ph_cp[cur] ^= 1u;
@@ -774,6 +780,8 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.ximg = reinterpret_cast<const unsigned char*>(ximg);
     a.n_tiles = plan->n_tiles;
     const int grid = tile_bwd_grid(plan);
+    a.order = plan->tile_grid == grid ? plan->tile_order : nullptr;
+    a.order_grid = a.order ? grid : 0;
     a.FW = layer->Fp + EP;
     int64_t po = 0, rows_all = 0;
     for (int d = 0; d < 4; ++d) {
@@ -848,6 +856,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     MK_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
     {
         c.meta = a.meta; c.ehat_node = plan->ehat_node; c.n_tiles = plan->n_tiles;
+        c.order = a.order; c.order_grid = a.order_grid;
         for (int d = 0; d < 4; ++d) {
             c.L[d] = layer->L[d]; c.koff[d] = layer->koff[d]; c.scoff[d] = scoff[d];
             c.part_off[d] = part_off[d];

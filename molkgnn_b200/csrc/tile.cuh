@@ -85,6 +85,24 @@ struct __align__(16) TileMetaG {
 };
 static_assert(sizeof(TileMetaG) % 16 == 0, "TileMetaG must be a multiple of 16 bytes");
 
+// ---- balanced tile schedule of the tile-major kernels (k_coef_tile, k_conv_bwd_tile) ------------------------------------
+// With n tiles on G persistent CTAs (n = q G + r) CTAs 0..r-1 walk q + 1 tiles and the others q.  Without an order array
+// CTA b walks tiles b, b + G, ... (round robin: per-CTA node totals differ by ~6 %, and the r CTAs with one tile more decide
+// the kernel time).  With plan->tile_order (k_tile_order, bucket.cu: tiles sorted by node count, the r long CTAs take the
+// smallest (q + 1) r tiles, the others the rest, boustrophedon inside each group) CTA b walks order[beg .. beg + cnt).
+struct TileWalk {
+    int beg, cnt, b, G;
+    const int* order;
+    __device__ __forceinline__ TileWalk(const int* order_, int order_grid, int n_tiles) {
+        b = (int)blockIdx.x; G = (int)gridDim.x;
+        const int q = n_tiles / G, r = n_tiles - q * G;
+        cnt = q + (b < r ? 1 : 0);
+        beg = b < r ? b * (q + 1) : r * (q + 1) + (b - r) * q;
+        order = (order_ && order_grid == G) ? order_ : nullptr;
+    }
+    __device__ __forceinline__ int tile(int k) const { return order ? __ldg(order + beg + k) : b + k * G; }
+};
+
 // ---- bulk async copy global -> shared with mbarrier completion ---------------------------------------------------------
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(tc::smem_u32(bar)), "r"(bytes) : "memory");

@@ -34,7 +34,8 @@ class BucketPlan(object):
                ("in_src", torch.int32, lambda N, E: 4 * N), ("in_j", torch.int32, lambda N, E: 4 * N),
                ("tile_start", torch.int32, lambda N, E: N // 32 + 4), ("tile_meta", torch.uint8, None),
                ("ehat_node", torch.float32, lambda N, E: max(E, 1) * EDGE_PAD),
-               ("node_tile", torch.int32, lambda N, E: max(N, 1)))
+               ("node_tile", torch.int32, lambda N, E: max(N, 1)),
+               ("tile_order", torch.int32, lambda N, E: N // 32 + 4))
     _SHAPES = {"ehat": (-1, EDGE_PAD), "ehat_node": (-1, EDGE_PAD), "in_src": (-1, 4), "in_j": (-1, 4)}
     _layout_cache = {}
 

@@ -156,3 +156,42 @@ def test_molecule_tiles(n_mol, seed):
         assert ts[t + 1] - ts[t] + sizes[m] > 128
     if n_mol >= 300:
         assert np.diff(ts).mean() > 105
+
+
+@pytest.mark.parametrize("n_mol,seed", [(1, 0), (7, 3), (300, 1), (4096, 2), (4096, 6000)])
+def test_tile_schedule_is_a_balanced_permutation(n_mol, seed):
+    """plan.tile_order (k_tile_order): every tile exactly once; CTA b of the G-CTA tile-major kernels walks a contiguous
+    slice of q or q + 1 entries (csrc/tile.cuh TileWalk); the per-CTA node totals are much closer than round robin's; the
+    schedule is deterministic.  Seed 6000 is the 8-GPU shard whose 892 tiles overflow 6 rounds of 148 SMs by four."""
+    from molkgnn_b200 import synth, _lib
+    b = synth.make_batch(n_mol, seed=seed)
+    N = b["x"].shape[0]
+    sms = _lib.lib().molkgnn_num_sms()
+    plan = _plan(b["edge_index"], b["p"], b["edge_attr"], N)          # default mode: only where a few CTAs walk one tile more
+    rem = plan.n_tiles % min(plan.n_tiles, sms)
+    assert plan.c.tile_grid == (min(plan.n_tiles, sms) if 0 < rem <= min(plan.n_tiles, sms) // 2 else 0)
+    old = _lib.lib().molkgnn_set_tile_order(2)                         # always
+    try:
+        plan = _plan(b["edge_index"], b["p"], b["edge_attr"], N)
+        plan2 = _plan(b["edge_index"], b["p"], b["edge_attr"], N)
+    finally:
+        _lib.lib().molkgnn_set_tile_order(old)
+    T, G = plan.n_tiles, plan.c.tile_grid
+    assert G == min(T, sms)
+    order = plan.tile_order.cpu().numpy()[:T]
+    assert np.array_equal(np.sort(order), np.arange(T))
+    assert np.array_equal(plan2.tile_order.cpu().numpy()[:T], order)
+    nn = np.diff(plan.tile_start.cpu().numpy()[:T + 1])
+    q, r = divmod(T, G)
+    load, load_rr = np.zeros(G), np.zeros(G)
+    pos = 0
+    for c in range(G):
+        cnt = q + (1 if c < r else 0)
+        load[c] = nn[order[pos:pos + cnt]].sum()
+        pos += cnt
+    for t in range(T):
+        load_rr[t % G] += nn[t]
+    assert pos == T
+    if T >= 4 * G:
+        assert load.max() / load.mean() < 1.03
+        assert load.max() <= load_rr.max()

@@ -117,3 +117,25 @@ def test_molecule_independence_and_shard_additivity(setup):
     for n in full[2]:
         if n.rsplit(".", 1)[-1] in GRAD_NAMES[:3]:
             assert _rel(r_lo[2][n] + r_hi[2][n], full[2][n]) < TOL, n
+
+
+def test_balanced_tile_schedule_changes_only_the_summation_order(setup):
+    """The balanced tile schedule (plan.tile_order, csrc/tile.cuh TileWalk) only changes WHICH persistent CTA walks which
+    tile in the tile-major backward kernels: h and grad_x are per-tile quantities and stay bitwise the same; the
+    kernel-parameter gradients are sums over tiles in another order and agree to 1e-5."""
+    from molkgnn_b200 import _lib
+    _, t, net, wout = setup
+    lib = _lib.lib()
+    old = lib.molkgnn_set_tile_order(0)
+    try:
+        a = _run(net, t, wout)
+        lib.molkgnn_set_tile_order(2)
+        b = _run(net, t, wout)
+        b2 = _run(net, t, wout)
+    finally:
+        lib.molkgnn_set_tile_order(old)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for n in a[2]:
+        assert torch.equal(b[2][n], b2[2][n]), n                       # still deterministic
+        if n.rsplit(".", 1)[-1] in GRAD_NAMES[:3]:
+            assert _rel(b[2][n], a[2][n]) < TOL, n
