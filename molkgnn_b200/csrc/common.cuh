@@ -167,6 +167,7 @@ private:
 #define MK_PH(i_)
 #define MK_PH_FLUSH(arr_)
 #endif
+extern bool g_fwd_counters_zeroed;   // conv_fwd_tile.cu: the caller (stack.cu) zeroed the tile queues of all layers already
 int device_num_sms();
 int device_max_smem_optin();
 

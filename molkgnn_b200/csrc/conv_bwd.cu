@@ -526,7 +526,7 @@ extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, c
         tot_tile += (int64_t)tgrid * (d + 2) * layer->L[d] * (layer->Fp + EP);
         rows += (int64_t)(d + 2) * layer->L[d];
     }
-    return std::max(tot, tot_tile) + 2 * rows + 16;
+    return std::max(tot, tot_tile) + 2 * rows + 16 + 512;      // + per-CTA max |coef| of k_coef_tile (tile path)
 }
 
 extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,

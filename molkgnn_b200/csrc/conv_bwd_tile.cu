@@ -62,7 +62,7 @@ struct CoefTileArgs {
     int nch[4];                                // node chunks per degree for the bond gradients
     const uint8_t* amT_in;                     // tile-ordered arg-max written by the forward (nullable: read `argmax`, write amT)
     float* partials; long long part_off[4]; int FW, Fp;
-    float* amax;                               // device scalar (zeroed by the launcher): max |coef|
+    float* amax;                               // [gridDim.x] max |coef| seen by every CTA (no zeroing, no atomics)
     int buf_bytes, sm_grad, sm_eh, sm_am, sm_coef, sm_inv;   // per-buffer size / offsets inside a buffer / pair arrays
 };
 
@@ -249,7 +249,16 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
     cp_async_wait<0>();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if ((tid & 31) == 0 && amax > 0.f) atomicMax(reinterpret_cast<unsigned int*>(a.amax), __float_as_uint(amax));
+    {
+        __shared__ float s_amax[CT_THREADS / 32];
+        if ((tid & 31) == 0) s_amax[tid >> 5] = amax;
+        __syncthreads();
+        if (tid == 0) {
+            float m = s_amax[0];
+            for (int w = 1; w < CT_THREADS / 32; ++w) m = fmaxf(m, s_amax[w]);
+            a.amax[blockIdx.x] = m;
+        }
+    }
     // one partial copy per CTA: bond columns of the support rows (chunks combined in chunk order through shared memory,
     // the tile buffers are free now); the centre rows carry no bond part
     __syncthreads();
@@ -305,7 +314,7 @@ struct BwdTileArgs {
     int img_one, x_one;
     const float* coefT;                // chi * g per (node, kernel) pair, tile order (k_coef_tile)
     const uint8_t* amT; int stride, stride_am;
-    const float* amax;                 // device scalar: max |coef| (k_coef_tile)
+    const float* amax;                 // [gridDim.x] per-CTA max |coef| of k_coef_tile (same grid)
     float* partials; long long part_off[4]; int FW;
     float* scratch;                    // [N, Fk] partial dxh handed from the first launch to the second
     float* gx; int ldgx;
@@ -443,6 +452,14 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             s_seg[bi][si] = c;
         }
     }
+    __shared__ float s_gmax;
+    if (warp == 3) {                                      // max |coef| over the per-CTA values of k_coef_tile
+        float gm = 0.f;
+        for (int i = lane; i < (int)gridDim.x; i += 32) gm = fmaxf(gm, __ldg(a.amax + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        if (lane == 0) s_gmax = gm;
+    }
     unsigned char* wt = smem + a.sm_wt;
     for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
     tc::fence_before_sync();
@@ -456,7 +473,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     // power-of-two scale: |alpha * chi * g| / scale <= 2^10
     float scale, rscale;
     {
-        const float gm = fmaxf(*a.amax, 1e-30f);
+        const float gm = fmaxf(s_gmax, 1e-30f);
         int e;
         frexpf(gm, &e);                                   // gm < 2^e
         scale = ldexpf(1.0f, e - 10);
@@ -793,7 +810,8 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         rows_all += (int64_t)(d + 2) * layer->L[d];
     }
     *part_total = po;
-    float* amax = partials + po + 2 * rows_all + 8;   // spare floats behind k_param_finalize's Q scratch
+    float* amax = partials + po + 2 * rows_all + 16;  // [grid] floats behind k_param_finalize's Q scratch
+    MK_REQUIRE(grid <= 512, "conv_bwd_tile: %d CTAs (the per-CTA max |coef| array holds 512)", grid);
     a.img = reinterpret_cast<const unsigned char*>(layer->tile_img);
     a.img_one = tile_img_one(a.Fk);
     a.x_one = tile_img_one(a.Fk);
@@ -853,7 +871,6 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         s_attr_c = smem_c;
     }
-    MK_CHECK_CUDA(cudaMemsetAsync(amax, 0, sizeof(float), st));
     {
         c.meta = a.meta; c.ehat_node = plan->ehat_node; c.n_tiles = plan->n_tiles;
         c.order = a.order; c.order_grid = a.order_grid;

@@ -30,6 +30,10 @@ namespace mk {
 bool tile_layer_ok(const molkgnn_layer_t* layer);
 int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 
+// set by the stack driver while it runs the layer loop: it zeroes the tile queues of all layers with ONE memset up front
+// (a memset between two kernels of the chain costs ~3 us of stream time)
+bool g_fwd_counters_zeroed = false;
+
 constexpr int TF_THREADS = 512;
 constexpr int TF_STEAL_MIN = 8;                // tiles left in another block's queue that justify a block set-up
 constexpr int TF_WARPS = TF_THREADS / 32;
@@ -661,7 +665,7 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.sm_es = (int)off; off += 128 * 32;        // <= 128 support rows x 8 floats per block
     a.sm_dup = (int)off; off += 128;
     if (off > s_budget - 1024) return 0;
-    MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, TILE_MAXB * sizeof(int), st));
+    if (!g_fwd_counters_zeroed) MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, TILE_MAXB * sizeof(int), st));
     static int64_t s_attr = 0;
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));

@@ -101,6 +101,7 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     const int N = plan->N;
     int rc;
     if (!(flags & MOLKGNN_STACK_PACKED) && (rc = molkgnn_param_pack_layers(layers, nl, 7, stream))) return rc;
+    MK_CHECK_CUDA(cudaMemsetAsync(ws + lay->counter, 0, sizeof(int32_t) * 8 * (size_t)nl, (cudaStream_t)stream));
     float* h = reinterpret_cast<float*>(ws + lay->h[0]);
     float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);
     if (lay->ximg[0] >= 0 && layers[0].Fp <= 64) {      // one pass over x: padded copy, norms, tensor-core images
@@ -111,6 +112,11 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
             (rc = molkgnn_tile_ximg_build(plan, &layers[0], h, layers[0].Fp, hn, ws + lay->ximg[0], stream)))
             return rc;
     }
+    // tile queues of every layer: one memset for the whole stack, queued before the first kernel of the chain
+    struct CountersZeroed {
+        CountersZeroed() { mk::g_fwd_counters_zeroed = true; }
+        ~CountersZeroed() { mk::g_fwd_counters_zeroed = false; }
+    } counters_zeroed;
     for (int i = 0; i < nl; ++i) {
         const molkgnn_layer_t& ly = layers[i];
         const bool last = i == nl - 1;
