@@ -167,9 +167,19 @@ def main():
     import torch.distributed as dist
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries exactly ONE line (the JSON): until it is printed, file descriptor 1 points at stderr, so that banners
+    # native libraries write there (NCCL prints "NCCL version ..." at NCCL_DEBUG=VERSION and =WARN) cannot precede it
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line (NCCL prints its version banner there)
         dist.init_process_group("nccl", device_id=dev)
     from molkgnn_b200 import build as mkbuild
     if rank == 0:
@@ -357,7 +367,7 @@ def main():
                                 "sample": f"{mol} molecules as batch-16 mini-batches in {el:.1f} s, oracle/molkgnn_oracle.py "
                                           "(vectorised restatement of the reference; the reference's own Python loops "
                                           "measured ~25 molecules/s on 8 cores, BASELINE.md 2)"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
