@@ -42,14 +42,21 @@ def _to_dev(b):
 
 
 def _check_param_grads(net, ref_grad, tol=TOL):
-    """ref_grad(li, d, name) -> reference gradient (numpy / tensor)"""
+    """ref_grad(li, d, name) -> reference gradient (numpy / tensor), or None where the reference has none: a degree bucket
+    that is empty in the whole batch never runs its KernelConv (kernels.py:690), so autograd leaves .grad = None there and the
+    CUDA path must deliver None or exact zeros"""
     for li, layer in enumerate(net.layers):
         for d, kc in enumerate(layer.trainable_kernelconv_set):
+            trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
+            if ref_grad(li, d, "x_center") is None:
+                for nme in ["x_center", "x_support", "edge_attr_support"] + trip:
+                    got = getattr(kc, nme).grad
+                    assert got is None or float(got.abs().max()) == 0.0, (li, d, nme)
+                continue
             for nme in ["x_center", "x_support", "edge_attr_support"]:
                 got = getattr(kc, nme).grad
                 assert got is not None, (li, d, nme)
                 assert rel_err(got.cpu(), ref_grad(li, d, nme)) < tol, (li, d, nme)
-            trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
             refs = np.array([float(ref_grad(li, d, t)) for t in trip])
             got = np.array([getattr(kc, t).grad.item() for t in trip])
             assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (li, d, got, refs)
@@ -77,7 +84,9 @@ def test_tile_kernels_are_the_default_path(fwd_path):
     assert after["bwd_tile"] - before["bwd_tile"] == 3 and after["bwd_other"] == before["bwd_other"]
 
 
-@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer"])
+
+
+@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer", "molgcn_chains", "molgcn_stars"])
 def test_molgcn_vs_reference_golden(name):
     g = load_golden(name)
     net = module_from_golden(g, DEV)
@@ -102,10 +111,11 @@ def test_molgcn_vs_reference_golden(name):
             tot += n_
             ex += e_
             assert torch.equal(used[d - 1] & 0x7f, torch.from_numpy(g[f"argmax_l{li}_d{d}"]).to(torch.uint8))
-    assert ex / tot > 0.97, (ex, tot)
+    assert ex / tot > (0.75 if name == "molgcn_stars" else 0.97), (ex, tot)   # stars: all structural ties
     (h * torch.from_numpy(g["wout"]).to(DEV)).sum().backward()
     assert rel_err(x.grad.cpu(), g["grad_x"]) < TOL
-    _check_param_grads(net, lambda li, d, n: g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{n}"])
+    _check_param_grads(net, lambda li, d, n: g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{n}"]
+                       if f"grad_layers.{li}.trainable_kernelconv_set.{d}.{n}" in g else None)
 
 
 def _oracle_run(net, b, wout, force=None):
@@ -344,3 +354,70 @@ def test_inference_sweep_forward_only():
             hf = net(x=d["x"], edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False,
                      argmax_in=forced)
         assert rel_err(hf.cpu(), h_ref) < TOL
+
+
+def _batch_from_bonds(mols, seed):
+    """collated batch from a list of (n_atoms, [(i, j), ...]) molecules; bond b occupies edge rows 2b, 2b+1 (wrapper.py:152-156)"""
+    rng = np.random.default_rng(seed)
+    xs, ps, ei, ea, off = [], [], [], [], 0
+    for n, bonds in mols:
+        xs.append(rng.standard_normal((n, 28)).astype(np.float32))
+        ps.append((rng.standard_normal((n, 3)) * 1.5).astype(np.float32))
+        for (i, j) in bonds:
+            a = np.zeros(7, np.float32)
+            a[rng.integers(0, 4)] = 1.0
+            a[4:] = rng.integers(0, 2, 3)
+            ei += [(off + i, off + j), (off + j, off + i)]
+            ea += [a, a]
+        off += n
+    return dict(x=np.concatenate(xs), p=np.concatenate(ps), edge_index=np.array(ei, dtype=np.int64).T.copy(),
+                edge_attr=np.stack(ea))
+
+
+def _edge_case(name):
+    from molkgnn_b200 import synth
+    if name == "large_molecules":          # molecules that do not fit a 128-node tile: no tiling, bucket-order kernels
+        return synth.make_batch(3, seed=71, min_atoms=140, max_atoms=150)
+    if name == "largest_tileable_molecules":   # 97 atoms: the tiler needs a legal cut at least every 97 nodes (bucket.cu)
+        return synth.make_batch(3, seed=72, min_atoms=97, max_atoms=97)
+    if name == "molecules_of_128":             # fit a tile, but beyond the tiler's cut-gap bound: untiled, bucket-order kernels
+        return synth.make_batch(2, seed=72, min_atoms=128, max_atoms=128)
+    if name == "chains":                   # degrees 1 and 2 only: the degree-3 and degree-4 buckets are empty
+        return _batch_from_bonds([(n, [(i, i + 1) for i in range(n - 1)]) for n in (2, 5, 9, 2, 3)], 73)
+    if name == "stars":                    # degrees 1 and 4 only (+ a two-atom molecule)
+        return _batch_from_bonds([(5, [(0, 1), (0, 2), (0, 3), (0, 4)]), (2, [(0, 1)]),
+                                  (8, [(0, 1), (0, 2), (0, 3), (0, 4), (4, 5), (4, 6), (4, 7)])], 74)
+    if name == "two_atoms":                # the smallest legal graph
+        return _batch_from_bonds([(2, [(0, 1)])], 75)
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["large_molecules", "largest_tileable_molecules", "molecules_of_128", "chains", "stars",
+                                  "two_atoms"])
+def test_edge_case_graphs(name, fwd_path):
+    """Graph shapes at the edges of the bucket / tile logic, each against the oracle (forced arg-max, 1e-5): molecules larger
+    than a tile or than the tiler's cut-gap bound of 97 nodes (the plan carries no tiles and the bucket-order kernels run),
+    the largest molecules that are tiled, batches with empty degree buckets (kernels.py:702-721 skips them), the two-atom molecule."""
+    import molkgnn_b200 as mk
+    b = _edge_case(name)
+    torch.manual_seed(7)
+    net = mk.MolGCN(3, 10, 20, 30, 50, 10, 20, 30, 50, x_dim=28, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], 110)
+    h_ref, gx_ref, params_ref, auxs = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    x = d["x"].clone().requires_grad_(True)
+    plan = net.build_plan(d["edge_index"], d["p"], d["edge_attr"], x.shape[0])
+    if name in ("large_molecules", "molecules_of_128"):
+        assert plan.n_tiles == 0
+    else:
+        assert plan.n_tiles > 0
+    if name == "largest_tileable_molecules":
+        assert plan.c.tile_max_nodes == 97 and plan.n_tiles == 3
+    forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+    h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, plan=plan,
+            argmax_in=forced)
+    assert rel_err(h.detach().cpu(), h_ref) < TOL
+    (h * wout.to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), gx_ref) < TOL
+    _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)

@@ -34,7 +34,7 @@ def test_bucket_pass_bit_exact(name):
             assert np.array_equal(got, ref), (k, d)
 
 
-@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer"])
+@pytest.mark.parametrize("name", ["molgcn_small", "molgcn_readme", "molgcn_1layer", "molgcn_chains", "molgcn_stars"])
 def test_molgcn_forward_backward(name):
     g = load_golden(name)
     params = golden_params(g, requires_grad=True)
@@ -43,7 +43,10 @@ def test_molgcn_forward_backward(name):
     gb = golden_buckets(g)
     for d in range(1, 5):  # oracle bucket pass == what the reference consumed
         for k in gb[d]:
-            assert torch.equal(bk[d][k], gb[d][k])
+            if gb[d][k].numel() == 0:          # a bucket that is empty in every molecule (wrapper.py:627-630): shapes are not pinned
+                assert bk[d][k].numel() == 0
+            else:
+                assert torch.equal(bk[d][k], gb[d][k])
     x = torch.from_numpy(g["x"]).clone().requires_grad_(True)
     ei = torch.from_numpy(g["edge_index"])
     # teacher-forced on the reference's arg-max so that a flip inside a tie class cannot cascade (hard part 1)
@@ -58,11 +61,19 @@ def test_molgcn_forward_backward(name):
             n, e, _ = check_argmax(g[f"S_l{li}_d{d}"], g[f"argmax_l{li}_d{d}"], aux[d - 1]["argmax"])
             tot += n
             ex += e
-    assert ex / tot > 0.97
+    # bit-identical share outside the tie classes' free choice; the star fixture is ALL structural ties from layer 1 on (the four
+    # leaves of a centre carry identical features, every permutation scores the same and rounding picks the winner)
+    assert ex / tot > (0.75 if name == "molgcn_stars" else 0.97)
     (h * torch.from_numpy(g["wout"])).sum().backward()
     assert rel_err(x.grad, g["grad_x"]) < 2e-5
     for li, layer in enumerate(params):
         for d in range(4):
+            if f"grad_layers.{li}.trainable_kernelconv_set.{d}.x_center" not in g:
+                # empty bucket: the reference never ran this degree's KernelConv (kernels.py:690), autograd left .grad = None
+                assert f"S_l{li}_d{d + 1}" not in g
+                for nme in ["x_center", "x_support", "edge_attr_support"]:
+                    assert layer[d][nme].grad is None or float(layer[d][nme].grad.abs().max()) == 0.0
+                continue
             for nme in ["x_center", "x_support", "edge_attr_support"]:
                 ref = g[f"grad_layers.{li}.trainable_kernelconv_set.{d}.{nme}"]
                 assert rel_err(layer[d][nme].grad, ref) < 5e-5, (li, d, nme)

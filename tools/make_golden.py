@@ -66,7 +66,9 @@ def ref_bucket_collated(mols):
             if parts:
                 cat = torch.cat(parts, dim=-1 if "index" in key else 0)
             else:
-                cat = torch.zeros(0)
+                # every molecule's bucket is empty: the indices stay int64 (nonzero() / .to(torch.long), wrapper.py:600,632),
+                # the float attributes are the empty float tensor of wrapper.py:627-630
+                cat = torch.zeros(0, dtype=torch.int64) if "index" in key else torch.zeros(0)
             out[name] = cat.numpy()
     return out
 
@@ -89,8 +91,27 @@ class MaxSpy(object):
         torch.max = self._orig
 
 
-def molgcn_case(name, n_mol, seed, num_layers, L1, LN, dup=0.5):
-    mols = synth.make_molecules(n_mol, seed=seed, dup_leaf_prob=dup)
+def mols_from_bonds(specs, seed):
+    """hand-built molecules: list of (n_atoms, [(i, j), ...]); bond b -> edge rows 2b, 2b+1 (wrapper.py:152-156)"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for n, bonds in specs:
+        x = rng.standard_normal((n, synth.X_DIM)).astype(np.float32)
+        p = (rng.standard_normal((n, 3)) * 1.5).astype(np.float32)
+        ei, ea = [], []
+        for (i, j) in bonds:
+            a = np.zeros(synth.EDGE_DIM, np.float32)
+            a[rng.integers(0, 4)] = 1.0
+            a[4:] = rng.integers(0, 2, 3)
+            ei += [(i, j), (j, i)]
+            ea += [a, a]
+        out.append(synth.Molecule(x, p, np.array(ei, dtype=np.int64).T.copy(), np.stack(ea)))
+    return out
+
+
+def molgcn_case(name, n_mol, seed, num_layers, L1, LN, dup=0.5, mols=None):
+    if mols is None:
+        mols = synth.make_molecules(n_mol, seed=seed, dup_leaf_prob=dup)
     b = synth.collate(mols)
     bk = ref_bucket_collated(mols)
     torch.manual_seed(seed)
@@ -164,6 +185,12 @@ def main():
     molgcn_case("molgcn_small", n_mol=6, seed=1, num_layers=2, L1=(3, 4, 5, 6), LN=(2, 3, 4, 5))
     molgcn_case("molgcn_readme", n_mol=4, seed=2, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50))
     molgcn_case("molgcn_1layer", n_mol=5, seed=5, num_layers=1, L1=(4, 4, 4, 4), LN=(4, 4, 4, 4))
+    # 5. empty degree buckets (kernels.py:702-721 skips them; wrapper.py:627-630 stores empty tensors)
+    chains = mols_from_bonds([(n, [(i, i + 1) for i in range(n - 1)]) for n in (2, 5, 9, 2, 3)], 73)
+    molgcn_case("molgcn_chains", None, 73, num_layers=2, L1=(3, 4, 5, 6), LN=(2, 3, 4, 5), mols=chains)
+    stars = mols_from_bonds([(5, [(0, 1), (0, 2), (0, 3), (0, 4)]), (2, [(0, 1)]),
+                             (8, [(0, 1), (0, 2), (0, 3), (0, 4), (4, 5), (4, 6), (4, 7)])], 74)
+    molgcn_case("molgcn_stars", None, 74, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50), mols=stars)
 
 
 if __name__ == "__main__":
