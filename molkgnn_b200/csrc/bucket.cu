@@ -314,7 +314,9 @@ __global__ void __launch_bounds__(1024) k_tile_starts_greedy(int N, int cap, con
     if (tid == 0) s_fail = 0;
     __syncthreads();
     const int gap = tinfo[0];
-    if ((TILE_CAP + 1 - gap < TILE_MIN_STRIDE) || (tinfo[1] & 1)) { if (tid == 0) tinfo[2] = 0; return; }
+    // the greedy walk only needs every molecule to fit a tile (any two consecutive greedy tiles hold > TILE_CAP nodes
+    // together, so there are at most N / 64 + 1 of them whatever the molecule sizes -- inside the N / 32 + 4 capacity)
+    if (gap > TILE_CAP || (tinfo[1] & 1)) { if (tid == 0) tinfo[2] = 0; return; }
     const int P = max(1, min(GW, N / 2048));              // segments of >= 2048 nodes
     const int S = (N + P - 1) / P;
     const int seg_lo = warp * S, seg_hi = min(N, (warp + 1) * S);

@@ -378,10 +378,10 @@ def _edge_case(name):
     from molkgnn_b200 import synth
     if name == "large_molecules":          # molecules that do not fit a 128-node tile: no tiling, bucket-order kernels
         return synth.make_batch(3, seed=71, min_atoms=140, max_atoms=150)
-    if name == "largest_tileable_molecules":   # 97 atoms: the tiler needs a legal cut at least every 97 nodes (bucket.cu)
-        return synth.make_batch(3, seed=72, min_atoms=97, max_atoms=97)
-    if name == "molecules_of_128":             # fit a tile, but beyond the tiler's cut-gap bound: untiled, bucket-order kernels
+    if name == "molecules_of_128":             # one molecule fills a tile exactly
         return synth.make_batch(2, seed=72, min_atoms=128, max_atoms=128)
+    if name == "mixed_sizes":                  # 20 .. 128 atoms: tiles of very different fill
+        return synth.make_batch(12, seed=76, min_atoms=20, max_atoms=128)
     if name == "chains":                   # degrees 1 and 2 only: the degree-3 and degree-4 buckets are empty
         return _batch_from_bonds([(n, [(i, i + 1) for i in range(n - 1)]) for n in (2, 5, 9, 2, 3)], 73)
     if name == "stars":                    # degrees 1 and 4 only (+ a two-atom molecule)
@@ -392,12 +392,11 @@ def _edge_case(name):
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["large_molecules", "largest_tileable_molecules", "molecules_of_128", "chains", "stars",
-                                  "two_atoms"])
+@pytest.mark.parametrize("name", ["large_molecules", "molecules_of_128", "mixed_sizes", "chains", "stars", "two_atoms"])
 def test_edge_case_graphs(name, fwd_path):
     """Graph shapes at the edges of the bucket / tile logic, each against the oracle (forced arg-max, 1e-5): molecules larger
-    than a tile or than the tiler's cut-gap bound of 97 nodes (the plan carries no tiles and the bucket-order kernels run),
-    the largest molecules that are tiled, batches with empty degree buckets (kernels.py:702-721 skips them), the two-atom molecule."""
+    than a tile (the plan carries no tiles and the bucket-order kernels run), molecules that fill a tile exactly, mixed
+    sizes up to 128 atoms, batches with empty degree buckets (kernels.py:702-721 skips them), the two-atom molecule."""
     import molkgnn_b200 as mk
     b = _edge_case(name)
     torch.manual_seed(7)
@@ -408,12 +407,12 @@ def test_edge_case_graphs(name, fwd_path):
     d = _to_dev(b)
     x = d["x"].clone().requires_grad_(True)
     plan = net.build_plan(d["edge_index"], d["p"], d["edge_attr"], x.shape[0])
-    if name in ("large_molecules", "molecules_of_128"):
+    if name == "large_molecules":
         assert plan.n_tiles == 0
     else:
         assert plan.n_tiles > 0
-    if name == "largest_tileable_molecules":
-        assert plan.c.tile_max_nodes == 97 and plan.n_tiles == 3
+    if name == "molecules_of_128":
+        assert plan.c.tile_max_nodes == 128 and plan.n_tiles == 2
     forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
     h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, plan=plan,
             argmax_in=forced)
