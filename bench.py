@@ -361,6 +361,11 @@ def main():
         "roofline": roof,
         "nodes_per_gpu": N, "edges_per_gpu": E,
     }
+    if bucket is not None:
+        if bucket.oneshot is not None:
+            bucket.oneshot.check()               # raises if a peer's flag ever timed out
+        line["config"]["allreduce"] = ("one-shot kernel over NVLink peer memory (csrc/oneshot.cu)" if bucket.oneshot is not None
+                                       else "ncclAllReduce (ReduceOp.AVG) of the flat gradient buffer")
     if world == 1 and not args.no_cpu_baseline:
         mol, el, cores = cpu_stream(seconds=args.cpu_seconds)
         line["cpu_baseline"] = {"value": mol / el, "unit": "molecules/s", "cores": cores, "kind": "port",

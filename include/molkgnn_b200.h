@@ -292,6 +292,18 @@ int molkgnn_profile_read(char* buf, int cap);
 int molkgnn_tc_selftest(const void* A, const void* B, float* D, int32_t N, int32_t K, int32_t a_mn, int32_t b_mn,
                         int32_t swap, void* stream);
 
+/* ---- data-parallel step: one-shot all-reduce of the flat kernel-parameter gradient buffer over NVLink peer memory ----------
+ * (csrc/oneshot.cu; the reference has no counterpart -- it trains on one GPU; replaces the ncclAllReduce of SURVEY 8(e) for
+ * latency-sized buffers).  Every rank creates an exchange buffer, the 64-byte CUDA IPC handles are exchanged by the host
+ * (molkgnn_b200/dp.py: torch.distributed all_gather), every rank opens its peers' buffers, and then one kernel per step sums
+ * the W copies in rank order (bitwise identical results on all ranks).  Ranks must call _allreduce the same number of times. */
+int molkgnn_oneshot_create(int32_t rank, int32_t world, int64_t bytes, void** handle);
+int molkgnn_oneshot_ipc_handle(void* handle, void* out64);
+int molkgnn_oneshot_open(void* handle, const void* handles /* world x 64 bytes in rank order */);
+int molkgnn_oneshot_allreduce(void* handle, float* flat, int64_t n, int32_t average, void* stream);
+int molkgnn_oneshot_error(void* handle);      /* 0, or r + 1 if rank r's flag timed out since the last call; synchronises */
+int molkgnn_oneshot_destroy(void* handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,12 @@ EXPORTS = {
                                     i32, C.POINTER(vp), C.POINTER(i32), vp]),
     "molkgnn_stack_bwd": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), i32, C.POINTER(StackLayout), vp, vp, vp, i32, vp,
                                     vp, C.POINTER(i32), vp]),
+    "molkgnn_oneshot_create": (C.c_int, [i32, i32, i64, C.POINTER(vp)]),
+    "molkgnn_oneshot_ipc_handle": (C.c_int, [vp, vp]),
+    "molkgnn_oneshot_open": (C.c_int, [vp, vp]),
+    "molkgnn_oneshot_allreduce": (C.c_int, [vp, vp, i64, i32, vp]),
+    "molkgnn_oneshot_error": (C.c_int, [vp]),
+    "molkgnn_oneshot_destroy": (C.c_int, [vp]),
     "molkgnn_profile_enable": (C.c_int, [C.c_int]),
     "molkgnn_profile_only": (C.c_int, [C.c_char_p]),
     "molkgnn_profile_read": (C.c_int, [C.c_char_p, C.c_int]),

@@ -29,6 +29,75 @@ def shard_bounds(num_nodes_per_molecule, world):
     return [(cuts[i], cuts[i + 1]) for i in range(world)]
 
 
+class OneShotAllReduce(object):
+    """One-shot all-reduce over NVLink peer memory (csrc/oneshot.cu): every rank reads the other ranks' copies of the flat
+    gradient buffer straight out of their exchange buffers and sums them in rank order -- one kernel per step instead of the
+    2 (W - 1) hops of a ring, for a buffer that is latency sized.  ``create`` returns None (on EVERY rank) when the exchange
+    cannot be set up on some rank (no peer access, IPC refused), so that the caller falls back to NCCL consistently."""
+
+    def __init__(self, handle, world, cap_floats):
+        self.handle, self.world, self.cap_floats = handle, world, cap_floats
+
+    @classmethod
+    def create(cls, numel, group=None):
+        import ctypes as C
+        from . import _lib
+        if not (dist.is_initialized() and torch.cuda.is_available()):
+            return None
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world < 2 or world > 16:
+            return None
+        dev = torch.device("cuda", torch.cuda.current_device())
+        L = _lib.lib()
+        handle, mine, ok = C.c_void_p(), torch.zeros(64, dtype=torch.uint8), 1
+        try:
+            _lib.check(L.molkgnn_oneshot_create(rank, world, 4 * int(numel) + 64, C.byref(handle)))
+            buf = (C.c_ubyte * 64)()
+            _lib.check(L.molkgnn_oneshot_ipc_handle(handle, buf))
+            mine = torch.tensor(list(buf), dtype=torch.uint8)
+        except Exception:
+            ok = 0
+        # every rank learns every handle (and whether every rank got this far)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        gathered = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, mine.to(dev), group=group)
+        if int(flag.item()) == 1:
+            try:
+                allh = torch.stack(gathered).cpu().contiguous()
+                _lib.check(L.molkgnn_oneshot_open(handle, C.c_void_p(allh.data_ptr())))
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok if int(flag.item()) == 1 else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) != 1:
+            if handle.value:
+                L.molkgnn_oneshot_destroy(handle)
+            return None
+        return cls(handle, world, int(numel) + 16)
+
+    def allreduce(self, flat, average=True):
+        from . import _lib
+        if flat.numel() > self.cap_floats or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise _lib.MolKGNNError("OneShotAllReduce: buffer larger than the exchange slot or not a contiguous fp32 tensor")
+        _lib.check(_lib.lib().molkgnn_oneshot_allreduce(self.handle, _lib.ptr(flat), flat.numel(), 1 if average else 0,
+                                                        _lib.stream_ptr()))
+        return flat
+
+    def check(self):
+        """raises if a peer's flag timed out in some step since the last check (synchronises the device)"""
+        from . import _lib
+        e = _lib.lib().molkgnn_oneshot_error(self.handle)
+        if e:
+            raise _lib.MolKGNNError(f"OneShotAllReduce: the flag of rank {e - 1} did not arrive within the time limit")
+
+    def close(self):
+        from . import _lib
+        if self.handle is not None and self.handle.value:
+            _lib.lib().molkgnn_oneshot_destroy(self.handle)
+            self.handle = None
+
+
 def _native_flat_of(module):
     flats = [m._stack.last_grad_flat for m in module.modules()
              if getattr(m, "_stack", None) is not None and getattr(m._stack, "last_grad_flat", None) is not None]
@@ -38,7 +107,7 @@ def _native_flat_of(module):
 class GradBucket(object):
     """Flat all-reduce bucket over the gradients of the kernel parameters of a module."""
 
-    def __init__(self, module, world=None, average=True, group=None):
+    def __init__(self, module, world=None, average=True, group=None, oneshot=None):
         self.params = [p for n, p in module.named_parameters()
                        if p.requires_grad and n.rsplit(".", 1)[-1] in GRAD_PARAM_SUFFIXES]
         self.numel = sum(p.numel() for p in self.params)
@@ -47,6 +116,14 @@ class GradBucket(object):
         self.group = group
         self.flat = None
         self.module = module
+        # one-shot NVLink all-reduce of the native flat buffer: opt-in (oneshot=True or MOLKGNN_DP_ONESHOT=1) until it has
+        # been validated on the 8-GPU box; NCCL otherwise and whenever the exchange cannot be set up
+        import os
+        if oneshot is None:
+            oneshot = os.environ.get("MOLKGNN_DP_ONESHOT", "0") == "1"
+        self.oneshot = None
+        if oneshot and self.world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            self.oneshot = OneShotAllReduce.create(2 * self.numel + 4096, group)   # room for the native buffer's padding
 
     def _native_flat(self, ps):
         flat = _native_flat_of(self.module)
@@ -71,7 +148,9 @@ class GradBucket(object):
         # p.grad tensors are views of it (functional.MolGCNFn.backward) -> reduce that buffer in place, no gather/scatter
         flat = self._native_flat(ps)
         if flat is not None:
-            if self.world > 1:
+            if self.world > 1 and self.oneshot is not None and flat.is_cuda:
+                self.oneshot.allreduce(flat, self.average)
+            elif self.world > 1:
                 if self.average and flat.is_cuda:
                     # NCCL averages inside the collective: no separate scaling kernel behind it
                     dist.all_reduce(flat, op=dist.ReduceOp.AVG, group=self.group)
