@@ -121,3 +121,27 @@ def params_from_module(net, dtype=torch.float32, requires_grad=False):
                        for n in PARAM_NAMES})
         out.append(lp)
     return out
+
+
+def tile_schedule_model(nn, G):
+    """Plain-numpy model of k_tile_order (csrc/bucket.cu; no reference counterpart -- the tile schedule is internal to the
+    tile-major backward kernels).  nn[t] = nodes of tile t, G persistent CTAs.  Returns `order`: CTA c walks
+    order[beg_c : beg_c + cnt_c] with cnt_c = q + (c < r), n = q G + r (csrc/tile.cuh TileWalk).  Tiles are sorted by node
+    count (stable); the r long CTAs take the (q + 1) r smallest, the others the rest, dealt boustrophedon in each group."""
+    nn = np.asarray(nn)
+    n = len(nn)
+    q, r = divmod(n, G)
+    srt = np.argsort(nn, kind="stable")
+    order = np.full(n, -1, dtype=np.int64)
+    nlong, Gs = (q + 1) * r, G - r
+    for s, t in enumerate(srt):
+        if s < nlong:
+            k, i = divmod(s, r)
+            c = r - 1 - i if k & 1 else i
+            pos = c * (q + 1) + k
+        else:
+            k, i = divmod(s - nlong, Gs)
+            c = Gs - 1 - i if k & 1 else i
+            pos = nlong + c * q + k
+        order[pos] = t
+    return order

@@ -182,6 +182,8 @@ def test_tile_schedule_is_a_balanced_permutation(n_mol, seed):
     assert np.array_equal(np.sort(order), np.arange(T))
     assert np.array_equal(plan2.tile_order.cpu().numpy()[:T], order)
     nn = np.diff(plan.tile_start.cpu().numpy()[:T + 1])
+    from tests.helpers import tile_schedule_model
+    assert np.array_equal(order, tile_schedule_model(nn, G))           # the kernel against its plain-numpy model
     q, r = divmod(T, G)
     load, load_rr = np.zeros(G), np.zeros(G)
     pos = 0

@@ -101,3 +101,28 @@ def test_roofline_formula_matches_survey_worked_numbers():
     fwd, bwd = roofline.stack_bytes(N=25, E=54, n=(6, 11, 6, 2), x_dim=28, L1=(40, 80, 120, 200),
                                     LN=(40, 80, 120, 200), num_layers=5)
     assert (fwd, bwd) == (419440, 597940)
+
+
+def test_tile_schedule_model_properties():
+    """The balanced tile schedule (model of k_tile_order; the GPU test compares the kernel with this model entry by entry):
+    a permutation; and when a few CTAs walk one tile more than the rest, those CTAs get the small tiles, so that the largest
+    per-CTA node total stays close to the mean instead of one full tile above it."""
+    from tests.helpers import tile_schedule_model
+    rng = np.random.default_rng(0)
+    for n, G in [(1, 1), (5, 5), (148, 148), (149, 148), (887, 148), (892, 148), (890, 148), (3000, 148), (37, 8)]:
+        nn = rng.integers(97, 129, size=n)
+        order = tile_schedule_model(nn, G)
+        assert np.array_equal(np.sort(order), np.arange(n))
+        q, r = divmod(n, G)
+        load, pos = np.zeros(G), 0
+        for c in range(G):
+            cnt = q + (1 if c < r else 0)
+            load[c] = nn[order[pos:pos + cnt]].sum()
+            pos += cnt
+        rr = np.zeros(G)
+        for t in range(n):
+            rr[t % G] += nn[t]
+        if q >= 4:
+            assert load.max() <= rr.max()
+            if 0 < r <= G // 2:
+                assert load.max() / load.mean() < 1.03 < rr.max() / rr.mean()
