@@ -304,7 +304,7 @@ class KernelSetConvFn(torch.autograd.Function):
         xp, xnorm, argmax = ctx.saved_tensors
         pack = ctx.pack
         need_gp = any(ctx.needs_input_grad[7:])
-        gx, grads = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float(), 0, argmax, ctx.need_gx, need_gp,
+        gx, grads = conv_backward(ctx.plan, pack, xp, xnorm, grad_sc.float().contiguous(), 0, argmax, ctx.need_gx, need_gp,
                                   ximg=ctx.ximg)
         flat = _flatten_param_grads(grads, pack, ctx.needs_input_grad[7:])
         return (gx[:, :ctx.F] if gx is not None else None, None, None, None, None, None, None, *flat)

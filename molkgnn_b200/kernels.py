@@ -133,8 +133,8 @@ class BaseKernelSetConv(Module):
         for d in range(4):
             f, t = self.fixed_kernelconv_set[d], self.trainable_kernelconv_set[d]
             if f is not None and t is not None:
-                raise NotImplementedError('mixed fixed+trainable kernel sets for one degree are not supported yet '
-                                          '(SURVEY.md 8(f) N4)')
+                raise NotImplementedError('the native stack driver takes one KernelConv per degree; a layer with fixed AND '
+                                          'trainable kernels runs through BaseKernelSetConv.forward (two passes)')
             out.append(t if f is None else f)
         return out
 
@@ -148,8 +148,8 @@ class BaseKernelSetConv(Module):
             elif f is None or t is None:
                 out.append(_param_dict(t if f is None else f))
             else:
-                raise NotImplementedError('mixed fixed+trainable kernel sets for one degree are not supported yet '
-                                          '(SURVEY.md 8(f) N4)')
+                raise NotImplementedError('one parameter set per degree expected here; BaseKernelSetConv.forward runs a layer '
+                                          'with fixed AND trainable kernels as two passes')
         return out
 
     def forward(self, is_last_layer, *argv, **kwargv):
@@ -167,17 +167,37 @@ class BaseKernelSetConv(Module):
         pf = [g(f'p_focal_deg{d}') for d in range(1, 5)]
         pn = [g(f'nei_p_deg{d}') for d in range(1, 5)]
         ea = [g(f'nei_edge_attr_deg{d}') for d in range(1, 5)]
-        params = self._degree_params()
+        fixed, train = list(self.fixed_kernelconv_set), list(self.trainable_kernelconv_set)
         for d in range(4):
-            if sel[d] is not None and sel[d].numel() and params[d] is None:
+            if sel[d] is not None and sel[d].numel() and fixed[d] is None and train[d] is None:
                 raise Exception(f'kernels.py::BaseKernelSet:both fixed and trainable kernelconv_set are None for '
                                 f'degree {d + 1}')
         plan = kwargv.get('plan', None)
         if plan is None:
             plan = BucketPlan.from_reference_tensors(x.shape[0], sel, nei, pf, pn, ea)
-        Fe = next(int(p['edge_attr_support'].shape[-1]) for p in params if p is not None)
-        sc = KernelSetConvFn.apply(x, plan, params, Fe, bool(is_last_layer), kwargv.get('argmax_in', None),
-                                   kwargv.get('aux', None), *flat_params(params))
+
+        def run(params):
+            Fe = next(int(p['edge_attr_support'].shape[-1]) for p in params if p is not None)
+            return KernelSetConvFn.apply(x, plan, params, Fe, bool(is_last_layer), kwargv.get('argmax_in', None),
+                                         kwargv.get('aux', None), *flat_params(params))
+
+        if any(f is not None and t is not None for f, t in zip(fixed, train)):
+            # fixed AND trainable kernels for a degree (kernels.py:702-715): every KernelConv carries its own three mixing
+            # weights, so the two sets run as two passes of the same kernels and the score columns of a degree are laid
+            # side by side as [fixed ; trainable]
+            if kwargv.get('argmax_in', None) is not None or kwargv.get('aux', None) is not None:
+                raise NotImplementedError('argmax_in / aux are not available for mixed fixed+trainable kernel sets')
+            pf_, pt_ = [None if f is None else _param_dict(f) for f in fixed], [None if t is None else _param_dict(t)
+                                                                               for t in train]
+            sc_f, sc_t = run(pf_), run(pt_)
+            cols, of, ot = [], 0, 0
+            for d in range(4):
+                Lf, Lt = self.num_fixed_kernel_list[d] or 0, self.num_trainable_kernel_list[d] or 0
+                cols += [sc_f[:, of:of + Lf], sc_t[:, ot:ot + Lt]]
+                of, ot = of + Lf, ot + Lt
+            sc = torch.cat(cols, dim=1)
+        else:
+            sc = run(self._degree_params())
         if save_score:
             self.save_score(sc)
         return sc

@@ -420,3 +420,42 @@ def test_edge_case_graphs(name, fwd_path):
     (h * wout.to(DEV)).sum().backward()
     assert rel_err(x.grad.cpu(), gx_ref) < TOL
     _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
+
+
+def test_mixed_fixed_and_trainable_kernel_sets():
+    """BaseKernelSetConv with a fixed (requires_grad=False) AND a trainable KernelConv per degree (kernels.py:452-516,
+    702-715) against the unmodified reference (tests/golden/set_mixed.npz): score columns of a degree are [fixed ; trainable],
+    gradients reach x and the trainable kernels only."""
+    import types
+    import molkgnn_b200 as mk
+    g = load_golden("set_mixed")
+    Lf, Lt = [int(v) for v in g["Lf"]], [int(v) for v in g["Lt"]]
+    mk_kc = lambda L, d, rg: mk.KernelConv(L=L, D=3, num_supports=d, node_attr_dim=28, edge_attr_dim=7,  # noqa: E731
+                                           requires_grad=rg, weight_requires_grad=rg)
+    layer = mk.BaseKernelSetConv(*[mk_kc(Lf[d], d + 1, False) for d in range(4)],
+                                 *[mk_kc(Lt[d], d + 1, True) for d in range(4)])
+    sd = {k[len("param_"):]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("param_")}
+    layer.load_state_dict(sd, strict=True)
+    layer = layer.to(DEV)
+    x = torch.from_numpy(g["x"]).to(DEV).requires_grad_(True)
+    data = types.SimpleNamespace(x=x, edge_index=torch.from_numpy(g["edge_index"]).to(DEV),
+                                 edge_attr=torch.from_numpy(g["edge_attr"]).to(DEV), p=torch.from_numpy(g["p"]).to(DEV))
+    for k, v in g.items():
+        if k.startswith("bk_"):
+            t = torch.from_numpy(np.asarray(v))
+            setattr(data, k[3:], (t.long() if "index" in k else t.float()).to(DEV))
+    sc = layer(is_last_layer=True, data=data, save_score=False)
+    assert sc.shape == g["sc"].shape
+    assert rel_err(sc.detach().cpu(), g["sc"]) < TOL
+    (sc * torch.from_numpy(g["wout"]).to(DEV)).sum().backward()
+    assert rel_err(x.grad.cpu(), g["grad_x"]) < TOL
+    for d in range(4):
+        for p in layer.fixed_kernelconv_set[d].parameters():
+            assert p.grad is None
+        kc = layer.trainable_kernelconv_set[d]
+        for nme in ["x_center", "x_support", "edge_attr_support"]:
+            assert rel_err(getattr(kc, nme).grad.cpu(), g[f"grad_trainable_kernelconv_set.{d}.{nme}"]) < TOL, (d, nme)
+        trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
+        refs = np.array([float(g[f"grad_trainable_kernelconv_set.{d}.{t}"]) for t in trip])
+        got = np.array([getattr(kc, t).grad.item() for t in trip])
+        assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (d, got, refs)

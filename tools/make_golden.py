@@ -158,6 +158,45 @@ def molgcn_case(name, n_mol, seed, num_layers, L1, LN, dup=0.5, mols=None):
     print(name, "N=", b["x"].shape[0], "E=", b["edge_index"].shape[1], "K=", K, "h.abs.mean=", float(h.abs().mean()))
 
 
+def mixed_set_case(name, n_mol, seed, Lf, Lt):
+    """One BaseKernelSetConv layer with a FIXED (requires_grad=False) and a TRAINABLE KernelConv per degree
+    (kernels.py:702-715: the score rows of a degree are [fixed ; trainable]), last layer (chirality on)."""
+    from models.MolKGNN.kernels import BaseKernelSetConv
+    # no duplicated leaf rows: without structural ties the free-running arg-max is the reference's (a mixed layer runs as two
+    # passes and cannot be teacher-forced)
+    mols = synth.make_molecules(n_mol, seed=seed, dup_leaf_prob=0.0)
+    b = synth.collate(mols)
+    bk = ref_bucket_collated(mols)
+    torch.manual_seed(seed)
+    mk_kc = lambda L, d, rg: KernelConv(L=L, D=3, num_supports=d, node_attr_dim=synth.X_DIM,  # noqa: E731
+                                        edge_attr_dim=synth.EDGE_DIM, requires_grad=rg, weight_requires_grad=rg)
+    fixed = [mk_kc(Lf[d], d + 1, False) for d in range(4)]
+    train = [mk_kc(Lt[d], d + 1, True) for d in range(4)]
+    g = torch.Generator().manual_seed(seed + 7)
+    with torch.no_grad():
+        for kc in fixed + train:
+            for w in (kc.support_attr_sc_weight, kc.center_attr_sc_weight, kc.edge_attr_support_sc_weight):
+                w.add_(0.5 * torch.randn((), generator=g))
+    layer = BaseKernelSetConv(*fixed, *train)
+    x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+    data = Data(x=x, edge_index=torch.from_numpy(b["edge_index"]), edge_attr=torch.from_numpy(b["edge_attr"]),
+                p=torch.from_numpy(b["p"]), **{k: torch.from_numpy(v) for k, v in bk.items()})
+    sc = layer(is_last_layer=True, data=data, save_score=False)
+    wout = torch.randn(sc.shape, generator=torch.Generator().manual_seed(seed + 11))
+    (sc * wout).sum().backward()
+    save = dict(x=b["x"], p=b["p"], edge_index=b["edge_index"], edge_attr=b["edge_attr"], sc=sc.detach().numpy(),
+                wout=wout.numpy(), grad_x=x.grad.numpy(), Lf=np.asarray(Lf), Lt=np.asarray(Lt), seed=np.int64(seed))
+    for k, v in bk.items():
+        save["bk_" + k] = v
+    for k, v in layer.state_dict().items():
+        save["param_" + k] = v.numpy()
+    for k, v in layer.named_parameters():
+        if v.grad is not None:
+            save["grad_" + k] = v.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "N=", b["x"].shape[0], "K=", sc.shape[1], "grads:", sum(1 for k in save if k.startswith("grad_")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. docstring KAT (kernels.py:161-170)
@@ -191,6 +230,8 @@ def main():
     stars = mols_from_bonds([(5, [(0, 1), (0, 2), (0, 3), (0, 4)]), (2, [(0, 1)]),
                              (8, [(0, 1), (0, 2), (0, 3), (0, 4), (4, 5), (4, 6), (4, 7)])], 74)
     molgcn_case("molgcn_stars", None, 74, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50), mols=stars)
+    # 6. fixed + trainable kernel sets in one layer (kernels.py:452-516, 702-715)
+    mixed_set_case("set_mixed", n_mol=5, seed=9, Lf=(2, 3, 2, 3), Lt=(3, 2, 4, 2))
 
 
 if __name__ == "__main__":
