@@ -83,3 +83,33 @@ def test_molgcn_forward_backward(name):
             assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (li, d, got, refs)
             # parameters the reference never differentiates
             assert f"grad_layers.{li}.trainable_kernelconv_set.{d}.p_support" not in g
+
+
+def test_mixed_fixed_and_trainable_kernel_sets():
+    """A layer with a fixed AND a trainable KernelConv per degree (kernels.py:702-715: rows of a degree = [fixed ; trainable]):
+    the oracle, run once per set with the columns laid side by side, against the unmodified reference's BaseKernelSetConv."""
+    from tests.helpers import PARAM_NAMES
+    g = load_golden("set_mixed")
+
+    def params(kind, rg):
+        return [{n: torch.from_numpy(np.asarray(g[f"param_{kind}_kernelconv_set.{d}.{n}"])).clone().requires_grad_(rg)
+                 for n in PARAM_NAMES} for d in range(4)]
+
+    pf, pt = params("fixed", False), params("trainable", True)
+    bk = orc.buckets_to_torch(orc.bucket_pass(g["edge_index"], g["x"].shape[0], g["p"], g["edge_attr"]))
+    x = torch.from_numpy(g["x"]).clone().requires_grad_(True)
+    sc_f = orc.kernel_set_conv_forward(pf, x, bk, is_last_layer=True)
+    sc_t = orc.kernel_set_conv_forward(pt, x, bk, is_last_layer=True)
+    cols, of, ot = [], 0, 0
+    for d in range(4):
+        Lf, Lt = int(g["Lf"][d]), int(g["Lt"][d])
+        cols += [sc_f[:, of:of + Lf], sc_t[:, ot:ot + Lt]]
+        of, ot = of + Lf, ot + Lt
+    sc = torch.cat(cols, dim=1)
+    assert rel_err(sc.detach(), g["sc"]) < 1e-5
+    (sc * torch.from_numpy(g["wout"])).sum().backward()
+    assert rel_err(x.grad, g["grad_x"]) < 2e-5
+    for d in range(4):
+        for nme in ["x_center", "x_support", "edge_attr_support"]:
+            assert rel_err(pt[d][nme].grad, g[f"grad_trainable_kernelconv_set.{d}.{nme}"]) < 5e-5, (d, nme)
+            assert f"grad_fixed_kernelconv_set.{d}.{nme}" not in g
