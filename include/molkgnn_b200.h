@@ -108,6 +108,9 @@ int molkgnn_num_sms(void);
 /* ---- degree bucketing: replaces ToXAndPAndEdgeAttrForDeg.__call__ (wrapper.py:559-672) + PyG collation ---- */
 /* size of one per-tile metadata record (plan->tile_meta) */
 int64_t molkgnn_tile_meta_bytes(void);
+/* sizeof of the structs of this header as compiled into the library: 0 molkgnn_plan_t, 1 molkgnn_layer_t,
+ * 2 molkgnn_layer_grads_t, 3 molkgnn_stack_layout_t (-1 otherwise).  A binding checks its mirror against these. */
+int64_t molkgnn_struct_bytes(int32_t which);
 /* Tile schedule of the tile-major backward kernels (plan->tile_order): 0 = round robin, 1 = balanced schedule for plans where
  * a few persistent CTAs would walk one tile more than the rest (default; env MOLKGNN_TILE_ORDER), 2 = always.  Returns the
  * previous mode.  Takes effect for plans built afterwards. */

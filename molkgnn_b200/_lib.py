@@ -52,6 +52,7 @@ EXPORTS = {
     "molkgnn_launch_count": (i64, []),
     "molkgnn_bucket_scratch_bytes": (i64, [i32, i32]),
     "molkgnn_tile_meta_bytes": (i64, []),
+    "molkgnn_struct_bytes": (i64, [i32]),
     "molkgnn_set_tile_order": (C.c_int, [C.c_int]),
     "molkgnn_tile_ximg_bytes": (i64, [C.POINTER(Plan), C.POINTER(Layer)]),
     "molkgnn_tile_ximg_build": (C.c_int, [C.POINTER(Plan), C.POINTER(Layer), vp, i32, vp, vp, vp]),

@@ -239,3 +239,13 @@ extern "C" int molkgnn_stack_bwd(const molkgnn_plan_t* plan, const molkgnn_layer
         if (side && used[pb]) MK_CHECK_CUDA(cudaStreamWaitEvent(main_st, side->done[pb], 0));
     return 0;
 }
+
+extern "C" int64_t molkgnn_struct_bytes(int32_t which) {
+    switch (which) {
+        case 0: return (int64_t)sizeof(molkgnn_plan_t);
+        case 1: return (int64_t)sizeof(molkgnn_layer_t);
+        case 2: return (int64_t)sizeof(molkgnn_layer_grads_t);
+        case 3: return (int64_t)sizeof(molkgnn_stack_layout_t);
+        default: return -1;
+    }
+}

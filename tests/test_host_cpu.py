@@ -26,6 +26,9 @@ def test_cabi_exports_every_declared_symbol():
     l = _lib.lib()
     assert l.molkgnn_version() >= 100
     assert l.molkgnn_packed_floats(4, 50, 112) > 0 and l.molkgnn_packed_floats(5, 1, 4) == -1
+    # the ctypes mirrors of the header's structs have the compiled sizes
+    for which, cls in enumerate([_lib.Plan, _lib.Layer, _lib.LayerGrads, _lib.StackLayout]):
+        assert l.molkgnn_struct_bytes(which) == ctypes.sizeof(cls), cls.__name__
 
 
 def test_state_dict_keys_and_init_order_match_reference():
