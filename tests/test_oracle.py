@@ -1,4 +1,5 @@
 """CPU: pin oracle/molkgnn_oracle.py against the fixtures produced by the UNMODIFIED reference (tools/make_golden.py)."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -113,3 +114,21 @@ def test_mixed_fixed_and_trainable_kernel_sets():
         for nme in ["x_center", "x_support", "edge_attr_support"]:
             assert rel_err(pt[d][nme].grad, g[f"grad_trainable_kernelconv_set.{d}.{nme}"]) < 5e-5, (d, nme)
             assert f"grad_fixed_kernelconv_set.{d}.{nme}" not in g
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models/MolKGNN"), reason="the reference tree only exists in the build container")
+def test_oracle_against_the_live_reference_on_fresh_batches():
+    """Beyond the committed fixtures: tools/live_reference_check.py imports the UNMODIFIED reference (own process: it mocks
+    rdkit & co. in sys.modules) and compares it with the oracle on fresh random batches -- random molecule counts, layer
+    counts and kernel counts per seed."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "live_reference_check.py"), "6"], capture_output=True,
+                       text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert out["bucket_bit_exact"]
+    assert out["h"] < 1e-5 and out["grad_x"] < 2e-5 and out["grad_params"] < 5e-5
+    assert out["argmax_exact_share"] > 0.97
