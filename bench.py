@@ -10,8 +10,9 @@ One "step" = one pass of the hot path over one batch of synthetic molecules: GPU
 + NCCL all-reduce of the flat kernel-gradient bucket when N > 1 (molecules sharded per rank, weak scaling).
 Workload = BASELINE.json configs[1]: batch 4096 molecules per GPU.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference (oracle/, kind "port":
-the reference repo is not present on the GPU box) on the host cores.
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own unmodified modules (oracle/_ref, staged by
+tools/make_oracle_ref.py; kind "reference") on the host cores -- the oracle port (kind "port") only where they are not staged.
+`--molecules 65536` = one GPU's share of BASELINE configs[3]; `--forward-only` = configs[4] (inference sweep, h returned to the host).
 """
 import argparse
 import json
@@ -43,72 +44,131 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=None, help="synthetic-batch seed (default 1000 * rank, SURVEY 8(d))")
+    ap.add_argument("--forward-only", action="store_true",
+                    help="BASELINE configs[4] (inference sweep): bucket pass + forward under torch.no_grad; e2e returns h [N,K] to the host")
     return ap.parse_args()
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port of the reference algorithm on the host cores
+# CPU arm: the reference's own modules (oracle/_ref, staged by tools/make_oracle_ref.py) on the host cores; where they
+# are not staged, the oracle port of the same algorithm
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_stream(seconds=None, batches=None, batch=16, seed=123, warm=2):
-    """Stream of README-shape mini-batches (16 molecules) through the oracle's MolGCN fwd+bwd; returns
-    (molecules, seconds, cores).  The reference's own code is super-linear in batch size, so batch-16 is
-    the configuration it is quoted on."""
+def cpu_arm(kind=None, batch=16, seed=123):
+    """-> (kind, one(i), cores): `one(i)` runs MolGCN fwd + backward on the i-th README-shape mini-batch (16 molecules).
+
+    kind "reference": the UNMODIFIED reference modules (models/MolKGNN/{kernels,KernelLayer}.py, imported from oracle/_ref
+    through the torch_geometric stand-in of tests/stubs), exactly BASELINE.md 2.  The 20 per-degree tensors the reference
+    precomputes OFFLINE (pre_transform, data.py:19-30) are built outside the timed region.
+    kind "port": oracle/molkgnn_oracle.py (vectorised restatement, ~35x faster than the reference's Python loops).
+    The reference is super-linear in batch size (O(n4^2) chirality loop, ~30 MB/molecule of autograd state), so
+    batch 16 is the configuration it is quoted on and the only one that is feasible on a host."""
     from molkgnn_b200 import synth
     from oracle import molkgnn_oracle as orc
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import make_oracle_ref
+    if kind is None:
+        kind = "reference" if make_oracle_ref.available() else "port"
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(0)
-    params = orc.init_molgcn_params(NUM_LAYERS, L_BASE, L_BASE, X_DIM, requires_grad=True)
     pool = [synth.make_batch(batch, seed=seed + i) for i in range(8)]
+    if kind == "reference":
+        import warnings
+        warnings.filterwarnings("ignore", message="Using torch.cross without specifying the dim")
+        MolGCN = make_oracle_ref.load()["KernelLayer"].MolGCN
+        net = MolGCN(num_layers=NUM_LAYERS, num_kernel1_1hop=L_BASE[0], num_kernel2_1hop=L_BASE[1], num_kernel3_1hop=L_BASE[2],
+                     num_kernel4_1hop=L_BASE[3], num_kernel1_Nhop=L_BASE[0], num_kernel2_Nhop=L_BASE[1],
+                     num_kernel3_Nhop=L_BASE[2], num_kernel4_Nhop=L_BASE[3], x_dim=X_DIM, p_dim=3, edge_attr_dim=EDGE_DIM)
+        kws = []
+        for b in pool:
+            bk = orc.bucket_pass(b["edge_index"], b["x"].shape[0], b["p"], b["edge_attr"])    # offline in the reference
+            kw = dict(edge_index=torch.from_numpy(b["edge_index"]), edge_attr=torch.from_numpy(b["edge_attr"]),
+                      p=torch.from_numpy(b["p"]), save_score=False)
+            for d in range(1, 5):
+                for k, v in bk[d].items():
+                    kw[f"{k}_deg{d}"] = torch.from_numpy(v)
+            kws.append(kw)
 
-    def one(b):
-        N = b["x"].shape[0]
-        bk = orc.buckets_to_torch(orc.bucket_pass(b["edge_index"], N, b["p"], b["edge_attr"]))
-        x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
-        h = orc.molgcn_forward(params, x, torch.from_numpy(b["edge_index"]), bk)
-        h.sum().backward()
+        def one(i):
+            b, kw = pool[i % len(pool)], kws[i % len(pool)]
+            x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+            h = net(x=x, **kw)
+            h.sum().backward()
+            net.zero_grad(set_to_none=True)
+    else:
+        params = orc.init_molgcn_params(NUM_LAYERS, L_BASE, L_BASE, X_DIM, requires_grad=True)
 
+        def one(i):
+            b = pool[i % len(pool)]
+            N = b["x"].shape[0]
+            bk = orc.buckets_to_torch(orc.bucket_pass(b["edge_index"], N, b["p"], b["edge_attr"]))
+            x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+            h = orc.molgcn_forward(params, x, torch.from_numpy(b["edge_index"]), bk)
+            h.sum().backward()
+    return kind, one, cores
+
+
+def cpu_stream(seconds=None, batches=None, batch=16, warm=2, kind=None):
+    """-> (molecules, seconds, cores, kind) of a stream of batch-16 mini-batches through the CPU arm"""
+    kind, one, cores = cpu_arm(kind, batch)
     for i in range(warm):
-        one(pool[i % len(pool)])
+        one(i)
     t0 = time.perf_counter()
     n = 0
     while True:
-        one(pool[n % len(pool)])
+        one(n)
         n += 1
         el = time.perf_counter() - t0
         if (batches is not None and n >= batches) or (seconds is not None and el >= seconds):
             break
-    return n * batch, el, cores
+    return n * batch, el, cores, kind
+
+
+CPU_SAMPLE = {"reference": "UNMODIFIED reference models/MolKGNN/{kernels,KernelLayer}.py (oracle/_ref) MolGCN fwd + autograd bwd, torch CPU, "
+                           "all host threads",
+              "port": "oracle/molkgnn_oracle.py (vectorised restatement; oracle/_ref not staged on this box), torch CPU, all host threads"}
 
 
 def run_reference(args):
-    """`--impl reference`: CPU port on all host threads; a step = 8 mini-batches of 16 molecules."""
+    """`--impl reference`: the reference's own CPU implementation of the path on all host threads.  A step = a bounded sample of
+    the workload: 2 mini-batches of 16 molecules (the reference runs ~25 molecules/s, so 20 steps take ~30 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_step = 8
-    cpu_stream(batches=args.warmup * per_step, warm=0)
-    mol, el, cores = cpu_stream(batches=args.steps * per_step, warm=0)
-    v = mol / el
+    kind, one, cores = cpu_arm()
+    per_step = 2 if kind == "reference" else 8
+    for i in range(args.warmup * per_step):
+        one(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps * per_step):
+        one(i)
+    el = time.perf_counter() - t0
+    v = args.steps * per_step * 16 / el
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "molecules/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.molecules),
-        "cpu_baseline": {"value": v, "unit": "molecules/s", "cores": cores, "kind": "port",
+        "config": workload_config(args.molecules, args.forward_only),
+        "cpu_baseline": {"value": v, "unit": "molecules/s", "cores": cores, "kind": kind,
                          "sample": f"{args.steps} steps x {per_step} mini-batches x 16 molecules (README batch shape), "
-                                   "oracle/molkgnn_oracle.py MolGCN fwd+bwd, torch CPU, all host threads"},
+                                   + CPU_SAMPLE[kind]},
         "e2e": {"value": v, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def workload_config(B):
-    return {"workload": f"BASELINE configs[1]: MolGCN conv stack fwd+bwd, {NUM_LAYERS} layers, kernels 10/20/30/50 "
+def workload_config(B, fwd_only=False):
+    which = ("BASELINE configs[4] (inference sweep): MolGCN conv stack forward only" if fwd_only else
+             "BASELINE configs[1]: MolGCN conv stack fwd+bwd" if B == 4096 else
+             "BASELINE configs[3] (one GPU's share of the sharded training step): MolGCN conv stack fwd+bwd" if B == 65536 else
+             "MolGCN conv stack fwd+bwd")
+    return {"workload": f"{which}, {NUM_LAYERS} layers, kernels 10/20/30/50 "
                         f"(1-hop and N-hop), node_dim 28, edge_dim 7, batch {B} synthetic 3D molecules per GPU "
                         "(18-32 atoms, degrees 1-4), GPU degree-bucket pass included",
-            "molecules_per_gpu": B, "layers": NUM_LAYERS, "kernels": list(L_BASE),
+            "molecules_per_gpu": B, "layers": NUM_LAYERS, "kernels": list(L_BASE), "forward_only": bool(fwd_only),
+            "cpu_arms": "the CPU arms (cpu_baseline, --impl reference) time a stream of batch-16 mini-batches of the same model and "
+                        "generator: the reference is super-linear in batch size and cannot run this batch on a host (SURVEY 6)",
             "pipeline": "the GPU bucket pass of step i+1 is queued on a side stream while step i computes (one pass per step, "
                         "inside the timed region)",
             "l2": "no explicit flush: per-step working set (activations+gradients of 3 layers, ~0.5 GB) exceeds the 126 MB L2"}
@@ -191,6 +251,7 @@ def main():
     from molkgnn_b200.dp import GradBucket
 
     B = args.molecules
+    fwd_only = args.forward_only
     batch = synth.make_batch(B, seed=1000 * rank if args.seed is None else args.seed)   # shard of this rank
     N, E = batch["x"].shape[0], batch["edge_index"].shape[1]
     host = {k: torch.from_numpy(batch[k]).pin_memory() for k in ("x", "p", "edge_index", "edge_attr")}
@@ -207,6 +268,9 @@ def main():
     def step(t, plan=None):
         """bucket pass (here, or already staged one step ahead on the prefetcher's stream: `plan`) + fwd + bwd
         (+ all-reduce) on device tensors `t`"""
+        if fwd_only:
+            with torch.no_grad():
+                return net(x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False, plan=plan)
         x = t["x"].detach().requires_grad_(True)
         h = net(x=x, edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False, plan=plan)
         h.backward(wout)                     # dL/dh handed in directly: no torch arithmetic inside the timed region
@@ -274,6 +338,7 @@ def main():
     # its loss back; the copy of step i+1 is issued on the prefetcher's side stream before step i's loss is waited for, the
     # way a pinned-memory DataLoader feeds the reference's training loop.
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_host = [torch.empty(N, K, dtype=torch.float32).pin_memory() for _ in range(2)] if fwd_only else None
 
     def e2e_run(k):
         nxt = pf.put(host_batch=host, build_plan=True)
@@ -283,18 +348,22 @@ def main():
             if i + 1 < k:
                 nxt = pf.put(host_batch=host, build_plan=True)
             h = step(t, plan)
-            loss = (h.detach() * wout).sum()
-            buf = loss_host[i & 1]
-            buf.copy_(loss, non_blocking=True)    # D2H read of the step's result into pinned memory ...
+            if fwd_only:                          # inference: the WHOLE result h [N, K] returns to the host
+                buf = h_host[i & 1]
+                buf.copy_(h, non_blocking=True)
+            else:
+                loss = (h.detach() * wout).sum()
+                buf = loss_host[i & 1]
+                buf.copy_(loss, non_blocking=True)    # D2H read of the step's result into pinned memory ...
             ev = torch.cuda.Event()
             ev.record()
             zero_grads()
             if pending is not None:               # ... consumed on the host one step later (asynchronous logging), so
                 pending[1].synchronize()          # the host can queue step i+1 while step i still runs
-                float(pending[0])
+                float(pending[0].view(-1)[0])
             pending = (buf, ev)
         pending[1].synchronize()
-        float(pending[0])
+        float(pending[0].view(-1)[0])
 
     e2e_run(3)
     sync_all()
@@ -330,6 +399,9 @@ def main():
     per_launch_ms = kms / max(cnt, 1)
     launches_per_step = cnt / args.steps
     achieved = (kbytes / max(launches_per_step, 1e-9)) / (per_launch_ms * 1e-3) / 1e9 if cnt else 0.0
+    if fwd_only:
+        fwd_b = roofline.stack_bytes(N, E, n, X_DIM, L_BASE, L_BASE, NUM_LAYERS, EDGE_DIM, training=False)[0]
+        bwd_b, bwd_f = 0, 0
     step_gbs = (fwd_b + bwd_b) * args.steps / (ms * 1e-3) / 1e9
     # DRAM bytes per launch of that kernel from the committed ncu --set full capture (profiles/traffic.json), or null
     traffic, traffic_src = None, None
@@ -349,10 +421,10 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "molecules/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, fwd_only),
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": N * K * 4 if fwd_only else 4, "ms_per_step": ms_e2e / args.steps,
                 "api": "molkgnn_b200.MolGCN.forward/backward; every step's x/p/edge_index/edge_attr copied from pinned host "
                        "memory and bucketed (molkgnn_b200.data.DevicePrefetcher: side stream, one step ahead), every step's loss "
                        "copied to pinned host memory and consumed by the host one step later; all K copies and K reads are "
@@ -364,14 +436,15 @@ def main():
     if bucket is not None:
         if bucket.oneshot is not None:
             bucket.oneshot.check()               # raises if a peer's flag ever timed out
-        line["config"]["allreduce"] = ("one-shot kernel over NVLink peer memory (csrc/oneshot.cu)" if bucket.oneshot is not None
+        line["allreduce"] = ("one-shot kernel over NVLink peer memory (csrc/oneshot.cu)" if bucket.oneshot is not None
                                        else "ncclAllReduce (ReduceOp.AVG) of the flat gradient buffer")
     if world == 1 and not args.no_cpu_baseline:
-        mol, el, cores = cpu_stream(seconds=args.cpu_seconds)
-        line["cpu_baseline"] = {"value": mol / el, "unit": "molecules/s", "cores": cores, "kind": "port",
-                                "sample": f"{mol} molecules as batch-16 mini-batches in {el:.1f} s, oracle/molkgnn_oracle.py "
-                                          "(vectorised restatement of the reference; the reference's own Python loops "
-                                          "measured ~25 molecules/s on 8 cores, BASELINE.md 2)"}
+        mol, el, cores, kind = cpu_stream(seconds=args.cpu_seconds)
+        line["cpu_baseline"] = {"value": mol / el, "unit": "molecules/s", "cores": cores, "kind": kind,
+                                "sample": f"{mol} molecules as batch-16 mini-batches (fwd+bwd) in {el:.1f} s, " + CPU_SAMPLE[kind]}
+        if kind == "reference":                  # second figure: the vectorised port of the same algorithm (the stricter baseline)
+            mol2, el2, _, _ = cpu_stream(seconds=min(4.0, args.cpu_seconds), kind="port")
+            line["cpu_baseline"]["port_value"] = mol2 / el2
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -129,6 +129,15 @@ int molkgnn_bucket_build_begin(molkgnn_plan_t* plan, const int64_t* edge_index, 
                                const float* edge_attr, int32_t Fe, void* scratch, void* stream);
 int molkgnn_bucket_build_finish(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                                 const float* edge_attr, int32_t Fe, void* scratch, void* stream);
+/* _finish for a batch that carries the reference's precomputed per-degree DATA tensors (kernels.py:628-645).  The reference
+ * convolves those raw tensors (BaseKernelSetConv.forward, kernels.py:679: nei_edge_attr_deg*; KernelConv, kernels.py:356:
+ * nei_p_deg* - p_focal_deg*), never the edge_attr handed to MolGCN.forward -- which MolKGNNNet batch-normalises first
+ * (MolKGNNNet.py:116-119).  Topology still comes from edge_index (bit-exact with the index tensors, wrapper.py:595-635);
+ * the bond rows of bucket row r, slot j are nei_edge_attr[d-1][(r*d + j)*Fe ..], n_rows[d-1] = rows the caller holds
+ * (must equal n_d * d, checked); p_focal4 [n_4,3] / nei_p4 [n_4,4,3] (nullable: use p) feed the chirality sign. */
+int molkgnn_bucket_build_finish_ref(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                    const float* const nei_edge_attr[4], const int64_t n_rows[4], int32_t Fe,
+                                    const float* p_focal4, const float* nei_p4, void* scratch, void* stream);
 /* Writes the reference-format attributes of degree d (int64 indices, raw fp32 gathers), bit-exact with
  * wrapper.py:595-635 after PyG collation: selected_index[n_d], nei_index[n_d*d], p_focal[n_d,p_dim],
  * nei_p[n_d,d,p_dim], nei_edge_attr[n_d,d,Fe].  Any output pointer may be NULL. */

@@ -61,21 +61,29 @@ class MolGCN(Module):
             raise Exception('Kernel does not take positional argument, use keyword argument instead. e.g. '
                             'model(data=data)')
         x = kwargv['x']
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            # the native calls take torch's CURRENT stream and allocate through torch: run them on the tensors' device
+            with torch.cuda.device(x.device):
+                return self.forward(**kwargv)
         edge_index = kwargv['edge_index']
         edge_attr = kwargv['edge_attr']
         p = kwargv['p']
         save_score = kwargv.get('save_score', False)
-        # The precomputed per-degree tensors (p_focal_deg*, nei_*_deg*, *_index_deg*) of the reference protocol are
-        # accepted and ignored: the buckets are rebuilt on the GPU from edge_index (bit-exact, tests/test_bucket_gpu.py).
-        # The bond attributes gathered for the conv are the RAW ones the pre-transform stored (kernels.py:679), so a
-        # caller that batch-normalises edge_attr (MolKGNNNet.py:116) may pass the raw tensor as raw_edge_attr=.
+        # Reference protocol (KernelLayer.py:63-101): the 20 precomputed per-degree tensors arrive as kwargs.  The index tensors
+        # (selected_index_deg*, nei_index_deg*) are rebuilt on the GPU from edge_index (bit-exact, tests/test_bucket_gpu.py);
+        # the DATA tensors are honoured: the conv reads its bond rows from nei_edge_attr_deg* and the degree-4 coordinates from
+        # p_focal_deg4 / nei_p_deg4 exactly like the reference (kernels.py:679, 356) -- NOT from `edge_attr`, which MolKGNNNet
+        # batch-normalises before the call (MolKGNNNet.py:116-119).  Without those kwargs (callers that never ran the
+        # pre-transform) the rows are gathered from `edge_attr` (or `raw_edge_attr=` if given), i.e. what the pre-transform
+        # would have stored (wrapper.py:578-593).
         raw_edge_attr = kwargv.get('raw_edge_attr', None)
         plan = kwargv.get('plan', None)
         if plan is None:
+            ref_rows = BucketPlan.ref_rows_from_kwargs(kwargv) if raw_edge_attr is None else None
             # first half of the GPU bucket pass: counting kernels queued; the host round trip for the bucket sizes happens
             # inside MolGCNFn.forward, after the host-side preparation below and the parameter packing were queued
             plan = BucketPlan.begin_from_edge_index(edge_index, p, edge_attr if raw_edge_attr is None else raw_edge_attr,
-                                                    x.shape[0])
+                                                    x.shape[0], ref_rows=ref_rows)
         # Host-side fast path: the 84 parameter tensors are fetched straight from the modules' _parameters dicts (the
         # slots are collected once; nn.Module.__getattr__ per parameter and step is what made a step host bound), and the
         # native layer descriptors are rebuilt only when a parameter tensor moved (new storage, device, dtype).
@@ -99,10 +107,33 @@ class MolGCN(Module):
             stack.key = key
             self.__dict__['_stack'] = stack
         stack.prepack()
-        h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), kwargv.get('aux', None), *flat)
+        # the packed (normalised) kernel rows are ONE workspace per module, rewritten by every forward: remember which
+        # parameter versions it holds, so that a backward running after a later forward with modified parameters is refused
+        # instead of silently differentiating with the wrong kernels (MolGCNFn.backward)
+        stack.versions = tuple(0 if t is None else t._version for t in flat)
+        aux = kwargv.get('aux', None)
+        if save_score and aux is None:
+            aux = {}
+        h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), aux, *flat)
         if save_score:
-            raise NotImplementedError('save_score=True: call the last KernelSetConv layer directly to obtain sim_sc')
+            # KernelLayer.py:117 hands save_score to every layer, each of which dumps its [N, K] score matrix (kernels.py:749-750,
+            # 594-608: scores.csv, rewritten layer after layer).  The stack keeps the compact scores; expand and dump them here.
+            for i, layer in enumerate(self.layers):
+                layer.save_score(self._dense_scores(plan, stack.packs[i], aux['sc'][i]))
         return h
+
+    @staticmethod
+    def _dense_scores(plan, pack, sc_compact):
+        """compact per-degree score blocks -> the reference's sim_sc [N, K] (kernels.py:743-747)."""
+        out = torch.zeros(plan.N, pack.K, dtype=torch.float32, device=sc_compact.device)
+        scoff, _ = plan.scoff(pack.L)
+        for d in range(4):
+            n, L = plan.n[d], pack.L[d]
+            if n == 0 or L == 0:
+                continue
+            rows = plan.sel[plan.boff[d]:plan.boff[d] + n].long()
+            out[rows, pack.koff[d]:pack.koff[d] + L] = sc_compact[scoff[d]:scoff[d] + n * L].view(n, L)
+        return out
 
     def message(self, sim_sc_j):
         return sim_sc_j

@@ -204,7 +204,8 @@ extern "C" int molkgnn_propagate_fwd(const molkgnn_plan_t* plan, const molkgnn_l
         t.ximg = reinterpret_cast<unsigned char*>(ximg);
         t.Fk = tile_fk(ldh); t.x_one = tile_img_one(t.Fk);
         const int smem = (int)((sizeof(TileMetaG) + 15) / 16 * 16) + TNODES * ldh * 4;
-        static int s_attr = 0;
+        static int s_attr_dev[16] = {0};
+        int& s_attr = s_attr_dev[device_index()];          // function attributes are per device
         if (smem > s_attr) {
             MK_CHECK_CUDA(cudaFuncSetAttribute(k_propagate_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
             s_attr = smem;

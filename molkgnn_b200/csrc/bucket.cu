@@ -8,6 +8,7 @@
 //   k_scan_blocks  exclusive scan of the block histograms -> stable bucket positions (ascending node id,
 //                  wrapper.py:599-600) and the bucket sizes
 //   k_assign       writes sel / pos / nei / nei_eid / ehat / tsign / in-lists
+#include <cstring>
 #include "common.cuh"
 #include "tile.cuh"
 
@@ -105,12 +106,17 @@ __global__ void __launch_bounds__(160) k_scan_blocks(int nblk, const int* __rest
     }
 }
 
+// Optional source of the raw per-degree data tensors a reference batch carries (nei_edge_attr_deg*, p_focal_deg4, nei_p_deg4,
+// kernels.py:628-645): the reference convolves THOSE (kernels.py:679), never the edge_attr / p handed to MolGCN.forward --
+// MolKGNNNet passes a batch-normalised edge_attr there (MolKGNNNet.py:116-119).  Bucket row r, slot j = row r * d + j.
+struct RefRows { const float* nea[4]; const float* pf4; const float* np4; };
+
 __global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int* __restrict__ deg,
                          const int* __restrict__ out_eid, const int* __restrict__ in_cnt,
                          const int* __restrict__ in_eid, const int* __restrict__ blk_off,
                          const int* __restrict__ totals, const float* __restrict__ p, int p_dim,
                          const float* __restrict__ edge_attr, int Fe, int* pos, int* sel, int* nei, int* nei_eid,
-                         float* ehat, int8_t* tsign, int* in_src, int* in_j) {
+                         float* ehat, int8_t* tsign, int* in_src, int* in_j, const RefRows ref) {
     __shared__ int warp_cnt[BT / 32][4];
     int v = blockIdx.x * BT + threadIdx.x;
     int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -139,7 +145,7 @@ __global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int
         nei[row] = u;
         nei_eid[row] = e;
         // bond attributes of the undirected bond: row 2*(eid/2) (wrapper.py:586-591), normalised for the cosine
-        const float* ea = edge_attr + (size_t)(2 * (e / 2)) * Fe;
+        const float* ea = ref.nea[cls] ? ref.nea[cls] + ((size_t)r * d + j) * Fe : edge_attr + (size_t)(2 * (e / 2)) * Fe;
         float t[EP];
         float ss = 0.f;
 #pragma unroll
@@ -152,7 +158,9 @@ __global__ void k_assign(int N, int E, const int64_t* __restrict__ ei, const int
         // sign of p2 . (p0 x p1) on neighbour coordinates calibrated by the focal atom (kernels.py:336,356)
         float q[3][3];
         for (int j = 0; j < 3; ++j)
-            for (int c = 0; c < 3; ++c) q[j][c] = __fsub_rn(p[(size_t)nb[j] * 3 + c], p[(size_t)v * 3 + c]);
+            for (int c = 0; c < 3; ++c)
+                q[j][c] = (ref.pf4 && ref.np4) ? __fsub_rn(ref.np4[((size_t)r * 4 + j) * 3 + c], ref.pf4[(size_t)r * 3 + c])
+                                               : __fsub_rn(p[(size_t)nb[j] * 3 + c], p[(size_t)v * 3 + c]);
         float cx = __fsub_rn(__fmul_rn(q[0][1], q[1][2]), __fmul_rn(q[0][2], q[1][1]));
         float cy = __fsub_rn(__fmul_rn(q[0][2], q[1][0]), __fmul_rn(q[0][0], q[1][2]));
         float cz = __fsub_rn(__fmul_rn(q[0][0], q[1][1]), __fmul_rn(q[0][1], q[1][0]));
@@ -730,7 +738,8 @@ __global__ void __launch_bounds__(1024) k_tile_order(int n_tiles, int G, const i
 
 // phases: bit 0 = counting kernels (asynchronous), bit 1 = host round trip of the bucket sizes + assignment kernels
 static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
-                               const float* edge_attr, int32_t Fe, void* scratch, void* stream_, int phases) {
+                               const float* edge_attr, int32_t Fe, void* scratch, void* stream_, int phases,
+                               const RefRows* ref_rows = nullptr, const int64_t* ref_nrows = nullptr) {
     cudaStream_t st = (cudaStream_t)stream_;
     const int N = plan->N, E = plan->E;
     MK_REQUIRE(N > 0 && E >= 0, "bucket_build: empty batch (N=%d E=%d)", N, E);
@@ -777,7 +786,8 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
         static int s_budget = 0;
         if (!s_budget) s_budget = device_max_smem_optin();
         if (bitmap <= s_budget - 16384) {                  // + the kernel's static tables
-            static int64_t s_attr = 0;
+            static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
             if (bitmap > s_attr) {
                 MK_CHECK_CUDA(cudaFuncSetAttribute(k_tile_starts_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bitmap));
                 s_attr = bitmap;
@@ -813,9 +823,21 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
                "8=node with out-degree 0 or >4; %d offending nodes)", host[16], host[4]);
     for (int d = 0; d < 4; ++d) { plan->n[d] = host[d]; plan->boff[d] = host[5 + d]; plan->eoff[d] = host[9 + d]; }
     ProfScope prof2("bucket_assign", st);
+    RefRows ref;
+    memset(&ref, 0, sizeof(ref));
+    if (ref_rows) ref = *ref_rows;
+    for (int d = 0; d < 4; ++d)
+        MK_REQUIRE(!ref_rows || plan->n[d] == 0 || ref.nea[d],
+                   "bucket_build: the batch has %d nodes of degree %d but no nei_edge_attr_deg%d tensor was given", plan->n[d],
+                   d + 1, d + 1);
+    for (int d = 0; d < 4 && ref_nrows; ++d)      // checked BEFORE the kernel reads the rows
+        MK_REQUIRE(ref_nrows[d] == (int64_t)plan->n[d] * (d + 1),
+                   "bucket_build: nei_edge_attr_deg%d has %lld rows but edge_index gives %d nodes of degree %d (inconsistent batch)",
+                   d + 1, (long long)ref_nrows[d], plan->n[d], d + 1);
+    MK_REQUIRE(ref.nea[0] || ref.nea[1] || ref.nea[2] || ref.nea[3] || edge_attr, "bucket_build: no bond attributes");
     k_assign<<<nblk, BT, 0, st>>>(N, E, edge_index, plan->deg, out_eid, plan->in_cnt, in_eid, blk_off, totals, p, p_dim,
                                   edge_attr, Fe, plan->pos, plan->sel, plan->nei, plan->nei_eid, plan->ehat,
-                                  plan->tsign, plan->in_src, plan->in_j);
+                                  plan->tsign, plan->in_src, plan->in_j, ref);
     if (plan->n_tiles > 0 && plan->tile_meta && plan->ehat_node) {
         count_launches(1);
         k_tile_meta<<<plan->n_tiles, TNODES, 0, st>>>(N, plan->tile_start, plan->deg, plan->pos, plan->nei, plan->ehat,
@@ -855,6 +877,17 @@ extern "C" int molkgnn_bucket_build_begin(molkgnn_plan_t* plan, const int64_t* e
 extern "C" int molkgnn_bucket_build_finish(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                                            const float* edge_attr, int32_t Fe, void* scratch, void* stream) {
     return bucket_build_phases(plan, edge_index, p, p_dim, edge_attr, Fe, scratch, stream, 2);
+}
+
+// _finish with the reference batch's own data tensors as the source of the bond rows / degree-4 coordinates (see RefRows).
+// n_rows[d] = rows of nei_edge_attr[d] the caller holds (n_d * (d+1), checked against the bucket sizes found on the GPU).
+extern "C" int molkgnn_bucket_build_finish_ref(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
+                                               const float* const nei_edge_attr[4], const int64_t n_rows[4], int32_t Fe,
+                                               const float* p_focal4, const float* nei_p4, void* scratch, void* stream) {
+    RefRows ref;
+    for (int d = 0; d < 4; ++d) ref.nea[d] = nei_edge_attr[d];
+    ref.pf4 = p_focal4; ref.np4 = nei_p4;
+    return bucket_build_phases(plan, edge_index, p, p_dim, nullptr, Fe, scratch, stream, 2, &ref, n_rows);
 }
 
 extern "C" int molkgnn_set_tile_order(int mode) {
@@ -900,7 +933,8 @@ extern "C" int molkgnn_plan_from_buckets(molkgnn_plan_t* plan, const int64_t* co
     MK_REQUIRE(eo == plan->E, "plan_from_buckets: plan->E=%d but buckets hold %d neighbour rows", plan->E, eo);
     // in_j doubles as the key scratch (4 ints per node) until the in-lists are decoded; err flag lives in in_cnt? no:
     // use the last int of nei_eid's allocation is not safe either -> use a static device flag.
-    static int* d_err = nullptr;
+    static int* d_err_dev[16] = {nullptr};
+    int*& d_err = d_err_dev[device_index()];                  // one error word per device
     if (!d_err) MK_CHECK_CUDA(cudaMalloc(&d_err, sizeof(int)));
     MK_CHECK_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int), st));
     MK_CHECK_CUDA(cudaMemsetAsync(plan->in_cnt, 0, sizeof(int) * (size_t)N, st));

@@ -169,6 +169,7 @@ private:
 #endif
 extern bool g_fwd_counters_zeroed;   // conv_fwd_tile.cu: the caller (stack.cu) zeroed the tile queues of all layers already
 int device_num_sms();
+int device_index();          // current CUDA device, clipped to 0..15 (index of the per-device caches)
 int device_max_smem_optin();
 
 }  // namespace mk

@@ -466,7 +466,8 @@ __global__ void __launch_bounds__(BX_THREADS, 1) k_bwd_x(const __grid_constant__
 
 template <int LPN, int NACC>
 static int launch_bwd_x(const BwdXArgs& a, int grid, int64_t smem, cudaStream_t st) {
-    static int64_t s_attr = 0;
+    static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
     if (smem > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_x<LPN, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s_attr = smem;
@@ -575,7 +576,8 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     w.grad = grad; w.ldg = ldg; w.grad_mode = grad_mode;
     w.argmax = argmax; w.coef = coef; w.partials = partials;
     if (cb > 0 && (phases & 1)) {
-        static int64_t s_attr = 0;
+        static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
         if (smem_w > s_attr) {
             MK_CHECK_CUDA(cudaFuncSetAttribute(k_bwd_w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
             s_attr = smem_w;

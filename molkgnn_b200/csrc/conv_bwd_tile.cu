@@ -862,7 +862,9 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     if (!do_launch) return 1;
     MK_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(coef) & 15) == 0,
                "conv_bwd_tile: grad and coef must be 16-byte aligned");
-    static int64_t s_attr = 0, s_attr_c = 0;
+    static int64_t s_attr_dev[16] = {0}, s_attr_c_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];
+    int64_t& s_attr_c = s_attr_c_dev[device_index()];   // function attributes are per device
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;

@@ -492,7 +492,8 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     a.counter = counter;
     if (tb == 0) return 0;
     MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    static int64_t s_attr = 0;
+    static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
     if (smem > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s_attr = smem;

@@ -586,7 +586,8 @@ int launch_conv_fwd_tc(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer,
     a.counter = counter;
     if (ub == 0) return 1;
     MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
-    static int64_t s_attr = 0;
+    static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
     if (smem > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         s_attr = smem;

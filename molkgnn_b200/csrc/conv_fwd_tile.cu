@@ -666,7 +666,8 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.sm_dup = (int)off; off += 128;
     if (off > s_budget - 1024) return 0;
     if (!g_fwd_counters_zeroed) MK_CHECK_CUDA(cudaMemsetAsync(counter, 0, TILE_MAXB * sizeof(int), st));
-    static int64_t s_attr = 0;
+    static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fwd_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));

@@ -61,7 +61,8 @@ __device__ __forceinline__ float4 os_load_peer(const float4* p) {
 
 // header layout (unsigned ints): [0 .. 2 W)  flags[parity][rank];  [64] CTA counter;  [65] error word
 __global__ void __launch_bounds__(OS_THREADS) k_oneshot_allreduce(const __grid_constant__ OneShotArgs a) {
-    __shared__ int s_last;
+    __shared__ int s_last, s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
     const int par = (int)(a.epoch & 1u);
     unsigned int* hdr = reinterpret_cast<unsigned int*>(a.peer[a.rank]);
     float4* mine = reinterpret_cast<float4*>(a.peer[a.rank] + OS_HDR_BYTES + par * a.slot_off);
@@ -88,11 +89,19 @@ __global__ void __launch_bounds__(OS_THREADS) k_oneshot_allreduce(const __grid_c
         const unsigned int* f = hdr + par * OS_MAX_WORLD + threadIdx.x;
         const unsigned long long t0 = os_now();
         while (os_load_acquire_sys(f) != a.epoch) {
-            if (os_now() - t0 > a.timeout_ns) { atomicExch(&hdr[65], 1u + (unsigned int)threadIdx.x); break; }
+            if (os_now() - t0 > a.timeout_ns) { atomicExch(&hdr[65], 1u + (unsigned int)threadIdx.x); s_bad = 1; break; }
             __nanosleep(100);
         }
     }
     __syncthreads();
+    // A flag that never arrived: the peers' slots hold stale or partial data.  Never reduce them into the gradients --
+    // poison this rank's buffer with NaN instead, so that no optimizer step can silently consume a wrong, rank-divergent
+    // sum (the error word says which rank was missing; GradBucket.check() / molkgnn_oneshot_error raise on it).
+    if (s_bad) {
+        const float qnan = __int_as_float(0x7fc00000);
+        for (long long i = i0; i < a.n4; i += stride) a.flat[i] = make_float4(qnan, qnan, qnan, qnan);
+        return;
+    }
     // 4. sum the W copies in rank order
     for (long long i = i0; i < a.n4; i += stride) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);

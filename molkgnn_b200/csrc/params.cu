@@ -62,6 +62,11 @@ int device_num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
     return n;
 }
+int device_index() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 0;
+    return dev < 16 ? dev : 15;
+}
 int device_max_smem_optin() {
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return -1;

@@ -50,6 +50,11 @@ class OneShotAllReduce(object):
         dev = torch.device("cuda", torch.cuda.current_device())
         L = _lib.lib()
         handle, mine, ok = C.c_void_p(), torch.zeros(64, dtype=torch.uint8), 1
+        # the slot size must be the same on every rank (validated collectively, once)
+        sizes = torch.tensor([int(numel), -int(numel)], dtype=torch.int64, device=dev)
+        dist.all_reduce(sizes, op=dist.ReduceOp.MAX, group=group)
+        if int(sizes[0].item()) != -int(sizes[1].item()):
+            return None
         try:
             _lib.check(L.molkgnn_oneshot_create(rank, world, 4 * int(numel) + 64, C.byref(handle)))
             buf = (C.c_ubyte * 64)()
@@ -79,6 +84,9 @@ class OneShotAllReduce(object):
     def allreduce(self, flat, average=True):
         from . import _lib
         if flat.numel() > self.cap_floats or flat.dtype != torch.float32 or not flat.is_contiguous():
+            # rank-local failure: the peers time out on this rank's flag, poison their buffers with NaN and raise at their next
+            # check() -- they never reduce without this rank.  create() validated the slot size collectively, so with the same
+            # model on every rank this cannot be reached on one rank only.
             raise _lib.MolKGNNError("OneShotAllReduce: buffer larger than the exchange slot or not a contiguous fp32 tensor")
         _lib.check(_lib.lib().molkgnn_oneshot_allreduce(self.handle, _lib.ptr(flat), flat.numel(), 1 if average else 0,
                                                         _lib.stream_ptr()))
@@ -122,8 +130,17 @@ class GradBucket(object):
         if oneshot is None:
             oneshot = os.environ.get("MOLKGNN_DP_ONESHOT", "0") == "1"
         self.oneshot = None
+        self.check_every = int(os.environ.get("MOLKGNN_DP_CHECK_EVERY", "64"))
+        self._steps = 0
         if oneshot and self.world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
             self.oneshot = OneShotAllReduce.create(2 * self.numel + 4096, group)   # room for the native buffer's padding
+
+    def check(self):
+        """Raises if the one-shot exchange ever timed out (a rank that died or raised before its launch leaves the others
+        with NaN-poisoned gradients, csrc/oneshot.cu).  Synchronises the device: call it where the loop synchronises anyway
+        (logging, before a checkpoint); ``allreduce`` itself calls it every ``check_every`` steps."""
+        if self.oneshot is not None:
+            self.oneshot.check()
 
     def _native_flat(self, ps):
         flat = _native_flat_of(self.module)
@@ -150,6 +167,9 @@ class GradBucket(object):
         if flat is not None:
             if self.world > 1 and self.oneshot is not None and flat.is_cuda:
                 self.oneshot.allreduce(flat, self.average)
+                self._steps += 1
+                if self.check_every > 0 and self._steps % self.check_every == 0:
+                    self.check()
             elif self.world > 1:
                 if self.average and flat.is_cuda:
                     # NCCL averages inside the collective: no separate scaling kernel behind it

@@ -373,21 +373,6 @@ class StackPack(object):
         as_strided = flat.as_strided
         return [None if sp is None else as_strided(sp[1], sp[2], sp[0]) for sp in specs]
 
-    def _grad_views_reference(self, lay, flat):
-        out = []
-        for i, pk in enumerate(self.packs):
-            for d in range(4):
-                Ld = pk.L[d]
-                if not Ld:
-                    out += [None] * 7
-                    continue
-                oc, os_, oe, ow = lay.g_x_center[i][d], lay.g_x_support[i][d], lay.g_edge_attr_support[i][d], lay.g_w[i][d]
-                out += [flat[oc:oc + Ld * pk.F].view(Ld, pk.F),
-                        flat[os_:os_ + Ld * (d + 1) * pk.F].view(Ld, d + 1, pk.F),
-                        flat[oe:oe + Ld * (d + 1) * pk.Fe].view(Ld, d + 1, pk.Fe),
-                        None, flat[ow], flat[ow + 1], flat[ow + 2]]
-        return out
-
 
 FLAG_KEEP_SC, FLAG_WANT_FREE, FLAG_PACKED = 1, 2, 4
 
@@ -436,6 +421,7 @@ class MolGCNFn(torch.autograd.Function):
                 aux.setdefault("argmax_free", []).append(ws[lay.argmax_free[i]:lay.argmax_free[i] + max(n, 1)])
                 aux.setdefault("sc", []).append(ws[lay.sc[i]:lay.sc[i] + 4 * max(n, 1)].view(torch.float32))
         ctx.plan, ctx.stack, ctx.lay = plan, stack, lay
+        ctx.versions = getattr(stack, "versions", None)
         ctx.save_for_backward(ws)
         ctx.need_gx = x.requires_grad
         ctx.F0 = x.shape[1]
@@ -443,9 +429,21 @@ class MolGCNFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_h):
-        L = _lib.lib()
         (ws,) = ctx.saved_tensors
+        if ws.device.index != torch.cuda.current_device():
+            with torch.cuda.device(ws.device):          # autograd may call from another current device
+                return MolGCNFn._backward(ctx, grad_h, ws)
+        return MolGCNFn._backward(ctx, grad_h, ws)
+
+    @staticmethod
+    def _backward(ctx, grad_h, ws):
+        L = _lib.lib()
         plan, stack, lay = ctx.plan, ctx.stack, ctx.lay
+        if ctx.versions != getattr(stack, "versions", None):
+            raise _lib.MolKGNNError(
+                "MolGCN backward: the kernel parameters were modified in place and re-packed by a later forward of the same "
+                "module before this backward ran (forward A, optimizer.step(), forward B, backward A).  The packed kernel rows "
+                "are one workspace per module; run backward A before the parameters change, or use a second module copy.")
         dev = ws.device
         g = grad_h
         if g.dtype != torch.float32:

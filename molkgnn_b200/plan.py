@@ -84,15 +84,28 @@ class BucketPlan(object):
 
     # ---- constructors -------------------------------------------------------------------------------------
     @classmethod
-    def from_edge_index(cls, edge_index, p, edge_attr, num_nodes):
+    def from_edge_index(cls, edge_index, p, edge_attr, num_nodes, ref_rows=None):
         """One GPU CSR->degree-bucket pass over the collated ``edge_index`` (replaces wrapper.py:637-672)."""
-        return cls.begin_from_edge_index(edge_index, p, edge_attr, num_nodes).finish()
+        return cls.begin_from_edge_index(edge_index, p, edge_attr, num_nodes, ref_rows=ref_rows).finish()
+
+    @staticmethod
+    def ref_rows_from_kwargs(kw):
+        """The raw per-degree DATA tensors of the reference's forward protocol (kernels.py:628-645), if the caller handed all of
+        them: the conv must read ITS bond rows / coordinates from these (kernels.py:679, 356), not from ``edge_attr`` / ``p``
+        (MolKGNNNet batch-normalises ``edge_attr`` before calling MolGCN, MolKGNNNet.py:116-119).  -> dict or None."""
+        names = [f"nei_edge_attr_deg{d}" for d in range(1, 5)]
+        if not all(n in kw and kw[n] is not None for n in names):
+            return None
+        return dict(nei_edge_attr=[kw[n] for n in names], p_focal4=kw.get("p_focal_deg4"), nei_p4=kw.get("nei_p_deg4"))
 
     @classmethod
-    def begin_from_edge_index(cls, edge_index, p, edge_attr, num_nodes):
+    def begin_from_edge_index(cls, edge_index, p, edge_attr, num_nodes, ref_rows=None):
         """First half of the pass: the counting kernels are queued, nothing is waited for.  ``finish()`` (called by
         ``from_edge_index`` / by the MolGCN forward) does the one host round trip for the bucket sizes; whatever the caller
-        queues or computes in between overlaps with the counting kernels."""
+        queues or computes in between overlaps with the counting kernels.
+
+        ``ref_rows`` (``ref_rows_from_kwargs``): take the bond rows and the degree-4 coordinates from the reference batch's
+        own per-degree tensors instead of gathering them from ``edge_attr`` / ``p``."""
         for t, nme in ((edge_index, "edge_index"), (p, "p"), (edge_attr, "edge_attr")):
             _require_cuda(t, nme)
         if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
@@ -107,6 +120,31 @@ class BucketPlan(object):
         check(L.molkgnn_bucket_build_begin(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], ptr(edge_attr),
                                            edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
         self._keep = (edge_index, p, edge_attr)
+        self._ref = None
+        if ref_rows is not None:
+            dev = edge_index.device
+            nea, nrows = (C.c_void_p * 4)(), (C.c_int64 * 4)()
+            keep = []
+            for d in range(4):
+                t = ref_rows["nei_edge_attr"][d]
+                if t is None or t.numel() == 0:           # empty bucket: torch.Tensor() in the reference (wrapper.py:627-630)
+                    nea[d], nrows[d] = None, 0
+                    continue
+                if t.shape[-1] != edge_attr.shape[1]:
+                    raise _lib.MolKGNNError(f"nei_edge_attr_deg{d + 1} has {t.shape[-1]} columns, edge_attr {edge_attr.shape[1]}")
+                t = t.to(device=dev, dtype=torch.float32).contiguous()
+                keep.append(t)
+                nea[d], nrows[d] = t.data_ptr(), t.numel() // t.shape[-1]
+            pf4, np4 = ref_rows.get("p_focal4"), ref_rows.get("nei_p4")
+            if pf4 is not None and np4 is not None and pf4.numel() and np4.numel() and p.shape[1] == 3:
+                pf4 = pf4.to(device=dev, dtype=torch.float32).contiguous()
+                np4 = np4.to(device=dev, dtype=torch.float32).contiguous()
+                if np4.numel() != 4 * pf4.numel() or nrows[3] != 4 * (pf4.numel() // 3):
+                    raise _lib.MolKGNNError("p_focal_deg4 / nei_p_deg4 / nei_edge_attr_deg4 disagree on the number of degree-4 nodes")
+                keep += [pf4, np4]
+            else:
+                pf4 = np4 = None
+            self._ref = (nea, nrows, pf4, np4, keep)
         self._pending = True
         return self
 
@@ -114,8 +152,14 @@ class BucketPlan(object):
         if self.__dict__.get("_pending"):
             edge_index, p, edge_attr = self._keep
             self._pending = False
-            check(_lib.lib().molkgnn_bucket_build_finish(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1],
-                                                         ptr(edge_attr), edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
+            if self._ref is not None:
+                nea, nrows, pf4, np4, _ = self._ref
+                check(_lib.lib().molkgnn_bucket_build_finish_ref(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1], nea, nrows,
+                                                                 edge_attr.shape[1], ptr(pf4), ptr(np4), self.scratch_ptr,
+                                                                 stream_ptr()))
+            else:
+                check(_lib.lib().molkgnn_bucket_build_finish(C.byref(self.c), ptr(edge_index), ptr(p), p.shape[1],
+                                                             ptr(edge_attr), edge_attr.shape[1], self.scratch_ptr, stream_ptr()))
             self.n = list(self.c.n)
             self.n_tiles = int(self.c.n_tiles)      # 0: no molecule tiling (bucket-order kernels are used)
         return self

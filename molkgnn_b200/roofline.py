@@ -6,20 +6,21 @@ Per layer, each tensor touched once, int32 topology, uint8 arg-max, kernel param
 """
 
 
-def layer_bytes(N, E, n, F, L, Fe=7, last=False):
+def layer_bytes(N, E, n, F, L, Fe=7, last=False, training=True):
     K = sum(L)
     am = sum(nd * ld for nd, ld in zip(n, L))
-    fwd = 4 * N * F + 4 * E * Fe + 4 * E + 4 * N + 4 * N * K + am + (12 * N if last else 0)
+    fwd = 4 * N * F + 4 * E * Fe + 4 * E + 4 * N + 4 * N * K + (am if training else 0) + (12 * N if last else 0)
     bwd = 4 * N * K + 4 * N * F + am + 4 * E * Fe + 4 * E + 4 * N + 4 * N * F
     return fwd, bwd
 
 
-def stack_bytes(N, E, n, x_dim, L1, LN, num_layers, Fe=7):
+def stack_bytes(N, E, n, x_dim, L1, LN, num_layers, Fe=7, training=True):
+    """training=False: forward-only sweep (BASELINE configs[4]) -- no arg-max store"""
     fwd = bwd = 0
     F = x_dim
     for i in range(num_layers):
         L = L1 if i == 0 else LN
-        f, b = layer_bytes(N, E, n, F, L, Fe, last=(i == num_layers - 1))
+        f, b = layer_bytes(N, E, n, F, L, Fe, last=(i == num_layers - 1), training=training)
         fwd += f
         bwd += b
         F = sum(L)

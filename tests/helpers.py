@@ -145,3 +145,53 @@ def tile_schedule_model(nn, G):
             pos = nlong + c * q + k
         order[pos] = t
     return order
+
+
+def oracle_chunked(net, b, wout, chunk=32):
+    """The CPU oracle over a LARGE batch in chunks of whole molecules (molecules are independent graphs, so h / grad_x are
+    per-chunk and kernel-parameter gradients add over chunks -- tests/test_fullsize_gpu.py proves both for the CUDA path).
+
+    b: numpy batch of synth.collate (needs "ptr"; edges grouped molecule by molecule); wout [N, K] dL/dh.
+    Returns dict(h, grad_x, grads {(li, d, name): tensor}, argmax [layer][d-1] -> [L_d, n_d] int64 (or None),
+    S [layer][d-1] -> [L_d, P_d, n_d] fp32 (or None)) in FULL-batch bucket order (chunks are contiguous node ranges and
+    bucket rows ascend with the node id, so per-degree concatenation over chunks is the full batch's order)."""
+    params = params_from_module(net, requires_grad=True)
+    ptr = np.asarray(b["ptr"])
+    src = b["edge_index"][0]
+    nl = len(params)
+    hs, gxs = [], []
+    am = [[[] for _ in range(4)] for _ in range(nl)]
+    Ss = [[[] for _ in range(4)] for _ in range(nl)]
+    for m0 in range(0, len(ptr) - 1, chunk):
+        m1 = min(m0 + chunk, len(ptr) - 1)
+        n0, n1 = int(ptr[m0]), int(ptr[m1])
+        e0, e1 = int(np.searchsorted(src, n0, side="left")), int(np.searchsorted(src, n1, side="left"))
+        ei = b["edge_index"][:, e0:e1] - n0
+        assert ei.min() >= 0 and ei.max() < n1 - n0, "edges must be grouped molecule by molecule"
+        bk = orc.buckets_to_torch(orc.bucket_pass(ei, n1 - n0, b["p"][n0:n1], b["edge_attr"][e0:e1]))
+        x = torch.from_numpy(b["x"][n0:n1]).clone().requires_grad_(True)
+        h, auxs = orc.molgcn_forward(params, x, torch.from_numpy(ei), bk, return_aux=True)
+        (h * wout[n0:n1]).sum().backward()          # parameter .grad accumulates over the chunks
+        hs.append(h.detach())
+        gxs.append(x.grad)
+        for li in range(nl):
+            for d in range(4):
+                if auxs[li][d] is not None:
+                    am[li][d].append(auxs[li][d]["argmax"].detach())
+                    Ss[li][d].append(auxs[li][d]["S"].detach().float())
+    cat = lambda lst, dim: torch.cat(lst, dim=dim) if lst else None  # noqa: E731
+    grads = {(li, d, n): params[li][d][n].grad for li in range(nl) for d in range(4) for n in PARAM_NAMES
+             if params[li][d][n].grad is not None}
+    return dict(h=torch.cat(hs), grad_x=torch.cat(gxs), grads=grads,
+                argmax=[[cat(am[li][d], 1) for d in range(4)] for li in range(nl)],
+                S=[[cat(Ss[li][d], 2) for d in range(4)] for li in range(nl)])
+
+
+def elementwise_close(a, b, rtol=1e-5, floor_frac=1e-5):
+    """Element-wise check beside the max-normalised one: |a - b| <= rtol |b| + floor_frac * max|b|.  The absolute floor is the
+    rounding of an fp32 sum whose terms are O(max|b|) (entries that cancel to ~0 cannot be relatively exact).
+    -> (ok, worst excess ratio)"""
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    bound = rtol * b.abs() + floor_frac * float(b.abs().max().clamp_min(1e-30))
+    ratio = float(((a - b).abs() / bound).max())
+    return ratio <= 1.0, ratio

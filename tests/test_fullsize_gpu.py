@@ -1,5 +1,12 @@
-"""Full-size (BASELINE configs[1]: 4096 molecules, 3 layers, 10/20/30/50) checks of the CUDA path through properties that do
-not need the CPU oracle at that size (it would take minutes):
+"""Full-size (BASELINE configs[1]: 4096 molecules, 3 layers, 10/20/30/50) checks of the CUDA path.
+
+  * against the CPU ORACLE at full size (test_configs1_matches_oracle_at_full_size; the wide 5-layer model at 256 molecules in
+    test_wide_config_matches_oracle): the oracle runs over the batch in chunks of 32 molecules (tests/helpers.oracle_chunked,
+    ~10 s); h, grad_x and every kernel-parameter gradient within 1e-5 (max-normalised AND element-wise with an absolute
+    floor) with the arg-max teacher-forced, the free-running arg-max tie-aware against the oracle's S with the measured
+    exact-match share PRINTED per layer and degree;
+
+and through properties that need no oracle:
 
   * two independent implementations agree: molecule-tile tcgen05 kernels vs bucket-order fp32 SIMT kernels (same arg-max
     forced on both) -- scores and every gradient within 1e-5 relative (max |err| / max |ref| per tensor);
@@ -139,3 +146,72 @@ def test_balanced_tile_schedule_changes_only_the_summation_order(setup):
         assert torch.equal(b[2][n], b2[2][n]), n                       # still deterministic
         if n.rsplit(".", 1)[-1] in GRAD_NAMES[:3]:
             assert _rel(b[2][n], a[2][n]) < TOL, n
+
+
+def _oracle_parity(net, b, t, wout_cpu, label):
+    from tests.helpers import (oracle_chunked, compact_from_kernel_major, kernel_major_from_compact, check_argmax, rel_err,
+                               elementwise_close)
+    ref = oracle_chunked(net.cpu(), b, wout_cpu, chunk=32)
+    net.to(DEV)
+    forced = [compact_from_kernel_major(ref["argmax"][li], DEV) for li in range(len(net.layers))]
+    h, gx, grads, aux = _run(net, t, wout_cpu.to(DEV), argmax_in=forced, want_aux=True)
+    # ---- scores / gradients, teacher-forced on the oracle's arg-max ----
+    worst = {}
+    for name, got, want in [("h", h.cpu(), ref["h"]), ("grad_x", gx.cpu(), ref["grad_x"])]:
+        ok, ratio = elementwise_close(got, want)
+        worst[name] = (rel_err(got, want), ratio)
+        assert rel_err(got, want) < TOL and ok, (name, worst[name])
+    trip = ["support_attr_sc_weight", "center_attr_sc_weight", "edge_attr_support_sc_weight"]
+    for li in range(len(net.layers)):
+        for d in range(4):
+            for n in ("x_center", "x_support", "edge_attr_support"):
+                got = grads[f"layers.{li}.trainable_kernelconv_set.{d}.{n}"].cpu()
+                want = ref["grads"][(li, d, n)]
+                ok, ratio = elementwise_close(got, want)
+                e = rel_err(got, want)
+                worst[n] = max(worst.get(n, (0.0, 0.0)), (e, ratio))
+                assert e < TOL and ok, (li, d, n, e, ratio)
+            r = np.array([float(ref["grads"][(li, d, w)]) for w in trip])
+            g_ = np.array([float(grads[f"layers.{li}.trainable_kernelconv_set.{d}.{w}"]) for w in trip])
+            assert np.abs(g_ - r).max() <= 1e-4 * max(np.abs(r).max(), 1e-6), (li, d, g_, r)
+    print(f"\n[{label}] N={t['x'].shape[0]}: " + ", ".join(f"{k}: rel {v[0]:.1e} elem {v[1]:.2f}" for k, v in worst.items()))
+    # ---- free-running arg-max vs the oracle's S (tie-aware), exact-match share per layer and degree ----
+    from molkgnn_b200.plan import BucketPlan
+    plan = BucketPlan.from_edge_index(t["edge_index"], t["p"], t["edge_attr"], t["x"].shape[0])
+    tot = ex = 0
+    for li, layer in enumerate(net.layers):
+        free = kernel_major_from_compact(aux["argmax_free"][li], plan.n, layer.num_kernel_list)
+        used = kernel_major_from_compact(aux["argmax"][li], plan.n, layer.num_kernel_list)
+        line = []
+        for d in range(4):
+            if free[d] is None:
+                continue
+            n_, e_, tie_ = check_argmax(ref["S"][li][d], ref["argmax"][li][d], free[d])     # asserts tie-class membership
+            assert torch.equal(used[d] & 0x7f, ref["argmax"][li][d].to(torch.uint8))
+            tot, ex = tot + n_, ex + e_
+            line.append(f"d{d + 1} {e_ / n_:.4%} ({n_ - e_} in tie class)")
+        print(f"[{label}] layer {li} free-running arg-max identical to the oracle: " + "; ".join(line))
+    print(f"[{label}] overall {ex}/{tot} = {ex / tot:.4%}")
+    assert ex / tot > 0.97
+
+
+def test_configs1_matches_oracle_at_full_size(setup):
+    """BASELINE configs[1] pinned against the oracle at the bench size (VERDICT r1 weak #2)."""
+    b, t, net, wout = setup
+    try:
+        _oracle_parity(net, b, t, wout.cpu(), "configs[1] 4096 molecules")
+    finally:
+        net.to(DEV)
+
+
+def test_wide_config_matches_oracle():
+    """BASELINE configs[2]: kernels 40/80/120/200, 5 layers, 256 molecules, against the oracle."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    LW = (40, 80, 120, 200)
+    b = synth.make_batch(256, seed=9)
+    t = {k: torch.from_numpy(b[k]).to(DEV) for k in ("x", "p", "edge_index", "edge_attr")}
+    torch.manual_seed(9)
+    net = mk.MolGCN(5, *LW, *LW, x_dim=28, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], sum(LW))
+    _oracle_parity(net, b, t, wout, "configs[2] wide, 256 molecules")

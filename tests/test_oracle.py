@@ -132,3 +132,35 @@ def test_oracle_against_the_live_reference_on_fresh_batches():
     assert out["bucket_bit_exact"]
     assert out["h"] < 1e-5 and out["grad_x"] < 2e-5 and out["grad_params"] < 5e-5
     assert out["argmax_exact_share"] > 0.97
+
+
+def test_oracle_at_the_molkgnnnet_call_site():
+    """The reference's real call site (MolKGNNNet.py:115-146): BatchNorm1d on x and on edge_attr, conv stack on the RAW
+    precomputed bond rows (kernels.py:679), swish-MLP, global_add_pool.  The fixture is the unmodified MolKGNNNet."""
+    g = load_golden("molkgnnnet_call")
+    sd = {k[len("param_"):]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("param_")}
+    nl = int(g["num_layers"])
+    params = []
+    for i in range(nl):
+        layer = []
+        for d in range(4):
+            layer.append({n: sd[f"gnn.layers.{i}.trainable_kernelconv_set.{d}.{n}"].clone().requires_grad_(True)
+                          for n in ["x_center", "x_support", "edge_attr_support", "p_support", "length_sc_weight",
+                                    "angle_sc_weight", "center_attr_sc_weight", "support_attr_sc_weight",
+                                    "edge_attr_support_sc_weight"]})
+        params.append(layer)
+    x = torch.from_numpy(g["x"]).clone().requires_grad_(True)
+    xb = torch.nn.functional.batch_norm(x, None, None, sd["node_batch_norm.weight"], sd["node_batch_norm.bias"], True)
+    bk = golden_buckets(g)                       # raw bond rows / coordinates, as the reference consumed them
+    h = orc.molgcn_forward(params, xb, torch.from_numpy(g["edge_index"]), bk)
+    z = torch.nn.functional.linear(h, sd["graph_embedding_lin1.weight"], sd["graph_embedding_lin1.bias"])
+    z = torch.nn.functional.linear(z * torch.sigmoid(z), sd["graph_embedding_lin2.weight"], sd["graph_embedding_lin2.bias"])
+    batch = torch.from_numpy(g["batch"])
+    out = torch.zeros(int(batch.max()) + 1, z.shape[1]).index_add(0, batch, z)
+    (out * torch.from_numpy(g["wout"])).sum().backward()
+    assert rel_err(out.detach(), g["out"]) < 1e-5
+    assert rel_err(x.grad, g["grad_x"]) < 1e-5
+    for i in range(nl):
+        for d in range(4):
+            for n in ("x_center", "x_support", "edge_attr_support"):
+                assert rel_err(params[i][d][n].grad, g[f"grad_gnn.layers.{i}.trainable_kernelconv_set.{d}.{n}"]) < 1e-5

@@ -39,6 +39,7 @@ import wrapper as ref_wrapper  # noqa: E402
 from molkgnn_b200 import synth  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
+ONLY = None
 DEG_KEYS = ["p_focal", "nei_p", "nei_edge_attr", "selected_index", "nei_index"]
 
 
@@ -197,6 +198,70 @@ def mixed_set_case(name, n_mol, seed, Lf, Lt):
     print(name, "N=", b["x"].shape[0], "K=", sc.shape[1], "grads:", sum(1 for k in save if k.startswith("grad_")))
 
 
+def no_sibling_leaves(m):
+    """True if no two degree-1 atoms of the molecule share their neighbour (such leaves carry bit-identical features from
+    layer 1 on, which ties permutations structurally -- SURVEY.md 7 hard part 1)."""
+    src, dst = m.edge_index
+    deg = np.bincount(src, minlength=m.num_nodes)
+    parents = [int(dst[np.nonzero(src == v)[0][0]]) for v in range(m.num_nodes) if deg[v] == 1]
+    return len(parents) == len(set(parents))
+
+
+def molkgnnnet_case(name, n_mol, seed, num_layers, L1, LN, emb=32):
+    """The reference's REAL call site of the hot path: the unmodified MolKGNNNet (MolKGNNNet.py:69-149) -- BatchNorm1d on x
+    AND on edge_attr (the latter is what reaches MolGCN.forward as `edge_attr`, MolKGNNNet.py:115-119), the conv stack, the
+    swish-MLP and global_add_pool.  Train mode (batch statistics), dropout 0 so the run is deterministic.  Molecules without
+    sibling leaves, so that the free-running arg-max has no structural ties: the fixture records the smallest top-2 gap."""
+    from models.MolKGNN.MolKGNNNet import MolKGNNNet
+    cand = synth.make_molecules(8 * n_mol, seed=seed, dup_leaf_prob=0.0)
+    mols = [m for m in cand if no_sibling_leaves(m)][:n_mol]
+    assert len(mols) == n_mol, "not enough molecules without sibling leaves"
+    b = synth.collate(mols)
+    bk = ref_bucket_collated(mols)
+    torch.manual_seed(seed)
+    net = MolKGNNNet(num_layers=num_layers, num_kernel1_1hop=L1[0], num_kernel2_1hop=L1[1], num_kernel3_1hop=L1[2],
+                     num_kernel4_1hop=L1[3], num_kernel1_Nhop=LN[0], num_kernel2_Nhop=LN[1], num_kernel3_Nhop=LN[2],
+                     num_kernel4_Nhop=LN[3], x_dim=synth.X_DIM, p_dim=3, edge_attr_dim=synth.EDGE_DIM, drop_ratio=0.0,
+                     graph_embedding_dim=emb)
+    net.train()
+    g = torch.Generator().manual_seed(seed + 7)
+    with torch.no_grad():
+        for layer in net.gnn.layers:
+            for kc in layer.trainable_kernelconv_set:
+                for w in (kc.support_attr_sc_weight, kc.center_attr_sc_weight, kc.edge_attr_support_sc_weight):
+                    w.add_(0.5 * torch.randn((), generator=g))
+        net.node_batch_norm.weight.add_(0.3 * torch.randn(synth.X_DIM, generator=g))
+        net.node_batch_norm.bias.add_(0.3 * torch.randn(synth.X_DIM, generator=g))
+        net.edge_batch_norm.weight.add_(0.3 * torch.randn(synth.EDGE_DIM, generator=g))
+        net.edge_batch_norm.bias.add_(0.3 * torch.randn(synth.EDGE_DIM, generator=g))
+    x = torch.from_numpy(b["x"]).clone().requires_grad_(True)
+    data = Data(x=x, p=torch.from_numpy(b["p"]), edge_index=torch.from_numpy(b["edge_index"]),
+                edge_attr=torch.from_numpy(b["edge_attr"]), batch=torch.from_numpy(b["batch"]),
+                **{k: torch.from_numpy(v) for k, v in bk.items()})
+    with MaxSpy() as spy:
+        out = net(data)
+    wout = torch.randn(out.shape, generator=torch.Generator().manual_seed(seed + 11))
+    (out * wout).sum().backward()
+    gap = np.inf
+    for S, am in spy.records:
+        if S.shape[1] > 1:
+            top2 = torch.topk(S.double(), 2, dim=1).values
+            gap = min(gap, float((top2[:, 0] - top2[:, 1]).min()))
+    save = dict(x=b["x"], p=b["p"], edge_index=b["edge_index"], edge_attr=b["edge_attr"], batch=b["batch"],
+                out=out.detach().numpy(), wout=wout.numpy(), grad_x=x.grad.numpy(), num_layers=np.int64(num_layers),
+                L1=np.asarray(L1), LN=np.asarray(LN), seed=np.int64(seed), emb=np.int64(emb), min_top2_gap=np.float64(gap))
+    for k, v in bk.items():
+        save["bk_" + k] = v
+    for k, v in net.state_dict().items():
+        save["param_" + k] = v.numpy()
+    for k, v in net.named_parameters():
+        if v.grad is not None:
+            save["grad_" + k] = v.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **save)
+    print(name, "N=", b["x"].shape[0], "graphs=", out.shape[0], "min top-2 gap=", gap,
+          "grads:", sum(1 for k in save if k.startswith("grad_")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     # 1. docstring KAT (kernels.py:161-170)
@@ -232,7 +297,15 @@ def main():
     molgcn_case("molgcn_stars", None, 74, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50), mols=stars)
     # 6. fixed + trainable kernel sets in one layer (kernels.py:452-516, 702-715)
     mixed_set_case("set_mixed", n_mol=5, seed=9, Lf=(2, 3, 2, 3), Lt=(3, 2, 4, 2))
+    # 7. the real call site: unmodified MolKGNNNet around the stack (BatchNorm'd edge_attr reaches MolGCN.forward)
+    if ONLY in (None, "molkgnnnet"):
+        molkgnnnet_case("molkgnnnet_call", n_mol=6, seed=29, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "molkgnnnet":      # only the new fixture (the others are unchanged)
+        ONLY = "molkgnnnet"
+        os.makedirs(OUT, exist_ok=True)
+        molkgnnnet_case("molkgnnnet_call", n_mol=6, seed=29, num_layers=3, L1=(10, 20, 30, 50), LN=(10, 20, 30, 50))
+    else:
+        main()
