@@ -198,11 +198,13 @@ int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, c
  * bulk copy instead of per-pair reads of the bucket-order array.  0 if the plan / layer is not eligible. */
 int64_t molkgnn_tile_argmax_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 
-/* Selects the forward kernel: 2 = molecule-tile tcgen05 kernel (default; needs ximg, a tiled plan and an eligible layer,
- * else falls back to 1), 1 = bucket-order tcgen05 kernel (falls back to 0 for layers whose kernel set does not fit shared
- * memory), 0 = fp32 SIMT kernel.  Returns the previous setting (-1 = not yet chosen). */
+/* Selects the forward kernel: 3 = layer-fused molecule-tile tcgen05 kernel for molkgnn_stack_fwd (default: ONE launch for all
+ * layers, csrc/stack_fwd_fused.cu; needs a tiled plan and eligible layers, else -- and for the per-layer entry point -- 2),
+ * 2 = per-layer molecule-tile tcgen05 kernel (needs ximg, a tiled plan and an eligible layer, else falls back to 1),
+ * 1 = bucket-order tcgen05 kernel (falls back to 0 for layers whose kernel set does not fit shared memory), 0 = fp32 SIMT
+ * kernel.  Returns the previous setting (-1 = not yet chosen). */
 int molkgnn_set_fwd_path(int path);
-/* the forward kernel currently selected (0, 1 or 2; resolves the MOLKGNN_FWD environment override on first use) */
+/* the forward kernel currently selected (0 .. 3; resolves the MOLKGNN_FWD environment override on first use) */
 int molkgnn_get_fwd_path(void);
 
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
@@ -248,6 +250,7 @@ void molkgnn_path_counts(int64_t out[4]);
 #define MOLKGNN_STACK_KEEP_SC 1      /* flags: keep every layer's compact scores (else one buffer is reused) */
 #define MOLKGNN_STACK_WANT_FREE 2    /* flags: also record the free-running arg-max of every layer */
 #define MOLKGNN_STACK_PACKED 4       /* flags: molkgnn_param_pack() already ran for every layer on this stream */
+#define MOLKGNN_STACK_INFERENCE 8    /* flags: no backward follows (torch.no_grad): the layer-fused forward writes only h_out */
 typedef struct molkgnn_stack_layout {
     int64_t fwd_bytes;                          /* forward workspace: lives from stack_fwd to stack_bwd */
     int64_t bwd_bytes;                          /* backward scratch: only during stack_bwd */

@@ -2,5 +2,7 @@
 from .kernels import KernelConv, BaseKernelSetConv, KernelSetConv  # noqa: F401
 from .KernelLayer import MolGCN  # noqa: F401
 from .plan import BucketPlan, ToXAndPAndEdgeAttrForDeg  # noqa: F401
+from ._lib import MolKGNNError  # noqa: F401
 
-__all__ = ["KernelConv", "BaseKernelSetConv", "KernelSetConv", "MolGCN", "BucketPlan", "ToXAndPAndEdgeAttrForDeg"]
+__all__ = ["KernelConv", "BaseKernelSetConv", "KernelSetConv", "MolGCN", "BucketPlan", "ToXAndPAndEdgeAttrForDeg",
+           "MolKGNNError"]

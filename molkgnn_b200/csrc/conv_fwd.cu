@@ -416,14 +416,15 @@ using namespace mk;
 static int g_fwd_path = -1;
 extern "C" int molkgnn_set_fwd_path(int path) {
     const int old = g_fwd_path;
-    g_fwd_path = path < 0 ? 0 : path > 2 ? 2 : path;
+    g_fwd_path = path < 0 ? 0 : path > 3 ? 3 : path;
     return old;
 }
 
 static void resolve_fwd_path() {
     if (g_fwd_path < 0) {
         const char* e = getenv("MOLKGNN_FWD");
-        g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : 2;   // simt | bucket-order tc | tile (default)
+        // simt | bucket-order tc | tile (per layer) | layer-fused tile kernel for the stack, per-layer tile kernel otherwise (default)
+        g_fwd_path = (e && e[0] == 's') ? 0 : (e && e[0] == 'b') ? 1 : (e && e[0] == 't') ? 2 : 3;
     }
 }
 extern "C" int molkgnn_get_fwd_path(void) {
@@ -454,7 +455,7 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
     }
     ProfScope prof("conv_fwd", st);
     resolve_fwd_path();
-    if (g_fwd_path == 2) {
+    if (g_fwd_path >= 2) {
         const int rc = launch_conv_fwd_tile(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, ld_sc, scoff, argmax,
                                             argmax_free, argmax_in, argmax_tile, counter, st);
         if (rc > 0) ++g_path_counts[0];

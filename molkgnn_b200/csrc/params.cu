@@ -243,7 +243,28 @@ __global__ void __launch_bounds__(256) k_param_pack_tile(const __grid_constant__
     if (!a.img) return;
     const int nch = a.Fk / 8;
     const int it = blockIdx.x * 256 + threadIdx.x;
-    if (it >= a.tb.nb * 128 * nch) return;
+    if (it >= a.tb.nb * 128 * nch) {
+        // bond-support table of the layer-fused forward: block by block, segment by segment, [slot][half][kernel] float4
+        int e = it - a.tb.nb * 128 * nch;
+        if (e >= tile_es_f4(a.L)) return;
+        float4* es = reinterpret_cast<float4*>(a.img + tile_es_off(a.tb.nb, a.Fk));
+        const int e_out = e;
+        for (int blk = 0; blk < a.tb.nb; ++blk)
+            for (int sgi = 0; sgi < a.tb.nseg[blk]; ++sgi) {
+                const TileSeg sg = a.tb.seg[blk][sgi];
+                const int cnt = sg.d * 2 * sg.nk;
+                if (e >= 0 && e < cnt) {
+                    const int kl = e % sg.nk, sh = e / sg.nk;               // sh = slot * 2 + half
+                    const int L = a.L[sg.d - 1];
+                    const PackedLayout pl(sg.d, L, a.Fp);
+                    es[e_out] = *reinterpret_cast<const float4*>(a.packed[sg.d - 1] + pl.es +
+                                                                 (size_t)((sh >> 1) * L + sg.k0 + kl) * EP + (sh & 1) * 4);
+                    return;
+                }
+                e -= cnt;
+            }
+        return;
+    }
     const int c = it % nch;
     const int row = (it / nch) % 128;
     const int blk = it / (nch * 128);
@@ -272,6 +293,11 @@ __global__ void __launch_bounds__(256) k_param_pack_tile(const __grid_constant__
     const uint32_t off = tc::il_off(row, 8 * c, a.Fk);
     *reinterpret_cast<uint4*>(base + off) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(base + one + off) = *reinterpret_cast<const uint4*>(lo);
+    // K-step-major copy (tile.cuh): K step ks = c / 2 of block blk is one contiguous 8 KB stage [hi | lo]
+    unsigned char* ks = a.img + tile_img_ks_off(a.tb.nb, a.Fk) + ((size_t)blk * (a.Fk >> 4) + (c >> 1)) * TILE_KS_BYTES +
+                        (size_t)(row >> 3) * 256 + (size_t)(c & 1) * 128 + (size_t)(row & 7) * 16;
+    *reinterpret_cast<uint4*>(ks) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(ks + TILE_KS_BYTES / 2) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -495,7 +521,8 @@ bool tile_layer_ok(const molkgnn_layer_t* layer) {
 extern "C" int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer) {
     TileBlocks tb;
     if (!tile_layer_ok(layer) || !tb.build(layer->L)) return 0;
-    return (int64_t)tb.nb * 2 * tile_img_one(tile_fk(layer->Fp));
+    // block-major images + K-step-major copy + bond-support table (tile.cuh)
+    return tile_es_off(tb.nb, tile_fk(layer->Fp)) + ((int64_t)tile_es_f4(layer->L) * 16 + 127) / 128 * 128;
 }
 
 // what: bit 0 = normalised rows / weights / signs, bit 1 = bucket-order tensor-core images, bit 2 = tile images
@@ -554,7 +581,7 @@ extern "C" int molkgnn_param_pack_layers(const molkgnn_layer_t* layers, int32_t 
                 for (int d = 0; d < 4; ++d) { ta.L[d] = layer->L[d]; ta.packed[d] = layer->packed[d]; }
                 ta.tb.build(layer->L);
                 ta.img = reinterpret_cast<unsigned char*>(layer->tile_img);
-                items_max = std::max(items_max, ta.tb.nb * 128 * (ta.Fk / 8));
+                items_max = std::max(items_max, ta.tb.nb * 128 * (ta.Fk / 8) + tile_es_f4(layer->L));
             }
         }
         ProfScope prof("param_pack", st);

@@ -11,6 +11,14 @@
 
 using namespace mk;
 
+namespace mk {
+int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int nl, const float* x, int32_t ldx,
+                           void* const* ximg, float* const* hnorm, uint8_t* const* amT, float* hgate, int32_t ld_hgate,
+                           float* h_out, int32_t ldh, float* const* sc, uint8_t* const* argmax, uint8_t* const* argmax_free,
+                           const uint8_t* const* argmax_in, const int64_t (*scoff)[4], cudaStream_t st);
+extern long long g_path_counts[4];
+}
+
 namespace {
 inline int64_t al128(int64_t v) { return (v + 127) / 128 * 128; }
 inline int rup4(int v) { return (v + 3) / 4 * 4; }
@@ -101,6 +109,37 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     const int N = plan->N;
     int rc;
     if (!(flags & MOLKGNN_STACK_PACKED) && (rc = molkgnn_param_pack_layers(layers, nl, 7, stream))) return rc;
+    // ---- layer-fused path: the whole stack in ONE launch (csrc/stack_fwd_fused.cu) ----
+    if (molkgnn_get_fwd_path() >= 3) {
+        bool all_img = true;
+        for (int i = 0; i < nl; ++i) all_img = all_img && lay->ximg[i] >= 0 && lay->argmax_tile[i] >= 0;
+        if (all_img && nl <= MOLKGNN_MAX_LAYERS) {
+            void* ximg[MOLKGNN_MAX_LAYERS]; float* hnorm[MOLKGNN_MAX_LAYERS]; uint8_t* amT[MOLKGNN_MAX_LAYERS];
+            float* scp[MOLKGNN_MAX_LAYERS]; uint8_t* am[MOLKGNN_MAX_LAYERS]; uint8_t* amf[MOLKGNN_MAX_LAYERS];
+            const uint8_t* amin[MOLKGNN_MAX_LAYERS];
+            const bool aux = (flags & MOLKGNN_STACK_KEEP_SC) || (flags & MOLKGNN_STACK_WANT_FREE) || argmax_in;
+            const bool train = !(flags & MOLKGNN_STACK_INFERENCE);
+            for (int i = 0; i < nl; ++i) {
+                ximg[i] = train ? ws + lay->ximg[i] : nullptr;
+                hnorm[i] = train ? reinterpret_cast<float*>(ws + lay->hnorm[i]) : nullptr;
+                amT[i] = train ? ws + lay->argmax_tile[i] : nullptr;
+                scp[i] = (flags & MOLKGNN_STACK_KEEP_SC) ? reinterpret_cast<float*>(ws + lay->sc[i]) : nullptr;
+                am[i] = aux ? ws + lay->argmax[i] : nullptr;
+                amf[i] = lay->argmax_free[i] >= 0 ? ws + lay->argmax_free[i] : nullptr;
+                amin[i] = argmax_in ? argmax_in[i] : nullptr;
+            }
+            float* hgate = nl > 1 ? reinterpret_cast<float*>(ws + lay->h[nl - 1]) : nullptr;
+            rc = launch_stack_fwd_fused(plan, layers, nl, x, ldx, ximg, hnorm, amT, hgate, nl > 1 ? layers[nl - 1].Fp : 0, h_out, ldh,
+                                        aux ? scp : nullptr, aux ? am : nullptr, aux ? amf : nullptr, argmax_in ? amin : nullptr,
+                                        lay->scoff, (cudaStream_t)stream);
+            if (rc < 0) return rc;
+            if (rc > 0) {
+                mk::g_path_counts[0] += nl;
+                for (int i = 0; i < nl && tile_fwd; ++i) tile_fwd[i] = train ? 1 : 0;
+                return 0;
+            }
+        }
+    }
     MK_CHECK_CUDA(cudaMemsetAsync(ws + lay->counter, 0, sizeof(int32_t) * 8 * (size_t)nl, (cudaStream_t)stream));
     float* h = reinterpret_cast<float*>(ws + lay->h[0]);
     float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);

@@ -1,0 +1,657 @@
+// Layer-fused, tile-major forward of the whole conv stack (sm_100a, tcgen05 + TMEM): ONE launch runs, for every molecule
+// tile, all layers of MolGCN.forward (reference KernelLayer.py:107-120: `sim_sc = layer(...)`, `h = propagate(...)`) with the
+// activations of the tile resident in shared memory from the raw input rows to the final h.
+//
+// A tile is a run of <= 128 consecutive nodes holding whole molecules (tile.cuh), so the conv of a layer (one dense GEMM per
+// kernel block on the tensor cores, T = khat . xhat^T, then the reference arithmetic per (node, kernel) pair -- kernels.py:353-425,
+// exactly as in conv_fwd_tile.cu) AND the neighbour sum that follows it (KernelLayer.py:119) only touch tile-local rows: the
+// next layer's normalised fp16 (hi, lo) operand image is rebuilt in place in shared memory.  HBM sees the raw x rows, the
+// per-tile metadata and bond rows, the final h -- and, in training, what the backward needs: per layer the operand image
+// (4 bytes per feature = the fp32 activation it replaces), the row norms and the arg-max bytes.  No score matrix, no
+// intermediate activations, no per-layer launches (7 launches of the per-layer path become 1).
+//
+// CTA = 16 consumer warps + 2 producer warps, persistent over its tiles (TileWalk):
+//   ring warp  streams the kernel-block images of every (tile, layer, block), one K step (8 KB: hi | lo) per stage, through a
+//              ring of bulk copies -- a pure function of the sequence number, so it runs ahead across blocks, layers and tiles;
+//   MMA warp   per (tile, layer): waits for the tile's operand image, then per block and K step 3 tcgen05.mma (hi*hi, lo*hi,
+//              hi*lo) into the block's own TMEM accumulator (4 x 128 columns), releasing ring stages by tcgen05.commit;
+//   consumers  per block: accumulator -> shared memory ([column][row]), one thread per (node, kernel) pair, scores into a
+//              compact shared-memory tile; per layer: neighbour sum from that tile, norm, next operand image (+ its bulk
+//              store to HBM for the backward).  Thread 0 also issues the bulk copies of the next layer's bond-support table
+//              and of the next tile's metadata / bond rows / raw x rows at the points where their buffers fall free.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include "common.cuh"
+#include "tc.cuh"
+#include "tile.cuh"
+
+namespace mk {
+
+bool tile_layer_ok(const molkgnn_layer_t* layer);
+int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+
+constexpr int SF_MAXL = 4;                 // layers the fused kernel takes (kernel-parameter space)
+constexpr int SF_CONS = 512;               // consumer threads
+constexpr int SF_CWARPS = SF_CONS / 32;
+constexpr int SF_THREADS = SF_CONS + 64;   // + ring warp + MMA warp
+constexpr int SF_MAXSTAGES = 8;
+
+struct SFLayer {
+    int F, Fp, Fk, K, Kp;
+    int L[4], koff[4];
+    const float* packed[4];
+    const unsigned char* img_ks;           // K-step-major kernel-block images (tile.cuh)
+    const float4* es_img; int es_f4;       // bond-support table of the layer
+    TileBlocks tb;
+    int x_one;                             // bytes of one operand image (hi or lo) of this layer's INPUT
+    unsigned char* ximg; float* hnorm;     // out (training): image / row norms of this layer's input, nullable
+    uint8_t* amT; int stride_am;           // out (training): tile-ordered arg-max bytes, nullable
+    float* sc; uint8_t* argmax; uint8_t* argmax_free; const uint8_t* argmax_in;   // parity harness / replay, nullable
+    long long scoff[4];
+};
+
+struct StackFwdArgs {
+    int nl;
+    SFLayer ly[SF_MAXL];
+    const float* x; int ldx; int x_stage;  // raw input rows; x_stage: rows of a tile are bulk-copied to shared memory
+    const TileMetaG* meta; const float* ehat_node; int n_tiles;
+    const int* order; int order_grid;
+    float* hgate; int ld_hgate;            // fp32 input rows of the LAST layer (chirality gate, kernels.py:310-317); nl == 1: = x
+    const float* hgate_r;
+    float* h_out; int ldh;
+    int nstages;
+    int sm_x, sm_dump, sm_ring, sm_meta, sm_eh, sm_es, sm_sc, sm_dup;
+};
+static_assert(sizeof(StackFwdArgs) <= 4000, "StackFwdArgs must fit the kernel-parameter space");
+
+struct SFSeg {                             // per (layer, block, segment) constants, shared memory
+    float ws, wc, we, W, rW, rnk;
+    int d, k0, nk, rowbase, L, es_off;
+    const int8_t* supsign;
+};
+
+__device__ __forceinline__ void sf_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SF_CONS) : "memory"); }
+__device__ __forceinline__ void sf_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+// shared -> global bulk store (async proxy), tracked by the issuing thread's bulk group
+__device__ __forceinline__ void sf_bulk_s2g(void* dst, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(tc::smem_u32(src_smem)), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void sf_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void sf_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// accumulator of block `blk` -> dump[column][row]: warp (quadrant q, column block cb) moves 32 rows x 32 columns
+__device__ __forceinline__ void sf_dump(float* dump, uint32_t tmem, int blk, int nn) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp & 3, cb = warp >> 2;
+    if (cb * 32 >= nn) return;
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * TNODES + cb * 32);
+    tc::tmem_ld16(taddr, v);
+    tc::tmem_ld16(taddr + 16, v + 16);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+    float* dst = dump + (size_t)(cb * 32) * 128 + q * 32 + lane;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]);
+}
+
+template <int D> __device__ __forceinline__ uint32_t sf_perm_code_rt(int p) {
+    uint32_t c = 0;
+#pragma unroll
+    for (int q = 0; q < Perm<D>::P; ++q) if (q == p) c = perm_code<D>(q);
+    return c;
+}
+
+struct SFPairOut { float sc; size_t cidx; int tidx; uint8_t am, free; };
+
+// one (node, kernel) pair: the reference arithmetic on its d x d similarity tile (same operation order as conv_fwd_tile.cu)
+template <int D, bool FORCED>
+__device__ __forceinline__ SFPairOut sf_pair(const SFLayer& ly, const TileMetaG& m, const float* dump, const float* ehS,
+                                             const float4* estab, const unsigned char* dupf, const SFSeg& sg, int doff,
+                                             bool is_last, int nl_, int kl) {
+    constexpr int P = Perm<D>::P;
+    const uint32_t nw = m.nl[nl_];
+    const int e0 = m.eslot[nl_];
+    const int k = sg.k0 + kl;
+    const float* col0 = dump + sg.rowbase + kl;
+    float T[D][D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float* c = col0 + ((nw >> (8 * j)) & 0xffu) * 128;
+#pragma unroll
+        for (int s = 0; s < D; ++s) T[j][s] = c[s * sg.nk];
+    }
+    const float cdot = col0[nl_ * 128 + D * sg.nk];
+    SFPairOut o;
+    o.cidx = FORCED ? (size_t)ly.scoff[D - 1] + (size_t)m.posl[nl_] * sg.L + k : 0;
+    o.tidx = doff + m.lidx[nl_] * sg.L + k;             // tile order: degree blocks, node-of-degree major, kernel minor
+    const int forced = FORCED && ly.argmax_in ? (ly.argmax_in[o.cidx] & 0x7f) : -1;
+    // mean over j for every permutation: sequential sum, then true division (kernels.py:194)
+    float best = 0.f, used = 0.f;
+    int bi = 0;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        float s = T[0][Perm<D>::at(p, 0)];
+#pragma unroll
+        for (int j = 1; j < D; ++j) s += T[j][Perm<D>::at(p, j)];
+        s = div_deg<D>(s);
+        if (p == 0 || s > best) { best = s; bi = p; }   // first maximum wins (torch.max, kernels.py:373)
+        if (FORCED && p == forced) used = s;
+    }
+    o.free = (uint8_t)bi;
+    if (FORCED && forced >= 0 && forced < P) { bi = forced; best = used; }
+    // bond-attribute cosine at the chosen permutation (kernels.py:382-390)
+    const uint32_t code = sf_perm_code_rt<D>(bi);
+    float esum = 0.f;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const int s = (code >> (2 * j)) & 3;
+        const float4 e0v = *reinterpret_cast<const float4*>(ehS + (size_t)(e0 + j) * EP);
+        const float4 e1v = *reinterpret_cast<const float4*>(ehS + (size_t)(e0 + j) * EP + 4);
+        const float4 s0 = estab[sg.es_off + (s * 2 + 0) * sg.nk + kl];
+        const float4 s1 = estab[sg.es_off + (s * 2 + 1) * sg.nk + kl];
+        float dd = 0.f;
+        dd = fmaf(e0v.x, s0.x, dd); dd = fmaf(e0v.y, s0.y, dd); dd = fmaf(e0v.z, s0.z, dd); dd = fmaf(e0v.w, s0.w, dd);
+        dd = fmaf(e1v.x, s1.x, dd); dd = fmaf(e1v.y, s1.y, dd); dd = fmaf(e1v.z, s1.z, dd); dd = fmaf(e1v.w, s1.w, dd);
+        esum = j == 0 ? dd : esum + dd;
+    }
+    const float E = div_deg<D>(esum);
+    float sc = div_by((best * sg.ws + cdot * sg.wc) + E * sg.we, sg.W, sg.rW);
+    uint8_t am = (uint8_t)bi;
+    if (D == 4 && is_last) {
+        // chirality (kernels.py:279-350): +1 if any two neighbours are identical, else sign agreement
+        int chi = 1;
+        if (!dupf[nl_]) chi = (m.tsg[nl_] == sg.supsign[k * 12 + bi]) ? 1 : -1;
+        if (chi < 0) { sc = -sc; am |= 0x80; }
+    }
+    o.sc = sc; o.am = am;
+    return o;
+}
+
+template <bool FORCED>
+__device__ __forceinline__ void sf_store(const SFLayer& ly, float* scS, uint8_t* amT_tile, const SFPairOut& o) {
+    scS[o.tidx] = o.sc;
+    if (amT_tile) amT_tile[o.tidx] = o.am;
+    if (FORCED) {
+        if (ly.argmax_free) ly.argmax_free[o.cidx] = o.free;
+        if (ly.argmax) ly.argmax[o.cidx] = o.am;
+        if (ly.sc) ly.sc[o.cidx] = o.sc;
+    }
+}
+
+template <int D, bool FORCED>
+__device__ __forceinline__ void sf_pairs_of_thread(const SFLayer& ly, const TileMetaG& m, const float* dump, const float* ehS,
+                                                   const float4* estab, const unsigned char* dupf, const SFSeg& sg, int doff,
+                                                   bool is_last, float* scS, uint8_t* amT_tile) {
+    const int np = m.cnt[D - 1] * sg.nk;
+    // the segment's pairs (node-major, then kernel), two per thread and iteration so that their dependency chains interleave
+    for (int p = (int)threadIdx.x; p < np; p += 2 * SF_CONS) {
+        const int p2 = p + SF_CONS;
+        const int ni = (int)(((float)p + 0.5f) * sg.rnk);
+        const SFPairOut o1 = sf_pair<D, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni], p - ni * sg.nk);
+        SFPairOut o2;
+        const bool has2 = p2 < np;
+        if (has2) {
+            const int ni2 = (int)(((float)p2 + 0.5f) * sg.rnk);
+            o2 = sf_pair<D, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni2], p2 - ni2 * sg.nk);
+        }
+        sf_store<FORCED>(ly, scS, amT_tile, o1);
+        if (has2) sf_store<FORCED>(ly, scS, amT_tile, o2);
+    }
+}
+
+// chirality gate of the degree-4 nodes of a tile: any two of the four neighbour feature rows bit-equal (torch.equal,
+// kernels.py:310-317); one warp per node, raw fp32 rows of the last layer's input from global memory
+__device__ __forceinline__ void sf_dup_flags(const float* rows, int ld, int F, const TileMetaG& m, unsigned char* dupf) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n4 = m.cnt[3], t0 = m.t0;
+    for (int i = warp; i < n4; i += SF_CWARPS) {
+        const int nl_ = m.list[3][i];
+        const uint32_t w = m.nl[nl_];
+        unsigned neq = 0;
+        for (int f = lane; f < F; f += 32) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = __ldcg(rows + (size_t)(t0 + ((w >> (8 * j)) & 0xff)) * ld + f);
+            int b = 0;
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+#pragma unroll
+                for (int q = p + 1; q < 4; ++q, ++b) if (!(v[p] == v[q])) neq |= 1u << b;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) neq |= __shfl_xor_sync(0xffffffffu, neq, o);
+        if (lane == 0) dupf[nl_] = (neq != 0x3fu) ? 1 : 0;
+    }
+}
+
+#ifdef MK_PHASE_CLOCKS
+__device__ unsigned long long g_ph_sfwd[16];
+#endif
+
+template <bool FORCED>
+__global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_constant__ StackFwdArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_meta[2], bar_eh, bar_es, bar_x, bar_mma[4], bar_tfree[4], bar_rfull[SF_MAXSTAGES], bar_rfree[SF_MAXSTAGES];
+    __shared__ uint32_t tslot;
+    __shared__ SFSeg s_seg[SF_MAXL][4][TILE_MAXSEG];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    MK_PH_DECL(tid == 0)
+    if (tid == 0) {
+        tc::mbar_init(&bar_meta[0], 1); tc::mbar_init(&bar_meta[1], 1);
+        tc::mbar_init(&bar_eh, 1); tc::mbar_init(&bar_es, 1); tc::mbar_init(&bar_x, 1);
+        for (int i = 0; i < 4; ++i) { tc::mbar_init(&bar_mma[i], 1); tc::mbar_init(&bar_tfree[i], 1); }
+        for (int i = 0; i < SF_MAXSTAGES; ++i) { tc::mbar_init(&bar_rfull[i], 1); tc::mbar_init(&bar_rfree[i], 1); }
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tslot, 512);
+    // per (layer, block, segment) constants
+    for (int i = tid; i < a.nl * 4 * TILE_MAXSEG; i += SF_THREADS) {
+        const int l = i / (4 * TILE_MAXSEG), blk = (i / TILE_MAXSEG) % 4, si = i % TILE_MAXSEG;
+        const SFLayer& ly = a.ly[l];
+        if (blk < ly.tb.nb && si < ly.tb.nseg[blk]) {
+            const TileSeg sg = ly.tb.seg[blk][si];
+            const int L = ly.L[sg.d - 1];
+            const PackedLayout pl(sg.d, L, ly.Fp);
+            const float* pk = ly.packed[sg.d - 1];
+            SFSeg c;
+            c.ws = pk[pl.w + 0]; c.wc = pk[pl.w + 1]; c.we = pk[pl.w + 2]; c.W = pk[pl.w + 3];
+            c.rW = 1.0f / c.W; c.rnk = 1.0f / (float)sg.nk;
+            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
+            int es_off = 0;                       // float4 offset of the segment inside the layer's bond-support table
+            for (int b2 = 0; b2 <= blk; ++b2)
+                for (int s2 = 0; s2 < (b2 == blk ? si : ly.tb.nseg[b2]); ++s2) es_off += ly.tb.seg[b2][s2].d * 2 * ly.tb.seg[b2][s2].nk;
+            c.es_off = es_off;
+            c.supsign = reinterpret_cast<const int8_t*>(pk + pl.sign);
+            s_seg[l][blk][si] = c;
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tslot;
+    const TileWalk walk(a.order, a.order_grid, a.n_tiles);
+    const int NS = a.nstages;
+    unsigned char* Xs = smem + a.sm_x;
+    unsigned char* ring = smem + a.sm_ring;
+
+    if (warp == SF_CWARPS) {
+        // ================= ring warp: kernel-block images, one K step per stage =================
+        if (lane == 0) {
+            uint32_t q = 0;
+            for (int wk = 0; wk < walk.cnt; ++wk)
+                for (int l = 0; l < a.nl; ++l) {
+                    const SFLayer& ly = a.ly[l];
+                    const int nks = ly.Fk >> 4, nst = ly.tb.nb * nks;
+                    for (int s = 0; s < nst; ++s, ++q) {
+                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        tc::mbar_wait(&bar_rfree[slot], (use & 1u) ^ 1u);
+                        mbar_expect_tx(&bar_rfull[slot], TILE_KS_BYTES);
+                        bulk_g2s(ring + (size_t)slot * TILE_KS_BYTES, ly.img_ks + (size_t)s * TILE_KS_BYTES, TILE_KS_BYTES, &bar_rfull[slot]);
+                    }
+                }
+        }
+    } else if (warp == SF_CWARPS + 1) {
+        // ================= MMA warp =================
+        if (lane == 0) {
+            uint32_t q = 0, xseq = 0, use_t[4] = {0u, 0u, 0u, 0u};
+            for (int wk = 0; wk < walk.cnt; ++wk) {
+                const int b = wk & 1;
+                tc::mbar_wait(&bar_meta[b], (uint32_t)(wk >> 1) & 1u);
+                const int nn = reinterpret_cast<const TileMetaG*>(smem + a.sm_meta + (size_t)b * sizeof(TileMetaG))->nn;
+                const int N = max(16, (nn + 15) & ~15);
+                const uint32_t idesc = tc::idesc_f16(128, N, 0, 0);
+                for (int l = 0; l < a.nl; ++l) {
+                    const SFLayer& ly = a.ly[l];
+                    const int nks = ly.Fk >> 4;
+                    const uint32_t sbo = (uint32_t)(ly.Fk >> 3) * 128u;
+                    const uint32_t xhi = tc::smem_u32(Xs), xlo = xhi + (uint32_t)ly.x_one;
+                    tc::mbar_wait(&bar_x, xseq & 1u);
+                    ++xseq;
+                    tc::fence_after_sync();
+                    for (int blk = 0; blk < ly.tb.nb; ++blk) {
+                        tc::mbar_wait(&bar_tfree[blk], (use_t[blk] & 1u) ^ 1u);
+                        ++use_t[blk];
+                        tc::fence_after_sync();
+                        const uint32_t d = tmem + (uint32_t)(blk * TNODES);
+                        for (int ks = 0; ks < nks; ++ks, ++q) {
+                            const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                            tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                            const uint32_t aH = tc::smem_u32(ring + (size_t)slot * TILE_KS_BYTES), aL = aH + TILE_KS_BYTES / 2;
+                            const uint64_t dAh = tc::smem_desc(aH, 128u, 256u), dAl = tc::smem_desc(aL, 128u, 256u);
+                            const uint32_t o = (uint32_t)ks * 256u;
+                            const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
+                            tc::umma_f16(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
+                            tc::umma_f16(d, dAl, dBh, idesc, 1u);
+                            tc::umma_f16(d, dAh, dBl, idesc, 1u);
+                            tc::umma_commit(&bar_rfree[slot]);          // the stage is free once these MMAs have read it
+                        }
+                        tc::umma_commit(&bar_mma[blk]);
+                    }
+                }
+            }
+        }
+    } else {
+        // ================= consumers =================
+        float* dump = reinterpret_cast<float*>(smem + a.sm_dump);
+        float* ehS = reinterpret_cast<float*>(smem + a.sm_eh);
+        float4* estab = reinterpret_cast<float4*>(smem + a.sm_es);
+        float* scS = reinterpret_cast<float*>(smem + a.sm_sc);
+        unsigned char* dupf = smem + a.sm_dup;
+        uint32_t cm[4] = {0u, 0u, 0u, 0u}, esseq = 0;
+        // thread 0 issues the bulk copies whose buffers the consumers themselves release
+        auto issue_meta = [&](int wk) {
+            uint64_t* bar = &bar_meta[wk & 1];
+            mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG));
+            bulk_g2s(smem + a.sm_meta + (size_t)(wk & 1) * sizeof(TileMetaG), a.meta + walk.tile(wk), (uint32_t)sizeof(TileMetaG), bar);
+        };
+        auto issue_es = [&](int l) {
+            const SFLayer& ly = a.ly[l];
+            mbar_expect_tx(&bar_es, (uint32_t)ly.es_f4 * 16u);
+            bulk_g2s(estab, ly.es_img, (uint32_t)ly.es_f4 * 16u, &bar_es);
+        };
+        auto issue_tile_data = [&](int wk) {          // bond rows + raw x rows of tile wk (its metadata must have landed)
+            const TileMetaG* mm = reinterpret_cast<const TileMetaG*>(smem + a.sm_meta + (size_t)(wk & 1) * sizeof(TileMetaG));
+            const uint32_t eb = (uint32_t)mm->ne * EP * 4u;
+            const uint32_t xb = a.x_stage ? (uint32_t)mm->nn * (uint32_t)a.ldx * 4u : 0u;
+            mbar_expect_tx(&bar_eh, eb + xb);
+            if (eb) bulk_g2s(ehS, a.ehat_node + (size_t)mm->e0 * EP, eb, &bar_eh);
+            if (xb) bulk_g2s(dump, a.x + (size_t)mm->t0 * a.ldx, xb, &bar_eh);
+        };
+        if (tid == 0 && walk.cnt > 0) {
+            issue_meta(0);
+            issue_es(0);
+            tc::mbar_wait(&bar_meta[0], 0u);
+            issue_tile_data(0);
+        }
+        MK_PH(0);
+        for (int wk = 0; wk < walk.cnt; ++wk) {
+            const int b = wk & 1;
+            const int tile = walk.tile(wk);
+            tc::mbar_wait(&bar_meta[b], (uint32_t)(wk >> 1) & 1u);
+            tc::mbar_wait(&bar_eh, (uint32_t)wk & 1u);
+            const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(smem + a.sm_meta + (size_t)b * sizeof(TileMetaG));
+            const int nn = m.nn, t0 = m.t0;
+            const int rend = min(TNODES, (nn + 15) & ~15);
+            MK_PH(1);
+            // ---- operand image of layer 0 from the raw x rows: a warp per row, norm with k_pad_norm's summation order ----
+            {
+                const SFLayer& ly = a.ly[0];
+                unsigned char* Xhi = Xs;
+                unsigned char* Xlo = Xs + ly.x_one;
+                const float* xs = a.x_stage ? dump : a.x + (size_t)t0 * a.ldx;
+                for (int r = warp; r < rend; r += SF_CWARPS) {
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (r < nn) {
+                        const float* xr = xs + (size_t)r * a.ldx;
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) if (lane + 32 * h < ly.F) v[h] = xr[lane + 32 * h];
+                    }
+                    float ss = v[0] * v[0];
+#pragma unroll
+                    for (int h = 1; h < 4; ++h) if (lane + 32 * h < ly.Fp) ss += v[h] * v[h];
+                    ss = warp_sum(ss);
+                    const float nrm = sqrtf(ss);
+                    const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
+                    if (r < nn && lane == 0 && ly.hnorm) ly.hnorm[t0 + r] = nrm;
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const int col = lane + 32 * h;
+                        if (col < ly.Fk) {
+                            const float xv = v[h] * rinv;
+                            const __half hi = __float2half_rn(xv);
+                            const __half lo = __float2half_rn(xv - __half2float(hi));
+                            const uint32_t off = tc::il_off(r, col, ly.Fk);
+                            *reinterpret_cast<__half*>(Xhi + off) = hi;
+                            *reinterpret_cast<__half*>(Xlo + off) = lo;
+                        }
+                    }
+                }
+            }
+            tc::fence_async_smem();
+            sf_consumer_sync();                                   // (S0) image complete; every warp has left the previous tile
+            if (tid == 0) {
+                sf_arrive(&bar_x);
+                if (a.ly[0].ximg) sf_bulk_s2g(a.ly[0].ximg + (size_t)tile * 2 * a.ly[0].x_one, Xs, 2u * (uint32_t)a.ly[0].x_one);
+                if (wk + 1 < walk.cnt) issue_meta(wk + 1);        // into the other metadata buffer (free since S0)
+            }
+            MK_PH(2);
+            for (int l = 0; l < a.nl; ++l) {
+                const SFLayer& ly = a.ly[l];
+                const bool is_last = l == a.nl - 1;
+                int doff[4];
+                doff[0] = 0;
+#pragma unroll
+                for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * ly.L[d - 1];
+                uint8_t* amT_tile = ly.amT ? ly.amT + (size_t)tile * ly.stride_am : nullptr;
+                tc::mbar_wait(&bar_es, esseq & 1u);
+                ++esseq;
+                for (int blk = 0; blk < ly.tb.nb; ++blk) {
+                    tc::mbar_wait(&bar_mma[blk], cm[blk] & 1u);
+                    ++cm[blk];
+                    tc::fence_after_sync();
+                    MK_PH(3);
+                    sf_dump(dump, tmem, blk, nn);
+                    if (blk == 0 && is_last && ly.L[3] > 0) sf_dup_flags(a.hgate_r, a.ld_hgate, ly.F, m, dupf);
+                    if (tid == 0) sf_bulk_wait_read();            // the image's bulk store has read shared memory (long ago)
+                    tc::fence_before_sync();
+                    sf_consumer_sync();                           // (S1) dump complete, accumulator drained
+                    if (tid == 0) sf_arrive(&bar_tfree[blk]);
+                    MK_PH(4);
+                    const int nseg = ly.tb.nseg[blk];
+                    for (int si = 0; si < nseg; ++si) {
+                        const SFSeg sg = s_seg[l][blk][si];
+                        switch (sg.d) {
+                            case 1: sf_pairs_of_thread<1, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[0], is_last, scS, amT_tile); break;
+                            case 2: sf_pairs_of_thread<2, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[1], is_last, scS, amT_tile); break;
+                            case 3: sf_pairs_of_thread<3, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[2], is_last, scS, amT_tile); break;
+                            default: sf_pairs_of_thread<4, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[3], is_last, scS, amT_tile); break;
+                        }
+                    }
+                    MK_PH(5);
+                    sf_consumer_sync();                           // (S2) scores of the block written; dump free
+                    MK_PH(6);
+                }
+                if (tid == 0) {
+                    // the bond-support table, and after the last layer the bond rows / x staging area, are free now
+                    if (!is_last) issue_es(l + 1);
+                    else if (wk + 1 < walk.cnt) {
+                        issue_es(0);
+                        tc::mbar_wait(&bar_meta[b ^ 1], (uint32_t)((wk + 1) >> 1) & 1u);
+                        issue_tile_data(wk + 1);
+                    }
+                }
+                // ---- neighbour sum h[v] = sum over in-edges of sc[source] (KernelLayer.py:119), norm, next operand image ----
+                {
+                    const int c0 = 4 * lane;
+                    const int Kp = ly.Kp;
+                    const SFLayer& nx = a.ly[is_last ? l : l + 1];
+                    unsigned char* Xhi = Xs;
+                    unsigned char* Xlo = Xs + nx.x_one;
+                    const bool gate_rows = !is_last && l + 1 == a.nl - 1 && a.hgate;
+                    for (int v = warp; v < nn; v += SF_CWARPS) {
+                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                        const int cnt = min((int)m.incnt[v], 4);
+                        const uint32_t w = m.inl[v];
+                        if (c0 < Kp) {
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {          // edge order
+                                if (t < cnt) {
+                                    const int j = (int)((w >> (8 * t)) & 0xffu);
+                                    const int dj = m.degl[j] - 1;
+                                    const int ko = ly.koff[dj], Lj = ly.L[dj];
+                                    const float* row = scS + doff[dj] + (int)m.lidx[j] * Lj - ko;
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const int c = c0 + u;
+                                        if (c >= ko && c < ko + Lj) acc[u] += row[c];
+                                    }
+                                }
+                            }
+                        }
+                        const int i = t0 + v;
+                        if (is_last) {
+                            if (c0 < a.ldh) {
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) if (c0 + u >= ly.K) acc[u] = 0.f;
+                                st4(a.h_out + (size_t)i * a.ldh + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+                            }
+                            continue;
+                        }
+                        float ss = 0.f;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) { if (c0 + u >= ly.K) acc[u] = 0.f; ss += acc[u] * acc[u]; }
+                        ss = warp_sum(ss);
+                        const float nrm = sqrtf(ss);
+                        if (lane == 0 && nx.hnorm) nx.hnorm[i] = nrm;
+                        if (gate_rows && c0 < a.ld_hgate) st4(a.hgate + (size_t)i * a.ld_hgate + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
+                        if (c0 < nx.Fk) {
+                            const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
+                            __align__(8) __half2 hi[2];
+                            __align__(8) __half2 lo[2];
+                            tc::split_u2(acc[0] * rinv, acc[1] * rinv, hi[0], lo[0]);
+                            tc::split_u2(acc[2] * rinv, acc[3] * rinv, hi[1], lo[1]);
+                            const uint32_t off = tc::il_off(v, c0, nx.Fk);
+                            *reinterpret_cast<uint2*>(Xhi + off) = *reinterpret_cast<const uint2*>(hi);
+                            *reinterpret_cast<uint2*>(Xlo + off) = *reinterpret_cast<const uint2*>(lo);
+                        }
+                    }
+                    if (!is_last && c0 < nx.Fk) {                  // pad rows up to the next multiple of 16 (the MMA's N extent)
+                        for (int rr = nn + warp; rr < rend; rr += SF_CWARPS) {
+                            const uint32_t off = tc::il_off(rr, c0, nx.Fk);
+                            *reinterpret_cast<uint2*>(Xhi + off) = make_uint2(0u, 0u);
+                            *reinterpret_cast<uint2*>(Xlo + off) = make_uint2(0u, 0u);
+                        }
+                    }
+                    if (!is_last) {
+                        tc::fence_async_smem();
+                        sf_consumer_sync();                       // (S3) next layer's image complete
+                        if (tid == 0) {
+                            sf_arrive(&bar_x);
+                            if (nx.ximg) sf_bulk_s2g(nx.ximg + (size_t)tile * 2 * nx.x_one, Xs, 2u * (uint32_t)nx.x_one);
+                        }
+                    }
+                }
+                MK_PH(7);
+            }
+        }
+        if (tid == 0) sf_bulk_wait_all();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    MK_PH(8);
+#ifdef MK_PHASE_CLOCKS
+    MK_PH_FLUSH(g_ph_sfwd);
+#endif
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+// One launch for the whole stack.  Returns 1 if launched, 0 if the plan / stack is not eligible (the caller runs the per-layer
+// path), < 0 on error.  `ximg[l]`, `hnorm[l]`, `amT[l]` (nullable: inference) receive what the tile backward reads;
+// sc / argmax / argmax_free / argmax_in per layer serve the parity harness.
+int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* layers, int nl, const float* x, int32_t ldx,
+                           void* const* ximg, float* const* hnorm, uint8_t* const* amT, float* hgate, int32_t ld_hgate,
+                           float* h_out, int32_t ldh, float* const* sc, uint8_t* const* argmax, uint8_t* const* argmax_free,
+                           const uint8_t* const* argmax_in, const int64_t (*scoff)[4], cudaStream_t st) {
+    if (nl < 1 || nl > SF_MAXL) return 0;
+    if (!(plan->n_tiles > 0 && plan->tile_start && plan->tile_meta && plan->ehat_node && plan->tile_max_nodes <= TNODES)) return 0;
+    static int s_budget = 0, s_sms = 0;
+    if (!s_budget) {
+        s_budget = device_max_smem_optin();
+        s_sms = device_num_sms();
+        MK_REQUIRE(s_budget > 0 && s_sms > 0, "stack_fwd_fused: no CUDA device");
+    }
+    StackFwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.nl = nl;
+    int64_t x_max = 0, es_max = 0, sc_max = 0;
+    bool forced = false;
+    for (int l = 0; l < nl; ++l) {
+        const molkgnn_layer_t& ly = layers[l];
+        SFLayer& s = a.ly[l];
+        if (!ly.tile_img || !tile_layer_ok(&ly)) return 0;
+        if (!s.tb.build(ly.L) || s.tb.nb > 4) return 0;
+        if (l > 0 && ly.F != layers[l - 1].K) return 0;
+        s.F = ly.F; s.Fp = ly.Fp; s.Fk = tile_fk(ly.Fp); s.K = ly.K; s.Kp = (ly.K + 3) / 4 * 4;
+        if (s.Kp > 128 || s.Fp > 128) return 0;
+        for (int d = 0; d < 4; ++d) { s.L[d] = ly.L[d]; s.koff[d] = ly.koff[d]; s.packed[d] = ly.packed[d]; s.scoff[d] = scoff ? scoff[l][d] : 0; }
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(ly.tile_img);
+        s.img_ks = img + tile_img_ks_off(s.tb.nb, s.Fk);
+        s.es_img = reinterpret_cast<const float4*>(img + tile_es_off(s.tb.nb, s.Fk));
+        s.es_f4 = tile_es_f4(ly.L);
+        s.x_one = tile_img_one(s.Fk);
+        s.ximg = ximg ? reinterpret_cast<unsigned char*>(ximg[l]) : nullptr;
+        s.hnorm = hnorm ? hnorm[l] : nullptr;
+        s.amT = amT ? amT[l] : nullptr;
+        s.stride_am = tile_argmax_stride(plan, &ly);
+        s.sc = sc ? sc[l] : nullptr;
+        s.argmax = argmax ? argmax[l] : nullptr;
+        s.argmax_free = argmax_free ? argmax_free[l] : nullptr;
+        s.argmax_in = argmax_in ? argmax_in[l] : nullptr;
+        if (s.sc || s.argmax || s.argmax_free || s.argmax_in) forced = true;
+        x_max = std::max<int64_t>(x_max, 2 * (int64_t)s.x_one);
+        es_max = std::max<int64_t>(es_max, (int64_t)s.es_f4 * 16);
+        sc_max = std::max<int64_t>(sc_max, (int64_t)s.stride_am * 4);      // stride_am >= pairs of the fullest tile
+        if (s.ximg && (reinterpret_cast<uintptr_t>(s.ximg) & 127)) return 0;
+    }
+    a.x = x; a.ldx = ldx;
+    a.x_stage = (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (int64_t)TNODES * ldx * 4 <= (int64_t)TNODES * 128 * 4) ? 1 : 0;
+    a.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
+    a.ehat_node = plan->ehat_node;
+    a.n_tiles = plan->n_tiles;
+    const int grid = std::min(plan->n_tiles, s_sms);
+    a.order = plan->tile_grid == grid ? plan->tile_order : nullptr;
+    a.order_grid = a.order ? grid : 0;
+    if (nl == 1) { a.hgate = nullptr; a.hgate_r = x; a.ld_hgate = ldx; }
+    else {
+        MK_REQUIRE(hgate && ld_hgate % 4 == 0 && ld_hgate >= layers[nl - 1].F, "stack_fwd_fused: hgate buffer missing");
+        a.hgate = hgate; a.hgate_r = hgate; a.ld_hgate = ld_hgate;
+    }
+    a.h_out = h_out; a.ldh = ldh;
+    MK_REQUIRE(ldh % 4 == 0 && ldh >= layers[nl - 1].K && ldh <= 128, "stack_fwd_fused: ldh=%d", ldh);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 127) / 128 * 128; return (int)o; };
+    a.sm_x = take(x_max);
+    a.sm_dump = take((int64_t)TNODES * 128 * 4);
+    a.sm_meta = take(2 * (int64_t)sizeof(TileMetaG));
+    a.sm_eh = take((int64_t)TILE_ESLOTS * EP * 4);
+    a.sm_es = take(es_max);
+    a.sm_sc = take(sc_max);
+    a.sm_dup = take(128);
+    a.sm_ring = take(0);
+    const int64_t room = (int64_t)s_budget - 5120 - off;          // static shared memory: barriers + segment constants
+    a.nstages = (int)std::min<int64_t>(SF_MAXSTAGES, room / TILE_KS_BYTES);
+    if (a.nstages < 3) return 0;
+    off += (int64_t)a.nstages * TILE_KS_BYTES;
+    static int64_t s_attr_dev[16] = {0};
+    int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
+    if (off > s_attr) {
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        s_attr = off;
+    }
+    count_launches(1);
+    ProfScope prof("stack_fwd_fused", st);
+    if (forced) k_stack_fwd_fused<true><<<grid, SF_THREADS, off, st>>>(a);     // parity harness / replay
+    else k_stack_fwd_fused<false><<<grid, SF_THREADS, off, st>>>(a);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace mk
+
+#ifdef MK_PHASE_CLOCKS
+extern "C" int molkgnn_debug_phase_clocks_sfwd(unsigned long long* out16) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out16, mk::g_ph_sfwd, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
+    unsigned long long z[16] = {0};
+    return cudaMemcpyToSymbol(mk::g_ph_sfwd, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif

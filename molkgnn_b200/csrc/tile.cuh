@@ -58,6 +58,14 @@ struct TileBlocks {
 __host__ __device__ inline int tile_fk(int Fp) { return (Fp + 15) / 16 * 16; }
 // one fp16 image (hi or lo) of a 128-row block / of a node tile: [16 row groups][Fk/8 chunks][8 rows][8 elements]
 __host__ __device__ inline int tile_img_one(int Fk) { return 16 * (Fk / 8) * 128; }
+// K-step-major copy of the kernel-block images for the layer-fused forward (stack_fwd_fused.cu): one K step (16 features) of
+// one block is 8 KB contiguous -- [hi: 16 row groups x 2 chunks x 128 B][lo: same] -- so that a CTA streams a block through
+// a ring of small stages (K-major operand: LBO = 128, SBO = 256).  It lives behind the block-major images in layer->tile_img,
+// followed by the bond-support table of the layer: for every block, every segment: [slot][half][kernel] float4.
+constexpr int TILE_KS_BYTES = 8192;
+__host__ __device__ inline int64_t tile_img_ks_off(int nb, int Fk) { return (int64_t)nb * 2 * tile_img_one(Fk); }
+__host__ __device__ inline int64_t tile_es_off(int nb, int Fk) { return 2 * tile_img_ks_off(nb, Fk); }
+__host__ __device__ inline int tile_es_f4(const int* L) { return 2 * (L[0] + 2 * L[1] + 3 * L[2] + 4 * L[3]); }
 // Images in global memory: kernel blocks [block][hi | lo]; node tiles [tile][hi | lo].  v = hi + lo, BOTH halves unscaled
 // (lo is usually an fp16 subnormal, which tcgen05 honours): one fp32 accumulator receives hi*hi + lo*hi + hi*lo.
 

@@ -345,7 +345,7 @@ class StackPack(object):
         """Queues the parameter packing of every layer (normalised kernel rows, tensor-core images) on the current stream."""
         # layers that run the molecule-tile kernels do not need the bucket-order tensor-core images (what = 1 | 4); should
         # the plan turn out untiled, MolGCNFn.forward lets the native forward pack everything again
-        self.packed_all = any(pk.tile_img is None for pk in self.packs) or _lib.lib().molkgnn_get_fwd_path() != 2
+        self.packed_all = any(pk.tile_img is None for pk in self.packs) or _lib.lib().molkgnn_get_fwd_path() < 2
         check(_lib.lib().molkgnn_param_pack_layers(self.arr, self.nl, 7 if self.packed_all else 5, stream_ptr()))
 
     def layout(self, plan: BucketPlan, flags):
@@ -374,7 +374,7 @@ class StackPack(object):
         return [None if sp is None else as_strided(sp[1], sp[2], sp[0]) for sp in specs]
 
 
-FLAG_KEEP_SC, FLAG_WANT_FREE, FLAG_PACKED = 1, 2, 4
+FLAG_KEEP_SC, FLAG_WANT_FREE, FLAG_PACKED, FLAG_INFERENCE = 1, 2, 4, 8
 
 
 class MolGCNFn(torch.autograd.Function):
@@ -390,6 +390,8 @@ class MolGCNFn(torch.autograd.Function):
         flags = (FLAG_KEEP_SC | FLAG_WANT_FREE) if aux is not None else 0
         if stack.packed_all or plan.n_tiles > 0:
             flags |= FLAG_PACKED
+        if not any(ctx.needs_input_grad):            # torch.no_grad() / nothing requires a gradient: inference
+            flags |= FLAG_INFERENCE
         lay = stack.layout(plan, flags)
         xc = x.detach()
         if xc.dtype != torch.float32:

@@ -59,7 +59,9 @@ def kernel_bytes_per_step(kernel, N, E, n, x_dim, L1, LN, num_layers, Fe=7):
         K = sum(L)
         am = sum(nd * ld for nd, ld in zip(n, L))
         topo = 4 * E + 4 * N
-        if kernel == "conv_fwd":
+        if kernel == "stack_fwd_fused":      # layer-fused forward: the whole forward formula (per-layer contract)
+            tot += layer_bytes(N, E, n, F, L, Fe, last=(i == num_layers - 1))[0]
+        elif kernel == "conv_fwd":
             tot += 4 * N * F + 4 * E * Fe + topo + am + (12 * N if i == num_layers - 1 else 0)
         elif kernel == "propagate_fwd":
             tot += 4 * N * K

@@ -21,18 +21,19 @@ TOL = 1e-5
 DEV = "cuda"
 
 
-PATHS = {"simt": 0, "bucket_tc": 1, "tile": 2}
+PATHS = {"simt": 0, "bucket_tc": 1, "tile": 2, "fused": 3}
 
 
-@pytest.fixture(autouse=True, params=["tile", "bucket_tc", "simt"])
+@pytest.fixture(autouse=True, params=["fused", "tile", "bucket_tc", "simt"])
 def fwd_path(request):
-    """Every test runs three times: with the molecule-tile tcgen05 forward (default product path), with the
-    bucket-order tcgen05 forward (plans without tiles) and with the fp32 SIMT forward (wide layers)."""
+    """Every test runs four times: with the layer-fused molecule-tile tcgen05 forward (default product path: the whole stack in
+    one launch), the per-layer molecule-tile forward, the bucket-order tcgen05 forward (plans without tiles) and the fp32 SIMT
+    forward (wide layers)."""
     from molkgnn_b200 import _lib
     old = _lib.lib().molkgnn_set_fwd_path(PATHS[request.param])
-    oldb = _lib.lib().molkgnn_set_bwd_path(1 if request.param == "tile" else 0)   # tile backward with the tile forward
+    oldb = _lib.lib().molkgnn_set_bwd_path(1 if request.param in ("tile", "fused") else 0)   # tile backward with the tile forwards
     yield request.param
-    _lib.lib().molkgnn_set_fwd_path(2 if old < 0 else old)
+    _lib.lib().molkgnn_set_fwd_path(3 if old < 0 else old)
     _lib.lib().molkgnn_set_bwd_path(oldb)
 
 
@@ -67,8 +68,8 @@ def _check_param_grads(net, ref_grad, tol=TOL):
 
 def test_tile_kernels_are_the_default_path(fwd_path):
     """The base model on a tiled plan must run the molecule-tile tcgen05 kernels (no silent fall back)."""
-    if fwd_path != "tile":
-        pytest.skip("path selection is only asserted for the default path")
+    if fwd_path not in ("tile", "fused"):
+        pytest.skip("path selection is only asserted for the tile paths")
     import molkgnn_b200 as mk
     from molkgnn_b200 import synth, functional
     b = _to_dev(synth.make_batch(64, seed=11))

@@ -61,13 +61,13 @@ def _run(net, t, wout, paths=None, argmax_in=None, want_aux=False, scale=1.0):
         return h.detach().clone(), x.grad.clone(), grads, aux
     finally:
         if old is not None:
-            lib.molkgnn_set_fwd_path(2 if old[0] < 0 else old[0])
+            lib.molkgnn_set_fwd_path(3 if old[0] < 0 else old[0])
             lib.molkgnn_set_bwd_path(old[1])
 
 
 def test_tile_and_simt_paths_agree_at_full_size(setup):
     _, t, net, wout = setup
-    h1, gx1, g1, aux = _run(net, t, wout, paths=(2, 1), want_aux=True)
+    h1, gx1, g1, aux = _run(net, t, wout, paths=(3, 1), want_aux=True)
     forced = [a.clone() for a in aux["argmax"]]          # the permutation + chirality bits the tile path used
     h0, gx0, g0, _ = _run(net, t, wout, paths=(0, 0), argmax_in=forced)
     assert _rel(h1, h0) < TOL
@@ -83,6 +83,27 @@ def test_tile_and_simt_paths_agree_at_full_size(setup):
             ref = torch.stack([g0[k] for k in trip])
             got = torch.stack([g1[k] for k in trip])
             assert float((got - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-6), (li, d)
+
+
+def test_fused_forward_equals_per_layer_tile_forward_bitwise(setup):
+    """The layer-fused forward (one launch, activations resident in shared memory) performs the same fp32 operations in the
+    same order as the per-layer tile kernels (conv_fwd_tile + propagate_tile): h, the arg-max bytes and every gradient that
+    the shared backward derives from its outputs are BITWISE identical."""
+    _, t, net, wout = setup
+    a = _run(net, t, wout, paths=(3, 1), want_aux=True)
+    b = _run(net, t, wout, paths=(2, 1), want_aux=True)
+    assert torch.equal(a[0], b[0])
+    for li in range(3):
+        assert torch.equal(a[3]["argmax"][li], b[3]["argmax"][li]), li
+        assert torch.equal(a[3]["sc"][li], b[3]["sc"][li]), li
+    assert torch.equal(a[1], b[1])
+    for n in a[2]:
+        assert torch.equal(a[2][n], b[2][n]), n
+    c = _run(net, t, wout, paths=(3, 1))             # product configuration (no aux outputs): same h again
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    with torch.no_grad():                            # inference: nothing is kept for a backward, same h
+        h_inf = net(x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False)
+    assert torch.equal(a[0], h_inf)
 
 
 def test_step_is_bitwise_deterministic_at_full_size(setup):
