@@ -54,7 +54,8 @@ struct SFLayer {
 struct StackFwdArgs {
     int nl;
     SFLayer ly[SF_MAXL];
-    const float* x; int ldx; int x_stage;  // raw input rows; x_stage: rows of a tile are bulk-copied to shared memory
+    const float* x; int ldx; int x_stage;  // raw input rows; x_stage: rows of a tile are bulk-copied to shared memory ...
+    int xs_off;                            // ... behind the layer-0 image inside the operand-image buffer (free between tiles)
     const TileMetaG* meta; const float* ehat_node; int n_tiles;
     const int* order; int order_grid;
     float* hgate; int ld_hgate;            // fp32 input rows of the LAST layer (chirality gate, kernels.py:310-317); nl == 1: = x
@@ -232,7 +233,7 @@ __device__ __forceinline__ void sf_dup_flags(const float* rows, int ld, int F, c
 }
 
 #ifdef MK_PHASE_CLOCKS
-__device__ unsigned long long g_ph_sfwd[16];
+__device__ unsigned long long g_ph_sfwd[48];     // [0..15] consumer thread 0, [16..31] ring lane, [32..47] MMA lane
 #endif
 
 template <bool FORCED>
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
     __shared__ uint32_t tslot;
     __shared__ SFSeg s_seg[SF_MAXL][4][TILE_MAXSEG];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    MK_PH_DECL(tid == 0)
+    MK_PH_DECL(tid == 0 || tid == SF_CONS || tid == SF_CONS + 32)
     if (tid == 0) {
         tc::mbar_init(&bar_meta[0], 1); tc::mbar_init(&bar_meta[1], 1);
         tc::mbar_init(&bar_eh, 1); tc::mbar_init(&bar_es, 1); tc::mbar_init(&bar_x, 1);
@@ -291,7 +292,9 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                     const int nks = ly.Fk >> 4, nst = ly.tb.nb * nks;
                     for (int s = 0; s < nst; ++s, ++q) {
                         const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        MK_PH(0);
                         tc::mbar_wait(&bar_rfree[slot], (use & 1u) ^ 1u);
+                        MK_PH(1);                                         // ring: waiting for a free stage
                         mbar_expect_tx(&bar_rfull[slot], TILE_KS_BYTES);
                         bulk_g2s(ring + (size_t)slot * TILE_KS_BYTES, ly.img_ks + (size_t)s * TILE_KS_BYTES, TILE_KS_BYTES, &bar_rfull[slot]);
                     }
@@ -312,17 +315,22 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                     const int nks = ly.Fk >> 4;
                     const uint32_t sbo = (uint32_t)(ly.Fk >> 3) * 128u;
                     const uint32_t xhi = tc::smem_u32(Xs), xlo = xhi + (uint32_t)ly.x_one;
+                    MK_PH(0);
                     tc::mbar_wait(&bar_x, xseq & 1u);
+                    MK_PH(1);                                             // MMA: waiting for the layer's operand image
                     ++xseq;
                     tc::fence_after_sync();
                     for (int blk = 0; blk < ly.tb.nb; ++blk) {
                         tc::mbar_wait(&bar_tfree[blk], (use_t[blk] & 1u) ^ 1u);
+                        MK_PH(2);                                         // MMA: waiting for the accumulator to be drained
                         ++use_t[blk];
                         tc::fence_after_sync();
                         const uint32_t d = tmem + (uint32_t)(blk * TNODES);
                         for (int ks = 0; ks < nks; ++ks, ++q) {
                             const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                            MK_PH(4);
                             tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                            MK_PH(3);                                     // MMA: waiting for a ring stage to land
                             const uint32_t aH = tc::smem_u32(ring + (size_t)slot * TILE_KS_BYTES), aL = aH + TILE_KS_BYTES / 2;
                             const uint64_t dAh = tc::smem_desc(aH, 128u, 256u), dAl = tc::smem_desc(aL, 128u, 256u);
                             const uint32_t o = (uint32_t)ks * 256u;
@@ -362,7 +370,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
             const uint32_t xb = a.x_stage ? (uint32_t)mm->nn * (uint32_t)a.ldx * 4u : 0u;
             mbar_expect_tx(&bar_eh, eb + xb);
             if (eb) bulk_g2s(ehS, a.ehat_node + (size_t)mm->e0 * EP, eb, &bar_eh);
-            if (xb) bulk_g2s(dump, a.x + (size_t)mm->t0 * a.ldx, xb, &bar_eh);
+            if (xb) bulk_g2s(Xs + a.xs_off, a.x + (size_t)mm->t0 * a.ldx, xb, &bar_eh);
         };
         if (tid == 0 && walk.cnt > 0) {
             issue_meta(0);
@@ -385,7 +393,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                 const SFLayer& ly = a.ly[0];
                 unsigned char* Xhi = Xs;
                 unsigned char* Xlo = Xs + ly.x_one;
-                const float* xs = a.x_stage ? dump : a.x + (size_t)t0 * a.ldx;
+                const float* xs = a.x_stage ? reinterpret_cast<const float*>(Xs + a.xs_off) : a.x + (size_t)t0 * a.ldx;
                 for (int r = warp; r < rend; r += SF_CWARPS) {
                     float v[4] = {0.f, 0.f, 0.f, 0.f};
                     if (r < nn) {
@@ -468,9 +476,30 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                     }
                 }
                 // ---- neighbour sum h[v] = sum over in-edges of sc[source] (KernelLayer.py:119), norm, next operand image ----
+                // The compact scores are first expanded into a dense [node][column] block (the accumulator dump area is free
+                // now): every output row is then <= 4 conflict-free float4 row reads in edge order -- the same fp32 sums,
+                // element by element, as k_propagate_tile (activations.cu).
                 {
                     const int c0 = 4 * lane;
                     const int Kp = ly.Kp;
+                    float* dense = dump;
+                    for (int i = tid; i < nn * (Kp >> 2); i += SF_CONS) reinterpret_cast<float4*>(dense)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    sf_consumer_sync();
+#pragma unroll
+                    for (int d = 1; d <= 4; ++d) {
+                        const int L = ly.L[d - 1];
+                        if (L == 0) continue;
+                        const int np = m.cnt[d - 1] * L;
+                        const float rL = 1.0f / (float)L;
+                        const int ko = ly.koff[d - 1];
+                        const float* src = scS + doff[d - 1];
+#pragma unroll 4
+                        for (int p = tid; p < np; p += SF_CONS) {
+                            const int i = (int)(((float)p + 0.5f) * rL);
+                            dense[(int)m.list[d - 1][i] * Kp + ko + (p - i * L)] = src[p];
+                        }
+                    }
+                    sf_consumer_sync();
                     const SFLayer& nx = a.ly[is_last ? l : l + 1];
                     unsigned char* Xhi = Xs;
                     unsigned char* Xlo = Xs + nx.x_one;
@@ -483,15 +512,8 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {          // edge order
                                 if (t < cnt) {
-                                    const int j = (int)((w >> (8 * t)) & 0xffu);
-                                    const int dj = m.degl[j] - 1;
-                                    const int ko = ly.koff[dj], Lj = ly.L[dj];
-                                    const float* row = scS + doff[dj] + (int)m.lidx[j] * Lj - ko;
-#pragma unroll
-                                    for (int u = 0; u < 4; ++u) {
-                                        const int c = c0 + u;
-                                        if (c >= ko && c < ko + Lj) acc[u] += row[c];
-                                    }
+                                    const float4 s4 = *reinterpret_cast<const float4*>(dense + (int)((w >> (8 * t)) & 0xffu) * Kp + c0);
+                                    acc[0] += s4.x; acc[1] += s4.y; acc[2] += s4.z; acc[3] += s4.w;
                                 }
                             }
                         }
@@ -547,7 +569,7 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
     __syncthreads();
     MK_PH(8);
 #ifdef MK_PHASE_CLOCKS
-    MK_PH_FLUSH(g_ph_sfwd);
+    MK_PH_FLUSH(g_ph_sfwd + (tid == 0 ? 0 : tid == SF_CONS ? 16 : 32));
 #endif
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
@@ -602,7 +624,11 @@ int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* la
         if (s.ximg && (reinterpret_cast<uintptr_t>(s.ximg) & 127)) return 0;
     }
     a.x = x; a.ldx = ldx;
-    a.x_stage = (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (int64_t)TNODES * ldx * 4 <= (int64_t)TNODES * 128 * 4) ? 1 : 0;
+    // raw x rows of the NEXT tile are staged behind the layer-0 image in the operand-image buffer (no MMA reads it between the
+    // last layer's MMAs and the next tile's layer-0 image)
+    a.xs_off = (2 * a.ly[0].x_one + 127) / 128 * 128;
+    a.x_stage = (ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && a.xs_off + (int64_t)TNODES * ldx * 4 <= 64 * 1024) ? 1 : 0;
+    if (a.x_stage) x_max = std::max<int64_t>(x_max, a.xs_off + (int64_t)TNODES * ldx * 4);
     a.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta);
     a.ehat_node = plan->ehat_node;
     a.n_tiles = plan->n_tiles;
@@ -648,10 +674,10 @@ int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* la
 }  // namespace mk
 
 #ifdef MK_PHASE_CLOCKS
-extern "C" int molkgnn_debug_phase_clocks_sfwd(unsigned long long* out16) {
+extern "C" int molkgnn_debug_phase_clocks_sfwd(unsigned long long* out48) {
     cudaDeviceSynchronize();
-    if (cudaMemcpyFromSymbol(out16, mk::g_ph_sfwd, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
-    unsigned long long z[16] = {0};
+    if (cudaMemcpyFromSymbol(out48, mk::g_ph_sfwd, sizeof(unsigned long long) * 48) != cudaSuccess) return -1;
+    unsigned long long z[48] = {0};
     return cudaMemcpyToSymbol(mk::g_ph_sfwd, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 #endif

@@ -203,8 +203,11 @@ def test_save_score_passthrough(tmp_path, monkeypatch):
     for li, lp in enumerate(params):
         sc = orc.kernel_set_conv_forward(lp, hh, bk, is_last_layer=(li == len(params) - 1))
         hh = orc.propagate(ei, sc)
-    assert rel_err(got.T, sc.numpy()) < 1e-2              # free-running arg-max on a fixture with ties: coarse bound ...
-    assert np.median(np.abs(got.T - sc.numpy())) < 1e-6   # ... and exact to rounding on the bulk
+    # free-running arg-max on a fixture WITH structural ties (duplicated leaves): a flipped tie changes single entries by O(0.1)
+    # (the edge term of another permutation), everything else is exact to rounding
+    close = np.abs(got.T - sc.numpy()) <= 1e-5 * np.abs(sc.numpy()).max()
+    assert close.mean() > 0.97, close.mean()
+    assert np.median(np.abs(got.T - sc.numpy())) < 1e-6
 
 
 def test_backward_after_repack_with_modified_parameters_is_refused():

@@ -25,6 +25,7 @@ net = mk.MolGCN(3, 10, 20, 30, 50, 10, 20, 30, 50, x_dim=28, p_dim=3, edge_attr_
 wout = torch.randn(t["x"].shape[0], 110, device=dev)
 L = _lib.lib()
 has_clk = hasattr(L, "molkgnn_debug_phase_clocks_bwd")
+has_sf = hasattr(L, "molkgnn_debug_phase_clocks_sfwd")
 
 
 def step(plan=None):
@@ -49,6 +50,8 @@ if has_clk:
     read("molkgnn_debug_phase_clocks_bwd", 16)
     read("molkgnn_debug_phase_clocks_fwd", 32)
     read("molkgnn_debug_phase_clocks_coef", 16)
+    if has_sf:
+        read("molkgnn_debug_phase_clocks_sfwd", 48)
 out = {}
 # (1) full step, plan rebuilt every step (one stream sync inside the bucket pass)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -73,6 +76,15 @@ if has_clk:
     out["bwd_tile_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_b, bw)}
     out["fwd_tile_consumer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_fc, fw[:16])}
     out["fwd_tile_producer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_fp, fw[16:])}
+    if has_sf:
+        sf = read("molkgnn_debug_phase_clocks_sfwd", 48)
+        names_sc = ["prologue", "wait meta/bonds/x", "layer-0 image + S0", "wait MMA", "dump + S1", "pairs", "S2", "propagate + S3",
+                    "teardown"]
+        names_sr = ["issue", "wait free stage"]
+        names_sm = ["issue / loop", "wait image", "wait accumulator", "wait ring stage", "MMA issue"]
+        out["stack_fwd_consumer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sc, sf[:16])}
+        out["stack_fwd_ring_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sr, sf[16:32])}
+        out["stack_fwd_mma_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sm, sf[32:])}
 # (2) plan reused: no host sync inside the loop -> wall time of the issue loop = host cost when the GPU is the bottleneck
 plan = net.build_plan(t["edge_index"], t["p"], t["edge_attr"], t["x"].shape[0])
 for _ in range(2):
