@@ -324,6 +324,8 @@ struct BwdTileArgs {
     int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
     int buf_bytes;
     int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
+    // pipelined kernel (k_conv_bwd_pipe): ring of K-step stages, two Wt buffers, two tile buffers [meta | coef | arg-max]
+    int nstages, stage_bytes, sm_ring, tbuf_bytes, tb_a, tb_am, cs;   // cs: TMEM column stride of an accumulator
 };
 
 struct BSeg {
@@ -735,6 +737,461 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// =============================================================================================================
+// k_conv_bwd_pipe: the same computation as k_conv_bwd_tile, software pipelined
+// =============================================================================================================
+// k_conv_bwd_tile runs scatter -> MMA -> clear strictly one after the other (every thread waits for the 48 MMAs of a visit).
+// Here the coefficient block Wt is double buffered and the roles are split:
+//   16 worker warps  build Wt of visit i+1 (clear, rank-0 scatter, rank passes) while the tensor core consumes visit i; they
+//                    run the dxh epilogue of tile t-1 after handing over the first block of tile t (two dxh accumulators);
+//   MMA warp         per visit: G_b += Wt . xhat, dxh (+)= Wt^T . khat_b -- both B operands arrive K step by K step ...
+//   ring warp        ... through a ring of bulk copies straight out of the tile-ordered node images and the kernel-block
+//                    images (16 rows = 2 row groups of an image are contiguous), so neither image is resident in shared
+//                    memory: that is what makes room for the second Wt buffer.
+// The Jacobian reads xhat from the (L2 resident) global image, prefetched into registers before the accumulator is waited for.
+constexpr int TP_WORK = 512;
+constexpr int TP_THREADS = TP_WORK + 96;      // + two ring warps + MMA warp
+constexpr int TP_SPS = 2;                      // K steps (of 16 rows) per ring stage: bulk-copy issue is ~150 cycles a copy
+constexpr int TP_MAXSTAGES = 8;
+
+__device__ __forceinline__ void tp_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TP_WORK) : "memory"); }
+__device__ __forceinline__ void tp_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+#ifdef MK_PHASE_CLOCKS
+__device__ unsigned long long g_ph_bwdp[48];     // [0..15] worker thread 0, [16..31] ring lane, [32..47] MMA lane
+#endif
+
+__global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_constant__ BwdTileArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ uint64_t bar_cp[2], bar_wfull[2], bar_wfree[2], bar_dxrdy[2], bar_dxfree[2], bar_rfull[TP_MAXSTAGES],
+        bar_rfree[TP_MAXSTAGES], bar_done;
+    __shared__ uint32_t tslot;
+    __shared__ BSeg s_seg[4][TILE_MAXSEG];
+    __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
+    __shared__ float s_gmax;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    MK_PH_DECL(tid == 0 || tid == TP_WORK || tid == TP_WORK + 64)
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&bar_cp[i], 1); tc::mbar_init(&bar_wfull[i], 1); tc::mbar_init(&bar_wfree[i], 1);
+            tc::mbar_init(&bar_dxrdy[i], 1); tc::mbar_init(&bar_dxfree[i], 1);
+        }
+        for (int i = 0; i < TP_MAXSTAGES; ++i) { tc::mbar_init(&bar_rfull[i], 1); tc::mbar_init(&bar_rfree[i], 1); }
+        tc::mbar_init(&bar_done, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tslot, 512);
+    if (tid < 48) {
+        const int d = tid / 12 + 1, p = tid % 12;
+        uint32_t code = 0;
+        if (d == 2) code = p < 2 ? perm_code<2>(p) : 0;
+        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_code<3>(q); }
+        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
+        s_lut[d - 1][p] = (unsigned char)code;
+    }
+    if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
+        const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
+        if (bi < a.nbl && si < a.tb.nseg[a.blist[bi]]) {
+            const TileSeg sg = a.tb.seg[a.blist[bi]][si];
+            const int L = a.L[sg.d - 1];
+            const PackedLayout pl(sg.d, L, a.Fp);
+            const float* pk = a.packed[sg.d - 1];
+            BSeg c;
+            c.alpha = pk[pl.w + 0] / pk[pl.w + 3] / (float)sg.d;
+            c.beta = pk[pl.w + 1] / pk[pl.w + 3];
+            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
+            c.rnk = 1.0f / (float)sg.nk;
+            s_seg[bi][si] = c;
+        }
+    }
+    if (warp == 3) {                                      // max |coef| over the per-CTA values of k_coef_tile
+        float gm = 0.f;
+        for (int i = lane; i < (int)gridDim.x; i += 32) gm = fmaxf(gm, __ldg(a.amax + i));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+        if (lane == 0) s_gmax = gm;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = tslot;
+    const TileWalk walk(a.order, a.order_grid, a.n_tiles);
+    const int my_tiles = walk.cnt;
+    const int NS = a.nstages;
+    const uint32_t fgrp = (uint32_t)(a.Fk >> 3) * 128u;  // bytes of one 8-row group of an [R x Fk] image
+    unsigned char* ring = smem + a.sm_ring;
+    const int dxcol = a.nbl * a.cs;                       // dxh accumulators behind the G accumulators
+
+    if (warp == TP_WORK / 32 || warp == TP_WORK / 32 + 1) {
+        // ================= ring warps: per visit the node image (16 nodes per K step), then the kernel-block image (16 rows
+        // per K step), TP_SPS K steps per stage; the two warps issue alternate stages =================
+        if (lane == 0) {
+            const uint32_t rid = (uint32_t)(warp - TP_WORK / 32);
+            uint32_t q = 0;
+            for (int wk = 0; wk < my_tiles; ++wk) {
+                const int tile = walk.tile(wk);
+                const int nn = __ldg(&a.meta[tile].nn);
+                const int nkg = max(16, (nn + 15) & ~15) >> 4;
+                const int nsg = (nkg + TP_SPS - 1) / TP_SPS;
+                for (int bi = 0; bi < a.nbl; ++bi) {
+                    const int blk = a.blist[bi];
+                    const int nkx = max(16, (a.tb.rows[blk] + 15) & ~15) >> 4;
+                    const int nsx = (nkx + TP_SPS - 1) / TP_SPS;
+                    for (int s = 0; s < nsg + nsx; ++s, ++q) {
+                        if ((q & 1u) != rid) continue;
+                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        const bool isx = s < nsg;
+                        const int s2 = isx ? s : s - nsg;
+                        const int steps = min(TP_SPS, (isx ? nkg : nkx) - s2 * TP_SPS);
+                        const unsigned char* src = (isx ? a.ximg + (size_t)tile * 2 * a.x_one : a.img + (size_t)blk * 2 * a.img_one) +
+                                                   (size_t)s2 * TP_SPS * 2 * fgrp;
+                        const uint32_t one = (uint32_t)(isx ? a.x_one : a.img_one);
+                        const uint32_t bytes = (uint32_t)steps * 2u * fgrp;
+                        MK_PH(0);
+                        tc::mbar_wait(&bar_rfree[slot], (use & 1u) ^ 1u);
+                        MK_PH(1);
+                        unsigned char* dst = ring + (size_t)slot * a.stage_bytes;
+                        mbar_expect_tx(&bar_rfull[slot], 2u * bytes);
+                        bulk_g2s(dst, src, bytes, &bar_rfull[slot]);
+                        bulk_g2s(dst + (uint32_t)TP_SPS * 2u * fgrp, src + one, bytes, &bar_rfull[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == TP_WORK / 32 + 2) {
+        // ================= MMA warp =================
+        if (lane == 0) {
+            uint32_t q = 0, vis = 0;
+            const uint32_t idesc_g = tc::idesc_f16(128, a.Fk, 0, 1);  // A = Wt K-major (K = node), B = xhat MN-major (N = feature)
+            const uint32_t idesc_x = tc::idesc_f16(128, a.Fk, 1, 1);  // A = Wt MN-major (M = node, K = row), B = khat MN-major
+            for (int wk = 0; wk < my_tiles; ++wk) {
+                const int tile = walk.tile(wk);
+                const int nn = __ldg(&a.meta[tile].nn);
+                const int nkg = max(16, (nn + 15) & ~15) >> 4;
+                const uint32_t par_t = (uint32_t)wk & 1u;
+                const uint32_t dX = tmem + (uint32_t)(dxcol + (int)par_t * a.cs);
+                for (int bi = 0; bi < a.nbl; ++bi, ++vis) {
+                    const int blk = a.blist[bi];
+                    const int nkx = max(16, (a.tb.rows[blk] + 15) & ~15) >> 4;
+                    const uint32_t buf = vis & 1u;
+                    const uint32_t whi = tc::smem_u32(smem + a.sm_wt + (size_t)buf * 2 * WT_ONE), wlo = whi + WT_ONE;
+                    MK_PH(0);
+                    tc::mbar_wait(&bar_wfull[buf], (vis >> 1) & 1u);
+                    MK_PH(1);                                             // MMA: waiting for the workers' Wt
+                    if (bi == 0) tc::mbar_wait(&bar_dxfree[par_t], (((uint32_t)wk >> 1) & 1u) ^ 1u);
+                    tc::fence_after_sync();
+                    const uint32_t dG = tmem + (uint32_t)(bi * a.cs);
+                    const uint32_t lo_off = (uint32_t)TP_SPS * 2u * fgrp;     // lo half of a stage
+                    for (int ks0 = 0; ks0 < nkg; ks0 += TP_SPS, ++q) {        // G_bi += Wt . xhat   (K = nodes, 16 per step)
+                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        MK_PH(3);
+                        tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                        MK_PH(2);                                         // MMA: waiting for a ring stage
+                        const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
+                        for (int ks = ks0; ks < min(ks0 + TP_SPS, nkg); ++ks) {
+                            const uint32_t so = (uint32_t)(ks - ks0) * 2u * fgrp;
+                            const uint64_t dAh = tc::smem_desc(whi + ks * 256u, 128u, 2048u), dAl = tc::smem_desc(wlo + ks * 256u, 128u, 2048u);
+                            const uint64_t dBh = tc::smem_desc(st + so, fgrp, 128u), dBl = tc::smem_desc(st + lo_off + so, fgrp, 128u);
+                            tc::umma_f16(dG, dAh, dBh, idesc_g, (wk == 0 && ks == 0) ? 0u : 1u);
+                            tc::umma_f16(dG, dAl, dBh, idesc_g, 1u);
+                            tc::umma_f16(dG, dAh, dBl, idesc_g, 1u);
+                        }
+                        tc::umma_commit(&bar_rfree[slot]);
+                    }
+                    for (int ks0 = 0; ks0 < nkx; ks0 += TP_SPS, ++q) {        // dxh (+)= Wt^T . khat   (K = kernel rows, 16 per step)
+                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        MK_PH(3);
+                        tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                        MK_PH(2);
+                        const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
+                        for (int ks = ks0; ks < min(ks0 + TP_SPS, nkx); ++ks) {
+                            const uint32_t so = (uint32_t)(ks - ks0) * 2u * fgrp;
+                            const uint64_t dAh = tc::smem_desc(whi + ks * 4096u, 2048u, 128u), dAl = tc::smem_desc(wlo + ks * 4096u, 2048u, 128u);
+                            const uint64_t dBh = tc::smem_desc(st + so, fgrp, 128u), dBl = tc::smem_desc(st + lo_off + so, fgrp, 128u);
+                            tc::umma_f16(dX, dAh, dBh, idesc_x, (bi == 0 && ks == 0) ? 0u : 1u);
+                            tc::umma_f16(dX, dAl, dBh, idesc_x, 1u);
+                            tc::umma_f16(dX, dAh, dBl, idesc_x, 1u);
+                        }
+                        tc::umma_commit(&bar_rfree[slot]);
+                    }
+                    tc::umma_commit(&bar_wfree[buf]);                     // Wt buffer free once these MMAs have read it
+                    if (bi == a.nbl - 1) tc::umma_commit(&bar_dxrdy[par_t]);
+                    MK_PH(3);
+                }
+            }
+            tc::umma_commit(&bar_done);
+        }
+    } else {
+        // ================= workers =================
+        float* red = reinterpret_cast<float*>(smem + a.sm_red);     // Jacobian reduction scratch
+        // power-of-two scale: |alpha * chi * g| / scale <= 2^10
+        float scale, rscale;
+        {
+            const float gm = fmaxf(s_gmax, 1e-30f);
+            int e;
+            frexpf(gm, &e);                                   // gm < 2^e
+            scale = ldexpf(1.0f, e - 10);
+            rscale = ldexpf(1.0f, 10 - e);
+        }
+        const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / 32-column part of this warp
+        auto issue_tile = [&](int wk) {                       // thread 0: metadata, coefficients, arg-max codes of tile wk
+            const int tile = walk.tile(wk);
+            const int np = tb_tile_pairs(a, tile);
+            unsigned char* buf = smem + a.sm_buf + (size_t)(wk & 1) * a.tbuf_bytes;
+            uint64_t* bar = &bar_cp[wk & 1];
+            const uint32_t cb = (uint32_t)((np * 4 + 15) & ~15), ab = (uint32_t)((np + 15) & ~15);
+            mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + cb + ab);
+            bulk_g2s(buf, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
+            if (np > 0) {
+                bulk_g2s(buf + a.tb_a, a.coefT + (size_t)tile * a.stride, cb, bar);
+                bulk_g2s(buf + a.tb_am, a.amT + (size_t)tile * a.stride_am, ab, bar);
+            }
+        };
+        // dxh epilogue of one tile (lane = node, 32 columns per warp): partial of the first launch / Jacobian + grad_x
+        auto epilogue = [&](int wk_t, int tile, int t0, int nn) {
+            const uint32_t par = (uint32_t)wk_t & 1u;
+            const int v = q * 32 + lane;
+            const int f0 = cpart * 32;
+            const bool colok = f0 < a.Fk;
+            const bool rowok = v < nn;
+            const int nf = min(32, a.Fk - f0);            // columns of this part (multiple of 16, or <= 0)
+            float dv[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dv[i] = 0.f;
+            float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
+            if (!a.first && rowok && colok) {             // partial dxh of the first launch
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nf) {
+                        const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
+                        dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
+                    }
+                }
+            }
+            float nrm = 1.f;
+            uint4 xh4[4], xl4[4];                          // xhat = hi + lo from the global node image (prefetched)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { xh4[c] = make_uint4(0u, 0u, 0u, 0u); xl4[c] = make_uint4(0u, 0u, 0u, 0u); }
+            if (a.last && rowok) {
+                nrm = a.xnorm[t0 + v];
+                if (colok) {
+                    const unsigned char* Xhi = a.ximg + (size_t)tile * 2 * a.x_one;
+                    const unsigned char* Xlo = Xhi + a.x_one;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        if (8 * c < nf) {
+                            const uint32_t off = tc::il_off(v, f0 + 8 * c, a.Fk);
+                            xh4[c] = __ldg(reinterpret_cast<const uint4*>(Xhi + off));
+                            xl4[c] = __ldg(reinterpret_cast<const uint4*>(Xlo + off));
+                        }
+                    }
+                }
+            }
+            tc::mbar_wait(&bar_dxrdy[par], ((uint32_t)wk_t >> 1) & 1u);
+            tc::fence_after_sync();
+            if (colok) {
+                uint32_t u[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(dxcol + (int)par * a.cs + f0);
+                tc::tmem_ld16(taddr, u);
+                if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
+                else {
+#pragma unroll
+                    for (int i = 16; i < 32; ++i) u[i] = 0u;
+                }
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = fmaf(__uint_as_float(u[i]), scale, dv[i]); }
+            }
+            float xh[32];
+            float dot = 0.f;
+            if (a.last) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const __half2* hh = reinterpret_cast<const __half2*>(&xh4[c]);
+                    const __half2* ll = reinterpret_cast<const __half2*>(&xl4[c]);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float2 fh = __half22float2(hh[t]), fl = __half22float2(ll[t]);
+                        xh[8 * c + 2 * t] = fh.x + fl.x;
+                        xh[8 * c + 2 * t + 1] = fh.y + fl.y;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dot = fmaf(dv[i], xh[i], dot);
+                red[cpart * 128 + v] = dot;
+            }
+            tc::fence_before_sync();
+            tp_worker_sync();                             // every worker has drained its part of the accumulator
+            if (tid == 0) tp_arrive(&bar_dxfree[par]);
+            if (!a.last) {
+                if (rowok && colok) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        if (i < nf) __stcg(reinterpret_cast<float4*>(sp + i), make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]));
+                }
+            } else {
+                // chain rule through xhat = x / max(|x|, eps):  gx = (g - (xhat . g) xhat) / |x|
+                dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
+                const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
+                const float rden = 1.0f / den;
+                const bool clamped = !(nrm > MOLKGNN_COS_EPS);
+                if (a.gx && rowok && colok) {
+                    float* out = a.gx + (size_t)(t0 + v) * a.ldgx + f0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (f0 + i + 4 <= a.Fp) {
+                            float o[4];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                o[c] = clamped ? dv[i + c] * rden : (dv[i + c] - dot * xh[i + c]) * rden;
+                                if (f0 + i + c >= a.F) o[c] = 0.f;
+                            }
+                            st4(out + i, make_float4(o[0], o[1], o[2], o[3]));
+                        }
+                    }
+                }
+                tp_worker_sync();                         // `red` is free again
+            }
+        };
+
+        if (tid == 0) {
+            if (my_tiles > 0) issue_tile(0);
+            if (my_tiles > 1) issue_tile(1);
+        }
+        MK_PH(0);
+        uint32_t vis = 0;
+        int t0p = 0, nnp = 0, tilep = 0;
+        for (int wk = 0; wk < my_tiles; ++wk) {
+            const int tile = walk.tile(wk);
+            const unsigned char* tbuf = smem + a.sm_buf + (size_t)(wk & 1) * a.tbuf_bytes;
+            const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(tbuf);
+            const float* a_s = reinterpret_cast<const float*>(tbuf + a.tb_a);
+            const unsigned char* am_s = tbuf + a.tb_am;
+            tc::mbar_wait(&bar_cp[wk & 1], ((uint32_t)wk >> 1) & 1u);
+            MK_PH(1);                                         // wait for the tile's metadata, coefficients, arg-max codes
+            const int t0c = m.t0, nnc = m.nn;                 // latched: the buffer is refilled at the end of the tile
+            int doff[4];                                      // first pair of degree d in the tile-ordered arrays
+            doff[0] = 0;
+#pragma unroll
+            for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * a.L[d - 1];
+            for (int bi = 0; bi < a.nbl; ++bi, ++vis) {
+                const int blk = a.blist[bi];
+                const int nseg = a.tb.nseg[blk];
+                unsigned char* wt = smem + a.sm_wt + (size_t)(vis & 1u) * 2 * WT_ONE;
+                int abase[TILE_MAXSEG];
+                for (int si = 0; si < nseg; ++si) abase[si] = doff[s_seg[bi][si].d - 1] + s_seg[bi][si].k0;
+                tc::mbar_wait(&bar_wfree[vis & 1u], ((vis >> 1) & 1u) ^ 1u);   // the MMAs of visit vis - 2 have read this buffer
+                MK_PH(2);
+                for (int i = tid * 16; i < 2 * WT_ONE; i += TP_WORK * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
+                tp_worker_sync();
+                MK_PH(3);                                     // Wt clear
+                // ---- rank 0: one thread per (node, kernel) pair -- centre entry, collision-free support entries ----
+                for (int si = 0; si < nseg; ++si) {
+                    const BSeg sg = s_seg[bi][si];
+                    const int np = m.cnt[sg.d - 1] * sg.nk;
+                    for (int p = tid; p < np; p += TP_WORK) {
+                        const int ni = (int)(((float)p + 0.5f) * sg.rnk);
+                        const int kl = p - ni * sg.nk;
+                        const int nl_ = m.list[sg.d - 1][ni];
+                        const int pi = abase[si] + ni * sg.L + kl;
+                        const float av = a_s[pi] * rscale;
+                        const uint32_t code = s_lut[sg.d - 1][am_s[pi] & 0x7f];
+                        const uint32_t nw = m.nl[nl_];
+                        const uint32_t cr = m.cr[nl_];
+                        wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
+                        const float as = av * sg.alpha;
+                        for (int j = 0; j < sg.d; ++j) {
+                            if (((cr >> (2 * j)) & 3u) == 0u)
+                                wt_store(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), as);
+                        }
+                    }
+                }
+                MK_PH(4);                                     // rank-0 scatter
+                // ---- ranks 1..3: one thread per (neighbour slot, kernel), read-modify-write after a barrier ----
+                for (int r = 1; r < 4; ++r) {
+                    bool more = false;
+                    for (int si = 0; si < nseg; ++si) {
+                        const int d = s_seg[bi][si].d;
+                        if (m.eoffs[d - 1][4] > m.eoffs[d - 1][r]) more = true;
+                    }
+                    if (!more) break;
+                    tp_worker_sync();
+                    for (int si = 0; si < nseg; ++si) {
+                        const BSeg sg = s_seg[bi][si];
+                        const int e0 = m.eoffs[sg.d - 1][r], e1 = m.eoffs[sg.d - 1][r + 1];
+                        const int ni_ = (e1 - e0) * sg.nk;
+                        for (int p = tid; p < ni_; p += TP_WORK) {
+                            const int ei = (int)(((float)p + 0.5f) * sg.rnk);
+                            const int kl = p - ei * sg.nk;
+                            const int ent = m.elist[e0 + ei];
+                            const int nl_ = ent >> 2, j = ent & 3;
+                            const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
+                            const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
+                            wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
+                        }
+                    }
+                }
+                tc::fence_async_smem();
+                tp_worker_sync();
+                if (tid == 0) tp_arrive(&bar_wfull[vis & 1u]);
+                MK_PH(5);                                     // ranks 1..3 + hand-over
+                // the MMAs of the previous tile's last block ran while this block was scattered: its dxh is (about) ready
+                if (bi == 0 && wk > 0) { epilogue(wk - 1, tilep, t0p, nnp); MK_PH(6); }
+            }
+            t0p = t0c; nnp = nnc; tilep = tile;
+            // this tile buffer is free (the hand-over barrier above ended the last reads): fetch the tile after the next
+            if (tid == 0 && wk + 2 < my_tiles) issue_tile(wk + 2);
+        }
+        if (my_tiles > 0) { epilogue(my_tiles - 1, tilep, t0p, nnp); MK_PH(6); }
+        // ---- kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks ----
+        if (my_tiles > 0) { tc::mbar_wait(&bar_done, 0u); tc::fence_after_sync(); }
+        for (int bi = 0; bi < a.nbl; ++bi) {
+            const int blk = a.blist[bi];
+            const int row = q * 32 + lane;
+            int d = 0, slot = 0, kk = 0, L = 0;
+            for (int si = 0; si < a.tb.nseg[blk]; ++si) {
+                const TileSeg sg = a.tb.seg[blk][si];
+                const int r = row - sg.rowbase;
+                if (r >= 0 && r < sg.nk * (sg.d + 1)) { d = sg.d; slot = r / sg.nk; kk = sg.k0 + r % sg.nk; L = a.L[sg.d - 1]; }
+            }
+            const int f0 = cpart * 32;
+            if (f0 < a.Fk) {
+                uint32_t u[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) u[i] = 0u;
+                if (my_tiles > 0) {
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * a.cs + f0);
+                    tc::tmem_ld16(taddr, u);
+                    if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
+                    tc::tmem_ld_wait();
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(u[i]));
+                if (d > 0) {
+                    const int rows_x = (d + 1) * L;
+                    float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
+                    const float sc2 = my_tiles > 0 ? scale : 0.f;     // a CTA without tiles never ran an MMA: zero partial sums
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (f0 + i + 4 <= a.Fp)
+                            st4(part + f0 + i, make_float4(__uint_as_float(u[i]) * sc2, __uint_as_float(u[i + 1]) * sc2,
+                                                           __uint_as_float(u[i + 2]) * sc2, __uint_as_float(u[i + 3]) * sc2));
+                    }
+                }
+            }
+        }
+        MK_PH(7);                                             // G partial sums -> global
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+#ifdef MK_PHASE_CLOCKS
+    MK_PH_FLUSH(g_ph_bwdp + (tid == 0 ? 0 : tid == TP_WORK ? 16 : 32));      // ring clocks: the first ring warp
+#endif
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------------
 static bool tile_plan_ok_b(const molkgnn_plan_t* plan) {
     return plan->n_tiles > 0 && plan->tile_start && plan->tile_meta && plan->ehat_node && plan->tile_max_nodes <= TNODES;
@@ -859,6 +1316,31 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     }
     const int64_t smem_c = c.sm_inv + ((int64_t)stride + 127) / 128 * 128;
     if (smem_c > s_budget - 2048) return 0;
+    // pipelined kernel (k_conv_bwd_pipe): two Wt buffers, two tile buffers [meta | coef | arg-max], ring of K-step stages
+    static int s_pipe = -1;
+    // opt-in (MOLKGNN_BWD_PIPE=1): measured equal to the serial kernel (0.653 vs 0.643 ms per step at 4096 molecules) -- the
+    // tcgen05.mma of both kernels read their operands from shared memory (SS mode: 7.5 KB per 128 x 112 x 16 MMA = the whole
+    // 128 B/cycle of the SM), so overlapping the scatter with the MMAs only makes both slower
+    if (s_pipe < 0) { const char* e = getenv("MOLKGNN_BWD_PIPE"); s_pipe = (e && e[0] == '1') ? 1 : 0; }
+    int64_t poff = 0;
+    bool use_pipe = s_pipe != 0;
+    BwdTileArgs pa = a;
+    {
+        pa.cs = a.Fk <= 32 ? 32 : a.Fk <= 64 ? 64 : 128;
+        if ((nbl_max + 2) * pa.cs > 512) use_pipe = false;
+        pa.sm_wt = (int)poff; poff += 2 * 2 * (int64_t)WT_ONE;
+        pa.tb_a = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
+        pa.tb_am = pa.tb_a + (int)(((int64_t)stride * 4 + 127) / 128 * 128);
+        pa.tbuf_bytes = pa.tb_am + (int)(((int64_t)stride_am + 127) / 128 * 128);
+        pa.sm_buf = (int)poff; poff += 2 * (int64_t)pa.tbuf_bytes;
+        pa.sm_red = (int)poff; poff += 4 * 128 * 4;
+        pa.sm_ring = (int)poff;
+        pa.stage_bytes = TP_SPS * 4 * (a.Fk >> 3) * 128;
+        const int64_t room = (int64_t)s_budget - 2048 - poff;
+        pa.nstages = (int)std::min<int64_t>(TP_MAXSTAGES, room / pa.stage_bytes);
+        if (pa.nstages < 3) use_pipe = false;
+        poff += (int64_t)std::max(pa.nstages, 0) * pa.stage_bytes;
+    }
     if (!do_launch) return 1;
     MK_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(coef) & 15) == 0,
                "conv_bwd_tile: grad and coef must be 16-byte aligned");
@@ -872,6 +1354,12 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     if (smem_c > s_attr_c) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
         s_attr_c = smem_c;
+    }
+    static int64_t s_attr_p_dev[16] = {0};
+    int64_t& s_attr_p = s_attr_p_dev[device_index()];
+    if (use_pipe && poff > s_attr_p) {
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_bwd_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)poff));
+        s_attr_p = poff;
     }
     {
         c.meta = a.meta; c.ehat_node = plan->ehat_node; c.n_tiles = plan->n_tiles;
@@ -915,7 +1403,13 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         a.first = l == 0; a.last = l == nlaunch - 1;
         count_launches(1);
         ProfScope prof("conv_bwd_tile", st);
-        k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
+        if (use_pipe) {
+            pa.nbl = a.nbl; pa.first = a.first; pa.last = a.last;
+            for (int i = 0; i < 4; ++i) pa.blist[i] = a.blist[i];
+            k_conv_bwd_pipe<<<grid, TP_THREADS, poff, st>>>(pa);
+        } else {
+            k_conv_bwd_tile<<<grid, TB_THREADS, off, st>>>(a);
+        }
         MK_CHECK_CUDA(cudaGetLastError());
     }
     return 1;
@@ -937,5 +1431,13 @@ extern "C" int molkgnn_debug_phase_clocks_bwd(unsigned long long* out16) {
     if (cudaMemcpyFromSymbol(out16, mk::g_ph_bwd, sizeof(unsigned long long) * 16) != cudaSuccess) return -1;
     unsigned long long z[16] = {0};
     return cudaMemcpyToSymbol(mk::g_ph_bwd, z, sizeof(z)) == cudaSuccess ? 0 : -1;
+}
+#endif
+#ifdef MK_PHASE_CLOCKS
+extern "C" int molkgnn_debug_phase_clocks_bwdp(unsigned long long* out48) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out48, mk::g_ph_bwdp, sizeof(unsigned long long) * 48) != cudaSuccess) return -1;
+    unsigned long long z[48] = {0};
+    return cudaMemcpyToSymbol(mk::g_ph_bwdp, z, sizeof(z)) == cudaSuccess ? 0 : -1;
 }
 #endif

@@ -52,6 +52,8 @@ if has_clk:
     read("molkgnn_debug_phase_clocks_coef", 16)
     if has_sf:
         read("molkgnn_debug_phase_clocks_sfwd", 48)
+    if hasattr(L, "molkgnn_debug_phase_clocks_bwdp"):
+        read("molkgnn_debug_phase_clocks_bwdp", 48)
 out = {}
 # (1) full step, plan rebuilt every step (one stream sync inside the bucket pass)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -85,6 +87,15 @@ if has_clk:
         out["stack_fwd_consumer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sc, sf[:16])}
         out["stack_fwd_ring_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sr, sf[16:32])}
         out["stack_fwd_mma_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sm, sf[32:])}
+    if hasattr(L, "molkgnn_debug_phase_clocks_bwdp"):
+        bp = read("molkgnn_debug_phase_clocks_bwdp", 48)
+        names_w = ["prologue", "wait tile data", "wait Wt buffer free", "Wt clear", "rank-0 scatter", "ranks 1-3 + hand-over",
+                   "dxh epilogue (incl. waiting for the MMAs)", "G store"]
+        names_r = ["issue", "wait free stage"]
+        names_m = ["loop", "wait Wt", "wait ring stage", "MMA issue"]
+        out["bwd_pipe_worker_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_w, bp[:16])}
+        out["bwd_pipe_ring_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_r, bp[16:32])}
+        out["bwd_pipe_mma_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_m, bp[32:])}
 # (2) plan reused: no host sync inside the loop -> wall time of the issue loop = host cost when the GPU is the bottleneck
 plan = net.build_plan(t["edge_index"], t["p"], t["edge_attr"], t["x"].shape[0])
 for _ in range(2):
