@@ -207,6 +207,23 @@ int molkgnn_set_fwd_path(int path);
 /* the forward kernel currently selected (0 .. 3; resolves the MOLKGNN_FWD environment override on first use) */
 int molkgnn_get_fwd_path(void);
 
+/* ---- batch assembly from a packed molecule store: replaces the PyG DataLoader collate the reference relies on
+ * (data.py:136-229; PyG Batch.from_data_list: attributes concatenated along __cat_dim__, keys containing "index" offset by
+ * the number of nodes in front of the graph).  Store: x [sumN,F], p [sumN,P], edge_attr [sumE,Fe], edge_index [2,sumE] with
+ * molecule-LOCAL node ids (row stride E_total), node_ptr / edge_ptr [M_total+1], optional targets y [M_total,Y].  ids [M]: the
+ * molecules of the batch (any order, repeats allowed).  Outputs (caller-sized from the host copies of the pointers): x_out
+ * [N_b,F], p_out [N_b,P], ea_out [E_b,Fe], ei_out [2,E_b] (row stride E_b, batch-global ids), batch_out [N_b], ptr_out [M+1],
+ * y_out [M,Y]; node_off / edge_off [M+1] scratch; err: device word, bit 0 = id out of range (checked by the caller). ---- */
+int molkgnn_collate(const int64_t* ids, int32_t M, int64_t M_total, const int64_t* node_ptr, const int64_t* edge_ptr,
+                    const float* x, int32_t F, const float* p, int32_t P, const float* edge_attr, int32_t Fe,
+                    const int64_t* edge_index, int64_t E_total, const float* y, int32_t Y, int64_t* node_off,
+                    int64_t* edge_off, float* x_out, float* p_out, float* ea_out, int64_t* ei_out, int64_t E_b,
+                    int64_t* batch_out, int64_t* ptr_out, float* y_out, int32_t* err, void* stream);
+
+/* global_add_pool of the caller of the stack (MolKGNNNet.py:59,144-146): out[g, :] = sum of rows ptr[g] .. ptr[g+1]-1 of z
+ * [N, C] (row stride ldz), added in node order -- deterministic, no atomics.  ptr [B+1] as produced by molkgnn_collate. */
+int molkgnn_segment_sum(const float* z, int32_t C, int32_t ldz, const int64_t* ptr, int32_t B, float* out, void* stream);
+
 /* ---- propagate: MolGCN.forward line `h = self.propagate(edge_index, sim_sc)` (KernelLayer.py:119-123) ---- */
 /* h[i, koff_d + k] = sum over in-edges (j -> i) in edge order of sc_{deg j}[pos j, k]; columns K..ldh-1 zeroed;
  * hnorm[i] = ||h_i|| (nullable).  ximg (nullable; needs a tiled plan and ldh <= 112): additionally writes the normalised

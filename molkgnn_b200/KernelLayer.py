@@ -84,6 +84,11 @@ class MolGCN(Module):
             # inside MolGCNFn.forward, after the host-side preparation below and the parameter packing were queued
             plan = BucketPlan.begin_from_edge_index(edge_index, p, edge_attr if raw_edge_attr is None else raw_edge_attr,
                                                     x.shape[0], ref_rows=ref_rows)
+        if any(layer._has_mixed_sets() for layer in self.layers):
+            # A layer that carries fixed (predefined, requires_grad=False) AND trainable kernels for a degree
+            # (kernels.py:452-516, 702-715) has two sets of mixing weights per degree: it runs through the layer modules
+            # (two passes of the same kernels per layer) and the native neighbour sum, layer by layer.
+            return self._forward_layerwise(x, plan.finish(), save_score, kwargv)
         # Host-side fast path: the 84 parameter tensors are fetched straight from the modules' _parameters dicts (the
         # slots are collected once; nn.Module.__getattr__ per parameter and step is what made a step host bound), and the
         # native layer descriptors are rebuilt only when a parameter tensor moved (new storage, device, dtype).
@@ -121,6 +126,37 @@ class MolGCN(Module):
             for i, layer in enumerate(self.layers):
                 layer.save_score(self._dense_scores(plan, stack.packs[i], aux['sc'][i]))
         return h
+
+    def _forward_layerwise(self, x, plan, save_score, kwargv):
+        """MolGCN.forward (KernelLayer.py:107-120) layer by layer: sim_sc = layer(...), h = propagate(edge_index, sim_sc)."""
+        if kwargv.get('argmax_in', None) is not None or kwargv.get('aux', None) is not None:
+            raise NotImplementedError('argmax_in / aux are not available for mixed fixed+trainable kernel sets')
+        # neighbour sum in edge order from the plan's in-lists (deterministic: <= 4 gathered rows added one after the other)
+        src = plan.in_src.long()
+        ok = (src >= 0).unsqueeze(-1)
+        src = src.clamp_min(0)
+        h = x
+        for i, layer in enumerate(self.layers):
+            sim_sc = layer(is_last_layer=(i == self.num_layers - 1), x=h, plan=plan, save_score=save_score,
+                           **{f'{k}_deg{d}': None for d in range(1, 5)
+                              for k in ('selected_index', 'nei_index', 'p_focal', 'nei_p', 'nei_edge_attr')})
+            h = torch.zeros_like(sim_sc)
+            for t in range(4):
+                h = h + torch.where(ok[:, t], sim_sc.index_select(0, src[:, t]), torch.zeros((), device=x.device))
+        return h
+
+    def save_kernels(self, dir, file_name):
+        """GNNModel.save_kernels (model.py:417-431): the first layer's trainable kernel sets, keys '{deg-1}.{param}' as read
+        by analyses/atom_encoder/kernel_reader.py:86."""
+        import os
+        if not os.path.exists(dir):
+            os.mkdir(dir)
+        torch.save(self.layers[0].trainable_kernelconv_set.state_dict(), dir + file_name)
+
+    def save_kernellayer(self, path, time_stamp):
+        """MolKGNNNet.save_kernellayer (MolKGNNNet.py:61-67): one state dict per layer."""
+        for i, layer in enumerate(self.layers):
+            torch.save(layer.state_dict(), f'{path}/{time_stamp}_{i}th_layer.pth')
 
     @staticmethod
     def _dense_scores(plan, pack, sc_compact):

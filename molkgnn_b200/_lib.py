@@ -63,6 +63,9 @@ EXPORTS = {
     "molkgnn_bucket_build_finish_ref": (C.c_int, [C.POINTER(Plan), vp, vp, i32, vp * 4, i64 * 4, i32, vp, vp, vp, vp]),
     "molkgnn_bucket_export": (C.c_int, [C.POINTER(Plan), i32, vp, i32, vp, i32, vp, vp, vp, vp, vp, vp]),
     "molkgnn_plan_from_buckets": (C.c_int, [C.POINTER(Plan), vp * 4, vp * 4, vp * 4, vp * 4, i32, vp * 4, i32, vp]),
+    "molkgnn_collate": (C.c_int, [vp, i32, i64, vp, vp, vp, i32, vp, i32, vp, i32, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, i64,
+                                  vp, vp, vp, vp, vp]),
+    "molkgnn_segment_sum": (C.c_int, [vp, i32, i32, vp, i32, vp, vp]),
     "molkgnn_pad_norm": (C.c_int, [vp, i32, i32, i32, vp, i32, vp, vp]),
     "molkgnn_packed_floats": (i64, [i32, i32, i32]),
     "molkgnn_param_pack": (C.c_int, [C.POINTER(Layer), vp]),

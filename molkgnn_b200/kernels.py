@@ -127,6 +127,9 @@ class BaseKernelSetConv(Module):
             headers += ['std_kernel'] * self.num_trainable_kernel_list[i]
         pd.DataFrame(sc_np, columns=headers).transpose().to_csv('scores.csv')
 
+    def _has_mixed_sets(self):
+        return any(f is not None and t is not None for f, t in zip(self.fixed_kernelconv_set, self.trainable_kernelconv_set))
+
     def _degree_owners(self):
         """Per degree: the KernelConv module that owns the parameters (None for a degree without kernels)."""
         out = []
@@ -162,6 +165,9 @@ class BaseKernelSetConv(Module):
             g = lambda k: kwargv[k]  # noqa: E731
         x = g('x')
         save_score = kwargv['save_score']
+        if x.is_cuda and x.device.index != torch.cuda.current_device():
+            with torch.cuda.device(x.device):        # the native calls take torch's CURRENT stream: run on the tensors' device
+                return self.forward(is_last_layer, **kwargv)
         sel = [g(f'selected_index_deg{d}') for d in range(1, 5)]
         nei = [g(f'nei_index_deg{d}') for d in range(1, 5)]
         pf = [g(f'p_focal_deg{d}') for d in range(1, 5)]

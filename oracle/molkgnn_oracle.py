@@ -255,3 +255,20 @@ def init_molgcn_params(num_layers, L_1hop, L_Nhop, x_dim, p_dim=3, edge_attr_dim
         layers.append(init_layer_params(L_Nhop, p_dim, f, edge_attr_dim, **kw))
         f = sum(L_Nhop)
     return layers
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# batch assembly (integer / byte work: bit-exact bar) -- PyG 2.0.x `Batch.from_data_list` as the reference's DataLoaders
+# use it (data.py:136-229): every attribute concatenated along its __cat_dim__ (dim 0; -1 for keys containing "index"),
+# keys containing "index" incremented by the number of nodes in front of the graph (__inc__), plus `batch` and `ptr`.
+# torch_geometric is not under /root/reference: restated from its documented behaviour (parity unpinned at that boundary).
+# ----------------------------------------------------------------------------------------------------------------
+def collate_pyg(mols):
+    """mols: sequence of objects with x [n,F], p [n,P], edge_index [2,e] (local ids), edge_attr [e,Fe] -> dict of numpy arrays"""
+    n = np.array([np.asarray(m.x).shape[0] for m in mols], dtype=np.int64)
+    ptr = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    return dict(x=np.concatenate([np.asarray(m.x) for m in mols], axis=0),
+                p=np.concatenate([np.asarray(m.p) for m in mols], axis=0),
+                edge_attr=np.concatenate([np.asarray(m.edge_attr) for m in mols], axis=0),
+                edge_index=np.concatenate([np.asarray(m.edge_index) + off for m, off in zip(mols, ptr[:-1])], axis=1),
+                batch=np.repeat(np.arange(len(mols), dtype=np.int64), n), ptr=ptr)

@@ -231,3 +231,86 @@ def test_backward_after_repack_with_modified_parameters_is_refused():
     with pytest.raises(mk.MolKGNNError):
         ha.sum().backward()
     del hb_same
+
+
+def test_molgcn_with_mixed_fixed_and_trainable_layer_and_save_kernels(tmp_path):
+    """a MolGCN whose layers carry fixed AND trainable kernel sets (kernels.py:452-516, 702-715) runs through
+    the drop-in (layer by layer) and equals the oracle; save_kernels writes the '{deg-1}.{param}' keys kernel_reader.py:86 reads."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    from oracle import molkgnn_oracle as orc
+    from tests.helpers import PARAM_NAMES
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(3)
+    b = synth.make_batch(12, seed=33, dup_leaf_prob=0.0)
+    net = mk.MolGCN(2, 3, 4, 5, 6, 2, 3, 4, 5, x_dim=28, p_dim=3, edge_attr_dim=7)
+    Lf = (2, 1, 2, 1)
+    fixed = [mk.KernelConv(L=Lf[d], D=3, num_supports=d + 1, node_attr_dim=28, edge_attr_dim=7, requires_grad=False,
+                           weight_requires_grad=False) for d in range(4)]
+    train = list(net.layers[0].trainable_kernelconv_set)
+    net.layers[0] = mk.BaseKernelSetConv(*fixed, *train)
+    K0 = sum(Lf) + 3 + 4 + 5 + 6
+    net.layers[1] = mk.KernelSetConv(2, 3, 4, 5, D=3, node_attr_dim=K0, edge_attr_dim=7)
+    net = net.to(dev)
+    t = {k: torch.from_numpy(b[k]).to(dev) for k in ("x", "p", "edge_index", "edge_attr")}
+    x = t["x"].clone().requires_grad_(True)
+    h = net(x=x, edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False)
+    h.sum().backward()
+    # oracle: a degree's score rows are [fixed ; trainable] (kernels.py:702-715)
+    bk = orc.buckets_to_torch(orc.bucket_pass(b["edge_index"], b["x"].shape[0], b["p"], b["edge_attr"]))
+    cpu = lambda kc: {n: getattr(kc, n).detach().cpu() for n in PARAM_NAMES}  # noqa: E731
+    xr = torch.from_numpy(b["x"])
+    ei = torch.from_numpy(b["edge_index"])
+    sc_f = orc.kernel_set_conv_forward([cpu(k) for k in fixed], xr, bk, is_last_layer=False)
+    sc_t = orc.kernel_set_conv_forward([cpu(k) for k in train], xr, bk, is_last_layer=False)
+    cols, of, ot = [], 0, 0
+    Lt = (3, 4, 5, 6)
+    for d in range(4):
+        cols += [sc_f[:, of:of + Lf[d]], sc_t[:, ot:ot + Lt[d]]]
+        of, ot = of + Lf[d], ot + Lt[d]
+    h1 = orc.propagate(ei, torch.cat(cols, dim=1))
+    sc2 = orc.kernel_set_conv_forward([cpu(k) for k in net.layers[1].trainable_kernelconv_set], h1, bk, is_last_layer=True)
+    h_ref = orc.propagate(ei, sc2)
+    close = (h.detach().cpu() - h_ref).abs() <= 1e-5 * h_ref.abs().max()
+    assert close.float().mean() > 0.97          # free-running arg-max: all but tie flips
+    assert x.grad is not None and all(p.grad is None for k in fixed for p in k.parameters())
+    net.save_kernels(str(tmp_path) + "/", "kernels.pt")
+    sd = torch.load(str(tmp_path) + "/kernels.pt")
+    assert set(sd) == {f"{d}.{n}" for d in range(4) for n in PARAM_NAMES}
+    assert sd["3.x_support"].shape == (6, 4, 28)
+
+
+def test_native_molkgnnnet_matches_the_reference_fixture():
+    """molkgnn_b200.MolKGNNNet (same ctor / state dict / forward protocol as MolKGNNNet.py:10-149, native conv
+    stack, deterministic native global_add_pool) against the fixture of the unmodified reference network."""
+    import molkgnn_b200 as mk
+    g = load_golden("molkgnnnet_call")
+    dev = torch.device("cuda", 0)
+    L1, LN = [int(v) for v in g["L1"]], [int(v) for v in g["LN"]]
+    net = mk.MolKGNNNet(num_layers=int(g["num_layers"]), num_kernel1_1hop=L1[0], num_kernel2_1hop=L1[1], num_kernel3_1hop=L1[2],
+                        num_kernel4_1hop=L1[3], num_kernel1_Nhop=LN[0], num_kernel2_Nhop=LN[1], num_kernel3_Nhop=LN[2],
+                        num_kernel4_Nhop=LN[3], x_dim=g["x"].shape[1], p_dim=3, edge_attr_dim=g["edge_attr"].shape[1],
+                        drop_ratio=0.0, graph_embedding_dim=int(g["emb"]))
+    sd = {k[len("param_"):]: torch.from_numpy(np.asarray(v)) for k, v in g.items() if k.startswith("param_")}
+    net.load_state_dict(sd, strict=True)               # identical state-dict keys
+    net = net.to(dev).train()
+    data = make_data(g, dev)
+    out = net(data)
+    (out * torch.from_numpy(g["wout"]).to(dev)).sum().backward()
+    assert rel_err(out.detach().cpu(), g["out"]) < 1e-5
+    assert rel_err(data.x.grad.cpu(), g["grad_x"]) < 1e-5
+    for name, prm in net.named_parameters():
+        if "grad_" + name in g and not name.endswith("_sc_weight"):
+            assert rel_err(prm.grad.cpu(), g["grad_" + name]) < 1e-5, name
+    # the same network on a batch WITHOUT the precomputed per-degree tensors (molkgnn_b200.store batches): same output
+    bare = Bag(x=data.x.detach(), p=data.p, edge_index=data.edge_index, edge_attr=data.edge_attr, batch=data.batch)
+    net.zero_grad()
+    with torch.no_grad():                              # (torch.no_grad does not switch BatchNorm to eval: still batch statistics)
+        out2 = net(bare)
+    assert rel_err(out2.cpu(), g["out"]) < 1e-5
+    # running statistics of BOTH batch norms advanced, like the reference's (the edge one is otherwise dead)
+    old = torch.from_numpy(g["param_edge_batch_norm.running_mean"])
+    mean = torch.from_numpy(g["edge_attr"]).mean(0)
+    assert rel_err(net.edge_batch_norm.running_mean.cpu(), 0.9 * (0.9 * old + 0.1 * mean) + 0.1 * mean) < 1e-5   # two train-mode calls
+    with pytest.raises(ValueError):
+        net(data, data)
