@@ -378,6 +378,59 @@ def main():
         ms_e2e = float(t.item())
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
+    # ---- end to end with the dataset RESIDENT in HBM (molkgnn_b200.store: packed molecule store + GPU batcher): the step's host
+    # input is the list of molecule ids of the batch (pinned), the batch is assembled on the GPU -- what the 180 GB are for ----
+    ms_store = None
+    if not fwd_only and not os.environ.get("MOLKGNN_BENCH_NO_STORE"):
+        from molkgnn_b200.store import MoleculeStore
+        ptr_h = batch["ptr"]
+        eptr = np.searchsorted(batch["edge_index"][0], ptr_h)            # edges are grouped molecule by molecule
+        local_ei = batch["edge_index"] - np.repeat(ptr_h[:-1], np.diff(eptr))[None, :]
+        store = MoleculeStore(devt["x"], devt["p"], torch.from_numpy(local_ei).to(dev), devt["edge_attr"],
+                              torch.from_numpy(ptr_h).to(dev), torch.from_numpy(eptr).to(dev))
+        gen = torch.Generator().manual_seed(rank)
+        id_bufs = [torch.randperm(B, generator=gen).pin_memory() for _ in range(4)]
+
+        def store_run(k):
+            pending = None
+            for i in range(k):
+                bt = store.collate(id_bufs[i & 3])            # H2D: B int64 ids; gather + rebasing on the GPU
+                h = step(bt)
+                loss = (h.detach() * wout).sum()
+                buf = loss_host[i & 1]
+                buf.copy_(loss, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                zero_grads()
+                if pending is not None:
+                    pending[1].synchronize()
+                    float(pending[0])
+                pending = (buf, ev)
+            pending[1].synchronize()
+            float(pending[0])
+
+        store_run(3)
+        sync_all()
+        e0.record()
+        store_run(args.steps)
+        e1.record()
+        sync_all()
+        ms_store = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_store], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_store = float(t.item())
+
+    # ---- multi-GPU self-check (outside the timed regions): sharded CUDA gradients after the all-reduce == full-batch gradients ----
+    dp_selfcheck = None
+    if world > 1 and not os.environ.get("MOLKGNN_BENCH_NO_SELFCHECK"):
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import dp_check
+        try:
+            dp_selfcheck = dp_check.run_check(64 * world)
+        except Exception as e:                       # reported, never fatal for the bench line
+            dp_selfcheck = {"error": repr(e)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -429,10 +482,18 @@ def main():
                        "memory and bucketed (molkgnn_b200.data.DevicePrefetcher: side stream, one step ahead), every step's loss "
                        "copied to pinned host memory and consumed by the host one step later; all K copies and K reads are "
                        "inside the timed region"},
+        "e2e_store": None if ms_store is None else {
+            "value": world * B * args.steps / (ms_store * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": 8 * B,
+            "d2h_bytes_per_step": 4, "ms_per_step": ms_store / args.steps,
+            "api": "molkgnn_b200.store.MoleculeStore.collate(ids) -> MolGCN.forward/backward: the dataset is packed in HBM once, "
+                   "every step copies only its (shuffled) molecule ids from pinned host memory, assembles the batch on the GPU "
+                   "(csrc/collate.cu), runs the bucket pass inside the forward and reads the loss back"},
         "gpu_launches": launches,
         "roofline": roof,
         "nodes_per_gpu": N, "edges_per_gpu": E,
     }
+    if dp_selfcheck is not None:
+        line["dp_selfcheck"] = dp_selfcheck
     if bucket is not None:
         if bucket.oneshot is not None:
             bucket.oneshot.check()               # raises if a peer's flag ever timed out

@@ -177,8 +177,12 @@ class MoleculeStore(object):
         Eb = int((self.edge_ptr_host[ids_host + 1] - self.edge_ptr_host[ids_host]).sum())
         dev = self.device
         with torch.cuda.device(dev):
-            ids_dev = ids.to(dev, torch.int64).contiguous() if torch.is_tensor(ids) and ids.is_cuda else \
-                torch.from_numpy(ids_host).pin_memory().to(dev, non_blocking=True)
+            if torch.is_tensor(ids) and ids.is_cuda:
+                ids_dev = ids.to(dev, torch.int64).contiguous()
+            elif torch.is_tensor(ids) and ids.dtype == torch.int64 and ids.is_pinned() and ids.is_contiguous():
+                ids_dev = ids.to(dev, non_blocking=True)          # the caller's pinned id buffer: the step's only H2D copy
+            else:
+                ids_dev = torch.from_numpy(ids_host).pin_memory().to(dev, non_blocking=True)
             F, P, Fe = self.x.shape[1], self.p.shape[1], self.edge_attr.shape[1]
             Y = 0 if self.y is None else self.y.shape[1]
             out = dict(x=torch.empty(Nb, F, device=dev), p=torch.empty(Nb, P, device=dev),
