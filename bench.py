@@ -393,9 +393,12 @@ def main():
 
         def store_run(k):
             pending = None
+            nxt = pf.put(store_batch=(store, id_bufs[0]), build_plan=True)    # H2D: B int64 ids; gather + rebasing on the GPU
             for i in range(k):
-                bt = store.collate(id_bufs[i & 3])            # H2D: B int64 ids; gather + rebasing on the GPU
-                h = step(bt)
+                bt, plan = pf.get(nxt)
+                if i + 1 < k:
+                    nxt = pf.put(store_batch=(store, id_bufs[(i + 1) & 3]), build_plan=True)
+                h = step(bt, plan)
                 loss = (h.detach() * wout).sum()
                 buf = loss_host[i & 1]
                 buf.copy_(loss, non_blocking=True)

@@ -22,9 +22,11 @@ class DevicePrefetcher(object):
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
 
-    def put(self, host_batch=None, device_batch=None, build_plan=False):
-        """Starts staging a batch given as a dict of (pinned) host tensors or of tensors already on the device; returns a
-        handle for ``get``.  With ``build_plan`` the counting half of the GPU bucket pass is queued behind the copies."""
+    def put(self, host_batch=None, device_batch=None, build_plan=False, store_batch=None):
+        """Starts staging a batch given as a dict of (pinned) host tensors, of tensors already on the device, or as
+        ``store_batch=(MoleculeStore, ids)`` (assembled on the GPU from the HBM-resident store: the only host->device copy is
+        the id list); returns a handle for ``get``.  With ``build_plan`` the counting half of the GPU bucket pass is queued
+        behind the copies."""
         from .plan import BucketPlan
         # Memory protocol: everything staged here is allocated from the side stream's pool and later used on the compute
         # stream WITHOUT record_stream (recorded blocks come back late, the pool keeps growing with synchronising
@@ -32,14 +34,17 @@ class DevicePrefetcher(object):
         # freed by the host (its last compute-stream use was queued before this point) is then safe to reuse here.
         self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
-            dev = device_batch if host_batch is None else {k: v.to(self.device, non_blocking=True)
-                                                            for k, v in host_batch.items()}
+            if store_batch is not None:
+                dev = store_batch[0].collate(store_batch[1])
+            else:
+                dev = device_batch if host_batch is None else {k: v.to(self.device, non_blocking=True)
+                                                                for k, v in host_batch.items()}
             plan = None
             if build_plan:
                 plan = BucketPlan.begin_from_edge_index(dev["edge_index"], dev["p"], dev["edge_attr"], dev["x"].shape[0])
             ev = torch.cuda.Event()
             ev.record(self.stream)
-        return dev, ev, plan, host_batch is not None
+        return dev, ev, plan, host_batch is not None or store_batch is not None
 
     def get(self, handle):
         """Finishes the plan (if any), makes the current stream wait for the staged batch and hands the tensors over to it.
