@@ -124,11 +124,14 @@ class GradBucket(object):
         self.group = group
         self.flat = None
         self.module = module
-        # one-shot NVLink all-reduce of the native flat buffer: opt-in (oneshot=True or MOLKGNN_DP_ONESHOT=1) until it has
-        # been validated on the 8-GPU box; NCCL otherwise and whenever the exchange cannot be set up
+        # one-shot NVLink all-reduce of the native flat buffer: the default on NCCL process groups since the 8-GPU measurement
+        # (profiles/r02j_bench_8gpu*.json, 4096 molecules per GPU: 1.376 ms per step against 1.539 ms with ncclAllReduce, i.e.
+        # 93 % against 83 % of 8x the one-GPU rate; tools/dp_check.py: sharded gradients == full-batch gradients on 8 GPUs for
+        # both paths).  MOLKGNN_DP_ONESHOT=0 / oneshot=False selects NCCL, which is also the fallback whenever the peer-memory
+        # exchange cannot be set up on some rank.
         import os
         if oneshot is None:
-            oneshot = os.environ.get("MOLKGNN_DP_ONESHOT", "0") == "1"
+            oneshot = os.environ.get("MOLKGNN_DP_ONESHOT", "1") != "0"
         self.oneshot = None
         self.check_every = int(os.environ.get("MOLKGNN_DP_CHECK_EVERY", "64"))
         self._steps = 0
