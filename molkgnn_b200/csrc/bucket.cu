@@ -441,12 +441,12 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
                                                       int* node_tile) {
     __shared__ int wsum[4][6];
     __shared__ int s_e0;
-    __shared__ int s_gcnt[16], s_goff[17], s_gfill[16];
+    __shared__ int s_ccnt[4], s_coff[5], s_cfill[4];
     const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t0 = tile_start[tile], t1 = tile_start[tile + 1];
     const int nn = t1 - t0;
     TileMetaG* m = meta + tile;
-    if (tid < 16) { s_gcnt[tid] = 0; s_gfill[tid] = 0; }
+    if (tid < 4) { s_ccnt[tid] = 0; s_cfill[tid] = 0; }
     // first bond slot of the tile = sum of the degrees of all nodes in front of it: whole 256-node blocks from the
     // class histogram of the bucket pass, the rest by a block reduction
     const int b0 = t0 / BT;
@@ -508,7 +508,6 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
                 if (deg[u] == d) ++r;
             }
             crank[j] = min(r, 3);
-            atomicAdd(&s_gcnt[(d - 1) * 4 + crank[j]], 1);
         }
         for (int j = 0; j < d; ++j) {
             w_nl |= (uint32_t)((nei[(size_t)base + j] - t0) & 0xff) << (8 * j);
@@ -535,21 +534,32 @@ __global__ void __launch_bounds__(TNODES) k_tile_meta(int N, const int* __restri
     m->incnt[tid] = (unsigned char)ic;
     m->lidx[tid] = (unsigned char)loff;
     m->cr[tid] = (unsigned char)(crank[0] | (crank[1] << 2) | (crank[2] << 4) | (crank[3] << 6));
+    // collision chains (tile.cuh): this thread is the TARGET v; per source degree dd the in-edges of v whose source has that
+    // degree, in in-edge order -- the first is the rank-0 store of its own pair thread, the others are the chain's followers
+    uint32_t chain[4] = {0u, 0u, 0u, 0u};
+    if (tid < nn) {
+        int seen[4] = {0, 0, 0, 0};
+        for (int t = 0; t < ic; ++t) {
+            const int ul = (int)((w_in >> (8 * t)) & 0xffu);
+            const int du = deg[t0 + ul];
+            if (du < 1 || du > 4) continue;
+            const int k = seen[du - 1]++;
+            if (k >= 1) chain[du - 1] |= (uint32_t)((ul << 2) | ij[t]) << (9 * (k - 1));
+        }
+        for (int dd = 0; dd < 4; ++dd)
+            if (seen[dd] >= 2) { chain[dd] |= (uint32_t)(seen[dd] - 2) << 27; atomicAdd(&s_ccnt[dd], 1); }
+            else chain[dd] = 0xffffffffu;
+    }
     __syncthreads();
     if (tid == 0) {
         int run = 0;
-        for (int g = 0; g < 16; ++g) { s_goff[g] = run; run += s_gcnt[g]; }
-        s_goff[16] = run;
-        for (int dd = 0; dd < 4; ++dd)
-            for (int r = 0; r < 5; ++r) m->eoffs[dd][r] = s_goff[min(dd * 4 + r, 16)];
+        for (int dd = 0; dd < 4; ++dd) { s_coff[dd] = run; m->choff[dd] = run; run += s_ccnt[dd]; }
+        s_coff[4] = run; m->choff[4] = run;
     }
     __syncthreads();
     if (tid < nn) {
-        for (int j = 0; j < d; ++j) {
-            const int g = (d - 1) * 4 + crank[j];
-            const int slot = s_goff[g] + atomicAdd(&s_gfill[g], 1);
-            m->elist[slot] = (unsigned short)((tid << 2) | j);
-        }
+        for (int dd = 0; dd < 4; ++dd)
+            if (chain[dd] != 0xffffffffu) m->chains[s_coff[dd] + atomicAdd(&s_cfill[dd], 1)] = chain[dd];
     }
 }
 

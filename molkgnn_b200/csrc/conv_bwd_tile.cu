@@ -511,6 +511,27 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         doff[0] = 0;
 #pragma unroll
         for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * a.L[d - 1];
+        // epilogue operands that come from global memory are fetched NOW (partial dxh of the first launch, row norm): their
+        // latency hides behind the scatter and the MMAs of the tile instead of sitting in front of the epilogue
+        float dv[32];
+        float nrm = 1.f;
+        {
+            const int v = q * 32 + lane, f0 = cpart * 32;
+            const int nf = min(32, a.Fk - f0);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) dv[i] = 0.f;
+            if (!a.first && v < nn && f0 < a.Fk) {
+                const float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < nf) {
+                        const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
+                        dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
+                    }
+                }
+            }
+            if (a.last && v < nn) nrm = __ldg(a.xnorm + t0 + v);
+        }
         for (int bi = 0; bi < a.nbl; ++bi) {
             const int blk = a.blist[bi];
             const int nseg = a.tb.nseg[blk];
@@ -538,27 +559,32 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 }
             }
             MK_PH(2);                                     // rank-0 scatter (thread 0's own share)
-            // ---- ranks 1..3: one thread per (neighbour slot, kernel), read-modify-write after a barrier ----
-            for (int r = 1; r < 4; ++r) {
+            // ---- collision chains: one thread per (chain, kernel) adds the chain's followers in in-edge order after ONE barrier ----
+            {
                 bool more = false;
                 for (int si = 0; si < nseg; ++si) {
                     const int d = s_seg[bi][si].d;
-                    if (m.eoffs[d - 1][4] > m.eoffs[d - 1][r]) more = true;
+                    if (m.choff[d] > m.choff[d - 1]) more = true;
                 }
-                if (!more) break;
-                __syncthreads();
-                for (int si = 0; si < nseg; ++si) {
-                    const BSeg sg = s_seg[bi][si];
-                    const int e0 = m.eoffs[sg.d - 1][r], e1 = m.eoffs[sg.d - 1][r + 1];
-                    const int ni_ = (e1 - e0) * sg.nk;
-                    for (int p = tid; p < ni_; p += TB_THREADS) {
-                        const int ei = (int)(((float)p + 0.5f) * sg.rnk);
-                        const int kl = p - ei * sg.nk;
-                        const int ent = m.elist[e0 + ei];
-                        const int nl_ = ent >> 2, j = ent & 3;
-                        const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
-                        const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
-                        wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
+                if (more) {
+                    __syncthreads();
+                    for (int si = 0; si < nseg; ++si) {
+                        const BSeg sg = s_seg[bi][si];
+                        const int c0 = m.choff[sg.d - 1];
+                        const int ni_ = (m.choff[sg.d] - c0) * sg.nk;
+                        for (int p = tid; p < ni_; p += TB_THREADS) {
+                            const int ci = (int)(((float)p + 0.5f) * sg.rnk);
+                            const int kl = p - ci * sg.nk;
+                            const uint32_t ch = m.chains[c0 + ci];
+                            const int nf = (int)((ch >> 27) & 3u) + 1;
+                            for (int f = 0; f < nf; ++f) {
+                                const int ent = (int)((ch >> (9 * f)) & 0x1ffu);
+                                const int nl_ = ent >> 2, j = ent & 3;
+                                const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
+                                const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
+                                wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
+                            }
+                        }
                     }
                 }
             }
@@ -596,21 +622,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             const bool colok = f0 < a.Fk;
             const bool rowok = v < nn;
             const int nf = min(32, a.Fk - f0);            // columns of this part (multiple of 16, or <= 0)
-            float dv[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) dv[i] = 0.f;
             float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
-            if (!a.first && rowok && colok) {             // partial dxh of the first launch
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nf) {
-                        const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
-                        dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
-                    }
-                }
-            }
-            float nrm = 1.f;
-            if (a.last && rowok) nrm = a.xnorm[t0 + v];
             if (colok) {
                 uint32_t u[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(a.dxcol + f0);
@@ -1109,27 +1121,32 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
                     }
                 }
                 MK_PH(4);                                     // rank-0 scatter
-                // ---- ranks 1..3: one thread per (neighbour slot, kernel), read-modify-write after a barrier ----
-                for (int r = 1; r < 4; ++r) {
+                // ---- collision chains: one thread per (chain, kernel) adds the followers in in-edge order after ONE barrier ----
+                {
                     bool more = false;
                     for (int si = 0; si < nseg; ++si) {
                         const int d = s_seg[bi][si].d;
-                        if (m.eoffs[d - 1][4] > m.eoffs[d - 1][r]) more = true;
+                        if (m.choff[d] > m.choff[d - 1]) more = true;
                     }
-                    if (!more) break;
-                    tp_worker_sync();
-                    for (int si = 0; si < nseg; ++si) {
-                        const BSeg sg = s_seg[bi][si];
-                        const int e0 = m.eoffs[sg.d - 1][r], e1 = m.eoffs[sg.d - 1][r + 1];
-                        const int ni_ = (e1 - e0) * sg.nk;
-                        for (int p = tid; p < ni_; p += TP_WORK) {
-                            const int ei = (int)(((float)p + 0.5f) * sg.rnk);
-                            const int kl = p - ei * sg.nk;
-                            const int ent = m.elist[e0 + ei];
-                            const int nl_ = ent >> 2, j = ent & 3;
-                            const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
-                            const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
-                            wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
+                    if (more) {
+                        tp_worker_sync();
+                        for (int si = 0; si < nseg; ++si) {
+                            const BSeg sg = s_seg[bi][si];
+                            const int c0 = m.choff[sg.d - 1];
+                            const int ni_ = (m.choff[sg.d] - c0) * sg.nk;
+                            for (int p = tid; p < ni_; p += TP_WORK) {
+                                const int ci = (int)(((float)p + 0.5f) * sg.rnk);
+                                const int kl = p - ci * sg.nk;
+                                const uint32_t ch = m.chains[c0 + ci];
+                                const int nf = (int)((ch >> 27) & 3u) + 1;
+                                for (int f = 0; f < nf; ++f) {
+                                    const int ent = (int)((ch >> (9 * f)) & 0x1ffu);
+                                    const int nl_ = ent >> 2, j = ent & 3;
+                                    const int pi = abase[si] + m.lidx[nl_] * sg.L + kl;
+                                    const int s = (s_lut[sg.d - 1][am_s[pi] & 0x7f] >> (2 * j)) & 3;
+                                    wt_add(wt, sg.rowbase + s * sg.nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * sg.alpha);
+                                }
+                            }
                         }
                     }
                 }

@@ -85,11 +85,14 @@ struct __align__(16) TileMetaG {
     unsigned char incnt[TNODES];
     unsigned char lidx[TNODES];       // index of the node inside list[deg - 1]
     unsigned char cr[TNODES];         // collision rank of the node's neighbour slots, 2 bits per j (see elist)
-    // neighbour slots (node << 2 | j) grouped by (degree d of the node, rank r): r = number of earlier in-edges of the
-    // same target whose source also has degree d.  Two slots of one group never share a target, so the backward scatter
-    // into (kernel row, target column) is collision free inside a group; groups of higher rank accumulate.
-    unsigned short elist[TILE_ESLOTS];
-    int eoffs[4][5];                  // elist range of group (d, r): [eoffs[d-1][r], eoffs[d-1][r+1])
+    // Collision chains of the backward scatter.  The neighbour slots (node n, j) of degree-d nodes that share a TARGET
+    // nei(n, j) = v write the same column of the coefficient block; their rank (cr) is the number of earlier in-edges of v whose
+    // source also has degree d.  Rank 0 is a plain store by the slot's own (node, kernel) thread; the FOLLOWERS (ranks 1..3) of
+    // one (target, degree) form a chain that ONE thread per kernel adds in in-edge order after a barrier -- deterministic, no
+    // atomics, one barrier.  chain word: follower f (0..2) in bits [9 f, 9 f + 9) as (node << 2 | j), count - 1 in bits [27, 29).
+    uint32_t chains[TILE_ESLOTS / 2];
+    int choff[5];                     // chains of degree d: [choff[d-1], choff[d])
+    int pad_[15];
 };
 static_assert(sizeof(TileMetaG) % 16 == 0, "TileMetaG must be a multiple of 16 bytes");
 
