@@ -34,7 +34,7 @@ int tile_argmax_stride(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer)
 constexpr int SF_MAXL = 4;                 // layers the fused kernel takes (kernel-parameter space)
 constexpr int SF_CONS = 512;               // consumer threads
 constexpr int SF_CWARPS = SF_CONS / 32;
-constexpr int SF_THREADS = SF_CONS + 64;   // + ring warp + MMA warp
+constexpr int SF_THREADS = SF_CONS + 96;   // + ring warp + two MMA warps
 constexpr int SF_MAXSTAGES = 8;
 
 struct SFLayer {
@@ -102,6 +102,29 @@ __device__ __forceinline__ void sf_dump(float* dump, uint32_t tmem, int blk, int
     for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]);
 }
 
+// Transposed variant (TS kernel: D[node, kernel row], lane = node): thread = node v moves 32 consecutive kernel rows of its
+// lane into dumpT[v][row], with the 16-byte chunk index XOR-swizzled by (v & 7) so that the float4 stores of a quarter warp
+// (8 nodes, 512 B apart) and the pair epilogue's reads (consecutive rows of one node) are both bank-conflict free.
+__device__ __forceinline__ int sf_dt_idx(int node, int r) { return node * 128 + ((((r >> 2) ^ (node & 7)) << 2) | (r & 3)); }
+__device__ __forceinline__ void sf_dump_t(float* dump, uint32_t tmem, int buf, int nn, int rows) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int q = warp & 3, cb = warp >> 2;
+    if (cb * 32 >= rows || q * 32 >= nn) return;
+    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + cb * 32);
+    tc::tmem_ld16(taddr, v);
+    tc::tmem_ld16(taddr + 16, v + 16);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
+    const int node = q * 32 + lane;
+    float* base = dump + node * 128;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(base + (((cb * 8 + i) ^ (node & 7)) << 2)) =
+            make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
+}
+
 template <int D> __device__ __forceinline__ uint32_t sf_perm_code_rt(int p) {
     uint32_t c = 0;
 #pragma unroll
@@ -112,7 +135,7 @@ template <int D> __device__ __forceinline__ uint32_t sf_perm_code_rt(int p) {
 struct SFPairOut { float sc; size_t cidx; int tidx; uint8_t am, free; };
 
 // one (node, kernel) pair: the reference arithmetic on its d x d similarity tile (same operation order as conv_fwd_tile.cu)
-template <int D, bool FORCED>
+template <int D, bool FORCED, bool TS>
 __device__ __forceinline__ SFPairOut sf_pair(const SFLayer& ly, const TileMetaG& m, const float* dump, const float* ehS,
                                              const float4* estab, const unsigned char* dupf, const SFSeg& sg, int doff,
                                              bool is_last, int nl_, int kl) {
@@ -124,11 +147,12 @@ __device__ __forceinline__ SFPairOut sf_pair(const SFLayer& ly, const TileMetaG&
     float T[D][D];
 #pragma unroll
     for (int j = 0; j < D; ++j) {
-        const float* c = col0 + ((nw >> (8 * j)) & 0xffu) * 128;
+        const int nj = (int)((nw >> (8 * j)) & 0xffu);
+        const float* c = col0 + nj * 128;
 #pragma unroll
-        for (int s = 0; s < D; ++s) T[j][s] = c[s * sg.nk];
+        for (int s = 0; s < D; ++s) T[j][s] = TS ? dump[sf_dt_idx(nj, sg.rowbase + s * sg.nk + kl)] : c[s * sg.nk];
     }
-    const float cdot = col0[nl_ * 128 + D * sg.nk];
+    const float cdot = TS ? dump[sf_dt_idx(nl_, sg.rowbase + D * sg.nk + kl)] : col0[nl_ * 128 + D * sg.nk];
     SFPairOut o;
     o.cidx = FORCED ? (size_t)ly.scoff[D - 1] + (size_t)m.posl[nl_] * sg.L + k : 0;
     o.tidx = doff + m.lidx[nl_] * sg.L + k;             // tile order: degree blocks, node-of-degree major, kernel minor
@@ -186,7 +210,7 @@ __device__ __forceinline__ void sf_store(const SFLayer& ly, float* scS, uint8_t*
     }
 }
 
-template <int D, bool FORCED>
+template <int D, bool FORCED, bool TS>
 __device__ __forceinline__ void sf_pairs_of_thread(const SFLayer& ly, const TileMetaG& m, const float* dump, const float* ehS,
                                                    const float4* estab, const unsigned char* dupf, const SFSeg& sg, int doff,
                                                    bool is_last, float* scS, uint8_t* amT_tile) {
@@ -195,12 +219,12 @@ __device__ __forceinline__ void sf_pairs_of_thread(const SFLayer& ly, const Tile
     for (int p = (int)threadIdx.x; p < np; p += 2 * SF_CONS) {
         const int p2 = p + SF_CONS;
         const int ni = (int)(((float)p + 0.5f) * sg.rnk);
-        const SFPairOut o1 = sf_pair<D, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni], p - ni * sg.nk);
+        const SFPairOut o1 = sf_pair<D, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni], p - ni * sg.nk);
         SFPairOut o2;
         const bool has2 = p2 < np;
         if (has2) {
             const int ni2 = (int)(((float)p2 + 0.5f) * sg.rnk);
-            o2 = sf_pair<D, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni2], p2 - ni2 * sg.nk);
+            o2 = sf_pair<D, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff, is_last, m.list[D - 1][ni2], p2 - ni2 * sg.nk);
         }
         sf_store<FORCED>(ly, scS, amT_tile, o1);
         if (has2) sf_store<FORCED>(ly, scS, amT_tile, o2);
@@ -236,7 +260,16 @@ __device__ __forceinline__ void sf_dup_flags(const float* rows, int ld, int F, c
 __device__ unsigned long long g_ph_sfwd[48];     // [0..15] consumer thread 0, [16..31] ring lane, [32..47] MMA lane
 #endif
 
-template <bool FORCED>
+// TS = true (MOLKGNN_FWD_TS=1): the NODE image is the MMA's A operand, copied once per (tile, layer) from shared to tensor memory by
+// tcgen05.cp, the kernel-block K steps of the ring are the B operand, the accumulator is D[node, kernel row] (3 buffers of 128
+// columns).  Per MMA the tensor core then reads 4 KB of shared memory instead of 8 KB (A and B of an SS-mode 128 x 128 x 16 MMA
+// are exactly the SM's 128 B/cycle, so every other shared-memory access -- dump, pairs, ring fill -- used to slow the MMAs).
+// Measured: no faster (0.420 vs 0.393 ms per step at 4096 molecules) -- the MMAs are bound by the ~120 cycles their issuing
+// thread needs per instruction, not by operand bandwidth.
+// TS = false (default): both operands from shared memory, D[kernel row, node] (4 buffers), TWO issuing warps.
+constexpr uint32_t SF_A_HI = 384u, SF_A_LO = 448u;     // TMEM columns of the node operand (Fk / 2 <= 56 each)
+
+template <bool FORCED, bool TS>
 __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_constant__ StackFwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar_meta[2], bar_eh, bar_es, bar_x, bar_mma[4], bar_tfree[4], bar_rfull[SF_MAXSTAGES], bar_rfree[SF_MAXSTAGES];
@@ -291,18 +324,28 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                     const SFLayer& ly = a.ly[l];
                     const int nks = ly.Fk >> 4, nst = ly.tb.nb * nks;
                     for (int s = 0; s < nst; ++s, ++q) {
+                        // stage order inside a layer: sequential (TS), or the K steps of a PAIR of blocks interleaved (the two
+                        // MMA warps work on the two blocks of a pair side by side)
+                        int src_stage = s;
+                        if (!TS) {
+                            const int p2 = s / (2 * nks), r = s - p2 * 2 * nks;
+                            const bool two = 2 * p2 + 1 < ly.tb.nb;
+                            src_stage = two ? (2 * p2 + (r & 1)) * nks + (r >> 1) : 2 * p2 * nks + r;
+                        }
                         const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
                         MK_PH(0);
                         tc::mbar_wait(&bar_rfree[slot], (use & 1u) ^ 1u);
                         MK_PH(1);                                         // ring: waiting for a free stage
                         mbar_expect_tx(&bar_rfull[slot], TILE_KS_BYTES);
-                        bulk_g2s(ring + (size_t)slot * TILE_KS_BYTES, ly.img_ks + (size_t)s * TILE_KS_BYTES, TILE_KS_BYTES, &bar_rfull[slot]);
+                        bulk_g2s(ring + (size_t)slot * TILE_KS_BYTES, ly.img_ks + (size_t)src_stage * TILE_KS_BYTES, TILE_KS_BYTES, &bar_rfull[slot]);
                     }
                 }
         }
-    } else if (warp == SF_CWARPS + 1) {
-        // ================= MMA warp =================
-        if (lane == 0) {
+    } else if (warp > SF_CWARPS) {
+        // ================= MMA warps: SS mode -- warp W issues the blocks 2 p + W (one tcgen05.mma costs its issuing thread
+        // ~120 cycles, twice the tensor time of a 128 x 128 x 16 MMA: two issuers keep the pipe busy); TS mode -- warp 0 alone ====
+        const int W = warp - (SF_CWARPS + 1);
+        if (lane == 0 && (!TS || W == 0)) {
             uint32_t q = 0, xseq = 0, use_t[4] = {0u, 0u, 0u, 0u};
             for (int wk = 0; wk < walk.cnt; ++wk) {
                 const int b = wk & 1;
@@ -320,28 +363,50 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                     MK_PH(1);                                             // MMA: waiting for the layer's operand image
                     ++xseq;
                     tc::fence_after_sync();
-                    for (int blk = 0; blk < ly.tb.nb; ++blk) {
-                        tc::mbar_wait(&bar_tfree[blk], (use_t[blk] & 1u) ^ 1u);
+                    if (TS) {
+                        // node image -> tensor memory (the MMAs of the previous layer are complete: the consumers waited for
+                        // all of them before they built this image)
+                        for (int ks = 0; ks < nks; ++ks) {
+                            tc::tmem_cp_128x256b(tmem + SF_A_HI + (uint32_t)ks * 8u, tc::smem_desc(xhi + (uint32_t)ks * 256u, 128u, sbo));
+                            tc::tmem_cp_128x256b(tmem + SF_A_LO + (uint32_t)ks * 8u, tc::smem_desc(xlo + (uint32_t)ks * 256u, 128u, sbo));
+                        }
+                    }
+                    for (int blk = TS ? 0 : W; blk < ly.tb.nb; blk += TS ? 1 : 2) {
+                        const int buf = TS ? blk % 3 : blk;
+                        tc::mbar_wait(&bar_tfree[buf], (use_t[buf] & 1u) ^ 1u);
                         MK_PH(2);                                         // MMA: waiting for the accumulator to be drained
-                        ++use_t[blk];
+                        ++use_t[buf];
                         tc::fence_after_sync();
-                        const uint32_t d = tmem + (uint32_t)(blk * TNODES);
-                        for (int ks = 0; ks < nks; ++ks, ++q) {
-                            const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
+                        const uint32_t d = tmem + (uint32_t)(buf * TNODES);
+                        const uint32_t idesc_b = tc::idesc_f16(128, max(16, (ly.tb.rows[blk] + 15) & ~15), 0, 0);
+                        for (int ks = 0; ks < nks; ++ks) {
+                            // ring stage of (blk, ks): sequential (TS) / interleaved inside the block pair (SS)
+                            const bool two = (blk | 1) < ly.tb.nb;
+                            const uint32_t qs = q + (uint32_t)(TS ? blk * nks + ks : (blk >> 1) * 2 * nks + (two ? 2 * ks + (blk & 1) : ks));
+                            const uint32_t slot = qs % (uint32_t)NS, use = qs / (uint32_t)NS;
                             MK_PH(4);
                             tc::mbar_wait(&bar_rfull[slot], use & 1u);
                             MK_PH(3);                                     // MMA: waiting for a ring stage to land
                             const uint32_t aH = tc::smem_u32(ring + (size_t)slot * TILE_KS_BYTES), aL = aH + TILE_KS_BYTES / 2;
-                            const uint64_t dAh = tc::smem_desc(aH, 128u, 256u), dAl = tc::smem_desc(aL, 128u, 256u);
-                            const uint32_t o = (uint32_t)ks * 256u;
-                            const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
-                            tc::umma_f16(d, dAh, dBh, idesc, ks > 0 ? 1u : 0u);
-                            tc::umma_f16(d, dAl, dBh, idesc, 1u);
-                            tc::umma_f16(d, dAh, dBl, idesc, 1u);
+                            const uint64_t dKh = tc::smem_desc(aH, 128u, 256u), dKl = tc::smem_desc(aL, 128u, 256u);
+                            if (TS) {
+                                // same three products, same order: khat_hi . xhat_hi, khat_lo . xhat_hi, khat_hi . xhat_lo
+                                const uint32_t xH = tmem + SF_A_HI + (uint32_t)ks * 8u, xL = tmem + SF_A_LO + (uint32_t)ks * 8u;
+                                tc::umma_f16_ts(d, xH, dKh, idesc_b, ks > 0 ? 1u : 0u);
+                                tc::umma_f16_ts(d, xH, dKl, idesc_b, 1u);
+                                tc::umma_f16_ts(d, xL, dKh, idesc_b, 1u);
+                            } else {
+                                const uint32_t o = (uint32_t)ks * 256u;
+                                const uint64_t dBh = tc::smem_desc(xhi + o, 128u, sbo), dBl = tc::smem_desc(xlo + o, 128u, sbo);
+                                tc::umma_f16(d, dKh, dBh, idesc, ks > 0 ? 1u : 0u);
+                                tc::umma_f16(d, dKl, dBh, idesc, 1u);
+                                tc::umma_f16(d, dKh, dBl, idesc, 1u);
+                            }
                             tc::umma_commit(&bar_rfree[slot]);          // the stage is free once these MMAs have read it
                         }
-                        tc::umma_commit(&bar_mma[blk]);
+                        tc::umma_commit(&bar_mma[buf]);
                     }
+                    q += (uint32_t)(ly.tb.nb * nks);
                 }
             }
         }
@@ -394,30 +459,39 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                 unsigned char* Xhi = Xs;
                 unsigned char* Xlo = Xs + ly.x_one;
                 const float* xs = a.x_stage ? reinterpret_cast<const float*>(Xs + a.xs_off) : a.x + (size_t)t0 * a.ldx;
-                for (int r = warp; r < rend; r += SF_CWARPS) {
-                    float v[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (r < nn) {
-                        const float* xr = xs + (size_t)r * a.ldx;
+                // Warp w owns the 8-row group w of the image; lane = (row of the group, 8-column chunk).  A lane then stores whole
+                // 16-byte core-matrix rows (rows 16 B apart, chunks 128 B apart: the 32 lanes of a store cover all banks) -- a
+                // warp-per-row split would hit 4 banks with every store (the chunks of ONE row are 128 B apart).
+                const int v = warp * 8 + (lane & 7), cq = lane >> 3;
+                if (warp * 8 < rend) {
+                    constexpr int NP = 4;                          // passes of 4 chunks: up to 128 columns
+                    float xv[NP][8];
+                    float ss = 0.f;
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) if (lane + 32 * h < ly.F) v[h] = xr[lane + 32 * h];
+                    for (int i = 0; i < NP; ++i) {
+                        const int c8 = (cq + 4 * i) * 8;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) {
+                            xv[i][u] = (v < nn && c8 + u < ly.F) ? xs[(size_t)v * a.ldx + c8 + u] : 0.f;
+                            ss += xv[i][u] * xv[i][u];
+                        }
                     }
-                    float ss = v[0] * v[0];
-#pragma unroll
-                    for (int h = 1; h < 4; ++h) if (lane + 32 * h < ly.Fp) ss += v[h] * v[h];
-                    ss = warp_sum(ss);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+                    ss += __shfl_xor_sync(0xffffffffu, ss, 16);
                     const float nrm = sqrtf(ss);
                     const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
-                    if (r < nn && lane == 0 && ly.hnorm) ly.hnorm[t0 + r] = nrm;
+                    if (v < nn && cq == 0 && ly.hnorm) ly.hnorm[t0 + v] = nrm;
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const int col = lane + 32 * h;
-                        if (col < ly.Fk) {
-                            const float xv = v[h] * rinv;
-                            const __half hi = __float2half_rn(xv);
-                            const __half lo = __float2half_rn(xv - __half2float(hi));
-                            const uint32_t off = tc::il_off(r, col, ly.Fk);
-                            *reinterpret_cast<__half*>(Xhi + off) = hi;
-                            *reinterpret_cast<__half*>(Xlo + off) = lo;
+                    for (int i = 0; i < NP; ++i) {
+                        const int c8 = (cq + 4 * i) * 8;
+                        if (c8 < ly.Fk) {
+                            __align__(16) __half2 hi[4];
+                            __align__(16) __half2 lo[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) tc::split_u2(xv[i][2 * u] * rinv, xv[i][2 * u + 1] * rinv, hi[u], lo[u]);
+                            const uint32_t off = tc::il_off(v, c8, ly.Fk);
+                            *reinterpret_cast<uint4*>(Xhi + off) = *reinterpret_cast<const uint4*>(hi);
+                            *reinterpret_cast<uint4*>(Xlo + off) = *reinterpret_cast<const uint4*>(lo);
                         }
                     }
                 }
@@ -441,25 +515,27 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                 tc::mbar_wait(&bar_es, esseq & 1u);
                 ++esseq;
                 for (int blk = 0; blk < ly.tb.nb; ++blk) {
-                    tc::mbar_wait(&bar_mma[blk], cm[blk] & 1u);
-                    ++cm[blk];
+                    const int buf = TS ? blk % 3 : blk;
+                    tc::mbar_wait(&bar_mma[buf], cm[buf] & 1u);
+                    ++cm[buf];
                     tc::fence_after_sync();
                     MK_PH(3);
-                    sf_dump(dump, tmem, blk, nn);
+                    if (TS) sf_dump_t(dump, tmem, buf, nn, ly.tb.rows[blk]);
+                    else sf_dump(dump, tmem, blk, nn);
                     if (blk == 0 && is_last && ly.L[3] > 0) sf_dup_flags(a.hgate_r, a.ld_hgate, ly.F, m, dupf);
                     if (tid == 0) sf_bulk_wait_read();            // the image's bulk store has read shared memory (long ago)
                     tc::fence_before_sync();
                     sf_consumer_sync();                           // (S1) dump complete, accumulator drained
-                    if (tid == 0) sf_arrive(&bar_tfree[blk]);
+                    if (tid == 0) sf_arrive(&bar_tfree[buf]);
                     MK_PH(4);
                     const int nseg = ly.tb.nseg[blk];
                     for (int si = 0; si < nseg; ++si) {
                         const SFSeg sg = s_seg[l][blk][si];
                         switch (sg.d) {
-                            case 1: sf_pairs_of_thread<1, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[0], is_last, scS, amT_tile); break;
-                            case 2: sf_pairs_of_thread<2, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[1], is_last, scS, amT_tile); break;
-                            case 3: sf_pairs_of_thread<3, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[2], is_last, scS, amT_tile); break;
-                            default: sf_pairs_of_thread<4, FORCED>(ly, m, dump, ehS, estab, dupf, sg, doff[3], is_last, scS, amT_tile); break;
+                            case 1: sf_pairs_of_thread<1, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff[0], is_last, scS, amT_tile); break;
+                            case 2: sf_pairs_of_thread<2, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff[1], is_last, scS, amT_tile); break;
+                            case 3: sf_pairs_of_thread<3, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff[2], is_last, scS, amT_tile); break;
+                            default: sf_pairs_of_thread<4, FORCED, TS>(ly, m, dump, ehS, estab, dupf, sg, doff[3], is_last, scS, amT_tile); break;
                         }
                     }
                     MK_PH(5);
@@ -480,11 +556,13 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                 // now): every output row is then <= 4 conflict-free float4 row reads in edge order -- the same fp32 sums,
                 // element by element, as k_propagate_tile (activations.cu).
                 {
-                    const int c0 = 4 * lane;
                     const int Kp = ly.Kp;
+                    const int DS = Kp + 4;                         // row stride of the dense block: 8 different rows -> 8 different bank groups
                     float* dense = dump;
-                    for (int i = tid; i < nn * (Kp >> 2); i += SF_CONS) reinterpret_cast<float4*>(dense)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    MK_PH(9);                                     // thread 0: bulk-copy issues for the next layer / tile
+                    for (int i = tid; i < nn * (DS >> 2); i += SF_CONS) reinterpret_cast<float4*>(dense)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                     sf_consumer_sync();
+                    MK_PH(10);                                    // zero fill of the dense score block
 #pragma unroll
                     for (int d = 1; d <= 4; ++d) {
                         const int L = ly.L[d - 1];
@@ -496,61 +574,83 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
 #pragma unroll 4
                         for (int p = tid; p < np; p += SF_CONS) {
                             const int i = (int)(((float)p + 0.5f) * rL);
-                            dense[(int)m.list[d - 1][i] * Kp + ko + (p - i * L)] = src[p];
+                            dense[(int)m.list[d - 1][i] * DS + ko + (p - i * L)] = src[p];
                         }
                     }
                     sf_consumer_sync();
+                    MK_PH(11);                                    // expansion of the compact scores
                     const SFLayer& nx = a.ly[is_last ? l : l + 1];
                     unsigned char* Xhi = Xs;
                     unsigned char* Xlo = Xs + nx.x_one;
                     const bool gate_rows = !is_last && l + 1 == a.nl - 1 && a.hgate;
-                    for (int v = warp; v < nn; v += SF_CWARPS) {
-                        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                        const int cnt = min((int)m.incnt[v], 4);
-                        const uint32_t w = m.inl[v];
-                        if (c0 < Kp) {
+                    // Warp w owns the 8-row group w; lane = (row of the group, 8-column chunk), 4 passes of 4 chunks.  Element by
+                    // element the same in-edge-order sums as k_propagate_tile; the image is stored as whole 16-byte core-matrix
+                    // rows (conflict free, see the layer-0 image above).
+                    const int v = warp * 8 + (lane & 7), cq = lane >> 3;
+                    if (warp * 8 < rend) {
+                        constexpr int NP = 4;
+                        float acc[NP][8];
+                        float ss = 0.f;
+                        const int cnt = v < nn ? min((int)m.incnt[v], 4) : 0;
+                        const uint32_t w = v < nn ? m.inl[v] : 0u;
 #pragma unroll
-                            for (int t = 0; t < 4; ++t) {          // edge order
-                                if (t < cnt) {
-                                    const float4 s4 = *reinterpret_cast<const float4*>(dense + (int)((w >> (8 * t)) & 0xffu) * Kp + c0);
-                                    acc[0] += s4.x; acc[1] += s4.y; acc[2] += s4.z; acc[3] += s4.w;
+                        for (int i = 0; i < NP; ++i) {
+                            const int c8 = (cq + 4 * i) * 8;
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) acc[i][u] = 0.f;
+                            if (c8 < Kp) {
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {      // edge order
+                                    if (t < cnt) {
+                                        const float* row = dense + (int)((w >> (8 * t)) & 0xffu) * DS + c8;
+                                        const float4 s0 = *reinterpret_cast<const float4*>(row);
+                                        acc[i][0] += s0.x; acc[i][1] += s0.y; acc[i][2] += s0.z; acc[i][3] += s0.w;
+                                        if (c8 + 4 < Kp) {
+                                            const float4 s1 = *reinterpret_cast<const float4*>(row + 4);
+                                            acc[i][4] += s1.x; acc[i][5] += s1.y; acc[i][6] += s1.z; acc[i][7] += s1.w;
+                                        }
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { if (c8 + u >= ly.K) acc[i][u] = 0.f; ss += acc[i][u] * acc[i][u]; }
+                        }
+                        const int gi = t0 + v;
+                        if (is_last) {
+                            if (v < nn) {
+#pragma unroll
+                                for (int i = 0; i < NP; ++i) {
+                                    const int c8 = (cq + 4 * i) * 8;
+                                    if (c8 < a.ldh) st4(a.h_out + (size_t)gi * a.ldh + c8, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+                                    if (c8 + 4 < a.ldh) st4(a.h_out + (size_t)gi * a.ldh + c8 + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+                                }
+                            }
+                        } else {
+                            ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+                            ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+                            const float nrm = sqrtf(ss);
+                            const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
+                            if (v < nn && cq == 0 && nx.hnorm) nx.hnorm[gi] = nrm;
+#pragma unroll
+                            for (int i = 0; i < NP; ++i) {
+                                const int c8 = (cq + 4 * i) * 8;
+                                if (gate_rows && v < nn) {
+                                    if (c8 < a.ld_hgate) st4(a.hgate + (size_t)gi * a.ld_hgate + c8, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]));
+                                    if (c8 + 4 < a.ld_hgate) st4(a.hgate + (size_t)gi * a.ld_hgate + c8 + 4, make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
+                                }
+                                if (c8 < nx.Fk) {                  // rows nn .. rend-1 (the MMA's N extent) receive zeros
+                                    __align__(16) __half2 hi[4];
+                                    __align__(16) __half2 lo[4];
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) tc::split_u2(acc[i][2 * u] * rinv, acc[i][2 * u + 1] * rinv, hi[u], lo[u]);
+                                    const uint32_t off = tc::il_off(v, c8, nx.Fk);
+                                    *reinterpret_cast<uint4*>(Xhi + off) = *reinterpret_cast<const uint4*>(hi);
+                                    *reinterpret_cast<uint4*>(Xlo + off) = *reinterpret_cast<const uint4*>(lo);
                                 }
                             }
                         }
-                        const int i = t0 + v;
-                        if (is_last) {
-                            if (c0 < a.ldh) {
-#pragma unroll
-                                for (int u = 0; u < 4; ++u) if (c0 + u >= ly.K) acc[u] = 0.f;
-                                st4(a.h_out + (size_t)i * a.ldh + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-                            }
-                            continue;
-                        }
-                        float ss = 0.f;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) { if (c0 + u >= ly.K) acc[u] = 0.f; ss += acc[u] * acc[u]; }
-                        ss = warp_sum(ss);
-                        const float nrm = sqrtf(ss);
-                        if (lane == 0 && nx.hnorm) nx.hnorm[i] = nrm;
-                        if (gate_rows && c0 < a.ld_hgate) st4(a.hgate + (size_t)i * a.ld_hgate + c0, make_float4(acc[0], acc[1], acc[2], acc[3]));
-                        if (c0 < nx.Fk) {
-                            const float rinv = 1.0f / fmaxf(nrm, MOLKGNN_COS_EPS);
-                            __align__(8) __half2 hi[2];
-                            __align__(8) __half2 lo[2];
-                            tc::split_u2(acc[0] * rinv, acc[1] * rinv, hi[0], lo[0]);
-                            tc::split_u2(acc[2] * rinv, acc[3] * rinv, hi[1], lo[1]);
-                            const uint32_t off = tc::il_off(v, c0, nx.Fk);
-                            *reinterpret_cast<uint2*>(Xhi + off) = *reinterpret_cast<const uint2*>(hi);
-                            *reinterpret_cast<uint2*>(Xlo + off) = *reinterpret_cast<const uint2*>(lo);
-                        }
                     }
-                    if (!is_last && c0 < nx.Fk) {                  // pad rows up to the next multiple of 16 (the MMA's N extent)
-                        for (int rr = nn + warp; rr < rend; rr += SF_CWARPS) {
-                            const uint32_t off = tc::il_off(rr, c0, nx.Fk);
-                            *reinterpret_cast<uint2*>(Xhi + off) = make_uint2(0u, 0u);
-                            *reinterpret_cast<uint2*>(Xlo + off) = make_uint2(0u, 0u);
-                        }
-                    }
+                    MK_PH(12);                                    // neighbour sums, norms, next image
                     if (!is_last) {
                         tc::fence_async_smem();
                         sf_consumer_sync();                       // (S3) next layer's image complete
@@ -659,14 +759,23 @@ int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* la
     static int64_t s_attr_dev[16] = {0};
     int64_t& s_attr = s_attr_dev[device_index()];      // function attributes are per device
     if (off > s_attr) {
-        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
-        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_stack_fwd_fused<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;
     }
+    static int s_ts = -1;
+    if (s_ts < 0) { const char* e = getenv("MOLKGNN_FWD_TS"); s_ts = (e && e[0] == '1') ? 1 : 0; }
     count_launches(1);
     ProfScope prof("stack_fwd_fused", st);
-    if (forced) k_stack_fwd_fused<true><<<grid, SF_THREADS, off, st>>>(a);     // parity harness / replay
-    else k_stack_fwd_fused<false><<<grid, SF_THREADS, off, st>>>(a);
+    if (s_ts) {
+        if (forced) k_stack_fwd_fused<true, true><<<grid, SF_THREADS, off, st>>>(a);      // parity harness / replay
+        else k_stack_fwd_fused<false, true><<<grid, SF_THREADS, off, st>>>(a);
+    } else {
+        if (forced) k_stack_fwd_fused<true, false><<<grid, SF_THREADS, off, st>>>(a);
+        else k_stack_fwd_fused<false, false><<<grid, SF_THREADS, off, st>>>(a);
+    }
     MK_CHECK_CUDA(cudaGetLastError());
     return 1;
 }

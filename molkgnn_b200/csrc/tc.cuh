@@ -121,6 +121,12 @@ __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// shared memory -> tensor memory: 128 rows x 256 bits (= one K = 16 step of an fp16 A operand: lane = row, 8 columns) described by
+// a K-major SWIZZLE_NONE matrix descriptor (two 16-byte chunks per row, LBO apart; 8-row groups SBO apart).  Issued by ONE
+// thread; ordered with the tcgen05.mma instructions the same thread issues afterwards (implicit tensor-core pipeline).
+__device__ __forceinline__ void tmem_cp_128x256b(uint32_t taddr, uint64_t sdesc) {
+    asm volatile("tcgen05.cp.cta_group::1.128x256b [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
 // arrive on `bar` when every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(SelfArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5;
     const int M = 128, N = a.N, K = a.K;
     // tile geometry: K-major operand is [rows = M|N][cols = K]; MN-major operand is [rows = K][cols = M|N]
-    const int aR = a.a_mn == 1 ? K : M, aC = a.a_mn == 1 ? M : K;
+    const int aR = a.a_mn == 1 ? K : M, aC = a.a_mn == 1 ? M : K;      // a_mn 2 / 3: staged K-major like 0
     const int bR = a.b_mn ? K : N, bC = a.b_mn ? N : K;
     unsigned char* As = smem;
     unsigned char* Bs = smem + tc::il_tile_bytes(aR, aC);
@@ -54,8 +54,12 @@ __global__ void __launch_bounds__(128, 1) k_tc_selftest(SelfArgs a) {
         __syncthreads();
         tc::fence_after_sync();
     }
-    if (tid == 0 && a_tmem) {
+    const bool a_cp = a.a_mn == 3;               // A operand copied shared -> tensor memory by tcgen05.cp (stack_fwd_fused.cu)
+    if (tid == 0 && (a_tmem || a_cp)) {
         const uint32_t idesc = tc::idesc_f16(M, N, 0, a.b_mn);
+        if (a_cp)
+            for (int ks = 0; ks < K / 16; ++ks)
+                tc::tmem_cp_128x256b(tmem + 256u + (uint32_t)(ks * 8), tc::smem_desc(tc::smem_u32(As) + ks * 256u, 128u, (aC / 8) * 128u));
         const uint32_t b_lbo = a.b_mn ? (bC / 8) * 128 : 128, b_sbo = a.b_mn ? 128 : (bC / 8) * 128;
         const uint32_t b_step = a.b_mn ? 2 * (bC / 8) * 128 : 256;
         for (int ks = 0; ks < K / 16; ++ks) {

@@ -43,3 +43,12 @@ def test_umma_a_operand_in_tensor_memory(N, K, b_mn):
     """A operand read from TMEM (a_mn = 2: lane = row, fp16 pairs packed per 32-bit column)."""
     err, mag = run(N, K, 2, b_mn)
     assert err < 1e-3 * max(mag, 1.0), f"UMMA (A in TMEM) mismatch: max err {err} (|ref| max {mag})"
+
+
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("N,K", [(16, 16), (128, 112), (80, 32), (128, 128)])
+def test_umma_a_operand_copied_to_tensor_memory_by_tcgen05_cp(N, K, b_mn):
+    """A staged in shared memory (K-major core-matrix layout), moved to TMEM with tcgen05.cp.128x256b per K step, then read by
+    the MMA as its TMEM operand (a_mn = 3) -- the operand path of the layer-fused forward."""
+    err, mag = run(N, K, 3, b_mn)
+    assert err < 1e-3 * max(mag, 1.0), f"UMMA (A via tcgen05.cp) mismatch: max err {err} (|ref| max {mag})"

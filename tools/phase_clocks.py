@@ -80,8 +80,8 @@ if has_clk:
     out["fwd_tile_producer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_fp, fw[16:])}
     if has_sf:
         sf = read("molkgnn_debug_phase_clocks_sfwd", 48)
-        names_sc = ["prologue", "wait meta/bonds/x", "layer-0 image + S0", "wait MMA", "dump + S1", "pairs", "S2", "propagate + S3",
-                    "teardown"]
+        names_sc = ["prologue", "wait meta/bonds/x", "layer-0 image + S0", "wait MMA", "dump + S1", "pairs", "S2",
+                    "pad rows + S3 + hand-over", "teardown", "t0: bulk issues", "zero fill", "expand scores", "row sums + image"]
         names_sr = ["issue", "wait free stage"]
         names_sm = ["issue / loop", "wait image", "wait accumulator", "wait ring stage", "MMA issue"]
         out["stack_fwd_consumer_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_sc, sf[:16])}
