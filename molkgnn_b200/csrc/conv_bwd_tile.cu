@@ -603,7 +603,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             }
             ++use;
             MK_PH(5);                                     // image wait + MMA issue
-            tc::mbar_wait(&bar_mma, ph_mma);
+            // the issuing thread alone polls for completion, everybody else sleeps in the hardware barrier: 511 threads
+            // spinning on try_wait take issue slots from the one thread that feeds the tensor core
+            if (tid == 0) tc::mbar_wait(&bar_mma, ph_mma);
+            __syncthreads();
             ph_mma ^= 1u;
             tc::fence_after_sync();
             MK_PH(6);                                     // MMA completion

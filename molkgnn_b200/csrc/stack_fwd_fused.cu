@@ -516,7 +516,10 @@ __global__ void __launch_bounds__(SF_THREADS, 1) k_stack_fwd_fused(const __grid_
                 ++esseq;
                 for (int blk = 0; blk < ly.tb.nb; ++blk) {
                     const int buf = TS ? blk % 3 : blk;
-                    tc::mbar_wait(&bar_mma[buf], cm[buf] & 1u);
+                    // ONE warp polls the mbarrier, the other 15 sleep in the hardware barrier: 512 threads spinning on
+                    // try_wait take issue slots from the ring / MMA warps that they are waiting for
+                    if (warp == 0) tc::mbar_wait(&bar_mma[buf], cm[buf] & 1u);
+                    sf_consumer_sync();
                     ++cm[buf];
                     tc::fence_after_sync();
                     MK_PH(3);
