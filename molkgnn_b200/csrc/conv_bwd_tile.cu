@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MK_PH_DECL(tid == 0)
     if (tid == 0) {
-        tc::mbar_init(&bar_mma, 1);
+        tc::mbar_init(&bar_mma, 2);                       // one commit per issuing thread (G group, dxh group)
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_img[i], 1);
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
         tc::fence_mbar_init();
@@ -593,9 +593,15 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             __syncthreads();
             MK_PH(4);                                     // barrier before the MMAs
             // ---- tensor cores ----
+            // TWO issuing threads: a tcgen05.mma costs the thread that issues it ~100 cycles (descriptor set-up, uniform-register
+            // moves), about twice the tensor time of these shapes; the G MMAs and the dxh MMAs write different accumulators, so
+            // warp 0 issues the first and warp 1 the second group and the tensor pipe sees both streams (bar_mma counts 2)
             if (tid == 0) {
                 tc::fence_after_sync();
                 tb_issue_mma_g(a, smem, nn, bi, fresh, tmem);
+                tc::umma_commit(&bar_mma);
+            } else if (tid == 32) {
+                tc::fence_after_sync();
                 const int ib = resident ? use % a.nbl : use % a.nimg;
                 if (!resident) tc::mbar_wait(&bar_img[ib], (uint32_t)(use / a.nimg) & 1u);
                 else if (use < a.nbl) tc::mbar_wait(&bar_img[ib], 0u);
@@ -765,8 +771,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
 //                    memory: that is what makes room for the second Wt buffer.
 // The Jacobian reads xhat from the (L2 resident) global image, prefetched into registers before the accumulator is waited for.
 constexpr int TP_WORK = 512;
-constexpr int TP_THREADS = TP_WORK + 96;      // + two ring warps + MMA warp
-constexpr int TP_SPS = 2;                      // K steps (of 16 rows) per ring stage: bulk-copy issue is ~150 cycles a copy
+constexpr int TP_THREADS = TP_WORK + 128;     // + two ring warps + two MMA warps (G group, dxh group)
+constexpr int TP_SPS = 1;                      // K steps (of 16 rows) per ring stage
 constexpr int TP_MAXSTAGES = 8;
 
 __device__ __forceinline__ void tp_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(TP_WORK) : "memory"); }
@@ -787,14 +793,14 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
     __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     __shared__ float s_gmax;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    MK_PH_DECL(tid == 0 || tid == TP_WORK || tid == TP_WORK + 64)
+    MK_PH_DECL(tid == 0 || tid == TP_WORK || tid == TP_WORK + 64)      // worker 0, first ring lane, G-MMA lane
     if (tid == 0) {
         for (int i = 0; i < 2; ++i) {
-            tc::mbar_init(&bar_cp[i], 1); tc::mbar_init(&bar_wfull[i], 1); tc::mbar_init(&bar_wfree[i], 1);
+            tc::mbar_init(&bar_cp[i], 1); tc::mbar_init(&bar_wfull[i], 1); tc::mbar_init(&bar_wfree[i], 2);   // wfree: both MMA warps
             tc::mbar_init(&bar_dxrdy[i], 1); tc::mbar_init(&bar_dxfree[i], 1);
         }
         for (int i = 0; i < TP_MAXSTAGES; ++i) { tc::mbar_init(&bar_rfull[i], 1); tc::mbar_init(&bar_rfree[i], 1); }
-        tc::mbar_init(&bar_done, 1);
+        tc::mbar_init(&bar_done, 2);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc(&tslot, 512);
@@ -839,44 +845,43 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
     unsigned char* ring = smem + a.sm_ring;
     const int dxcol = a.nbl * a.cs;                       // dxh accumulators behind the G accumulators
 
+    // TWO independent rings (single producer, single consumer each): ring 0 carries the node-image K steps to the G warp, ring 1
+    // the kernel-block-image K steps to the dxh warp -- slots [0, NSh) and [NSh, 2 NSh).  (One shared ring with two consumers
+    // running at their own pace aliases the mbarrier phase parity: a consumer a whole ring ahead of the other sees "complete".)
+    const int NSh = NS / 2;
     if (warp == TP_WORK / 32 || warp == TP_WORK / 32 + 1) {
-        // ================= ring warps: per visit the node image (16 nodes per K step), then the kernel-block image (16 rows
-        // per K step), TP_SPS K steps per stage; the two warps issue alternate stages =================
+        // ================= ring warps =================
         if (lane == 0) {
-            const uint32_t rid = (uint32_t)(warp - TP_WORK / 32);
+            const bool isx = warp == TP_WORK / 32;                    // node image (true) / kernel-block image (false)
+            const uint32_t s0 = isx ? 0u : (uint32_t)NSh;
             uint32_t q = 0;
             for (int wk = 0; wk < my_tiles; ++wk) {
                 const int tile = walk.tile(wk);
                 const int nn = __ldg(&a.meta[tile].nn);
                 const int nkg = max(16, (nn + 15) & ~15) >> 4;
-                const int nsg = (nkg + TP_SPS - 1) / TP_SPS;
                 for (int bi = 0; bi < a.nbl; ++bi) {
                     const int blk = a.blist[bi];
-                    const int nkx = max(16, (a.tb.rows[blk] + 15) & ~15) >> 4;
-                    const int nsx = (nkx + TP_SPS - 1) / TP_SPS;
-                    for (int s = 0; s < nsg + nsx; ++s, ++q) {
-                        if ((q & 1u) != rid) continue;
-                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
-                        const bool isx = s < nsg;
-                        const int s2 = isx ? s : s - nsg;
-                        const int steps = min(TP_SPS, (isx ? nkg : nkx) - s2 * TP_SPS);
-                        const unsigned char* src = (isx ? a.ximg + (size_t)tile * 2 * a.x_one : a.img + (size_t)blk * 2 * a.img_one) +
-                                                   (size_t)s2 * TP_SPS * 2 * fgrp;
-                        const uint32_t one = (uint32_t)(isx ? a.x_one : a.img_one);
-                        const uint32_t bytes = (uint32_t)steps * 2u * fgrp;
+                    const int nk = isx ? nkg : (max(16, (a.tb.rows[blk] + 15) & ~15) >> 4);
+                    const unsigned char* base = isx ? a.ximg + (size_t)tile * 2 * a.x_one : a.img + (size_t)blk * 2 * a.img_one;
+                    const uint32_t one = (uint32_t)(isx ? a.x_one : a.img_one);
+                    for (int ks = 0; ks < nk; ++ks, ++q) {
+                        const uint32_t slot = s0 + q % (uint32_t)NSh, use = q / (uint32_t)NSh;
                         MK_PH(0);
                         tc::mbar_wait(&bar_rfree[slot], (use & 1u) ^ 1u);
                         MK_PH(1);
                         unsigned char* dst = ring + (size_t)slot * a.stage_bytes;
-                        mbar_expect_tx(&bar_rfull[slot], 2u * bytes);
-                        bulk_g2s(dst, src, bytes, &bar_rfull[slot]);
-                        bulk_g2s(dst + (uint32_t)TP_SPS * 2u * fgrp, src + one, bytes, &bar_rfull[slot]);
+                        const unsigned char* src = base + (size_t)ks * 2 * fgrp;
+                        mbar_expect_tx(&bar_rfull[slot], 4u * fgrp);
+                        bulk_g2s(dst, src, 2u * fgrp, &bar_rfull[slot]);
+                        bulk_g2s(dst + 2u * fgrp, src + one, 2u * fgrp, &bar_rfull[slot]);
                     }
                 }
             }
         }
-    } else if (warp == TP_WORK / 32 + 2) {
-        // ================= MMA warp =================
+    } else if (warp == TP_WORK / 32 + 2 || warp == TP_WORK / 32 + 3) {
+        // ================= MMA warps: warp G issues G_b += Wt . xhat, warp X issues dxh (+)= Wt^T . khat -- one thread needs ~100
+        // cycles per tcgen05.mma, two issuing threads keep the tensor pipe busy; bar_wfree / bar_done count both =================
+        const bool isG = warp == TP_WORK / 32 + 2;
         if (lane == 0) {
             uint32_t q = 0, vis = 0;
             const uint32_t idesc_g = tc::idesc_f16(128, a.Fk, 0, 1);  // A = Wt K-major (K = node), B = xhat MN-major (N = feature)
@@ -895,44 +900,40 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
                     MK_PH(0);
                     tc::mbar_wait(&bar_wfull[buf], (vis >> 1) & 1u);
                     MK_PH(1);                                             // MMA: waiting for the workers' Wt
-                    if (bi == 0) tc::mbar_wait(&bar_dxfree[par_t], (((uint32_t)wk >> 1) & 1u) ^ 1u);
+                    if (!isG && bi == 0) tc::mbar_wait(&bar_dxfree[par_t], (((uint32_t)wk >> 1) & 1u) ^ 1u);
                     tc::fence_after_sync();
-                    const uint32_t dG = tmem + (uint32_t)(bi * a.cs);
-                    const uint32_t lo_off = (uint32_t)TP_SPS * 2u * fgrp;     // lo half of a stage
-                    for (int ks0 = 0; ks0 < nkg; ks0 += TP_SPS, ++q) {        // G_bi += Wt . xhat   (K = nodes, 16 per step)
-                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
-                        MK_PH(3);
-                        tc::mbar_wait(&bar_rfull[slot], use & 1u);
-                        MK_PH(2);                                         // MMA: waiting for a ring stage
-                        const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
-                        for (int ks = ks0; ks < min(ks0 + TP_SPS, nkg); ++ks) {
-                            const uint32_t so = (uint32_t)(ks - ks0) * 2u * fgrp;
+                    if (isG) {
+                        const uint32_t dG = tmem + (uint32_t)(bi * a.cs);
+                        for (int ks = 0; ks < nkg; ++ks, ++q) {           // G_bi += Wt . xhat   (K = nodes, 16 per step)
+                            const uint32_t slot = q % (uint32_t)NSh, use = q / (uint32_t)NSh;
+                            MK_PH(3);
+                            tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                            MK_PH(2);                                     // MMA: waiting for a ring stage
+                            const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
                             const uint64_t dAh = tc::smem_desc(whi + ks * 256u, 128u, 2048u), dAl = tc::smem_desc(wlo + ks * 256u, 128u, 2048u);
-                            const uint64_t dBh = tc::smem_desc(st + so, fgrp, 128u), dBl = tc::smem_desc(st + lo_off + so, fgrp, 128u);
+                            const uint64_t dBh = tc::smem_desc(st, fgrp, 128u), dBl = tc::smem_desc(st + 2u * fgrp, fgrp, 128u);
                             tc::umma_f16(dG, dAh, dBh, idesc_g, (wk == 0 && ks == 0) ? 0u : 1u);
                             tc::umma_f16(dG, dAl, dBh, idesc_g, 1u);
                             tc::umma_f16(dG, dAh, dBl, idesc_g, 1u);
+                            tc::umma_commit(&bar_rfree[slot]);
                         }
-                        tc::umma_commit(&bar_rfree[slot]);
-                    }
-                    for (int ks0 = 0; ks0 < nkx; ks0 += TP_SPS, ++q) {        // dxh (+)= Wt^T . khat   (K = kernel rows, 16 per step)
-                        const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
-                        MK_PH(3);
-                        tc::mbar_wait(&bar_rfull[slot], use & 1u);
-                        MK_PH(2);
-                        const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
-                        for (int ks = ks0; ks < min(ks0 + TP_SPS, nkx); ++ks) {
-                            const uint32_t so = (uint32_t)(ks - ks0) * 2u * fgrp;
+                    } else {
+                        for (int ks = 0; ks < nkx; ++ks, ++q) {           // dxh (+)= Wt^T . khat   (K = kernel rows, 16 per step)
+                            const uint32_t slot = (uint32_t)NSh + q % (uint32_t)NSh, use = q / (uint32_t)NSh;
+                            MK_PH(3);
+                            tc::mbar_wait(&bar_rfull[slot], use & 1u);
+                            MK_PH(2);
+                            const uint32_t st = tc::smem_u32(ring + (size_t)slot * a.stage_bytes);
                             const uint64_t dAh = tc::smem_desc(whi + ks * 4096u, 2048u, 128u), dAl = tc::smem_desc(wlo + ks * 4096u, 2048u, 128u);
-                            const uint64_t dBh = tc::smem_desc(st + so, fgrp, 128u), dBl = tc::smem_desc(st + lo_off + so, fgrp, 128u);
+                            const uint64_t dBh = tc::smem_desc(st, fgrp, 128u), dBl = tc::smem_desc(st + 2u * fgrp, fgrp, 128u);
                             tc::umma_f16(dX, dAh, dBh, idesc_x, (bi == 0 && ks == 0) ? 0u : 1u);
                             tc::umma_f16(dX, dAl, dBh, idesc_x, 1u);
                             tc::umma_f16(dX, dAh, dBl, idesc_x, 1u);
+                            tc::umma_commit(&bar_rfree[slot]);
                         }
-                        tc::umma_commit(&bar_rfree[slot]);
                     }
-                    tc::umma_commit(&bar_wfree[buf]);                     // Wt buffer free once these MMAs have read it
-                    if (bi == a.nbl - 1) tc::umma_commit(&bar_dxrdy[par_t]);
+                    tc::umma_commit(&bar_wfree[buf]);                     // (both warps) Wt buffer free once these MMAs have read it
+                    if (!isG && bi == a.nbl - 1) tc::umma_commit(&bar_dxrdy[par_t]);
                     MK_PH(3);
                 }
             }
@@ -1358,7 +1359,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         pa.stage_bytes = TP_SPS * 4 * (a.Fk >> 3) * 128;
         const int64_t room = (int64_t)s_budget - 2048 - poff;
         pa.nstages = (int)std::min<int64_t>(TP_MAXSTAGES, room / pa.stage_bytes);
-        if (pa.nstages < 3) use_pipe = false;
+        if (pa.nstages < 6) use_pipe = false;                 // two rings of >= 3 stages
         poff += (int64_t)std::max(pa.nstages, 0) * pa.stage_bytes;
     }
     if (!do_launch) return 1;
