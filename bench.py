@@ -338,7 +338,11 @@ def main():
     # its loss back; the copy of step i+1 is issued on the prefetcher's side stream before step i's loss is waited for, the
     # way a pinned-memory DataLoader feeds the reference's training loop.
     loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
-    h_host = [torch.empty(N, K, dtype=torch.float32).pin_memory() for _ in range(2)] if fwd_only else None
+    # inference sweep (configs[4]): what returns to the host per step is the per-MOLECULE result, global_add_pool(h) [B, K]
+    # (MolKGNNNet.py:144-146 pools before anything leaves the model), through the native deterministic segmented sum
+    h_host = [torch.empty(B, K, dtype=torch.float32).pin_memory() for _ in range(2)] if fwd_only else None
+    ptr_dev = torch.from_numpy(batch["ptr"]).to(dev)
+    batch_dev = torch.from_numpy(batch["batch"]).to(dev)
 
     def e2e_run(k):
         nxt = pf.put(host_batch=host, build_plan=True)
@@ -348,9 +352,9 @@ def main():
             if i + 1 < k:
                 nxt = pf.put(host_batch=host, build_plan=True)
             h = step(t, plan)
-            if fwd_only:                          # inference: the WHOLE result h [N, K] returns to the host
+            if fwd_only:                          # inference: the pooled result [B, K] returns to the host
                 buf = h_host[i & 1]
-                buf.copy_(h, non_blocking=True)
+                buf.copy_(mk.global_add_pool(h, batch_dev, ptr_dev), non_blocking=True)
             else:
                 loss = (h.detach() * wout).sum()
                 buf = loss_host[i & 1]
@@ -381,7 +385,7 @@ def main():
     # ---- end to end with the dataset RESIDENT in HBM (molkgnn_b200.store: packed molecule store + GPU batcher): the step's host
     # input is the list of molecule ids of the batch (pinned), the batch is assembled on the GPU -- what the 180 GB are for ----
     ms_store = None
-    if not fwd_only and not os.environ.get("MOLKGNN_BENCH_NO_STORE"):
+    if not os.environ.get("MOLKGNN_BENCH_NO_STORE"):
         from molkgnn_b200.store import MoleculeStore
         ptr_h = batch["ptr"]
         eptr = np.searchsorted(batch["edge_index"][0], ptr_h)            # edges are grouped molecule by molecule
@@ -399,18 +403,22 @@ def main():
                 if i + 1 < k:
                     nxt = pf.put(store_batch=(store, id_bufs[(i + 1) & 3]), build_plan=True)
                 h = step(bt, plan)
-                loss = (h.detach() * wout).sum()
-                buf = loss_host[i & 1]
-                buf.copy_(loss, non_blocking=True)
+                if fwd_only:
+                    buf = h_host[i & 1]
+                    buf.copy_(mk.global_add_pool(h, bt["batch"], bt["ptr"]), non_blocking=True)
+                else:
+                    loss = (h.detach() * wout).sum()
+                    buf = loss_host[i & 1]
+                    buf.copy_(loss, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record()
                 zero_grads()
                 if pending is not None:
                     pending[1].synchronize()
-                    float(pending[0])
+                    float(pending[0].view(-1)[0])
                 pending = (buf, ev)
             pending[1].synchronize()
-            float(pending[0])
+            float(pending[0].view(-1)[0])
 
         store_run(3)
         sync_all()
@@ -480,14 +488,14 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(B, fwd_only),
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": N * K * 4 if fwd_only else 4, "ms_per_step": ms_e2e / args.steps,
+                "d2h_bytes_per_step": B * K * 4 if fwd_only else 4, "ms_per_step": ms_e2e / args.steps,
                 "api": "molkgnn_b200.MolGCN.forward/backward; every step's x/p/edge_index/edge_attr copied from pinned host "
                        "memory and bucketed (molkgnn_b200.data.DevicePrefetcher: side stream, one step ahead), every step's loss "
                        "copied to pinned host memory and consumed by the host one step later; all K copies and K reads are "
                        "inside the timed region"},
         "e2e_store": None if ms_store is None else {
             "value": world * B * args.steps / (ms_store * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": 8 * B,
-            "d2h_bytes_per_step": 4, "ms_per_step": ms_store / args.steps,
+            "d2h_bytes_per_step": B * K * 4 if fwd_only else 4, "ms_per_step": ms_store / args.steps,
             "api": "molkgnn_b200.store.MoleculeStore.collate(ids) -> MolGCN.forward/backward: the dataset is packed in HBM once, "
                    "every step copies only its (shuffled) molecule ids from pinned host memory, assembles the batch on the GPU "
                    "(csrc/collate.cu), runs the bucket pass inside the forward and reads the loss back"},
