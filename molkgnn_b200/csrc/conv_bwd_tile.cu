@@ -341,6 +341,11 @@ __device__ __forceinline__ void wt_store(unsigned char* wt, int row, int col, fl
     *reinterpret_cast<__half*>(wt + off) = hi;
     *reinterpret_cast<__half*>(wt + WT_ONE + off) = lo;
 }
+__device__ __forceinline__ void wt_store_hl(unsigned char* wt, int row, int col, __half hi, __half lo) {
+    const uint32_t off = tc::il_off(row, col, 128);
+    *reinterpret_cast<__half*>(wt + off) = hi;
+    *reinterpret_cast<__half*>(wt + WT_ONE + off) = lo;
+}
 __device__ __forceinline__ void wt_add(unsigned char* wt, int row, int col, float v) {
     const uint32_t off = tc::il_off(row, col, 128);
     __half* ph = reinterpret_cast<__half*>(wt + off);
@@ -353,12 +358,15 @@ __device__ __forceinline__ void wt_add(unsigned char* wt, int row, int col, floa
 
 // thread 0: metadata record, node images and the tile-ordered coefficients / arg-max codes of `tile` (np pairs).  The
 // coefficient arrays and the image buffer are single: the caller issues this only after the previous tile's last use of them.
+// The node images complete on their OWN barrier: only the first G MMA of the tile (and the Jacobian) need them, so the 57 KB
+// land while the tile's first block is scattered instead of being waited for at the top of the tile.
 __device__ __forceinline__ void tb_issue_copy(const BwdTileArgs& a, unsigned char* smem, unsigned char* buf, int tile, int np,
-                                              uint64_t* bar) {
+                                              uint64_t* bar, uint64_t* bar_x) {
     const uint32_t cb = (uint32_t)((np * 4 + 15) & ~15), ab = (uint32_t)((np + 15) & ~15);
-    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + 2u * (uint32_t)a.x_one + cb + ab);
+    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + cb + ab);
+    mbar_expect_tx(bar_x, 2u * (uint32_t)a.x_one);
     bulk_g2s(buf, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
-    bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar);
+    bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar_x);
     if (np > 0) {
         bulk_g2s(smem + a.sm_a, a.coefT + (size_t)tile * a.stride, cb, bar);
         bulk_g2s(smem + a.sm_am, a.amT + (size_t)tile * a.stride_am, ab, bar);
@@ -418,13 +426,14 @@ __device__ unsigned long long g_ph_bwd[16];
 
 __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_constant__ BwdTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_mma, bar_img[4], bar_cp[2];
+    __shared__ uint64_t bar_mma, bar_img[4], bar_cp[2], bar_xi;
     __shared__ uint32_t tslot;
     __shared__ BSeg s_seg[4][TILE_MAXSEG];
     __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     MK_PH_DECL(tid == 0)
     if (tid == 0) {
+        tc::mbar_init(&bar_xi, 1);
         tc::mbar_init(&bar_mma, 2);                       // one commit per issuing thread (G group, dxh group)
         for (int i = 0; i < 4; ++i) tc::mbar_init(&bar_img[i], 1);
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
@@ -489,7 +498,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     const bool resident = a.nbl <= a.nimg;
     int np_next = 0;
     if (tid == 0 && my_tiles > 0) {
-        tb_issue_copy(a, smem, smem + a.sm_buf, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0]);
+        tb_issue_copy(a, smem, smem + a.sm_buf, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0], &bar_xi);
         const int n0 = resident ? a.nbl : min(a.nimg, total_uses);
         for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, a.blist[u % a.nbl], u % a.nimg, &bar_img[u % a.nimg]);
     }
@@ -551,10 +560,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     const uint32_t nw = m.nl[nl_];
                     const uint32_t cr = m.cr[nl_];
                     wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
-                    const float as = av * sg.alpha;
+                    const float as = av * sg.alpha;           // the same value goes to all d support entries: split it once
+                    const __half ah = __float2half_rn(as);
+                    const __half al = __float2half_rn(as - __half2float(ah));
                     for (int j = 0; j < sg.d; ++j) {
                         if (((cr >> (2 * j)) & 3u) == 0u)
-                            wt_store(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), as);
+                            wt_store_hl(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), ah, al);
                     }
                 }
             }
@@ -597,6 +608,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             // moves), about twice the tensor time of these shapes; the G MMAs and the dxh MMAs write different accumulators, so
             // warp 0 issues the first and warp 1 the second group and the tensor pipe sees both streams (bar_mma counts 2)
             if (tid == 0) {
+                if (bi == 0) tc::mbar_wait(&bar_xi, (uint32_t)wk & 1u);      // node images of this tile (one completion per tile)
                 tc::fence_after_sync();
                 tb_issue_mma_g(a, smem, nn, bi, fresh, tmem);
                 tc::umma_commit(&bar_mma);
@@ -647,7 +659,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             }
             if (!a.last) {
                 if (tid == 0 && tnext < a.n_tiles)
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1]);
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1], &bar_xi);
                 if (rowok && colok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -660,6 +672,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 float dot = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) xh[i] = 0.f;
+                tc::mbar_wait(&bar_xi, (uint32_t)wk & 1u);                    // (complete since the first G MMA; acquire for this thread)
                 if (colok) {
                     const unsigned char* Xhi = smem + a.sm_x;
                     const unsigned char* Xlo = Xhi + a.x_one;
@@ -685,7 +698,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 red[cpart * 128 + v] = dot;
                 __syncthreads();
                 if (tid == 0 && tnext < a.n_tiles)      // every thread has read its xhat: the image buffer may be refilled
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1]);
+                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1], &bar_xi);
                 dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
                 const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
                 const float rden = 1.0f / den;
@@ -1117,10 +1130,12 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
                         const uint32_t nw = m.nl[nl_];
                         const uint32_t cr = m.cr[nl_];
                         wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
-                        const float as = av * sg.alpha;
+                        const float as = av * sg.alpha;           // the same value goes to all d support entries: split it once
+                        const __half ah = __float2half_rn(as);
+                        const __half al = __float2half_rn(as - __half2float(ah));
                         for (int j = 0; j < sg.d; ++j) {
                             if (((cr >> (2 * j)) & 3u) == 0u)
-                                wt_store(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), as);
+                                wt_store_hl(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), ah, al);
                         }
                     }
                 }

@@ -166,7 +166,10 @@ class MoleculeStore(object):
         if not self.x.is_cuda:
             raise _lib.MolKGNNError("MoleculeStore.collate: the store must live on a CUDA device (store.to('cuda')); "
                                     "there is no CPU fallback")
-        ids_host = np.asarray(ids.cpu() if torch.is_tensor(ids) else ids, dtype=np.int64).reshape(-1)
+        if torch.is_tensor(ids):
+            ids_host = (ids if not ids.is_cuda else ids.cpu()).numpy().astype(np.int64, copy=False).reshape(-1)
+        else:
+            ids_host = np.asarray(ids, dtype=np.int64).reshape(-1)
         M = int(ids_host.shape[0])
         if M == 0:
             raise _lib.MolKGNNError("MoleculeStore.collate: empty batch")
@@ -185,11 +188,22 @@ class MoleculeStore(object):
                 ids_dev = torch.from_numpy(ids_host).pin_memory().to(dev, non_blocking=True)
             F, P, Fe = self.x.shape[1], self.p.shape[1], self.edge_attr.shape[1]
             Y = 0 if self.y is None else self.y.shape[1]
-            out = dict(x=torch.empty(Nb, F, device=dev), p=torch.empty(Nb, P, device=dev),
-                       edge_attr=torch.empty(Eb, Fe, device=dev), edge_index=torch.empty(2, Eb, dtype=torch.int64, device=dev),
-                       batch=torch.empty(Nb, dtype=torch.int64, device=dev), ptr=torch.empty(M + 1, dtype=torch.int64, device=dev))
+            # ONE allocation for the whole batch, carved into the output tensors (16-byte aligned pieces)
+            al = lambda n: (n + 15) // 16 * 16  # noqa: E731
+            sizes = [("x", Nb * F * 4), ("p", Nb * P * 4), ("edge_attr", Eb * Fe * 4), ("edge_index", 2 * Eb * 8),
+                     ("batch", Nb * 8), ("ptr", (M + 1) * 8), ("y", M * Y * 4)]
+            offs, tot = {}, 0
+            for k, nb in sizes:
+                offs[k] = tot
+                tot += al(nb)
+            buf = torch.empty(tot, dtype=torch.uint8, device=dev)
+            cut = lambda k, nb, dt, shape: buf[offs[k]:offs[k] + nb].view(dt).view(*shape)  # noqa: E731
+            out = dict(x=cut("x", Nb * F * 4, torch.float32, (Nb, F)), p=cut("p", Nb * P * 4, torch.float32, (Nb, P)),
+                       edge_attr=cut("edge_attr", Eb * Fe * 4, torch.float32, (Eb, Fe)),
+                       edge_index=cut("edge_index", 2 * Eb * 8, torch.int64, (2, Eb)),
+                       batch=cut("batch", Nb * 8, torch.int64, (Nb,)), ptr=cut("ptr", (M + 1) * 8, torch.int64, (M + 1,)))
             if Y:
-                out["y"] = torch.empty(M, Y, device=dev)
+                out["y"] = cut("y", M * Y * 4, torch.float32, (M, Y))
             scratch = torch.empty(2 * (M + 1), dtype=torch.int64, device=dev)
             if self._err is None:
                 self._err = torch.zeros(1, dtype=torch.int32, device=dev)
