@@ -405,6 +405,10 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const int64_t scoff[4], uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in,
                          uint8_t* argmax_tile, int32_t* counter, cudaStream_t st);
 
+int launch_conv_fwd_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                         const void* ximg, int32_t is_last_layer, float* sc, int32_t sc_mode, const int64_t scoff[4],
+                         uint8_t* argmax, uint8_t* argmax_free, const uint8_t* argmax_in, cudaStream_t st);
+
 extern long long g_path_counts[4];
 
 }  // namespace mk
@@ -460,6 +464,11 @@ extern "C" int molkgnn_conv_fwd(const molkgnn_plan_t* plan, const molkgnn_layer_
                                             argmax_free, argmax_in, argmax_tile, counter, st);
         if (rc > 0) ++g_path_counts[0];
         if (rc != 0) return rc < 0 ? rc : 0;
+        // wide layers (more blocks / features than the resident-operand kernels take): both operands streamed
+        const int rw = launch_conv_fwd_wide(plan, layer, x, ldx, ximg, is_last_layer, sc, sc_mode, scoff, argmax, argmax_free,
+                                            argmax_in, st);
+        if (rw > 0) ++g_path_counts[0];
+        if (rw != 0) return rw < 0 ? rw : 0;
     }
     ++g_path_counts[1];
     if (g_fwd_path >= 1) {

@@ -685,13 +685,25 @@ int launch_conv_fwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 
 using namespace mk;
 
+namespace mk {
+bool wide_layer_ok(const molkgnn_layer_t* layer);
+int launch_x_images_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
+                         const float* xnorm, void* ximg, cudaStream_t st);
+}
+
 extern "C" int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
+    if (tile_plan_ok(plan) && wide_layer_ok(layer)) return (int64_t)(wide_fk(layer->Fp) / 32) * WIDE_STAGE;
     if (!tile_plan_ok(plan) || !tile_layer_ok(layer)) return 0;
     return 2 * (int64_t)tile_img_one(tile_fk(layer->Fp));
 }
 
 extern "C" int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                                        const float* xnorm, void* ximg, void* stream_) {
+    if (tile_plan_ok(plan) && wide_layer_ok(layer)) {
+        MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(ximg) & 127) == 0, "tile_ximg_build: bad alignment / ldx=%d", ldx);
+        return launch_x_images_wide(plan, layer, x, ldx, xnorm, ximg, (cudaStream_t)stream_);
+    }
     MK_REQUIRE(tile_plan_ok(plan) && tile_layer_ok(layer), "tile_ximg_build: plan or layer is not eligible for the tile kernels");
     MK_REQUIRE(ldx % 4 == 0 && ldx >= layer->Fp, "tile_ximg_build: ldx=%d must be a multiple of 4 and >= Fp=%d", ldx, layer->Fp);
     MK_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(ximg) & 127) == 0,

@@ -518,8 +518,15 @@ bool tile_layer_ok(const molkgnn_layer_t* layer) {
 }
 }  // namespace mk
 
+namespace mk {
+bool wide_layer_ok(const molkgnn_layer_t* layer);
+int64_t wide_img_bytes(const molkgnn_layer_t* layer);
+int launch_param_pack_wide(const molkgnn_layer_t* layer, cudaStream_t st);
+}
+
 extern "C" int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer) {
     TileBlocks tb;
+    if (wide_layer_ok(layer)) return wide_img_bytes(layer);      // wide layers: stage-major images (conv_fwd_wide.cu)
     if (!tile_layer_ok(layer) || !tb.build(layer->L)) return 0;
     // block-major images + K-step-major copy + bond-support table (tile.cuh)
     return tile_es_off(tb.nb, tile_fk(layer->Fp)) + ((int64_t)tile_es_f4(layer->L) * 16 + 127) / 128 * 128;
@@ -600,6 +607,11 @@ extern "C" int molkgnn_param_pack_layers(const molkgnn_layer_t* layers, int32_t 
             count_launches(1);
             MK_CHECK_CUDA(cudaGetLastError());
         }
+        if (what & 4)
+            for (int i = 0; i < n; ++i) {
+                const int rc = launch_param_pack_wide(layers + l0 + i, st);
+                if (rc) return rc;
+            }
     }
     return 0;
 }

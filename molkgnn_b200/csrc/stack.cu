@@ -17,6 +17,7 @@ int launch_stack_fwd_fused(const molkgnn_plan_t* plan, const molkgnn_layer_t* la
                            float* h_out, int32_t ldh, float* const* sc, uint8_t* const* argmax, uint8_t* const* argmax_free,
                            const uint8_t* const* argmax_in, const int64_t (*scoff)[4], cudaStream_t st);
 extern long long g_path_counts[4];
+bool tile_layer_ok(const molkgnn_layer_t* layer);
 }
 
 namespace {
@@ -143,7 +144,7 @@ extern "C" int molkgnn_stack_fwd(const molkgnn_plan_t* plan, const molkgnn_layer
     MK_CHECK_CUDA(cudaMemsetAsync(ws + lay->counter, 0, sizeof(int32_t) * 8 * (size_t)nl, (cudaStream_t)stream));
     float* h = reinterpret_cast<float*>(ws + lay->h[0]);
     float* hn = reinterpret_cast<float*>(ws + lay->hnorm[0]);
-    if (lay->ximg[0] >= 0 && layers[0].Fp <= 64) {      // one pass over x: padded copy, norms, tensor-core images
+    if (lay->ximg[0] >= 0 && layers[0].Fp <= 64 && mk::tile_layer_ok(&layers[0])) {      // one pass over x: padded copy, norms, tensor-core images
         if ((rc = molkgnn_tile_ximg_build_raw(plan, &layers[0], x, ldx, h, hn, ws + lay->ximg[0], stream))) return rc;
     } else {
         if ((rc = molkgnn_pad_norm(x, N, layers[0].F, ldx, h, layers[0].Fp, hn, stream))) return rc;

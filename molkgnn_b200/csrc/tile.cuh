@@ -66,6 +66,43 @@ constexpr int TILE_KS_BYTES = 8192;
 __host__ __device__ inline int64_t tile_img_ks_off(int nb, int Fk) { return (int64_t)nb * 2 * tile_img_one(Fk); }
 __host__ __device__ inline int64_t tile_es_off(int nb, int Fk) { return 2 * tile_img_ks_off(nb, Fk); }
 __host__ __device__ inline int tile_es_f4(const int* L) { return 2 * (L[0] + 2 * L[1] + 3 * L[2] + 4 * L[3]); }
+// ---- wide layers (conv_fwd_wide.cu, conv_bwd_wide.cu): more than TILE_MAXB blocks or more than 112 features -----------------
+// Blocks of ONE degree each (rows = slot * nk + (k - k0), slot d = centre row), degree 4 first.  Both operands are streamed in
+// STAGES of 16 KB = two K steps (32 features) of a 128-row operand: [K step][hi | lo][16 row groups][2 chunks][8 rows][8 elements]
+// (K-major UMMA operand per K step: LBO = 128, SBO = 256).
+constexpr int WIDE_MAXB = 16;
+constexpr int WIDE_STAGE = 16384;
+struct WideBlocks {
+    int nb;
+    int d[WIDE_MAXB], k0[WIDE_MAXB], nk[WIDE_MAXB];
+    __host__ __device__ bool build(const int* L) {
+        nb = 0;
+        for (int b = 0; b < WIDE_MAXB; ++b) { d[b] = 1; k0[b] = 0; nk[b] = 0; }
+        for (int dd = 4; dd >= 1; --dd) {
+            const int Ld = L[dd - 1];
+            if (Ld <= 0) continue;
+            const int per = 128 / (dd + 1);
+            const int need = (Ld + per - 1) / per;
+            if (nb + need > WIDE_MAXB) return false;
+            int k = 0;
+            for (int i = 0; i < need; ++i) {
+                const int n = (Ld - k + (need - i) - 1) / (need - i);
+                d[nb] = dd; k0[nb] = k; nk[nb] = n;
+                ++nb;
+                k += n;
+            }
+        }
+        return nb > 0;
+    }
+};
+__host__ __device__ inline int wide_fk(int Fp) { return (Fp + 31) / 32 * 32; }
+// byte offset of (row, 8-column chunk c = 0..3) inside a stage; the lo half lies WIDE_STAGE / 4 behind the hi half
+__host__ __device__ inline uint32_t wide_stage_off(int row, int c) {
+    return (uint32_t)(c >> 1) * (WIDE_STAGE / 2) + (uint32_t)(row >> 3) * 256u + (uint32_t)(c & 1) * 128u + (uint32_t)(row & 7) * 16u;
+}
+// kernel-block images [block][stage], then the bond-support table
+__host__ __device__ inline int64_t wide_es_off(int nb, int Fk) { return (int64_t)nb * (Fk / 32) * WIDE_STAGE; }
+
 // Images in global memory: kernel blocks [block][hi | lo]; node tiles [tile][hi | lo].  v = hi + lo, BOTH halves unscaled
 // (lo is usually an fp16 subnormal, which tcgen05 honours): one fp32 accumulator receives hi*hi + lo*hi + hi*lo.
 
