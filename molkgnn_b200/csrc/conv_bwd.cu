@@ -22,6 +22,12 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
                          const uint8_t* argmax, const int64_t scoff[4], float* coef, float* partials, float* scratch,
                          float* grad_x, int32_t ldgx, int64_t part_off[4], int ncta[4], int64_t* part_total, bool do_launch,
                          const uint8_t* argmax_tile, cudaStream_t st);
+int launch_conv_bwd_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx, const float* xnorm,
+                         const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode, const uint8_t* argmax,
+                         const int64_t scoff[4], float* coef, float* partials, float* grad_x, int32_t ldgx, int64_t part_off[4],
+                         int ncta[4], int64_t* part_total, bool do_launch, cudaStream_t st);
+int64_t wide_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
+int64_t wide_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 int tile_bwd_grid(const molkgnn_plan_t* plan);
 bool tile_bwd_ok(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 long long g_path_counts[4] = {0, 0, 0, 0};   // forward tile / other, backward tile / other
@@ -513,7 +519,7 @@ extern "C" int64_t molkgnn_tile_argmax_bytes(const molkgnn_plan_t* plan, const m
 extern "C" int64_t molkgnn_conv_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
     int64_t tot = 0;
     for (int d = 0; d < 4; ++d) tot += (int64_t)plan->n[d] * layer->L[d];
-    return std::max<int64_t>(std::max(tot, mk::tile_bwd_coef_floats(plan, layer)), 4);
+    return std::max<int64_t>(std::max(std::max(tot, mk::tile_bwd_coef_floats(plan, layer)), wide_bwd_coef_floats(plan, layer)), 4);
 }
 
 extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
@@ -527,7 +533,8 @@ extern "C" int64_t molkgnn_conv_bwd_partial_floats(const molkgnn_plan_t* plan, c
         tot_tile += (int64_t)tgrid * (d + 2) * layer->L[d] * (layer->Fp + EP);
         rows += (int64_t)(d + 2) * layer->L[d];
     }
-    return std::max(tot, tot_tile) + 2 * rows + 16 + 512;      // + per-CTA max |coef| of k_coef_tile (tile path)
+    return std::max(std::max(tot, tot_tile) + 2 * rows + 16 + 512,      // + per-CTA max |coef| of k_coef_tile (tile path)
+                    wide_bwd_partial_floats(plan, layer));
 }
 
 extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
@@ -546,6 +553,19 @@ extern "C" int molkgnn_conv_bwd(const molkgnn_plan_t* plan, const molkgnn_layer_
         const int rc = launch_conv_bwd_tile(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, argmax, scoff, coef,
                                             partials, scratch, grad_x, ldgx, t_off, t_ncta, &t_total, (phases & 1) != 0,
                                             argmax_tile, st);
+        if (rc < 0) return rc;
+        if (rc == 1) {
+            if (phases & 1) ++g_path_counts[2];
+            if (grads && (phases & 2)) return launch_param_finalize(layer, partials, t_off, t_ncta, partials + t_total, grads, 1, st);
+            return 0;
+        }
+    }
+    // ---------------- wide layers: tensor-core backward with streamed operands (conv_bwd_wide.cu) ----------------
+    if (ximg && g_bwd_path != 0 && (!grad_x || ldgx == layer->Fp)) {
+        int64_t t_off[4], t_total = 0;
+        int t_ncta[4];
+        const int rc = launch_conv_bwd_wide(plan, layer, x, ldx, xnorm, ximg, grad, ldg, grad_mode, argmax, scoff, coef, partials,
+                                            grad_x, ldgx, t_off, t_ncta, &t_total, (phases & 1) != 0, st);
         if (rc < 0) return rc;
         if (rc == 1) {
             if (phases & 1) ++g_path_counts[2];

@@ -26,6 +26,7 @@
 //                    epilogue; the last launch applies d(x/|x|)/dx and writes grad_x.
 // k_param_finalize (params.cu) reduces the per-CTA copies in fixed order.
 #include <algorithm>
+#include <cstring>
 #include "common.cuh"
 #include "tc.cuh"
 #include "tile.cuh"
@@ -33,6 +34,8 @@
 namespace mk {
 
 bool tile_layer_ok(const molkgnn_layer_t* layer);
+
+static int64_t g_coef_attr_dev[16] = {0};      // dynamic shared memory k_coef_tile is configured for, per device (two launchers)
 
 constexpr int TB_THREADS = 512;
 constexpr int WT_ONE = 16 * 16 * 128;          // one fp16 image of the 128 x 128 coefficient block
@@ -64,6 +67,11 @@ struct CoefTileArgs {
     float* partials; long long part_off[4]; int FW, Fp;
     float* amax;                               // [gridDim.x] max |coef| seen by every CTA (no zeroing, no atomics)
     int buf_bytes, sm_grad, sm_eh, sm_am, sm_coef, sm_inv;   // per-buffer size / offsets inside a buffer / pair arrays
+    // wide layers (conv_bwd_wide.cu): the gradient rows are read from global memory (a tile's rows do not fit shared memory)
+    // and coefT / amT are written in BLOCKED tile order -- the pairs of one kernel block (WideBlocks: degree d, kernels
+    // k0 .. k0+nk-1) contiguous: off_d + cnt_d * k0 + i * nk + (k - k0).  wb_base / wb_rem: kernels per block of degree d
+    // (the first wb_rem blocks hold wb_base + 1).
+    int wide, wb_base[4], wb_rem[4];
 };
 
 __device__ __forceinline__ void cp_async_n(void* dst, const void* src, int bytes) {
@@ -82,7 +90,7 @@ __device__ __forceinline__ void ct_issue(const CoefTileArgs& a, unsigned char* b
     const int tid = threadIdx.x;
     for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += CT_THREADS)
         cp_async_n(buf + i * 16, reinterpret_cast<const unsigned char*>(g) + i * 16, 16);
-    {
+    if (!a.wide) {
         // rows t0 .. t0+nn-1 of grad are contiguous: nn * ldg floats; the staged copy starts at the vec-aligned float below
         const long long first = (long long)hdr.x * a.ldg;
         const long long f0 = first - (first % a.vec);
@@ -116,11 +124,20 @@ __device__ __forceinline__ void ct_pairs(const CoefTileArgs& a, const TileMetaG&
     const int np = m.cnt[D - 1] * L;
     const float rL = 1.0f / (float)L;
     const int koff = a.koff[D - 1];
+    const int wbase = a.wb_base[D - 1], wrem = a.wb_rem[D - 1], cntd = m.cnt[D - 1];
 #pragma unroll 2
     for (int p = threadIdx.x; p < np; p += CT_THREADS) {
         const int i = (int)(((float)p + 0.5f) * rL);
         const int k = p - i * L;
         const int nl_ = m.list[D - 1][i];
+        int po = p;                                     // position inside the degree's part of the tile-ordered arrays
+        if (a.wide) {
+            const int big = wrem * (wbase + 1);
+            int k0, nk;
+            if (k < big) { const int j = k / (wbase + 1); k0 = j * (wbase + 1); nk = wbase + 1; }
+            else { const int j = (k - big) / wbase; k0 = big + j * wbase; nk = wbase; }
+            po = cntd * k0 + i * nk + (k - k0);
+        }
         const uint8_t am = amS ? amS[off + p] : a.argmax[(size_t)a.scoff[D - 1] + (size_t)m.posl[nl_] * L + k];
         float g;
         if (a.grad_mode == 0) {
@@ -133,8 +150,8 @@ __device__ __forceinline__ void ct_pairs(const CoefTileArgs& a, const TileMetaG&
         }
         const float av = (am & 0x80) ? -g : g;
         amax = fmaxf(amax, fabsf(av));
-        cT[off + p] = av;
-        if (aT) aT[off + p] = am & 0x7f;
+        cT[off + po] = av;
+        if (aT) aT[off + po] = am & 0x7f;
         coefS[off + p] = av;
         invS[off + p] = inv_lut[am & 0x7f];
     }
@@ -202,7 +219,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
         __syncthreads();                                 // this tile's buffer is complete; coefS / invS are free
         MK_PH(2);                                        // wait for this tile's data
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
-        const float* gS = reinterpret_cast<const float*>(buf + a.sm_grad) + (int)(((long long)m.t0 * a.ldg) % a.vec);
+        const float* gS = a.wide ? a.grad + (size_t)m.t0 * a.ldg
+                                 : reinterpret_cast<const float*>(buf + a.sm_grad) + (int)(((long long)m.t0 * a.ldg) % a.vec);
         const float4* ehS = reinterpret_cast<const float4*>(buf + a.sm_eh);
         int off[5];
         off[0] = 0;
@@ -1269,6 +1287,74 @@ int64_t tile_bwd_coef_floats(const molkgnn_plan_t* plan, const molkgnn_layer_t* 
     return (int64_t)plan->n_tiles * stride + ((int64_t)plan->n_tiles * stride_am + 3) / 4 + 4;
 }
 
+// k_coef_tile for wide layers (conv_bwd_wide.cu): coefficients / arg-max codes in blocked tile order, max |coef| per CTA, and the
+// bond-attribute sums as `grid` partial copies in bondP -- [degree][CTA][(d + 1) L_d rows][8 floats] (centre rows zero).
+// Returns the shared-memory bytes it needs (<= 0: does not fit) when `do_launch` is false.
+int64_t launch_coef_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* grad, int32_t ldg, int32_t grad_mode,
+                         const uint8_t* argmax, const int64_t scoff[4], float* coefT, uint8_t* amT, int stride, int stride_am,
+                         float* bondP, float* amax, int grid, bool do_launch, cudaStream_t st) {
+    CoefTileArgs c;
+    memset(&c, 0, sizeof(c));
+    WideBlocks wb;
+    if (!wb.build(layer->L)) return -1;
+    c.meta = reinterpret_cast<const TileMetaG*>(plan->tile_meta); c.ehat_node = plan->ehat_node; c.n_tiles = plan->n_tiles;
+    c.order = plan->tile_grid == grid ? plan->tile_order : nullptr;
+    c.order_grid = c.order ? grid : 0;
+    int64_t po = 0;
+    for (int d = 0; d < 4; ++d) {
+        c.L[d] = layer->L[d]; c.koff[d] = layer->koff[d]; c.scoff[d] = scoff[d];
+        c.part_off[d] = po;
+        po += (int64_t)grid * (d + 2) * layer->L[d] * EP;
+        int need = 0;
+        for (int b = 0; b < wb.nb; ++b) if (wb.d[b] == d + 1) ++need;
+        c.wb_base[d] = need ? layer->L[d] / need : 0;
+        c.wb_rem[d] = need ? layer->L[d] % need : 0;
+    }
+    c.wide = 1;
+    c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode; c.vec = 1;
+    c.argmax = argmax;
+    c.coefT = coefT; c.amT = amT; c.stride = stride; c.stride_am = stride_am;
+    c.amT_in = nullptr;
+    c.partials = bondP; c.FW = EP; c.Fp = 0;              // bond columns only: rows of 8 floats
+    c.amax = amax;
+    for (int div = 1;; ++div) {
+        int items = 0;
+        for (int d = 0; d < 4; ++d) {
+            c.nch[d] = std::max(1, std::min(8, ((plan->tile_max_deg[d] + CT_CHUNK - 1) / CT_CHUNK + div - 1) / div));
+            items += (d + 1) * layer->L[d] * c.nch[d];
+        }
+        if (items <= CT_MAXR * CT_THREADS) break;
+        if (div >= 64) return -1;
+    }
+    {
+        int64_t o = (sizeof(TileMetaG) + 127) / 128 * 128;
+        c.sm_grad = (int)o;
+        c.sm_eh = (int)o; o += (int64_t)TILE_ESLOTS * EP * 4;
+        c.sm_am = (int)o;
+        c.buf_bytes = (int)o;
+        c.sm_coef = (int)(2 * o);
+        c.sm_inv = c.sm_coef + (int)(((int64_t)stride * 4 + 127) / 128 * 128);
+    }
+    // the chunk sums are combined through shared memory at the end: 32 bytes per item
+    int items = 0;
+    for (int d = 0; d < 4; ++d) items += (d + 1) * layer->L[d] * c.nch[d];
+    const int64_t smem_c = std::max<int64_t>(c.sm_inv + ((int64_t)stride + 127) / 128 * 128, (int64_t)items * 32 + 128);
+    static int s_budget = 0;
+    if (!s_budget) s_budget = device_max_smem_optin();
+    if (smem_c > s_budget - 2048) return -1;
+    if (!do_launch) return smem_c;
+    int64_t& s_attr_c = g_coef_attr_dev[device_index()];
+    if (smem_c > s_attr_c) {
+        MK_CHECK_CUDA(cudaFuncSetAttribute(k_coef_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+        s_attr_c = smem_c;
+    }
+    count_launches(1);
+    ProfScope prof("coef_tile", st);
+    k_coef_tile<<<grid, CT_THREADS, smem_c, st>>>(c);
+    MK_CHECK_CUDA(cudaGetLastError());
+    return smem_c;
+}
+
 // returns 1 if launched, 0 if not eligible, <0 on error.  part_off / ncta describe the partial copies for k_param_finalize.
 int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                          const float* xnorm, const void* ximg, const float* grad, int32_t ldg, int32_t grad_mode,
@@ -1380,9 +1466,9 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     if (!do_launch) return 1;
     MK_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(coef) & 15) == 0,
                "conv_bwd_tile: grad and coef must be 16-byte aligned");
-    static int64_t s_attr_dev[16] = {0}, s_attr_c_dev[16] = {0};
+    static int64_t s_attr_dev[16] = {0};
     int64_t& s_attr = s_attr_dev[device_index()];
-    int64_t& s_attr_c = s_attr_c_dev[device_index()];   // function attributes are per device
+    int64_t& s_attr_c = g_coef_attr_dev[device_index()];   // function attributes are per device
     if (off > s_attr) {
         MK_CHECK_CUDA(cudaFuncSetAttribute(k_conv_bwd_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)off));
         s_attr = off;
@@ -1410,6 +1496,8 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         c.amT_in = argmax_tile; c.amT = argmax_tile ? nullptr : const_cast<uint8_t*>(a.amT);
         c.partials = partials; c.FW = a.FW; c.Fp = layer->Fp;
         c.amax = amax;
+        c.wide = 0;
+        for (int d = 0; d < 4; ++d) { c.wb_base[d] = 0; c.wb_rem[d] = 0; }
         // node chunks per degree: as many as the fullest tile needs, fewer if the items would exceed the threads' capacity
         for (int div = 1;; ++div) {
             int items = 0;

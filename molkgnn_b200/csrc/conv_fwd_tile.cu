@@ -692,7 +692,7 @@ int launch_x_images_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
 }
 
 extern "C" int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer) {
-    if (tile_plan_ok(plan) && wide_layer_ok(layer)) return (int64_t)(wide_fk(layer->Fp) / 32) * WIDE_STAGE;
+    if (tile_plan_ok(plan) && wide_layer_ok(layer)) return 2 * (int64_t)(wide_fk(layer->Fp) / 32) * WIDE_STAGE;   // forward + backward layouts
     if (!tile_plan_ok(plan) || !tile_layer_ok(layer)) return 0;
     return 2 * (int64_t)tile_img_one(tile_fk(layer->Fp));
 }

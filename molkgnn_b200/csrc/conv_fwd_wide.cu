@@ -29,7 +29,8 @@ bool tile_layer_ok(const molkgnn_layer_t* layer);
 
 constexpr int WF_CONS = 512;               // consumer threads
 constexpr int WF_CWARPS = WF_CONS / 32;
-constexpr int WF_THREADS = WF_CONS + 96;   // + ring warp + two MMA warps
+constexpr int WF_RINGS = 3;                // ring warps: node-image stages, stages of the pair's first / second block
+constexpr int WF_THREADS = WF_CONS + 32 * (WF_RINGS + 2);   // + ring warps + two MMA warps
 constexpr int WF_MAXSLOT = 4;
 
 bool wide_layer_ok(const molkgnn_layer_t* layer) {
@@ -40,7 +41,8 @@ bool wide_layer_ok(const molkgnn_layer_t* layer) {
 int64_t wide_img_bytes(const molkgnn_layer_t* layer) {
     WideBlocks wb;
     if (!wide_layer_ok(layer) || !wb.build(layer->L)) return 0;
-    return wide_es_off(wb.nb, wide_fk(layer->Fp)) + ((int64_t)tile_es_f4(layer->L) * 16 + 127) / 128 * 128;
+    const int Fk = wide_fk(layer->Fp);
+    return wide_img_bwd_off(wb.nb, Fk, layer->L) + (int64_t)wb.nb * 8 * Fk * 64;      // forward stages, bond table, backward stages
 }
 
 // ---- operand images ----------------------------------------------------------------------------------------------------
@@ -50,6 +52,7 @@ struct WideXArgs {
     const float* x; const float* xnorm; int ldx, Fp;
     const int* tile_start;
     unsigned char* ximg; int nk2;
+    unsigned char* ximg_bwd; int Fk;      // K-step-major MN-major copy for the backward (tile.cuh), [tile][8 stages]
 };
 
 __global__ void __launch_bounds__(512) k_x_images_wide(const WideXArgs a) {
@@ -73,10 +76,13 @@ __global__ void __launch_bounds__(512) k_x_images_wide(const WideXArgs a) {
     __align__(16) __half2 hi[4];
     __align__(16) __half2 lo[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) tc::split_u2(xv[2 * u], xv[2 * u + 1], hi[u], lo[u]);
+    for (int u = 0; u < 4; ++u) tc::split_u2(xv[2 * u] * WIDE_OPSCALE, xv[2 * u + 1] * WIDE_OPSCALE, hi[u], lo[u]);
     unsigned char* dst = a.ximg + ((size_t)tile * a.nk2 + kk) * WIDE_STAGE + wide_stage_off(v, c);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(dst + WIDE_STAGE / 4) = *reinterpret_cast<const uint4*>(lo);
+    unsigned char* db = a.ximg_bwd + (size_t)tile * 8 * a.Fk * 64 + wide_bstage_off(v, kk * 4 + c, a.Fk);
+    *reinterpret_cast<uint4*>(db) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(db + a.Fk * 32) = *reinterpret_cast<const uint4*>(lo);
 }
 
 int launch_x_images_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
@@ -86,7 +92,9 @@ int launch_x_images_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.x = x; a.xnorm = xnorm; a.ldx = ldx; a.Fp = layer->Fp;
     a.tile_start = plan->tile_start;
     a.ximg = reinterpret_cast<unsigned char*>(ximg);
-    a.nk2 = wide_fk(layer->Fp) / 32;
+    a.Fk = wide_fk(layer->Fp);
+    a.nk2 = a.Fk / 32;
+    a.ximg_bwd = a.ximg + wide_ximg_bwd_off(plan->n_tiles, a.Fk);
     count_launches(1);
     ProfScope prof("x_images", st);
     k_x_images_wide<<<dim3(plan->n_tiles, a.nk2), 512, 0, st>>>(a);
@@ -144,11 +152,14 @@ __global__ void __launch_bounds__(256) k_param_pack_wide(const __grid_constant__
         const int col = 8 * c + 2 * t;
         const float v0 = (src && col < a.Fp) ? src[col] : 0.f;
         const float v1 = (src && col + 1 < a.Fp) ? src[col + 1] : 0.f;
-        tc::split_u2(v0, v1, hi[t], lo[t]);
+        tc::split_u2(v0 * WIDE_OPSCALE, v1 * WIDE_OPSCALE, hi[t], lo[t]);
     }
     unsigned char* dst = a.img + ((size_t)blk * (a.Fk / 32) + (c >> 2)) * WIDE_STAGE + wide_stage_off(row, c & 3);
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(hi);
     *reinterpret_cast<uint4*>(dst + WIDE_STAGE / 4) = *reinterpret_cast<const uint4*>(lo);
+    unsigned char* db = a.img + wide_img_bwd_off(a.wb.nb, a.Fk, a.L) + (size_t)blk * 8 * a.Fk * 64 + wide_bstage_off(row, c, a.Fk);
+    *reinterpret_cast<uint4*>(db) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(db + a.Fk * 32) = *reinterpret_cast<const uint4*>(lo);
 }
 
 int launch_param_pack_wide(const molkgnn_layer_t* layer, cudaStream_t st) {
@@ -204,7 +215,7 @@ __device__ __forceinline__ void wf_dump(float* dump, uint32_t tmem, int buf, int
     for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(v[i]));
     float* dst = dump + (size_t)(cb * 32) * 128 + q * 32 + lane;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]);
+    for (int i = 0; i < 32; ++i) dst[i * 128] = __uint_as_float(v[i]) * (1.0f / (WIDE_OPSCALE * WIDE_OPSCALE));   // exact
 }
 
 template <int D> __device__ __forceinline__ uint32_t wf_perm_code_rt(int p) {
@@ -313,7 +324,7 @@ __device__ __forceinline__ void wf_dup_flags(const float* rows, int ld, int F, c
 }
 
 #ifdef MK_PHASE_CLOCKS
-__device__ unsigned long long g_ph_wfwd[48];     // [0..15] consumer thread 0, [16..31] ring lane, [32..47] MMA lane (warp 0)
+__device__ unsigned long long g_ph_wfwd[48];     // [0..15] consumer thread 0, [16..31] ring lane of block 2 g, [32..47] MMA lane (warp 0)
 #endif
 
 template <bool FORCED>
@@ -324,7 +335,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_conv_fwd_wide(const __grid_co
     __shared__ uint32_t tslot;
     __shared__ WFDeg s_deg[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    MK_PH_DECL(tid == 0 || tid == WF_CONS || tid == WF_CONS + 32)
+    MK_PH_DECL(tid == 0 || tid == WF_CONS + 32 || tid == WF_CONS + 32 * WF_RINGS)
     if (tid == 0) {
         tc::mbar_init(&bar_meta[0], 1); tc::mbar_init(&bar_meta[1], 1); tc::mbar_init(&bar_eh, 1);
         for (int i = 0; i < 4; ++i) { tc::mbar_init(&bar_mma[i], 1); tc::mbar_init(&bar_tfree[i], 1); }
@@ -353,42 +364,42 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_conv_fwd_wide(const __grid_co
     unsigned char* ringB = smem + a.sm_ringB;
     unsigned char* ringA = smem + a.sm_ringA;        // warp W's ring at + W * nA stages
 
-    if (warp == WF_CWARPS) {
-        // ================= ring warp =================
+    if (warp >= WF_CWARPS && warp < WF_CWARPS + WF_RINGS) {
+        // ================= ring warps: one per ring (issuing a bulk copy costs its thread ~300 cycles when many are in flight:
+        // one thread for all three rings was the bottleneck of the kernel) =================
+        const int R = warp - WF_CWARPS;                   // 0: node-image stages, 1 / 2: stages of block 2 g / 2 g + 1
         if (lane == 0) {
-            uint32_t qB = 0, qA[2] = {0u, 0u};
+            uint32_t q = 0;
             for (int wk = 0; wk < walk.cnt; ++wk) {
                 const unsigned char* xsrc = a.ximg + (size_t)walk.tile(wk) * nk2 * WIDE_STAGE;
-                for (int g = 0; g < ng; ++g)
-                    for (int kk = 0; kk < nk2; ++kk) {
-                        {
-                            const uint32_t slot = qB % (uint32_t)a.nB, use = qB / (uint32_t)a.nB;
+                for (int g = 0; g < ng; ++g) {
+                    const int blk = 2 * g + (R - 1);
+                    if (R > 0 && blk >= nb) continue;
+                    for (int kk = 0; kk < nk2; ++kk, ++q) {
+                        if (R == 0) {
+                            const uint32_t slot = q % (uint32_t)a.nB, use = q / (uint32_t)a.nB;
                             MK_PH(0);
                             tc::mbar_wait(&bar_Bfree[slot], (use & 1u) ^ 1u);
-                            MK_PH(1);                                     // ring: waiting for a free node-image stage
+                            MK_PH(1);                                     // ring: waiting for a free stage
                             mbar_expect_tx(&bar_Bfull[slot], WIDE_STAGE);
                             bulk_g2s(ringB + (size_t)slot * WIDE_STAGE, xsrc + (size_t)kk * WIDE_STAGE, WIDE_STAGE, &bar_Bfull[slot]);
-                            ++qB;
-                        }
-#pragma unroll
-                        for (int w = 0; w < 2; ++w) {
-                            const int blk = 2 * g + w;
-                            if (blk >= nb) continue;
-                            const uint32_t slot = qA[w] % (uint32_t)a.nA, use = qA[w] / (uint32_t)a.nA;
+                        } else {
+                            const int w = R - 1;
+                            const uint32_t slot = q % (uint32_t)a.nA, use = q / (uint32_t)a.nA;
                             MK_PH(0);
                             tc::mbar_wait(&bar_Afree[w][slot], (use & 1u) ^ 1u);
-                            MK_PH(2);                                     // ring: waiting for a free kernel-block stage
+                            MK_PH(1);
                             mbar_expect_tx(&bar_Afull[w][slot], WIDE_STAGE);
                             bulk_g2s(ringA + (size_t)(w * a.nA + (int)slot) * WIDE_STAGE,
                                      a.img + ((size_t)blk * nk2 + kk) * WIDE_STAGE, WIDE_STAGE, &bar_Afull[w][slot]);
-                            ++qA[w];
                         }
                     }
+                }
             }
         }
-    } else if (warp > WF_CWARPS) {
+    } else if (warp >= WF_CWARPS + WF_RINGS) {
         // ================= MMA warps: warp W issues block 2 g + W of every pair g =================
-        const int W = warp - (WF_CWARPS + 1);
+        const int W = warp - (WF_CWARPS + WF_RINGS);
         if (lane == 0) {
             uint32_t qB = 0, qA = 0, use_t[2] = {0u, 0u};
             for (int wk = 0; wk < walk.cnt; ++wk) {
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(WF_THREADS, 1) k_conv_fwd_wide(const __grid_co
     tc::fence_before_sync();
     __syncthreads();
 #ifdef MK_PHASE_CLOCKS
-    MK_PH_FLUSH(g_ph_wfwd + (tid == 0 ? 0 : tid == WF_CONS ? 16 : 32));
+    MK_PH_FLUSH(g_ph_wfwd + (tid == 0 ? 0 : tid == WF_CONS + 32 ? 16 : 32));
 #endif
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }

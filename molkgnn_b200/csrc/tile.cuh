@@ -72,6 +72,10 @@ __host__ __device__ inline int tile_es_f4(const int* L) { return 2 * (L[0] + 2 *
 // (K-major UMMA operand per K step: LBO = 128, SBO = 256).
 constexpr int WIDE_MAXB = 16;
 constexpr int WIDE_STAGE = 16384;
+// Both operands of the wide kernels are multiplied by 2^4 before the (hi, lo) split: the entries of a normalised 440-feature row
+// are ~0.05, whose fp16 remainder is a subnormal (absolute error 2^-25 = 2^-20.7 relative); scaled, the split keeps 4 more bits.
+// The accumulators then carry 2^8 (forward: both operands scaled) or 2^4 (backward: one), removed exactly in the epilogues.
+constexpr float WIDE_OPSCALE = 16.0f;
 struct WideBlocks {
     int nb;
     int d[WIDE_MAXB], k0[WIDE_MAXB], nk[WIDE_MAXB];
@@ -102,6 +106,18 @@ __host__ __device__ inline uint32_t wide_stage_off(int row, int c) {
 }
 // kernel-block images [block][stage], then the bond-support table
 __host__ __device__ inline int64_t wide_es_off(int nb, int Fk) { return (int64_t)nb * (Fk / 32) * WIDE_STAGE; }
+// Backward images (conv_bwd_wide.cu) behind them: the same 128-row operands as MN-major UMMA operands in K-step-major order --
+// stage ks = rows 16 ks .. 16 ks + 15: [hi | lo][2 row groups][Fk / 8 chunks][8 rows][8 elements] = Fk * 64 bytes, 8 stages per
+// operand (LBO = Fk / 8 * 128: next row group, SBO = 128: next 8-column chunk).
+__host__ __device__ inline int64_t wide_img_bwd_off(int nb, int Fk, const int* L) {
+    return wide_es_off(nb, Fk) + ((int64_t)tile_es_f4(L) * 16 + 127) / 128 * 128;
+}
+__host__ __device__ inline int64_t wide_ximg_bwd_off(int n_tiles, int Fk) { return (int64_t)n_tiles * (Fk / 32) * WIDE_STAGE; }
+// byte offset of (row, 8-column chunk c8) inside a 128-row backward operand; the lo half lies Fk * 32 behind the hi half
+__host__ __device__ inline uint32_t wide_bstage_off(int row, int c8, int Fk) {
+    return (uint32_t)(row >> 4) * (uint32_t)(Fk * 64) + (uint32_t)((row >> 3) & 1) * (uint32_t)(Fk >> 3) * 128u + (uint32_t)c8 * 128u +
+           (uint32_t)(row & 7) * 16u;
+}
 
 // Images in global memory: kernel blocks [block][hi | lo]; node tiles [tile][hi | lo].  v = hi + lo, BOTH halves unscaled
 // (lo is usually an fp16 subnormal, which tcgen05 honours): one fp32 accumulator receives hi*hi + lo*hi + hi*lo.
