@@ -340,6 +340,7 @@ struct BwdTileArgs {
     int gstride, dxcol;                // TMEM columns: G of block bi at bi * gstride, dxh at dxcol
     int nimg;                          // kernel-block image buffers in shared memory (1..4)
     int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
+    int gflush;                        // tiles per accumulation chunk of the G accumulators (see g_flush in k_conv_bwd_tile)
     int buf_bytes;
     int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
     // pipelined kernel (k_conv_bwd_pipe): ring of K-step stages, two Wt buffers, two tile buffers [meta | coef | arg-max]
@@ -523,6 +524,55 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     MK_PH(0);                                             // prologue
     int cur = 0, use = 0;
     bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
+    // Kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks, tensor memory ->
+    // the CTA's partial copy.  The tensor core TRUNCATES every accumulate (measured: against the fp32 SIMT backward the sums come
+    // out smaller in magnitude, the error growing with the batch: 4e-6 at 6 tiles per CTA, 5e-5 at 96), so the accumulators are
+    // flushed every `gflush` tiles -- chains of <= gflush * 24 MMAs -- and the chunks are added in fp32 (round to nearest) by
+    // fire-and-forget reductions; every element has one writer thread, the order of its reductions is program order.
+    auto g_flush = [&](bool add, bool valid) {
+        for (int bi = 0; bi < a.nbl; ++bi) {
+            const int blk = a.blist[bi];
+            const int row = q * 32 + lane;
+            int d = 0, slot = 0, kk = 0, L = 0;
+            for (int si = 0; si < a.tb.nseg[blk]; ++si) {
+                const TileSeg sg = a.tb.seg[blk][si];
+                const int r = row - sg.rowbase;
+                if (r >= 0 && r < sg.nk * (sg.d + 1)) { d = sg.d; slot = r / sg.nk; kk = sg.k0 + r % sg.nk; L = a.L[sg.d - 1]; }
+            }
+            const int f0 = cpart * 32;
+            if (f0 < a.Fk) {
+                uint32_t u[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) u[i] = 0u;
+                if (valid) {               // a CTA that saw no tile never ran an MMA: its accumulators are undefined, its sums zero
+                    const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * a.gstride + f0);
+                    tc::tmem_ld16(taddr, u);
+                    if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
+                    tc::tmem_ld_wait();
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(u[i]));
+                if (d > 0) {
+                    const int rows_x = (d + 1) * L;
+                    float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
+                    const float sc2 = valid ? scale : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (f0 + i + 4 <= a.Fp) {
+                            if (add) {
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) atomicAdd(part + f0 + i + c, __uint_as_float(u[i + c]) * sc2);
+                            } else {
+                                st4(part + f0 + i, make_float4(__uint_as_float(u[i]) * sc2, __uint_as_float(u[i + 1]) * sc2,
+                                                               __uint_as_float(u[i + 2]) * sc2, __uint_as_float(u[i + 3]) * sc2));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    };
+    int nflushed = 0;
 
     for (int wk = 0; wk < walk.cnt; ++wk) {
         const int tile = walk.tile(wk);
@@ -741,47 +791,18 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         tc::fence_before_sync();
         __syncthreads();                 // Jacobian scratch, TMEM dxh and this tile's buffer are free again
         MK_PH(8);                                         // dxh epilogue
+        if ((wk + 1) % a.gflush == 0 && wk + 1 < walk.cnt) {      // end of an accumulation chunk, more tiles follow
+            tc::fence_after_sync();
+            g_flush(nflushed > 0, true);
+            ++nflushed;
+            fresh = true;
+            tc::fence_before_sync();
+            __syncthreads();
+            MK_PH(9);
+        }
         cur ^= 1;
     }
-    // ---- kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks ----
-    for (int bi = 0; bi < a.nbl; ++bi) {
-        const int blk = a.blist[bi];
-        const int row = q * 32 + lane;
-        int d = 0, slot = 0, kk = 0, L = 0;
-        for (int si = 0; si < a.tb.nseg[blk]; ++si) {
-            const TileSeg sg = a.tb.seg[blk][si];
-            const int r = row - sg.rowbase;
-            if (r >= 0 && r < sg.nk * (sg.d + 1)) { d = sg.d; slot = r / sg.nk; kk = sg.k0 + r % sg.nk; L = a.L[sg.d - 1]; }
-        }
-        const int f0 = cpart * 32;
-        if (f0 < a.Fk) {
-            uint32_t u[32];
-            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(bi * a.gstride + f0);
-            tc::tmem_ld16(taddr, u);
-            if (f0 + 16 < a.Fk) tc::tmem_ld16(taddr + 16, u + 16);
-            else {
-#pragma unroll
-                for (int i = 16; i < 32; ++i) u[i] = 0u;
-            }
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(u[i]));
-            if (d > 0) {
-                const int rows_x = (d + 1) * L;
-                float* part = a.partials + a.part_off[d - 1] + ((size_t)blockIdx.x * rows_x + (size_t)slot * L + kk) * a.FW;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (f0 + i + 4 <= a.Fp) {
-                        // a CTA that saw no tile never ran an MMA: its accumulators are undefined, its partial sums zero
-                        const float sc2 = my_tiles > 0 ? scale : 0.f;
-                        st4(part + f0 + i, my_tiles > 0 ? make_float4(__uint_as_float(u[i]) * sc2, __uint_as_float(u[i + 1]) * sc2,
-                                                                      __uint_as_float(u[i + 2]) * sc2, __uint_as_float(u[i + 3]) * sc2)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f));
-                    }
-                }
-            }
-        }
-    }
+    g_flush(nflushed > 0, my_tiles > 0);
     tc::fence_before_sync();
     __syncthreads();
     MK_PH(9);                                             // G partial sums -> global
@@ -1463,6 +1484,10 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         if (pa.nstages < 6) use_pipe = false;                 // two rings of >= 3 stages
         poff += (int64_t)std::max(pa.nstages, 0) * pa.stage_bytes;
     }
+    static int s_gflush = -1;
+    if (s_gflush < 0) { const char* e = getenv("MOLKGNN_BWD_GFLUSH"); s_gflush = e ? std::max(1, atoi(e)) : 6; }
+    a.gflush = s_gflush;
+    if ((plan->n_tiles + grid - 1) / grid > s_gflush) use_pipe = false;      // the pipelined variant keeps ONE chain per CTA
     if (!do_launch) return 1;
     MK_REQUIRE((reinterpret_cast<uintptr_t>(grad) & 15) == 0 && (reinterpret_cast<uintptr_t>(coef) & 15) == 0,
                "conv_bwd_tile: grad and coef must be 16-byte aligned");
