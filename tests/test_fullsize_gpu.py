@@ -243,3 +243,64 @@ def test_wide_config_matches_oracle():
     net = mk.MolGCN(5, *LW, *LW, x_dim=28, p_dim=3, edge_attr_dim=7)
     wout = torch.randn(b["x"].shape[0], sum(LW))
     _oracle_parity(net, b, t, wout, "configs[2] wide, 256 molecules")
+
+
+def _agree(g1, g0, nl):
+    for n in g0:
+        if n.rsplit(".", 1)[-1] in GRAD_NAMES[:3]:
+            assert _rel(g1[n], g0[n]) < TOL, (n, _rel(g1[n], g0[n]))
+    for li in range(nl):
+        for d in range(4):
+            trip = [f"layers.{li}.trainable_kernelconv_set.{d}.{w}" for w in GRAD_NAMES[3:]]
+            ref = torch.stack([g0[k] for k in trip])
+            got = torch.stack([g1[k] for k in trip])
+            assert float((got - ref).abs().max()) <= 1e-4 * max(float(ref.abs().max()), 1e-6), (li, d)
+
+
+def test_long_accumulation_chains_do_not_drift():
+    """The tensor core truncates every accumulate, so ONE TMEM accumulator summed over all tiles of a persistent CTA drifts with
+    the batch size (kernel-parameter gradients were 5e-5 off at 65536 molecules).  16384 molecules = 24 tiles per CTA: the
+    accumulators are flushed every 6 tiles (conv_bwd_tile.cu g_flush) and the gradients stay within 1e-5 of the fp32 SIMT
+    backward (same forward, same arg-max: only the backward differs)."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    parts = [synth.make_batch(4096, seed=70 + i) for i in range(4)]
+    off, ei = 0, []
+    for p in parts:
+        ei.append(p["edge_index"] + off)
+        off += p["x"].shape[0]
+    t = {"x": torch.from_numpy(np.concatenate([p["x"] for p in parts])).to(DEV),
+         "p": torch.from_numpy(np.concatenate([p["p"] for p in parts])).to(DEV),
+         "edge_attr": torch.from_numpy(np.concatenate([p["edge_attr"] for p in parts])).to(DEV),
+         "edge_index": torch.from_numpy(np.concatenate(ei, axis=1)).to(DEV)}
+    torch.manual_seed(70)
+    net = mk.MolGCN(3, *L, *L, x_dim=28, p_dim=3, edge_attr_dim=7).to(DEV)
+    wout = torch.randn(t["x"].shape[0], sum(L), device=DEV)
+    h1, gx1, g1, _ = _run(net, t, wout, paths=(2, 1))          # per-layer tile forward, tensor-core backward
+    h0, gx0, g0, _ = _run(net, t, wout, paths=(2, 0))          # same forward, fp32 SIMT backward
+    assert torch.equal(h1, h0)
+    assert _rel(gx1, gx0) < TOL
+    _agree(g1, g0, 3)
+
+
+def test_wide_backward_chunked_accumulation_matches_simt():
+    """configs[2] model at 1536 molecules (~330 tiles: every CTA of the block-major kernel-gradient launch sees several
+    accumulation chunks, every tile of the input-gradient launch four): tensor-core wide backward (conv_bwd_wide.cu) against
+    the fp32 SIMT backward on the same forward."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth
+    from molkgnn_b200 import functional as Fn
+    LW = (40, 80, 120, 200)
+    b = synth.make_batch(1536, seed=11)
+    t = {k: torch.from_numpy(b[k]).to(DEV) for k in ("x", "p", "edge_index", "edge_attr")}
+    torch.manual_seed(11)
+    net = mk.MolGCN(3, *LW, *LW, x_dim=28, p_dim=3, edge_attr_dim=7).to(DEV)
+    wout = torch.randn(t["x"].shape[0], sum(LW), device=DEV)
+    pc0 = Fn.path_counts()
+    h1, gx1, g1, _ = _run(net, t, wout, paths=(3, 1))
+    pc1 = Fn.path_counts()
+    assert pc1["fwd_tile"] - pc0["fwd_tile"] == 3 and pc1["bwd_tile"] - pc0["bwd_tile"] == 3, "wide tensor-core kernels did not run"
+    h0, gx0, g0, _ = _run(net, t, wout, paths=(3, 0))
+    assert torch.equal(h1, h0)
+    assert _rel(gx1, gx0) < TOL
+    _agree(g1, g0, 3)
