@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=None, help="synthetic-batch seed (default 1000 * rank, SURVEY 8(d))")
+    ap.add_argument("--wide", action="store_true",
+                    help="BASELINE configs[2]: wide kernel sets 40/80/120/200 per degree, 5 layers (the streamed-operand tcgen05 kernels)")
     ap.add_argument("--forward-only", action="store_true",
                     help="BASELINE configs[4] (inference sweep): bucket pass + forward under torch.no_grad; e2e returns h [N,K] to the host")
     return ap.parse_args()
@@ -159,11 +161,13 @@ def run_reference(args):
 
 
 def workload_config(B, fwd_only=False):
-    which = ("BASELINE configs[4] (inference sweep): MolGCN conv stack forward only" if fwd_only else
+    which = ("BASELINE configs[2] (wide kernel sets): MolGCN conv stack " + ("forward only" if fwd_only else "fwd+bwd")
+             if tuple(L_BASE) != (10, 20, 30, 50) else
+             "BASELINE configs[4] (inference sweep): MolGCN conv stack forward only" if fwd_only else
              "BASELINE configs[1]: MolGCN conv stack fwd+bwd" if B == 4096 else
              "BASELINE configs[3] (one GPU's share of the sharded training step): MolGCN conv stack fwd+bwd" if B == 65536 else
              "MolGCN conv stack fwd+bwd")
-    return {"workload": f"{which}, {NUM_LAYERS} layers, kernels 10/20/30/50 "
+    return {"workload": f"{which}, {NUM_LAYERS} layers, kernels {'/'.join(str(v) for v in L_BASE)} "
                         f"(1-hop and N-hop), node_dim 28, edge_dim 7, batch {B} synthetic 3D molecules per GPU "
                         "(18-32 atoms, degrees 1-4), GPU degree-bucket pass included",
             "molecules_per_gpu": B, "layers": NUM_LAYERS, "kernels": list(L_BASE), "forward_only": bool(fwd_only),
@@ -218,6 +222,9 @@ class ClockSampler(object):
 
 def main():
     args = parse()
+    if args.wide:                                # configs[2]: the same protocol on the wide model
+        global L_BASE, NUM_LAYERS
+        L_BASE, NUM_LAYERS = (40, 80, 120, 200), 5
     if args.impl == "reference":
         return run_reference(args)
 

@@ -94,12 +94,30 @@ struct WBSeq {
     }
 };
 
-// 32 x 32 fp32 transpose through a per-warp shared-memory tile: lane r writes its 32 columns, then reads row i / column lane
+// Accumulation chunks (see k_conv_bwd_wide): position of a unit = block index inside the tile (phase X) / unit index (phase G);
+// the chunks of column half h are shifted by h * flush / 2 positions, so that the two halves are never flushed together
+// (while one half leaves tensor memory, the other half's MMA warp keeps the tensor cores busy).
+__device__ __forceinline__ bool wb_fresh(int flush, int pos, int h) { return pos == 0 || (pos + h * (flush >> 1)) % flush == 0; }
+__device__ __forceinline__ bool wb_chunk_end(int flush, int pos, int last, int h) { return pos == last || (pos + 1 + h * (flush >> 1)) % flush == 0; }
+__device__ __forceinline__ bool wb_chunk_add(int flush, int pos, int h) { return (pos + h * (flush >> 1)) / flush > 0; }
+
+// 32 x 32 fp32 transpose through a per-warp shared-memory tile in 16-byte units: lane r writes its 32 columns as 8 float4 (the
+// chunk index XOR-swizzled by r & 7: conflict free per quarter warp), then lane l reads the float4 (row 4 i + l / 8, chunk l & 7):
+// a warp instruction covers 4 rows x 128 contiguous bytes of the result.
 __device__ __forceinline__ void wb_tile_put(float* tb, int lane, const uint32_t* u, float scale) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) tb[lane * 32 + (i ^ lane)] = __uint_as_float(u[i]) * scale;
+    for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(tb + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_float4(__uint_as_float(u[4 * j]) * scale, __uint_as_float(u[4 * j + 1]) * scale, __uint_as_float(u[4 * j + 2]) * scale,
+                        __uint_as_float(u[4 * j + 3]) * scale);
 }
-__device__ __forceinline__ float wb_tile_get(const float* tb, int lane, int row) { return tb[row * 32 + (lane ^ row)]; }
+__device__ __forceinline__ float4 wb_tile_get4(const float* tb, int row, int j) {
+    return *reinterpret_cast<const float4*>(tb + row * 32 + ((j ^ (row & 7)) << 2));
+}
+// fire-and-forget 16-byte reduction (red.global.add.v4.f32, sm_90+): the L2 does the four round-to-nearest adds
+__device__ __forceinline__ void wb_red4(float* dst, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 
 #ifdef MK_PHASE_CLOCKS
 __device__ unsigned long long g_ph_wbwd[2][48];   // [phase][0..15 consumer thread 0 | 16..31 ring lane | 32..47 MMA lane (warp 0)]
@@ -107,7 +125,7 @@ __device__ unsigned long long g_ph_wbwd[2][48];   // [phase][0..15 consumer thre
 
 __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_constant__ WideBwdArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t bar_cp[2], bar_wt[2], bar_mma[2], bar_full[WB_MAXSTAGES], bar_free[WB_MAXSTAGES];
+    __shared__ uint64_t bar_cp[2], bar_wt[2], bar_mma[2], bar_fl[2], bar_full[WB_MAXSTAGES], bar_free[WB_MAXSTAGES];
     __shared__ uint32_t tslot;
     __shared__ unsigned char s_lut[4][12];               // packed permutation codes (2 bits per j) per degree
     __shared__ float s_alpha[4], s_beta[4], s_gmax;
@@ -117,7 +135,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
     MK_PH_DECL(tid == 0 || tid == WB_CONS || tid == WB_CONS + 32)
     if (tid == 0) {
         tc::mbar_init(&bar_cp[0], 1); tc::mbar_init(&bar_cp[1], 1);
-        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_wt[i], 1); tc::mbar_init(&bar_mma[i], (uint32_t)NI); }
+        for (int i = 0; i < 2; ++i) { tc::mbar_init(&bar_wt[i], 1); tc::mbar_init(&bar_mma[i], (uint32_t)NI); tc::mbar_init(&bar_fl[i], 1); }
         for (int i = 0; i < WB_MAXSTAGES; ++i) { tc::mbar_init(&bar_full[i], 1); tc::mbar_init(&bar_free[i], (uint32_t)NI); }
         tc::fence_mbar_init();
     }
@@ -211,7 +229,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
         // ================= MMA warps: warp W issues the column half W =================
         const int W = warp - (WB_CWARPS + 1);
         if (lane == 0 && W < NI) {
-            uint32_t q = 0;
+            uint32_t q = 0, nfl = 0;
             const int ncol = W == NI - 1 ? a.Fk - W * a.Nh : a.Nh;
             const uint32_t dcol = tmem + (uint32_t)(W * a.Nh);
             const uint32_t boff = (uint32_t)(W * (a.Nh >> 3)) * 128u;      // first 8-column chunk of this half inside a row group
@@ -226,11 +244,16 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
                 const uint32_t whi = tc::smem_u32(wt + (size_t)(u & 1) * 2 * WB_WT_ONE), wlo = whi + WB_WT_ONE;
                 int nks;
                 bool fresh;
-                if (a.phase == 0) { nks = ((a.wb.nk[un.blk] * (a.wb.d[un.blk] + 1) + 15) >> 4); fresh = un.blk % a.flush == 0; }
+                if (a.phase == 0) { nks = ((a.wb.nk[un.blk] * (a.wb.d[un.blk] + 1) + 15) >> 4); fresh = wb_fresh(a.flush, un.blk, W); }
                 else {
                     const int nn = __ldg(a.tile_start + un.tile + 1) - __ldg(a.tile_start + un.tile);
                     nks = max(1, (nn + 15) >> 4);
-                    fresh = u % a.flush == 0;
+                    fresh = wb_fresh(a.flush, u, W);
+                }
+                if (fresh && u > 0) {                                 // the previous chunk of this half has left tensor memory
+                    tc::mbar_wait(&bar_fl[W], nfl & 1u);
+                    ++nfl;
+                    tc::fence_after_sync();
                 }
                 for (int ks = 0; ks < nks; ++ks, ++q) {
                     const uint32_t slot = q % (uint32_t)NS, use = q / (uint32_t)NS;
@@ -285,14 +308,13 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
         // MMAs per chain, as in conv_bwd_tile.cu -- into the fp32 result in global memory (round-to-nearest adds; the rows are
         // L2 resident between the flushes of a tile / of a CTA's partial copy).
         // end_of_chunk(u): unit u is the last of its chunk; flush_unit(u): accumulator -> global (first chunk: store, later: add).
-        auto end_of_chunk = [&](int u) {
-            if (a.phase == 0) { const int blk = u % a.wb.nb; return (blk + 1) % a.flush == 0 || blk == a.wb.nb - 1; }
-            return (u + 1) % a.flush == 0 || u == seq.nunits - 1;
-        };
-        auto flush_unit = [&](int u) {
+        auto upos = [&](int u) { return a.phase == 0 ? u % a.wb.nb : u; };
+        const int last_pos = a.phase == 0 ? a.wb.nb - 1 : seq.nunits - 1;
+        auto flush_unit = [&](int u, int h) {
             float* tb = reinterpret_cast<float*>(wt + (size_t)(u & 1) * 2 * WB_WT_ONE) + warp * 1024;   // the unit's Wt buffer is free: transposition buffer
             const WBUnit pu = seq.at(u);
-            const bool add = a.phase == 0 ? (pu.blk / a.flush) > 0 : (u / a.flush) > 0;
+            const bool add = wb_chunk_add(a.flush, upos(u), h);
+            const int cbeg = h * (a.Nh >> 5), cend = (h == NI - 1 ? a.Fk : (h + 1) * a.Nh) >> 5;      // 32-column chunks of the half
             int t0p = 0, nnp = 0, nk = 1, k0 = 0, L = 0, rows = 0;
             float* part = nullptr;
             if (a.phase == 0) { t0p = __ldg(a.tile_start + pu.tile); nnp = __ldg(a.tile_start + pu.tile + 1) - t0p; }
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
                 nk = a.wb.nk[pu.blk]; k0 = a.wb.k0[pu.blk]; L = a.L[d - 1]; rows = nk * (d + 1);
                 part = a.partials + a.part_off[d - 1] + (size_t)seq.rank * (d + 1) * L * a.FW;
             }
-            for (int c = cpart; c * 32 < a.Fk; c += 4) {
+            for (int c = cbeg + cpart; c < cend; c += 4) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
                 tc::tmem_ld16(taddr, v);
@@ -309,30 +331,20 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
                 tc::tmem_ld_wait();
                 wb_tile_put(tb, lane, v, scale);
                 __syncwarp();
-                const int f = c * 32 + lane;
+                // Later chunks ADD with fire-and-forget reductions (the L2 does the round-to-nearest adds, no load latency on the SM);
+                // every element has ONE writer thread and the reductions of a thread to one address arrive in program order, so
+                // the result is deterministic.
+                const int j = lane & 7, f = c * 32 + 4 * j;
                 if (f < a.Fp) {
-                    // 32 rows of 128 contiguous bytes per warp.  Later chunks ADD with fire-and-forget reductions (red.global.add.f32:
-                    // the L2 does the round-to-nearest add, no load latency on the SM); every element has ONE writer thread, and
-                    // the reductions of a thread to one address arrive in program order, so the result is deterministic.
-                    if (a.phase == 0) {
-                        const int rmax = min(32, nnp - q * 32);
-                        float* dst = a.gx + (size_t)(t0p + q * 32) * a.ldgx + f;
-                        if (add) {
-#pragma unroll 8
-                            for (int r = 0; r < rmax; ++r) atomicAdd(dst + (size_t)r * a.ldgx, wb_tile_get(tb, lane, r));
-                        } else {
-#pragma unroll 8
-                            for (int r = 0; r < rmax; ++r) __stcg(dst + (size_t)r * a.ldgx, wb_tile_get(tb, lane, r));
-                        }
-                    } else {
-                        const int rmax = min(32, rows - q * 32);
-                        const int* ro = s_rowoff + q * 32;
-                        if (add) {
-#pragma unroll 8
-                            for (int r = 0; r < rmax; ++r) atomicAdd(part + ro[r] + f, wb_tile_get(tb, lane, r));
-                        } else {
-#pragma unroll 8
-                            for (int r = 0; r < rmax; ++r) __stcg(part + ro[r] + f, wb_tile_get(tb, lane, r));
+                    const int rmax = a.phase == 0 ? min(32, nnp - q * 32) : min(32, rows - q * 32);
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + (lane >> 3);
+                        if (r < rmax) {
+                            const float4 val = wb_tile_get4(tb, r, j);
+                            float* dst = a.phase == 0 ? a.gx + (size_t)(t0p + q * 32 + r) * a.ldgx + f : part + s_rowoff[q * 32 + r] + f;
+                            if (add) wb_red4(dst, val);
+                            else __stcg(reinterpret_cast<float4*>(dst), val);
                         }
                     }
                 }
@@ -415,17 +427,26 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
             tc::fence_async_smem();
             wb_consumer_sync();
             MK_PH(5);
-            // ---- the previous unit closed an accumulation chunk: its MMAs must be done, then the accumulator leaves tensor memory
-            // (before this unit's first MMA overwrites it) ----
-            if (u > 0 && end_of_chunk(u - 1)) {
-                if (warp == 0) tc::mbar_wait(&bar_mma[(u - 1) & 1], (uint32_t)((u - 1) >> 1) & 1u);
-                wb_consumer_sync();
-                tc::fence_after_sync();
-                MK_PH(7);                                 // waiting for the chunk's last MMAs
-                flush_unit(u - 1);
-                MK_PH(6);                                 // flush
+            if (tid == 0) wb_arrive(&bar_wt[u & 1]);      // the MMA warps may start this unit (a half whose chunk ended: after its flush)
+            // ---- the previous unit closed an accumulation chunk of a column half: its MMAs must be done, then that half of the
+            // accumulator leaves tensor memory; the other half's MMA warp is already working on this unit ----
+            if (u > 0) {
+                bool e[2];
+                e[0] = wb_chunk_end(a.flush, upos(u - 1), last_pos, 0);
+                e[1] = NI > 1 && wb_chunk_end(a.flush, upos(u - 1), last_pos, 1);
+                if (e[0] || e[1]) {
+                    if (warp == 0) tc::mbar_wait(&bar_mma[(u - 1) & 1], (uint32_t)((u - 1) >> 1) & 1u);
+                    wb_consumer_sync();
+                    tc::fence_after_sync();
+                    MK_PH(7);                             // waiting for the chunk's last MMAs
+                    for (int h = 0; h < NI; ++h)
+                        if (e[h]) {
+                            flush_unit(u - 1, h);
+                            if (tid == 0) wb_arrive(&bar_fl[h]);
+                        }
+                    MK_PH(6);                             // flush
+                }
             }
-            if (tid == 0) wb_arrive(&bar_wt[u & 1]);      // the MMA warps may start this unit
         }
         // ---- tail: the last unit's MMAs, then the accumulator that is still in tensor memory ----
         if (seq.nunits > 0) {
@@ -434,7 +455,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
             tc::fence_after_sync();
         }
         MK_PH(1);
-        if (seq.nunits > 0) flush_unit(seq.nunits - 1);
+        if (seq.nunits > 0)
+            for (int h = 0; h < NI; ++h) flush_unit(seq.nunits - 1, h);
         if (a.phase == 1) {
             // one partial copy per CTA of the block.  A CTA without tiles never ran an MMA: its sums are zero.  Bond columns: zeros
             // for the copies >= 1 (copy 0 receives the reduced bond sums from k_wide_bond_reduce)
@@ -608,7 +630,7 @@ int launch_conv_bwd_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.F = layer->F; a.Fp = layer->Fp; a.Fk = wide_fk(layer->Fp);
     a.nh = (a.Fk + 255) / 256;
     if (a.nh > 2) return 0;
-    a.Nh = a.nh == 1 ? a.Fk : ((a.Fk / 2 + 15) / 16 * 16);
+    a.Nh = a.nh == 1 ? a.Fk : ((a.Fk / 2 + 31) / 32 * 32);      // whole 32-column flush chunks per half
     a.stage_bytes = a.Fk * 64;
     a.FW = layer->Fp + EP;
     int cpb[4];
