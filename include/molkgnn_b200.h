@@ -166,11 +166,13 @@ int molkgnn_param_pack(const molkgnn_layer_t* layer, void* stream);
  * weights, signs; bit 1 = operand images of the bucket-order tensor-core forward; bit 2 = kernel-block images of the
  * molecule-tile kernels.  molkgnn_param_pack(layer) == molkgnn_param_pack_layers(layer, 1, 7). */
 int molkgnn_param_pack_layers(const molkgnn_layer_t* layers, int32_t nl, int32_t what, void* stream);
-/* bytes of the fp16 (hi, lo) tensor-core operand images of the whole kernel set used by the tile kernels;
- * 0 if the layer is not eligible (too many kernels per degree for two 128-row blocks per role, or F > 240) */
+/* bytes of the fp16 (hi, lo) tensor-core operand images of the whole kernel set used by the tile kernels: resident-operand
+ * layout for layers of <= 8 kernel blocks and <= 112 features; stage-major (forward) + K-step-major (backward) layouts for WIDE
+ * layers (<= 16 degree-pure blocks, <= 512 features: csrc/conv_fwd_wide.cu, conv_bwd_wide.cu); 0 if neither applies */
 int64_t molkgnn_tile_img_bytes(const molkgnn_layer_t* layer);
 /* Normalised fp16 (hi, lo) images of the activations in tile order, the tensor-core operand of the tile kernels:
- * ximg holds plan->n_tiles records of molkgnn_tile_ximg_bytes() bytes.  Built once per layer, read by forward and backward. */
+ * ximg holds plan->n_tiles records of molkgnn_tile_ximg_bytes() bytes (wide layers: the forward's and the backward's layouts,
+ * all tiles of the first, then all tiles of the second).  Built once per layer, read by forward and backward. */
 int64_t molkgnn_tile_ximg_bytes(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer);
 int molkgnn_tile_ximg_build(const molkgnn_plan_t* plan, const molkgnn_layer_t* layer, const float* x, int32_t ldx,
                             const float* xnorm, void* ximg, void* stream);

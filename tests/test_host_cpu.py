@@ -129,3 +129,33 @@ def test_tile_schedule_model_properties():
             assert load.max() <= rr.max()
             if 0 < r <= G // 2:
                 assert load.max() / load.mean() < 1.03 < rr.max() / rr.mean()
+
+
+def test_tile_image_sizes_for_base_wide_and_oversized_layers():
+    """Host logic of the layer classification (no GPU): the base model takes the resident-operand tile kernels, the configs[2]
+    model the streamed-operand wide kernels (stage-major forward + K-step-major backward images + bond table), a kernel set
+    beyond 16 blocks neither (the bucket-order kernels take it)."""
+    import ctypes as C
+    from molkgnn_b200 import _lib
+
+    def layer(F, L):
+        ly = _lib.Layer()
+        ly.F, ly.Fp, ly.Fe, ly.K = F, (F + 3) // 4 * 4, 7, sum(L)
+        ko = 0
+        for d in range(4):
+            ly.L[d] = L[d]
+            ly.koff[d] = ko
+            ko += L[d]
+        return ly
+
+    lib = _lib.lib()
+    base = lib.molkgnn_tile_img_bytes(C.byref(layer(110, (10, 20, 30, 50))))
+    assert base > 0
+    for F in (28, 440):
+        Fk = (F + 31) // 32 * 32
+        got = lib.molkgnn_tile_img_bytes(C.byref(layer(F, (40, 80, 120, 200))))
+        nb = 8 + 4 + 2 + 1                                         # 25 / 30 / 40 / 40 kernels per 128-row block
+        es = 2 * (40 + 2 * 80 + 3 * 120 + 4 * 200) * 16
+        want = nb * (Fk // 32) * 16384 + (es + 127) // 128 * 128 + nb * 8 * Fk * 64
+        assert got == want, (F, got, want)
+    assert lib.molkgnn_tile_img_bytes(C.byref(layer(440, (400, 800, 1200, 2000)))) == 0
