@@ -527,7 +527,9 @@ static int64_t tcf_configure(const molkgnn_layer_t* layer, int budget, FwdTcArgs
         cenb = std::max(cenb, pl.tc_cen_bytes);
         esb[d - 1] = ((int64_t)d * L * EP * 4 + 127) / 128 * 128;
         const int ds = tcf_ds(d);
-        const int krmax = 128 / ds;
+        // degree 3: a chunk of 3 kernels is loaded as 16 accumulator columns (12 used): the last chunk must end inside the 128
+        // columns of the job, i.e. at most 10 chunks = 30 kernels per range
+        const int krmax = d == 3 ? 30 : 128 / ds;
         const int align = d == 1 ? 8 : d == 2 ? 4 : 2;          // range starts on an 8-row boundary of the image
         const int nr = (L + krmax - 1) / krmax;
         int kr = ((L + nr - 1) / nr + align - 1) / align * align;

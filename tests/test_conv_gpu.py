@@ -460,3 +460,36 @@ def test_mixed_fixed_and_trainable_kernel_sets():
         refs = np.array([float(g[f"grad_trainable_kernelconv_set.{d}.{t}"]) for t in trip])
         got = np.array([getattr(kc, t).grad.item() for t in trip])
         assert np.abs(got - refs).max() <= 1e-4 * max(np.abs(refs).max(), 1e-6), (d, got, refs)
+
+
+@pytest.mark.parametrize("x_dim,L1,LN", [
+    (130, (10, 20, 30, 50), (10, 20, 30, 50)),      # few blocks, one column half (Fk = 160); second layer on the base tile kernels
+    (300, (10, 20, 30, 50), (10, 20, 30, 50)),      # two column halves of 160 columns
+    (500, (3, 5, 7, 9), (4, 6, 8, 10)),             # Fk = 512: the accumulator fills tensor memory
+    (28, (60, 90, 64, 52), (10, 20, 30, 50)),       # 9 uneven blocks (18/17/17, 32/32, 30/30/30, 60), then F = 266 -> halves 160 + 128
+])
+def test_wide_kernels_feature_widths_and_block_shapes(x_dim, L1, LN, fwd_path):
+    """The streamed-operand (wide) kernels on shapes other than configs[2]: feature widths with one and two column halves, a full
+    512-column accumulator, uneven kernel blocks (blocked tile order of the coefficients with a remainder)."""
+    import molkgnn_b200 as mk
+    from molkgnn_b200 import synth, functional
+    b = synth.make_batch(20, seed=61)
+    rng = np.random.default_rng(61)
+    b["x"] = rng.standard_normal((b["x"].shape[0], x_dim)).astype(np.float32)
+    torch.manual_seed(61)
+    net = mk.MolGCN(2, *L1, *LN, x_dim=x_dim, p_dim=3, edge_attr_dim=7)
+    wout = torch.randn(b["x"].shape[0], sum(LN))
+    h_ref, gx_ref, params_ref, auxs = _oracle_run(net, b, wout)
+    net = net.to(DEV)
+    d = _to_dev(b)
+    x = d["x"].clone().requires_grad_(True)
+    forced = [compact_from_kernel_major([None if a is None else a["argmax"] for a in aux], DEV) for aux in auxs]
+    pc0 = functional.path_counts()
+    h = net(x=x, edge_index=d["edge_index"], edge_attr=d["edge_attr"], p=d["p"], save_score=False, argmax_in=forced)
+    assert rel_err(h.detach().cpu(), h_ref) < TOL
+    (h * wout.to(DEV)).sum().backward()
+    pc1 = functional.path_counts()
+    if fwd_path in ("fused", "tile"):
+        assert pc1["fwd_tile"] - pc0["fwd_tile"] == 2 and pc1["bwd_tile"] - pc0["bwd_tile"] == 2, (pc0, pc1)
+    assert rel_err(x.grad.cpu(), gx_ref) < TOL
+    _check_param_grads(net, lambda li, dg, n: params_ref[li][dg][n].grad)
