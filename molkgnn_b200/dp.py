@@ -135,6 +135,11 @@ class GradBucket(object):
         self.oneshot = None
         self.check_every = int(os.environ.get("MOLKGNN_DP_CHECK_EVERY", "64"))
         self._steps = 0
+        # the one-shot kernel is a latency play: every rank reads EVERY rank's copy (world x the bytes of a ring all-reduce), so
+        # large buckets (the wide model: 12.7 MB of kernel gradients) go through NCCL
+        max_bytes = int(os.environ.get("MOLKGNN_DP_ONESHOT_MAX_BYTES", str(4 << 20)))
+        if 4 * self.numel > max_bytes:
+            oneshot = False
         if oneshot and self.world > 1 and dist.is_initialized() and dist.get_backend(group) == "nccl":
             self.oneshot = OneShotAllReduce.create(2 * self.numel + 4096, group)   # room for the native buffer's padding
 
