@@ -572,7 +572,12 @@ static void wide_bwd_partition(const molkgnn_plan_t* plan, const molkgnn_layer_t
         cpb[d] = 0;
         if (!nblk[d]) continue;
         const double pairs = (double)plan->n[d] / std::max(1, plan->n_tiles) * ((double)layer->L[d] / nblk[d]);
-        w[d] = 7000.0 + 6.0 * pairs;                       // ~cycles: clear + MMAs + barriers, scatter per pair
+        static double s_w0 = -1.0, s_w1 = 0.0;             // MOLKGNN_WIDE_GW="fixed,per_pair" overrides the cost model
+        if (s_w0 < 0.0) {
+            s_w0 = 14000.0; s_w1 = 3.0;      // measured: 2.97 ms for the 5 layers of configs[2]; (7000, 6) gave 4.1 ms
+            if (const char* e = getenv("MOLKGNN_WIDE_GW")) { s_w0 = std::max(1.0, atof(e)); const char* c = strchr(e, ','); if (c) s_w1 = atof(c + 1); }
+        }
+        w[d] = s_w0 + s_w1 * pairs;                        // ~cycles per unit (phase clocks): clear + MMAs + flush share + barriers, scatter / chains per pair
         cpb[d] = 1;
     }
     auto used = [&] { int u = 0; for (int d = 0; d < 4; ++d) u += nblk[d] * cpb[d]; return u; };
