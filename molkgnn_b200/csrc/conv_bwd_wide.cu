@@ -282,25 +282,14 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
     } else {
         // ================= consumers =================
         const int q = warp & 3, cpart = warp >> 2;            // TMEM lane quadrant / column part of this warp
-        // thread 0: [metadata | coefficients | arg-max codes] of unit u -> unit buffer u & 1
+        // thread 0: tile metadata of unit u -> unit buffer u & 1.  The unit's coefficients / arg-max codes (one contiguous run of
+        // the blocked tile order, L2 resident: k_coef_tile just wrote them) are read straight from global memory by the scatter --
+        // staging them in shared memory cost the room of a third ring stage, and it is the ring depth that bounds the kernel
         auto issue_unit = [&](int u) {
             const WBUnit un = seq.at(u);
-            const int4 c = __ldg(reinterpret_cast<const int4*>(&a.meta[un.tile].cnt[0]));
-            const int cn[4] = {c.x, c.y, c.z, c.w};
-            const int d = a.wb.d[un.blk];
-            int base = cn[d - 1] * a.wb.k0[un.blk];
-            for (int dd = 1; dd < d; ++dd) base += cn[dd - 1] * a.L[dd - 1];
-            const int np = cn[d - 1] * a.wb.nk[un.blk];
-            unsigned char* ub = smem + a.sm_unit + (size_t)(u & 1) * a.unit_bytes;
             uint64_t* bar = &bar_cp[u & 1];
-            const size_t fa = (size_t)un.tile * a.stride + base, ba = (size_t)un.tile * a.stride_am + base;
-            const uint32_t cb = (uint32_t)((((fa & 3) + np) * 4 + 15) & ~15), ab = (uint32_t)(((ba & 15) + np + 15) & ~15);
-            mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + (np > 0 ? cb + ab : 0u));
-            bulk_g2s(ub, a.meta + un.tile, (uint32_t)sizeof(TileMetaG), bar);
-            if (np > 0) {
-                bulk_g2s(ub + a.ub_a, a.coefT + (fa & ~(size_t)3), cb, bar);
-                bulk_g2s(ub + a.ub_am, a.amT + (ba & ~(size_t)15), ab, bar);
-            }
+            mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG));
+            bulk_g2s(smem + a.sm_unit + (size_t)(u & 1) * a.unit_bytes, a.meta + un.tile, (uint32_t)sizeof(TileMetaG), bar);
         };
         // Accumulation chunks.  The tensor core TRUNCATES every accumulate (measured: the raw sums come out smaller in magnitude by
         // ~2^-24 per tcgen05.mma that added to them), so a chain of 360 (phase X: 15 blocks x 24) or 2000+ (phase G: all tiles of
@@ -378,11 +367,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
             {
                 int base = m.cnt[d - 1] * k0;                 // first pair of the block in the tile's blocked order
                 for (int dd = 1; dd < d; ++dd) base += m.cnt[dd - 1] * a.L[dd - 1];
-                // the bulk copies start at the 16-byte boundary below the block's first coefficient / arg-max byte
-                const int fa = (int)(((size_t)un.tile * a.stride + base) & 3);
-                const int ba = (int)(((size_t)un.tile * a.stride_am + base) & 15);
-                const float* a_s = reinterpret_cast<const float*>(ub + a.ub_a) + fa;
-                const unsigned char* am_s = ub + a.ub_am + ba;
+                const float* a_s = a.coefT + (size_t)un.tile * a.stride + base;
+                const unsigned char* am_s = a.amT + (size_t)un.tile * a.stride_am + base;
                 const float alpha = s_alpha[d - 1], beta = s_beta[d - 1];
                 const float rnk = 1.0f / (float)nk;
                 const int np = m.cnt[d - 1] * nk;
@@ -391,8 +377,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
                     const int ni = (int)(((float)p + 0.5f) * rnk);
                     const int kl = p - ni * nk;
                     const int nl_ = m.list[d - 1][ni];
-                    const float av = a_s[p] * rscale;
-                    const uint32_t code = lut[am_s[p] & 0x7f];
+                    const float av = __ldg(a_s + p) * rscale;
+                    const uint32_t code = lut[__ldg(am_s + p) & 0x7f];
                     const uint32_t nw = m.nl[nl_];
                     const uint32_t cr = m.cr[nl_];
                     wbt_store(wtb, d * nk + kl, nl_, av * beta);
@@ -417,8 +403,8 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
                             const int ent = (int)((ch >> (9 * f)) & 0x1ffu);
                             const int nl_ = ent >> 2, j = ent & 3;
                             const int pi = m.lidx[nl_] * nk + kl;
-                            const int s = (lut[am_s[pi] & 0x7f] >> (2 * j)) & 3;
-                            wbt_add(wtb, s * nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (a_s[pi] * rscale) * alpha);
+                            const int s = (lut[__ldg(am_s + pi) & 0x7f] >> (2 * j)) & 3;
+                            wbt_add(wtb, s * nk + kl, (int)((m.nl[nl_] >> (8 * j)) & 0xffu), (__ldg(a_s + pi) * rscale) * alpha);
                         }
                     }
                 }
@@ -660,15 +646,12 @@ int launch_conv_bwd_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     bondP = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(bondP) + 15) & ~(uintptr_t)15);
     if (launch_coef_wide(plan, layer, grad, ldg, grad_mode, argmax, scoff, coefT, amT, stride, stride_am, bondP, amax, cgrid, false, st) <= 0)
         return 0;
-    // shared memory: Wt, two unit buffers [meta | coef | arg-max], ring of K-step stages
-    int maxpairs = 0;
-    for (int b = 0; b < a.wb.nb; ++b) maxpairs = std::max(maxpairs, plan->tile_max_deg[a.wb.d[b] - 1] * a.wb.nk[b]);
+    // shared memory: two Wt buffers, two tile-metadata buffers, ring of K-step stages
     int64_t off = 0;
     auto take = [&](int64_t bytes) { const int64_t o = off; off += (bytes + 127) / 128 * 128; return (int)o; };
     a.sm_wt = take(2 * 2 * (int64_t)WB_WT_ONE);          // two coefficient-block buffers
-    a.ub_a = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
-    a.ub_am = a.ub_a + (int)((((int64_t)maxpairs + 4) * 4 + 127) / 128 * 128);
-    a.unit_bytes = a.ub_am + (int)(((int64_t)maxpairs + 32 + 127) / 128 * 128);
+    a.ub_a = a.ub_am = 0;
+    a.unit_bytes = (int)((sizeof(TileMetaG) + 127) / 128 * 128);
     a.sm_unit = take(2 * (int64_t)a.unit_bytes);
     a.sm_ring = take(0);
     const int64_t room = (int64_t)s_budget - 2048 - off;
