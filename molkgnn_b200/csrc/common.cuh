@@ -65,6 +65,14 @@ template <int D> __host__ __device__ constexpr uint32_t perm_inv_code(int p) {
     for (int j = 0; j < D; ++j) c |= (uint32_t)j << (2 * Perm<D>::at(p, j));
     return c;
 }
+// The same codes as compile-time tables in constant memory, [degree - 1][permutation]: a kernel prologue copies them to shared
+// memory.  (Selecting perm_code<D>(q) with a run-time q materialises Perm<D>'s table on the thread's stack: ~700 local stores in
+// the prologue of k_conv_bwd_tile.)
+#define MK_PC3(f) f<3>(0), f<3>(1), f<3>(2), f<3>(3), f<3>(4), f<3>(5)
+#define MK_PC4(f) f<4>(0), f<4>(1), f<4>(2), f<4>(3), f<4>(4), f<4>(5), f<4>(6), f<4>(7), f<4>(8), f<4>(9), f<4>(10), f<4>(11)
+static __constant__ unsigned char c_perm_code[4][12] = {{0}, {perm_code<2>(0), perm_code<2>(1)}, {MK_PC3(perm_code)}, {MK_PC4(perm_code)}};
+static __constant__ unsigned char c_perm_inv_code[4][12] = {{0}, {perm_inv_code<2>(0), perm_inv_code<2>(1)}, {MK_PC3(perm_inv_code)},
+                                                            {MK_PC4(perm_inv_code)}};
 __host__ __device__ inline int num_perms(int d) { return d == 1 ? 1 : d == 2 ? 2 : d == 3 ? 6 : 12; }
 
 // ---- packed (normalised) kernel-set layout of one degree; all offsets in floats ----

@@ -59,7 +59,8 @@ struct CoefTileArgs {
     const int* order; int order_grid;          // balanced tile schedule (tile.cuh TileWalk), nullable
     int L[4], koff[4];
     long long scoff[4];
-    const float* grad; int ldg; int grad_mode; int vec;     // vec: floats per cp.async of the gradient rows (1, 2 or 4)
+    const float* grad; int ldg; int grad_mode; int vec;     // (vec: unused since the staging went to bulk copies)
+    long long grad_floats;                                  // floats of the gradient array the staging may read (N * ldg)
     const uint8_t* argmax;
     float* coefT; uint8_t* amT; int stride, stride_am;
     int nch[4];                                // node chunks per degree for the bond gradients
@@ -83,35 +84,36 @@ __device__ __forceinline__ void cp_async_n(void* dst, const void* src, int bytes
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// all threads: metadata record, gradient rows and bond rows of `tile` -> buffer
-__device__ __forceinline__ void ct_issue(const CoefTileArgs& a, unsigned char* buf, int tile) {
+// thread 0: metadata record, gradient rows, bond rows and arg-max codes of `tile` -> buffer, as bulk copies completing on `bar`
+// (the first version had all 512 threads issue 16-byte cp.async: 4.3 k cycles of pure issue per tile).  The gradient rows of a
+// tile are one contiguous range of `grad`; the copy starts at the 16-byte boundary below it and ends at the one above it -- or
+// at the last whole 16 bytes of the array, the <= 3 floats behind which are moved by plain loads / stores.
+__device__ __forceinline__ void ct_issue(const CoefTileArgs& a, unsigned char* buf, int tile, uint64_t* bar, const int4 hdr,
+                                         const int4 c) {               // hdr = (t0, nn, e0, ne), c = nodes per degree
     const TileMetaG* g = a.meta + tile;
-    const int4 hdr = __ldg(reinterpret_cast<const int4*>(g));          // t0, nn, e0, ne
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (int)(sizeof(TileMetaG) / 16); i += CT_THREADS)
-        cp_async_n(buf + i * 16, reinterpret_cast<const unsigned char*>(g) + i * 16, 16);
+    uint32_t tx = (uint32_t)sizeof(TileMetaG) + (uint32_t)hdr.w * 32u;
+    long long f0 = 0, f1 = 0, fend = 0;
     if (!a.wide) {
-        // rows t0 .. t0+nn-1 of grad are contiguous: nn * ldg floats; the staged copy starts at the vec-aligned float below
         const long long first = (long long)hdr.x * a.ldg;
-        const long long f0 = first - (first % a.vec);
-        const int nfl = (int)(first - f0) + hdr.y * a.ldg;
-        const int nv = (nfl + a.vec - 1) / a.vec;
-        float* dst = reinterpret_cast<float*>(buf + a.sm_grad);
-        const float* src = a.grad + f0;
-        const int bytes = a.vec * 4;
-        for (int i = tid; i < nv; i += CT_THREADS) cp_async_n(dst + i * a.vec, src + (size_t)i * a.vec, bytes);
+        fend = first + (long long)hdr.y * a.ldg;
+        f0 = first & ~3ll;
+        f1 = min((fend + 3) & ~3ll, a.grad_floats & ~3ll);
+        if (f1 > f0) tx += (uint32_t)(f1 - f0) * 4u;
     }
-    {
-        const float* src = a.ehat_node + (size_t)hdr.z * EP;
-        float* dst = reinterpret_cast<float*>(buf + a.sm_eh);
-        for (int i = tid; i < hdr.w * 2; i += CT_THREADS) cp_async_n(dst + i * 4, src + (size_t)i * 4, 16);
-    }
+    uint32_t ab = 0;
     if (a.amT_in) {
-        const int4 c = __ldg(reinterpret_cast<const int4*>(&g->cnt[0]));
-        const int np = c.x * a.L[0] + c.y * a.L[1] + c.z * a.L[2] + c.w * a.L[3];
-        const unsigned char* src = a.amT_in + (size_t)tile * a.stride_am;
-        for (int i = tid; i < (np + 15) / 16; i += CT_THREADS) cp_async_n(buf + a.sm_am + i * 16, src + (size_t)i * 16, 16);
+        ab = (uint32_t)((c.x * a.L[0] + c.y * a.L[1] + c.z * a.L[2] + c.w * a.L[3] + 15) & ~15);
+        tx += ab;
     }
+    mbar_expect_tx(bar, tx);
+    bulk_g2s(buf, g, (uint32_t)sizeof(TileMetaG), bar);
+    if (hdr.w > 0) bulk_g2s(buf + a.sm_eh, a.ehat_node + (size_t)hdr.z * EP, (uint32_t)hdr.w * 32u, bar);
+    if (!a.wide) {
+        float* dst = reinterpret_cast<float*>(buf + a.sm_grad);
+        if (f1 > f0) bulk_g2s(dst, a.grad + f0, (uint32_t)(f1 - f0) * 4u, bar);
+        for (long long f = max(f1, f0); f < fend; ++f) dst[f - f0] = __ldg(a.grad + f);       // tail of the array (<= 3 floats)
+    }
+    if (ab) bulk_g2s(buf + a.sm_am, a.amT_in + (size_t)tile * a.stride_am, ab, bar);
 }
 
 // (node, kernel) pairs of degree D of one tile: chi * g from the staged gradient rows, tile-ordered outputs
@@ -164,15 +166,15 @@ __device__ unsigned long long g_ph_coef[16];
 __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_constant__ CoefTileArgs a) {
     extern __shared__ __align__(128) unsigned char smem_c[];
     __shared__ unsigned char s_inv[4][12];               // inverse permutation codes per degree
+    __shared__ uint64_t bar_ct[2];                       // completion of the bulk copies into tile buffer 0 / 1
     const int tid = threadIdx.x;
     MK_PH_DECL(tid == 0)
+    if (tid == 0) {
+        tc::mbar_init(&bar_ct[0], 1); tc::mbar_init(&bar_ct[1], 1);
+        tc::fence_mbar_init();
+    }
     if (tid < 48) {
-        const int d = tid / 12 + 1, p = tid % 12;
-        uint32_t code = 0;
-        if (d == 2) code = p < 2 ? perm_inv_code<2>(p) : 0;
-        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_inv_code<3>(q); }
-        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_inv_code<4>(q); }
-        s_inv[d - 1][p] = (unsigned char)code;
+        s_inv[tid / 12][tid % 12] = c_perm_inv_code[tid / 12][tid % 12];
     }
     float* coefS = reinterpret_cast<float*>(smem_c + a.sm_coef);
     unsigned char* invS = smem_c + a.sm_inv;
@@ -204,23 +206,37 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
     float amax = 0.f;
     int cur = 0;
     const TileWalk walk(a.order, a.order_grid, a.n_tiles);
-    if (walk.cnt > 0) ct_issue(a, smem_c, walk.tile(0));
-    cp_async_commit();
+    // thread 0 keeps the header and the degree counts of the NEXT tile to issue in registers, loaded one tile earlier: the
+    // global-memory latency of the two loads stays off its (= every barrier's) critical path
+    int4 nh = make_int4(0, 0, 0, 0), nc = make_int4(0, 0, 0, 0);
+    auto ct_load_hdr = [&](int k) {
+        if (k < walk.cnt) {
+            const TileMetaG* g = a.meta + walk.tile(k);
+            nh = __ldg(reinterpret_cast<const int4*>(g));
+            nc = __ldg(reinterpret_cast<const int4*>(&g->cnt[0]));
+        }
+    };
+    if (tid == 0 && walk.cnt > 0) {
+        ct_load_hdr(0);
+        ct_issue(a, smem_c, walk.tile(0), &bar_ct[0], nh, nc);
+        ct_load_hdr(1);
+    }
     MK_PH(0);
     for (int wk = 0; wk < walk.cnt; ++wk) {
         const int tile = walk.tile(wk);
         unsigned char* buf = smem_c + (size_t)cur * a.buf_bytes;
         const int tnext = wk + 1 < walk.cnt ? walk.tile(wk + 1) : a.n_tiles;
-        __syncthreads();                                 // the previous tile's readers are done with the other buffer
-        if (tnext < a.n_tiles) ct_issue(a, smem_c + (size_t)(cur ^ 1) * a.buf_bytes, tnext);
-        cp_async_commit();
+        __syncthreads();                                 // the previous tile's readers are done with the other buffer; coefS / invS are free
+        if (tid == 0 && tnext < a.n_tiles) {
+            ct_issue(a, smem_c + (size_t)(cur ^ 1) * a.buf_bytes, tnext, &bar_ct[cur ^ 1], nh, nc);
+            ct_load_hdr(wk + 2);
+        }
         MK_PH(1);                                        // barrier + issue of the next tile's copies
-        cp_async_wait<1>();
-        __syncthreads();                                 // this tile's buffer is complete; coefS / invS are free
+        tc::mbar_wait(&bar_ct[cur], ((uint32_t)wk >> 1) & 1u);   // this tile's buffer is complete
         MK_PH(2);                                        // wait for this tile's data
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
         const float* gS = a.wide ? a.grad + (size_t)m.t0 * a.ldg
-                                 : reinterpret_cast<const float*>(buf + a.sm_grad) + (int)(((long long)m.t0 * a.ldg) % a.vec);
+                                 : reinterpret_cast<const float*>(buf + a.sm_grad) + (int)(((long long)m.t0 * a.ldg) & 3ll);
         const float4* ehS = reinterpret_cast<const float4*>(buf + a.sm_eh);
         int off[5];
         off[0] = 0;
@@ -264,7 +280,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) k_coef_tile(const __grid_consta
         MK_PH(5);                                        // bond sums (thread 0's rows)
         cur ^= 1;
     }
-    cp_async_wait<0>();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     {
@@ -343,6 +358,7 @@ struct BwdTileArgs {
     int gflush;                        // tiles per accumulation chunk of the G accumulators (see g_flush in k_conv_bwd_tile)
     int buf_bytes;
     int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
+    int dbuf, a_bytes, am_bytes;       // dbuf: the coefficient / arg-max arrays are double buffered (copy b at sm_a + b * a_bytes)
     // pipelined kernel (k_conv_bwd_pipe): ring of K-step stages, two Wt buffers, two tile buffers [meta | coef | arg-max]
     int nstages, stage_bytes, sm_ring, tbuf_bytes, tb_a, tb_am, cs;   // cs: TMEM column stride of an accumulator
 };
@@ -375,20 +391,69 @@ __device__ __forceinline__ void wt_add(unsigned char* wt, int row, int col, floa
     *pl = __float2half_rn(v - __half2float(hi));
 }
 
+// Rank-0 scatter of one segment (degree D): thread t owns the (node, kernel) pairs t, t + TB_THREADS, ...  A pair is one long
+// dependent chain (list -> neighbour words -> coefficient, arg-max code -> permutation -> conversions -> stores, ~130
+// instructions), and with 16 warps on 4 schedulers the phase is bound by that chain's latency times the pairs per thread.  The
+// pairs of a thread are therefore taken TB_NU at a time: all their loads first (the compiler cannot hoist loads over the
+// shared-memory stores of the previous pair on its own), then the conversions, then the stores.
+constexpr int TB_NU = 3;
+template <int D>
+__device__ __forceinline__ void tb_scatter_seg(const BSeg& sg, const TileMetaG& m, int np, int abase, const float* a_s,
+                                               const unsigned char* am_s, const unsigned char* lut, unsigned char* wt, float rscale,
+                                               int tid) {
+    for (int p0 = tid; p0 < np; p0 += TB_NU * TB_THREADS) {
+        int kl[TB_NU], nl_[TB_NU];
+        float av[TB_NU];
+        uint32_t code[TB_NU], nw[TB_NU], cr[TB_NU];
+        bool ok[TB_NU];
+#pragma unroll
+        for (int u = 0; u < TB_NU; ++u) {
+            const int p = p0 + u * TB_THREADS;
+            ok[u] = p < np;
+            const int pc = ok[u] ? p : p0;
+            const int ni = (int)(((float)pc + 0.5f) * sg.rnk);
+            kl[u] = pc - ni * sg.nk;
+            nl_[u] = m.list[D - 1][ni];
+            const int pi = abase + ni * sg.L + kl[u];
+            av[u] = a_s[pi] * rscale;
+            code[u] = lut[am_s[pi] & 0x7f];
+            nw[u] = m.nl[nl_[u]];
+            cr[u] = m.cr[nl_[u]];
+        }
+#pragma unroll
+        for (int u = 0; u < TB_NU; ++u) {
+            if (!ok[u]) continue;
+            wt_store(wt, sg.rowbase + D * sg.nk + kl[u], nl_[u], av[u] * sg.beta);
+            const float as = av[u] * sg.alpha;                // the same value goes to all D support entries: split it once
+            const __half ah = __float2half_rn(as);
+            const __half al = __float2half_rn(as - __half2float(ah));
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                if (((cr[u] >> (2 * j)) & 3u) == 0u)
+                    wt_store_hl(wt, sg.rowbase + (int)((code[u] >> (2 * j)) & 3u) * sg.nk + kl[u], (int)((nw[u] >> (8 * j)) & 0xffu), ah, al);
+            }
+        }
+    }
+}
+
 // thread 0: metadata record, node images and the tile-ordered coefficients / arg-max codes of `tile` (np pairs).  The
 // coefficient arrays and the image buffer are single: the caller issues this only after the previous tile's last use of them.
 // The node images complete on their OWN barrier: only the first G MMA of the tile (and the Jacobian) need them, so the 57 KB
 // land while the tile's first block is scattered instead of being waited for at the top of the tile.
-__device__ __forceinline__ void tb_issue_copy(const BwdTileArgs& a, unsigned char* smem, unsigned char* buf, int tile, int np,
-                                              uint64_t* bar, uint64_t* bar_x) {
-    const uint32_t cb = (uint32_t)((np * 4 + 15) & ~15), ab = (uint32_t)((np + 15) & ~15);
-    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + cb + ab);
+// Split in two: the node images (single buffer: issued once the previous tile's last reader is done) and the metadata +
+// coefficient arrays into buffer `b` -- with a.dbuf these are double buffered and fetched a whole tile ahead.
+__device__ __forceinline__ void tb_issue_x(const BwdTileArgs& a, unsigned char* smem, int tile, uint64_t* bar_x) {
     mbar_expect_tx(bar_x, 2u * (uint32_t)a.x_one);
-    bulk_g2s(buf, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
     bulk_g2s(smem + a.sm_x, a.ximg + (size_t)tile * 2 * a.x_one, 2u * (uint32_t)a.x_one, bar_x);
+}
+__device__ __forceinline__ void tb_issue_meta(const BwdTileArgs& a, unsigned char* smem, int b, int tile, int np, uint64_t* bar) {
+    const uint32_t cb = (uint32_t)((np * 4 + 15) & ~15), ab = (uint32_t)((np + 15) & ~15);
+    const int cb_i = a.dbuf ? b : 0;
+    mbar_expect_tx(bar, (uint32_t)sizeof(TileMetaG) + cb + ab);
+    bulk_g2s(smem + a.sm_buf + (size_t)b * a.buf_bytes, a.meta + tile, (uint32_t)sizeof(TileMetaG), bar);
     if (np > 0) {
-        bulk_g2s(smem + a.sm_a, a.coefT + (size_t)tile * a.stride, cb, bar);
-        bulk_g2s(smem + a.sm_am, a.amT + (size_t)tile * a.stride_am, ab, bar);
+        bulk_g2s(smem + a.sm_a + (size_t)cb_i * a.a_bytes, a.coefT + (size_t)tile * a.stride, cb, bar);
+        bulk_g2s(smem + a.sm_am + (size_t)cb_i * a.am_bytes, a.amT + (size_t)tile * a.stride_am, ab, bar);
     }
 }
 __device__ __forceinline__ int tb_tile_pairs(const BwdTileArgs& a, int tile) {
@@ -460,12 +525,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     }
     if (warp == 0) tc::tmem_alloc(&tslot, 512);
     if (tid < 48) {
-        const int d = tid / 12 + 1, p = tid % 12;
-        uint32_t code = 0;
-        if (d == 2) code = p < 2 ? perm_code<2>(p) : 0;
-        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_code<3>(q); }
-        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
-        s_lut[d - 1][p] = (unsigned char)code;
+        s_lut[tid / 12][tid % 12] = c_perm_code[tid / 12][tid % 12];
     }
     if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
         const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
@@ -496,8 +556,6 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = tslot;
-    const float* a_s = reinterpret_cast<const float*>(smem + a.sm_a);
-    const unsigned char* am_s = smem + a.sm_am;
     float* red = reinterpret_cast<float*>(smem + a.sm_red);     // Jacobian reduction scratch
     uint32_t ph_mma = 0u, ph_cp[2] = {0u, 0u};
     // power-of-two scale: |alpha * chi * g| / scale <= 2^10
@@ -517,10 +575,12 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     const bool resident = a.nbl <= a.nimg;
     int np_next = 0;
     if (tid == 0 && my_tiles > 0) {
-        tb_issue_copy(a, smem, smem + a.sm_buf, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0], &bar_xi);
+        tb_issue_meta(a, smem, 0, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0]);
+        tb_issue_x(a, smem, walk.tile(0), &bar_xi);
         const int n0 = resident ? a.nbl : min(a.nimg, total_uses);
         for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, a.blist[u % a.nbl], u % a.nimg, &bar_img[u % a.nimg]);
     }
+    if (tid == 64 && a.dbuf && my_tiles > 1) np_next = tb_tile_pairs(a, walk.tile(1));
     MK_PH(0);                                             // prologue
     int cur = 0, use = 0;
     bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
@@ -579,7 +639,9 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         unsigned char* buf = smem + a.sm_buf + cur * a.buf_bytes;
         const TileMetaG& m = *reinterpret_cast<const TileMetaG*>(buf);
         const int tnext = wk + 1 < walk.cnt ? walk.tile(wk + 1) : a.n_tiles;
-        if (tid == 0 && tnext < a.n_tiles) np_next = tb_tile_pairs(a, tnext);   // latency hidden behind this tile's work
+        if (!a.dbuf && tid == 0 && tnext < a.n_tiles) np_next = tb_tile_pairs(a, tnext);   // latency hidden behind this tile's work
+        const float* a_s = reinterpret_cast<const float*>(smem + a.sm_a + (size_t)(a.dbuf ? cur : 0) * a.a_bytes);
+        const unsigned char* am_s = smem + a.sm_am + (size_t)(a.dbuf ? cur : 0) * a.am_bytes;
         tc::mbar_wait(&bar_cp[cur], ph_cp[cur]);
         ph_cp[cur] ^= 1u;
         MK_PH(1);                                         // wait for the tile's metadata, node images, coefficients
@@ -588,56 +650,28 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         doff[0] = 0;
 #pragma unroll
         for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * a.L[d - 1];
-        // epilogue operands that come from global memory are fetched NOW (partial dxh of the first launch, row norm): their
-        // latency hides behind the scatter and the MMAs of the tile instead of sitting in front of the epilogue
         float dv[32];
         float nrm = 1.f;
-        {
-            const int v = q * 32 + lane, f0 = cpart * 32;
-            const int nf = min(32, a.Fk - f0);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) dv[i] = 0.f;
-            if (!a.first && v < nn && f0 < a.Fk) {
-                const float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    if (i < nf) {
-                        const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
-                        dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
-                    }
-                }
-            }
-            if (a.last && v < nn) nrm = __ldg(a.xnorm + t0 + v);
-        }
+        for (int i = 0; i < 32; ++i) dv[i] = 0.f;
         for (int bi = 0; bi < a.nbl; ++bi) {
             const int blk = a.blist[bi];
             const int nseg = a.tb.nseg[blk];
             int abase[TILE_MAXSEG];
             for (int si = 0; si < nseg; ++si) abase[si] = doff[s_seg[bi][si].d - 1] + s_seg[bi][si].k0;
+            MK_PH(14);                                    // tile / block set-up in front of the scatter
             // ---- rank 0: one thread per (node, kernel) pair -- centre entry, collision-free support entries ----
             for (int si = 0; si < nseg; ++si) {
                 const BSeg sg = s_seg[bi][si];
                 const int np = m.cnt[sg.d - 1] * sg.nk;
-                for (int p = tid; p < np; p += TB_THREADS) {
-                    const int ni = (int)(((float)p + 0.5f) * sg.rnk);
-                    const int kl = p - ni * sg.nk;
-                    const int nl_ = m.list[sg.d - 1][ni];
-                    const int pi = abase[si] + ni * sg.L + kl;
-                    const float av = a_s[pi] * rscale;
-                    const uint32_t code = s_lut[sg.d - 1][am_s[pi] & 0x7f];
-                    const uint32_t nw = m.nl[nl_];
-                    const uint32_t cr = m.cr[nl_];
-                    wt_store(wt, sg.rowbase + sg.d * sg.nk + kl, nl_, av * sg.beta);
-                    const float as = av * sg.alpha;           // the same value goes to all d support entries: split it once
-                    const __half ah = __float2half_rn(as);
-                    const __half al = __float2half_rn(as - __half2float(ah));
-                    for (int j = 0; j < sg.d; ++j) {
-                        if (((cr >> (2 * j)) & 3u) == 0u)
-                            wt_store_hl(wt, sg.rowbase + (int)((code >> (2 * j)) & 3u) * sg.nk + kl, (int)((nw >> (8 * j)) & 0xffu), ah, al);
-                    }
+                switch (sg.d) {
+                    case 1: tb_scatter_seg<1>(sg, m, np, abase[si], a_s, am_s, s_lut[0], wt, rscale, tid); break;
+                    case 2: tb_scatter_seg<2>(sg, m, np, abase[si], a_s, am_s, s_lut[1], wt, rscale, tid); break;
+                    case 3: tb_scatter_seg<3>(sg, m, np, abase[si], a_s, am_s, s_lut[2], wt, rscale, tid); break;
+                    default: tb_scatter_seg<4>(sg, m, np, abase[si], a_s, am_s, s_lut[3], wt, rscale, tid); break;
                 }
             }
-            MK_PH(2);                                     // rank-0 scatter (thread 0's own share)
+            MK_PH(10 + blk);                              // rank-0 scatter (thread 0's own share), per kernel block
             // ---- collision chains: one thread per (chain, kernel) adds the chain's followers in in-edge order after ONE barrier ----
             {
                 bool more = false;
@@ -686,9 +720,37 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 if (!resident) tc::mbar_wait(&bar_img[ib], (uint32_t)(use / a.nimg) & 1u);
                 else if (use < a.nbl) tc::mbar_wait(&bar_img[ib], 0u);
                 tb_issue_mma_x(a, smem, a.tb.rows[blk], bi == 0, ib, tmem, &bar_mma);
+            } else if (tid == 64 && bi == 0 && a.dbuf) {
+                // double buffered metadata / coefficients: the other buffer's readers finished with the previous tile.  Thread 64
+                // fetches the next tile's a whole tile ahead while its warp would only sleep in the barrier below (any work on
+                // thread 0 sits on every barrier's critical path), then loads the pair count of the tile after it.
+                if (tnext < a.n_tiles) tb_issue_meta(a, smem, cur ^ 1, tnext, np_next, &bar_cp[cur ^ 1]);
+                if (wk + 2 < walk.cnt) np_next = tb_tile_pairs(a, walk.tile(wk + 2));
             }
             ++use;
             MK_PH(5);                                     // image wait + MMA issue
+            // Epilogue operands that come from global memory (partial dxh of the first launch, row norm) are fetched while the
+            // tile's LAST block is in the tensor cores: ~3 k cycles ahead of the epilogue.  (Fetched at the top of the tile they cost
+            // 6 k cycles per tile in front of the first scatter -- measured with a phase clock between the two: 128 16-byte loads
+            // per warp ahead of the scatter's shared-memory loads in the same load / store queue.)
+            // The 57 KB of a tile take ~6 k cycles to get through the load / store unit, two tensor-core phases: the first half of the
+            // columns goes with the second-to-last block, the second half with the last.
+            if (bi >= a.nbl - 2) {
+                const int v = q * 32 + lane, f0 = cpart * 32;
+                const int nf = min(32, a.Fk - f0);
+                const bool h0 = a.nbl == 1 || bi == a.nbl - 2, h1 = bi == a.nbl - 1;
+                if (!a.first && v < nn && f0 < a.Fk) {
+                    const float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        if (i < nf && (i < 16 ? h0 : h1)) {
+                            const float4 o = __ldcg(reinterpret_cast<const float4*>(sp + i));
+                            dv[i] = o.x; dv[i + 1] = o.y; dv[i + 2] = o.z; dv[i + 3] = o.w;
+                        }
+                    }
+                }
+                if (h1 && a.last && v < nn) nrm = __ldg(a.xnorm + t0 + v);
+            }
             // the issuing thread alone polls for completion, everybody else sleeps in the hardware barrier: 511 threads
             // spinning on try_wait take issue slots from the one thread that feeds the tensor core
             if (tid == 0) tc::mbar_wait(&bar_mma, ph_mma);
@@ -726,8 +788,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = fmaf(__uint_as_float(u[i]), scale, dv[i]); }
             }
             if (!a.last) {
-                if (tid == 0 && tnext < a.n_tiles)
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1], &bar_xi);
+                if (tid == 0 && tnext < a.n_tiles) {
+                    if (!a.dbuf) tb_issue_meta(a, smem, cur ^ 1, tnext, np_next, &bar_cp[cur ^ 1]);
+                    tb_issue_x(a, smem, tnext, &bar_xi);
+                }
                 if (rowok && colok) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -765,8 +829,10 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 }
                 red[cpart * 128 + v] = dot;
                 __syncthreads();
-                if (tid == 0 && tnext < a.n_tiles)      // every thread has read its xhat: the image buffer may be refilled
-                    tb_issue_copy(a, smem, smem + a.sm_buf + (cur ^ 1) * a.buf_bytes, tnext, np_next, &bar_cp[cur ^ 1], &bar_xi);
+                if (tid == 0 && tnext < a.n_tiles) {    // every thread has read its xhat: the image buffer may be refilled
+                    if (!a.dbuf) tb_issue_meta(a, smem, cur ^ 1, tnext, np_next, &bar_cp[cur ^ 1]);
+                    tb_issue_x(a, smem, tnext, &bar_xi);
+                }
                 dot = (red[v] + red[128 + v]) + (red[256 + v] + red[384 + v]);
                 const float den = fmaxf(nrm, MOLKGNN_COS_EPS);
                 const float rden = 1.0f / den;
@@ -857,12 +923,7 @@ __global__ void __launch_bounds__(TP_THREADS, 1) k_conv_bwd_pipe(const __grid_co
     }
     if (warp == 0) tc::tmem_alloc(&tslot, 512);
     if (tid < 48) {
-        const int d = tid / 12 + 1, p = tid % 12;
-        uint32_t code = 0;
-        if (d == 2) code = p < 2 ? perm_code<2>(p) : 0;
-        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_code<3>(q); }
-        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
-        s_lut[d - 1][p] = (unsigned char)code;
+        s_lut[tid / 12][tid % 12] = c_perm_code[tid / 12][tid % 12];
     }
     if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
         const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
@@ -1333,6 +1394,7 @@ int64_t launch_coef_wide(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     }
     c.wide = 1;
     c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode; c.vec = 1;
+    c.grad_floats = (long long)plan->N * ldg;
     c.argmax = argmax;
     c.coefT = coefT; c.amT = amT; c.stride = stride; c.stride_am = stride_am;
     c.amT_in = nullptr;
@@ -1438,19 +1500,28 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     a.sm_x = (int)off; off += 2 * (int64_t)a.x_one;
     a.sm_wt = (int)off; off += 2 * (int64_t)WT_ONE;
     a.sm_buf = (int)off; off += 2 * (int64_t)a.buf_bytes;
-    a.sm_a = (int)off; off += ((int64_t)stride * 4 + 127) / 128 * 128;
-    a.sm_am = (int)off; off += ((int64_t)stride_am + 127) / 128 * 128;
+    a.a_bytes = (int)(((int64_t)stride * 4 + 127) / 128 * 128);
+    a.am_bytes = (int)(((int64_t)stride_am + 127) / 128 * 128);
+    // the static shared memory of the kernel is < 1 KB: dynamic budget = opt-in maximum - 1 KB
+    const int64_t budget = (int64_t)s_budget - 1024;
+    static int s_dbuf = -1;
+    if (s_dbuf < 0) { const char* e = getenv("MOLKGNN_BWD_DBUF"); s_dbuf = (e && e[0] == '0') ? 0 : 1; }
+    const int64_t fixed = off + 4 * 128 * 4 + 2 * (int64_t)a.img_one;
+    // double buffered coefficient / arg-max arrays (the next tile's arrive while this tile is scattered) when they fit
+    a.dbuf = (s_dbuf && fixed + 2 * ((int64_t)a.a_bytes + a.am_bytes) <= budget) ? 1 : 0;
+    a.sm_a = (int)off; off += (int64_t)(a.dbuf + 1) * a.a_bytes;
+    a.sm_am = (int)off; off += (int64_t)(a.dbuf + 1) * a.am_bytes;
     a.sm_red = (int)off; off += 4 * 128 * 4;
     a.sm_img = (int)off; off += 2 * (int64_t)a.img_one;
-    if (off > s_budget - 2048) return 0;
+    if (off > budget) return 0;
     a.nimg = 1;                      // as many image buffers as fit (all blocks resident if possible)
-    while (a.nimg < nbl_max && off + 2 * (int64_t)a.img_one <= s_budget - 2048) { ++a.nimg; off += 2 * (int64_t)a.img_one; }
+    while (a.nimg < nbl_max && off + 2 * (int64_t)a.img_one <= budget) { ++a.nimg; off += 2 * (int64_t)a.img_one; }
     // k_coef_tile: two tile buffers (metadata + gradient rows + bond rows) and the pair arrays of the current tile
     CoefTileArgs c;
     c.vec = ((int64_t)plan->N * ldg) % 4 == 0 ? 4 : ((int64_t)plan->N * ldg) % 2 == 0 ? 2 : 1;
     {
         int64_t o = (sizeof(TileMetaG) + 127) / 128 * 128;
-        c.sm_grad = (int)o; o += (((int64_t)TNODES * ldg + 4) * 4 + 127) / 128 * 128;
+        c.sm_grad = (int)o; o += (((int64_t)TNODES * ldg + 8) * 4 + 127) / 128 * 128;
         c.sm_eh = (int)o; o += (int64_t)TILE_ESLOTS * EP * 4;
         c.sm_am = (int)o; o += ((int64_t)stride_am + 127) / 128 * 128;
         c.buf_bytes = (int)o;
@@ -1516,6 +1587,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
             c.part_off[d] = part_off[d];
         }
         c.grad = grad; c.ldg = ldg; c.grad_mode = grad_mode;
+        c.grad_floats = (long long)plan->N * ldg;
         c.argmax = argmax;
         c.coefT = coef; c.stride = stride; c.stride_am = stride_am;
         c.amT_in = argmax_tile; c.amT = argmax_tile ? nullptr : const_cast<uint8_t*>(a.amT);

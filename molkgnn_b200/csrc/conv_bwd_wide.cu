@@ -141,12 +141,7 @@ __global__ void __launch_bounds__(WB_THREADS, 1) k_conv_bwd_wide(const __grid_co
     }
     if (warp == 0) tc::tmem_alloc(&tslot, 512);
     if (tid < 48) {
-        const int d = tid / 12 + 1, p = tid % 12;
-        uint32_t code = 0;
-        if (d == 2) code = p < 2 ? perm_code<2>(p) : 0;
-        else if (d == 3) { for (int q = 0; q < 6; ++q) if (q == p) code = perm_code<3>(q); }
-        else if (d == 4) { for (int q = 0; q < 12; ++q) if (q == p) code = perm_code<4>(q); }
-        s_lut[d - 1][p] = (unsigned char)code;
+        s_lut[tid / 12][tid % 12] = c_perm_code[tid / 12][tid % 12];
     }
     if (tid >= 64 && tid < 68 && a.L[tid - 64] > 0) {
         const int d = tid - 63;

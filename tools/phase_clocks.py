@@ -71,8 +71,9 @@ if has_clk:
     names_c = ["prologue", "barrier + issue next", "wait data", "pairs", "pairs barrier", "bond sums", "final"]
     ncta = 148
     out["coef_tile_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_c, cf)}
-    names_b = ["prologue", "wait tile copy", "rank-0 scatter", "ranks 1-3", "barrier before MMA", "img wait + MMA issue",
-               "MMA wait", "Wt clear", "dxh epilogue", "G store"]
+    names_b = ["prologue", "wait tile copy", "(unused)", "ranks 1-3", "barrier before MMA", "img wait + MMA issue",
+               "MMA wait", "Wt clear", "dxh epilogue", "G store", "rank-0 scatter block 0", "rank-0 scatter block 1",
+               "rank-0 scatter block 2", "rank-0 scatter block 3", "set-up in front of the scatter"]
     names_fc = ["block set-up", "wait copy", "wait MMA", "dump", "dupflags+sync", "epilogue", "sync", "teardown"]
     names_fp = ["block set-up", "wait bfree", "wait img buffer", "copy wait", "wait tfree", "MMA issue"]
     out["bwd_tile_kcycles_per_cta_per_step"] = {n: v / ncta / steps / 1e3 for n, v in zip(names_b, bw)}
