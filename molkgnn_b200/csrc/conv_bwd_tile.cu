@@ -358,6 +358,7 @@ struct BwdTileArgs {
     int gflush;                        // tiles per accumulation chunk of the G accumulators (see g_flush in k_conv_bwd_tile)
     int buf_bytes;
     int sm_img, sm_x, sm_wt, sm_buf, sm_a, sm_am, sm_red;
+    int dmask_first;                   // two-launch layers: bit d set if the FIRST launch's blocks hold kernels of degree d
     int dbuf, a_bytes, am_bytes;       // dbuf: the coefficient / arg-max arrays are double buffered (copy b at sm_a + b * a_bytes)
     // pipelined kernel (k_conv_bwd_pipe): ring of K-step stages, two Wt buffers, two tile buffers [meta | coef | arg-max]
     int nstages, stage_bytes, sm_ring, tbuf_bytes, tb_a, tb_am, cs;   // cs: TMEM column stride of an accumulator
@@ -650,6 +651,22 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         doff[0] = 0;
 #pragma unroll
         for (int d = 1; d < 4; ++d) doff[d] = doff[d - 1] + m.cnt[d - 1] * a.L[d - 1];
+        // Two-launch layers: the first launch's partial dxh is non-zero only in the rows its blocks touch -- nodes of those degrees
+        // (centre entries) and their neighbours (support entries).  With the first launch on the degree-4 blocks that is ~30 % of the
+        // rows for drug-like molecules; only those rows make the round trip through `scratch`.
+        bool touched = true;
+        if (a.first != a.last) {
+            const int v = q * 32 + lane;
+            touched = false;
+            if (v < nn) {
+                touched = ((a.dmask_first >> m.degl[v]) & 1) != 0;
+                const uint32_t iw = m.inl[v];
+                const int ic = m.incnt[v];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j < ic && ((a.dmask_first >> m.degl[(iw >> (8 * j)) & 0xffu]) & 1)) touched = true;
+            }
+        }
         float dv[32];
         float nrm = 1.f;
 #pragma unroll
@@ -739,7 +756,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 const int v = q * 32 + lane, f0 = cpart * 32;
                 const int nf = min(32, a.Fk - f0);
                 const bool h0 = a.nbl == 1 || bi == a.nbl - 2, h1 = bi == a.nbl - 1;
-                if (!a.first && v < nn && f0 < a.Fk) {
+                if (!a.first && touched && v < nn && f0 < a.Fk) {
                     const float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -792,7 +809,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                     if (!a.dbuf) tb_issue_meta(a, smem, cur ^ 1, tnext, np_next, &bar_cp[cur ^ 1]);
                     tb_issue_x(a, smem, tnext, &bar_xi);
                 }
-                if (rowok && colok) {
+                if (rowok && colok && touched) {
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         if (i < nf) __stcg(reinterpret_cast<float4*>(sp + i), make_float4(dv[i], dv[i + 1], dv[i + 2], dv[i + 3]));
@@ -1611,7 +1628,7 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
     }
     MK_REQUIRE(nlaunch == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than two kernel blocks");
     for (int l = 0; l < nlaunch; ++l) {
-        // blocks {0, 3} and {1, 2}: the scatter work of the two launches is about equal for the base model
+        // blocks {0, 1} first (base model: the two degree-4 blocks, whose partial dxh touches the fewest rows), then {2, 3}
         for (int i = 0; i < 4; ++i) a.blist[i] = 0;
         if (one_launch) {
             a.nbl = a.tb.nb;
@@ -1619,8 +1636,13 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
             a.gstride = a.tb.nb <= 2 ? 128 : a.Fk;
             a.dxcol = a.tb.nb <= 2 ? 256 : a.tb.nb * a.Fk;
         } else if (a.tb.nb == 3) { a.nbl = l == 0 ? 2 : 1; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 2; }
-        else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 1; a.blist[1] = l == 0 ? 3 : 2; }
+        else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 3; }
         if (!one_launch) { a.gstride = 128; a.dxcol = 256; }
+        if (l == 0) {
+            a.dmask_first = 0;
+            for (int i = 0; i < a.nbl; ++i)
+                for (int si = 0; si < a.tb.nseg[a.blist[i]]; ++si) a.dmask_first |= 1 << a.tb.seg[a.blist[i]][si].d;
+        }
         a.first = l == 0; a.last = l == nlaunch - 1;
         count_launches(1);
         ProfScope prof("conv_bwd_tile", st);
