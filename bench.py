@@ -173,7 +173,7 @@ def workload_config(B, fwd_only=False):
             "molecules_per_gpu": B, "layers": NUM_LAYERS, "kernels": list(L_BASE), "forward_only": bool(fwd_only),
             "cpu_arms": "the CPU arms (cpu_baseline, --impl reference) time a stream of batch-16 mini-batches of the same model and "
                         "generator: the reference is super-linear in batch size and cannot run this batch on a host (SURVEY 6)",
-            "pipeline": "the GPU bucket pass of step i+1 is queued on a side stream while step i computes (one pass per step, "
+            "pipeline": "the GPU bucket pass of step i+2 is queued on a side stream while step i computes (one pass per step, "
                         "inside the timed region)",
             "l2": "no explicit flush: per-step working set (activations+gradients of 3 layers, ~0.5 GB) exceeds the 126 MB L2"}
 
@@ -300,11 +300,11 @@ def main():
     def run_steps(k):
         """k steps on the device-resident batch.  Every step runs its own GPU bucket pass; it is queued one step ahead on
         the prefetcher's side stream, so its host round trip (bucket sizes) never drains the compute stream."""
-        nxt = pf.put(device_batch=devt, build_plan=True)
+        q = [pf.put(device_batch=devt, build_plan=True) for _ in range(min(pf.depth, k))]
         for i in range(k):
-            t, plan = pf.get(nxt)
-            if i + 1 < k:
-                nxt = pf.put(device_batch=devt, build_plan=True)
+            t, plan = pf.get(q.pop(0))
+            if i + pf.depth < k:
+                q.append(pf.put(device_batch=devt, build_plan=True))
             step(t, plan)
             zero_grads()
 
@@ -352,12 +352,12 @@ def main():
     batch_dev = torch.from_numpy(batch["batch"]).to(dev)
 
     def e2e_run(k):
-        nxt = pf.put(host_batch=host, build_plan=True)
+        q = [pf.put(host_batch=host, build_plan=True) for _ in range(min(pf.depth, k))]   # prefetch depth 2, as a DataLoader's
         pending = None
         for i in range(k):
-            t, plan = pf.get(nxt)
-            if i + 1 < k:
-                nxt = pf.put(host_batch=host, build_plan=True)
+            t, plan = pf.get(q.pop(0))
+            if i + pf.depth < k:
+                q.append(pf.put(host_batch=host, build_plan=True))
             h = step(t, plan)
             if fwd_only:                          # inference: the pooled result [B, K] returns to the host
                 buf = h_host[i & 1]
@@ -404,11 +404,12 @@ def main():
 
         def store_run(k):
             pending = None
-            nxt = pf.put(store_batch=(store, id_bufs[0]), build_plan=True)    # H2D: B int64 ids; gather + rebasing on the GPU
+            # H2D: B int64 ids per step; gather + rebasing on the GPU
+            q = [pf.put(store_batch=(store, id_bufs[j & 3]), build_plan=True) for j in range(min(pf.depth, k))]
             for i in range(k):
-                bt, plan = pf.get(nxt)
-                if i + 1 < k:
-                    nxt = pf.put(store_batch=(store, id_bufs[(i + 1) & 3]), build_plan=True)
+                bt, plan = pf.get(q.pop(0))
+                if i + pf.depth < k:
+                    q.append(pf.put(store_batch=(store, id_bufs[(i + pf.depth) & 3]), build_plan=True))
                 h = step(bt, plan)
                 if fwd_only:
                     buf = h_host[i & 1]
@@ -497,7 +498,7 @@ def main():
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "molecules/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": B * K * 4 if fwd_only else 4, "ms_per_step": ms_e2e / args.steps,
                 "api": "molkgnn_b200.MolGCN.forward/backward; every step's x/p/edge_index/edge_attr copied from pinned host "
-                       "memory and bucketed (molkgnn_b200.data.DevicePrefetcher: side stream, one step ahead), every step's loss "
+                       "memory and bucketed (molkgnn_b200.data.DevicePrefetcher: side streams, two steps ahead), every step's loss "
                        "copied to pinned host memory and consumed by the host one step later; all K copies and K reads are "
                        "inside the timed region"},
         "e2e_store": None if ms_store is None else {

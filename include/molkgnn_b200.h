@@ -123,7 +123,7 @@ int64_t molkgnn_bucket_scratch_bytes(int32_t N, int32_t E);
 int molkgnn_bucket_build(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                          const float* edge_attr, int32_t Fe, void* scratch, void* stream);
 /* The same pass in two halves, so that the host can queue other work (parameter packing, its own bookkeeping) behind the
- * counting kernels before it blocks: _begin enqueues the counting kernels and returns; _finish (same arguments) brings the
+ * counting kernels before it blocks: _begin enqueues the counting kernels and returns; _finish (same arguments, same stream) brings the
  * bucket sizes to the host (the one stream synchronisation), validates them and enqueues the assignment kernels. */
 int molkgnn_bucket_build_begin(molkgnn_plan_t* plan, const int64_t* edge_index, const float* p, int32_t p_dim,
                                const float* edge_attr, int32_t Fe, void* scratch, void* stream);

@@ -791,7 +791,6 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
         k_valid_cuts<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, far, cutpos, tinfo);
         k_cut_gaps<<<(N + 1 + 255) / 256, 256, 0, st>>>(N, cutpos, tinfo);
         MK_CHECK_CUDA(cudaStreamWaitEvent(st, side->deg_ready, 0));
-        (void)main_st;
         const int64_t bitmap = (int64_t)((N + 32) / 32) * 4;
         static int s_budget = 0;
         if (!s_budget) s_budget = device_max_smem_optin();
@@ -809,15 +808,14 @@ static int bucket_build_phases(molkgnn_plan_t* plan, const int64_t* edge_index, 
             k_tile_starts<<<(tile_cap + 3) / 4, 128, 0, st>>>(N, tile_cap, cutpos, plan->deg, plan->tile_start, tinfo);
         }
         MK_CHECK_CUDA(cudaEventRecord(side->done, st));
+        // The launching stream picks the cut chain's results up HERE, in the first half: the events are one set per device, and
+        // a second _begin (another batch staged ahead on another stream) re-records them before this batch's _finish runs --
+        // waiting there made _finish wait for the LATER batch's chain (and its host -> device copies).
+        MK_CHECK_CUDA(cudaStreamWaitEvent(main_st, side->done, 0));
     }
     MK_CHECK_CUDA(cudaGetLastError());
     }
     if (!(phases & 2)) return 0;
-    if (tiles) {                                           // the launching stream picks the cut chain's results up here
-        SideStream* side = side_stream();
-        MK_REQUIRE(side, "bucket_build: cannot create the side stream");
-        MK_CHECK_CUDA(cudaStreamWaitEvent(st, side->done, 0));
-    }
     int host[32];
     MK_CHECK_CUDA(cudaMemcpyAsync(host, totals, sizeof(int) * 32, cudaMemcpyDeviceToHost, st));
     MK_CHECK_CUDA(cudaStreamSynchronize(st));

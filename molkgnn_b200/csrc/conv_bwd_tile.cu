@@ -676,6 +676,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             const int nseg = a.tb.nseg[blk];
             int abase[TILE_MAXSEG];
             for (int si = 0; si < nseg; ++si) abase[si] = doff[s_seg[bi][si].d - 1] + s_seg[bi][si].k0;
+            // The image buffer the previous visit freed is refilled NOW, not at the start of that visit's Wt clear: the 57 KB of the
+            // bulk copy and the 64 KB of clearing stores shared the 128 B/cycle of shared-memory bandwidth (clear + set-up 1.9 k
+            // cycles per visit); the copy has the whole scatter to land.  Thread 96: not a thread the barriers wait for.
+            if (tid == 96 && !resident && use >= 1 && use - 1 + a.nimg < total_uses)
+                tb_issue_img(a, smem, a.blist[(use - 1 + a.nimg) % a.nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
             MK_PH(14);                                    // tile / block set-up in front of the scatter
             // ---- rank 0: one thread per (node, kernel) pair -- centre entry, collision-free support entries ----
             for (int si = 0; si < nseg; ++si) {
@@ -777,8 +782,6 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             MK_PH(6);                                     // MMA completion
             // the tensor cores are done with Wt and this block's images: fetch the images of a later use, clear Wt
             for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
-            if (tid == 0 && !resident && use - 1 + a.nimg < total_uses)
-                tb_issue_img(a, smem, a.blist[(use - 1 + a.nimg) % a.nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
             if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
             MK_PH(7);                                     // Wt clear
         }
