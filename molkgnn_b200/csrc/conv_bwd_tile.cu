@@ -351,7 +351,8 @@ struct BwdTileArgs {
     float* partials; long long part_off[4]; int FW;
     float* scratch;                    // [N, Fk] partial dxh handed from the first launch to the second
     float* gx; int ldgx;
-    int nbl, blist[4];                 // kernel blocks of this launch
+    int nbl, blist[4];                 // kernel blocks of this launch (k_conv_bwd_pipe; k_conv_bwd_tile reads the per-pass lists)
+    int npass, p_nbl[2], p_blist[2][4]; // k_conv_bwd_tile: passes of this launch and their kernel blocks
     int gstride, dxcol;                // TMEM columns: G of block bi at bi * gstride, dxh at dxcol
     int nimg;                          // kernel-block image buffers in shared memory (1..4)
     int first, last;                   // first: no partial dxh to add; last: apply the Jacobian and write grad_x
@@ -528,21 +529,6 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     if (tid < 48) {
         s_lut[tid / 12][tid % 12] = c_perm_code[tid / 12][tid % 12];
     }
-    if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
-        const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
-        if (bi < a.nbl && si < a.tb.nseg[a.blist[bi]]) {
-            const TileSeg sg = a.tb.seg[a.blist[bi]][si];
-            const int L = a.L[sg.d - 1];
-            const PackedLayout pl(sg.d, L, a.Fp);
-            const float* pk = a.packed[sg.d - 1];
-            BSeg c;
-            c.alpha = pk[pl.w + 0] / pk[pl.w + 3] / (float)sg.d;
-            c.beta = pk[pl.w + 1] / pk[pl.w + 3];
-            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
-            c.rnk = 1.0f / (float)sg.nk;
-            s_seg[bi][si] = c;
-        }
-    }
     __shared__ float s_gmax;
     if (warp == 3) {                                      // max |coef| over the per-CTA values of k_coef_tile
         float gm = 0.f;
@@ -572,27 +558,55 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     // image uses u = 0, 1, ...: block blist[u % nbl] in buffer u % nimg.  With nbl <= nimg the images stay resident.
     const TileWalk walk(a.order, a.order_grid, a.n_tiles);
     const int my_tiles = walk.cnt;
-    const int total_uses = my_tiles * a.nbl;
-    const bool resident = a.nbl <= a.nimg;
     int np_next = 0;
+    int cur = 0;
+    uint32_t ph_img = 0u;                                 // phase bit of every image barrier (thread 32 waits on them)
+    MK_PH(0);                                             // prologue
+  // One launch runs a.npass passes over the CTA's tiles, each over its own <= 2 kernel blocks (TMEM: 2 x G_b + dxh = 336 of the 512
+  // columns): a layer with 4 blocks at Fk = 112 is pass 0 over blocks {0, 1}, G flush, pass 1 over blocks {2, 3} -- the two
+  // LAUNCHES this used to be, without the second launch's prologue and without every CTA waiting for the slowest one in between.
+  // A pass hands its partial dxh to the next through `scratch` (rows written and re-read by the same thread).
+  for (int pass = 0; pass < a.npass; ++pass) {
+    const int nbl = a.p_nbl[pass];
+    const int* blist = a.p_blist[pass];
+    const bool pfirst = a.first && pass == 0, plast = a.last && pass == a.npass - 1;
+    __syncthreads();                                      // the previous pass is done with s_seg
+    if (tid >= 64 && tid < 64 + 4 * TILE_MAXSEG) {
+        const int bi = (tid - 64) / TILE_MAXSEG, si = (tid - 64) % TILE_MAXSEG;
+        if (bi < nbl && si < a.tb.nseg[blist[bi]]) {
+            const TileSeg sg = a.tb.seg[blist[bi]][si];
+            const int L = a.L[sg.d - 1];
+            const PackedLayout pl(sg.d, L, a.Fp);
+            const float* pk = a.packed[sg.d - 1];
+            BSeg c;
+            c.alpha = pk[pl.w + 0] / pk[pl.w + 3] / (float)sg.d;
+            c.beta = pk[pl.w + 1] / pk[pl.w + 3];
+            c.d = sg.d; c.k0 = sg.k0; c.nk = sg.nk; c.rowbase = sg.rowbase; c.L = L;
+            c.rnk = 1.0f / (float)sg.nk;
+            s_seg[bi][si] = c;
+        }
+    }
+    __syncthreads();
+    const int total_uses = my_tiles * nbl;
+    const bool resident = nbl <= a.nimg;
+    const uint32_t xi_base = (uint32_t)(pass * my_tiles);  // bar_xi completes once per tile, over all passes
     if (tid == 0 && my_tiles > 0) {
-        tb_issue_meta(a, smem, 0, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[0]);
+        tb_issue_meta(a, smem, cur, walk.tile(0), tb_tile_pairs(a, walk.tile(0)), &bar_cp[cur]);
         tb_issue_x(a, smem, walk.tile(0), &bar_xi);
-        const int n0 = resident ? a.nbl : min(a.nimg, total_uses);
-        for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, a.blist[u % a.nbl], u % a.nimg, &bar_img[u % a.nimg]);
+        const int n0 = resident ? nbl : min(a.nimg, total_uses);
+        for (int u = 0; u < n0; ++u) tb_issue_img(a, smem, blist[u % nbl], u % a.nimg, &bar_img[u % a.nimg]);
     }
     if (tid == 64 && a.dbuf && my_tiles > 1) np_next = tb_tile_pairs(a, walk.tile(1));
-    MK_PH(0);                                             // prologue
-    int cur = 0, use = 0;
-    bool fresh = true;                                    // first tile of this CTA: the G accumulators start from zero
+    int use = 0;
+    bool fresh = true;                                    // first tile of this pass: the G accumulators start from zero
     // Kernel-parameter partial sums of this CTA: node-attribute part of every row of this launch's blocks, tensor memory ->
     // the CTA's partial copy.  The tensor core TRUNCATES every accumulate (measured: against the fp32 SIMT backward the sums come
     // out smaller in magnitude, the error growing with the batch: 4e-6 at 6 tiles per CTA, 5e-5 at 96), so the accumulators are
     // flushed every `gflush` tiles -- chains of <= gflush * 24 MMAs -- and the chunks are added in fp32 (round to nearest) by
     // fire-and-forget reductions; every element has one writer thread, the order of its reductions is program order.
     auto g_flush = [&](bool add, bool valid) {
-        for (int bi = 0; bi < a.nbl; ++bi) {
-            const int blk = a.blist[bi];
+        for (int bi = 0; bi < nbl; ++bi) {
+            const int blk = blist[bi];
             const int row = q * 32 + lane;
             int d = 0, slot = 0, kk = 0, L = 0;
             for (int si = 0; si < a.tb.nseg[blk]; ++si) {
@@ -655,7 +669,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         // (centre entries) and their neighbours (support entries).  With the first launch on the degree-4 blocks that is ~30 % of the
         // rows for drug-like molecules; only those rows make the round trip through `scratch`.
         bool touched = true;
-        if (a.first != a.last) {
+        if (pfirst != plast) {
             const int v = q * 32 + lane;
             touched = false;
             if (v < nn) {
@@ -671,8 +685,8 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
         float nrm = 1.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) dv[i] = 0.f;
-        for (int bi = 0; bi < a.nbl; ++bi) {
-            const int blk = a.blist[bi];
+        for (int bi = 0; bi < nbl; ++bi) {
+            const int blk = blist[bi];
             const int nseg = a.tb.nseg[blk];
             int abase[TILE_MAXSEG];
             for (int si = 0; si < nseg; ++si) abase[si] = doff[s_seg[bi][si].d - 1] + s_seg[bi][si].k0;
@@ -680,7 +694,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             // bulk copy and the 64 KB of clearing stores shared the 128 B/cycle of shared-memory bandwidth (clear + set-up 1.9 k
             // cycles per visit); the copy has the whole scatter to land.  Thread 96: not a thread the barriers wait for.
             if (tid == 96 && !resident && use >= 1 && use - 1 + a.nimg < total_uses)
-                tb_issue_img(a, smem, a.blist[(use - 1 + a.nimg) % a.nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
+                tb_issue_img(a, smem, blist[(use - 1 + a.nimg) % nbl], (use - 1) % a.nimg, &bar_img[(use - 1) % a.nimg]);
             MK_PH(14);                                    // tile / block set-up in front of the scatter
             // ---- rank 0: one thread per (node, kernel) pair -- centre entry, collision-free support entries ----
             for (int si = 0; si < nseg; ++si) {
@@ -732,15 +746,17 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             // moves), about twice the tensor time of these shapes; the G MMAs and the dxh MMAs write different accumulators, so
             // warp 0 issues the first and warp 1 the second group and the tensor pipe sees both streams (bar_mma counts 2)
             if (tid == 0) {
-                if (bi == 0) tc::mbar_wait(&bar_xi, (uint32_t)wk & 1u);      // node images of this tile (one completion per tile)
+                if (bi == 0) tc::mbar_wait(&bar_xi, (xi_base + (uint32_t)wk) & 1u);   // node images of this tile (one completion per tile)
                 tc::fence_after_sync();
                 tb_issue_mma_g(a, smem, nn, bi, fresh, tmem);
                 tc::umma_commit(&bar_mma);
             } else if (tid == 32) {
                 tc::fence_after_sync();
-                const int ib = resident ? use % a.nbl : use % a.nimg;
-                if (!resident) tc::mbar_wait(&bar_img[ib], (uint32_t)(use / a.nimg) & 1u);
-                else if (use < a.nbl) tc::mbar_wait(&bar_img[ib], 0u);
+                const int ib = resident ? use % nbl : use % a.nimg;
+                if (!resident || use < nbl) {                 // (resident images are waited for once per pass)
+                    tc::mbar_wait(&bar_img[ib], (ph_img >> ib) & 1u);
+                    ph_img ^= 1u << ib;
+                }
                 tb_issue_mma_x(a, smem, a.tb.rows[blk], bi == 0, ib, tmem, &bar_mma);
             } else if (tid == 64 && bi == 0 && a.dbuf) {
                 // double buffered metadata / coefficients: the other buffer's readers finished with the previous tile.  Thread 64
@@ -757,11 +773,11 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             // per warp ahead of the scatter's shared-memory loads in the same load / store queue.)
             // The 57 KB of a tile take ~6 k cycles to get through the load / store unit, two tensor-core phases: the first half of the
             // columns goes with the second-to-last block, the second half with the last.
-            if (bi >= a.nbl - 2) {
+            if (bi >= nbl - 2) {
                 const int v = q * 32 + lane, f0 = cpart * 32;
                 const int nf = min(32, a.Fk - f0);
-                const bool h0 = a.nbl == 1 || bi == a.nbl - 2, h1 = bi == a.nbl - 1;
-                if (!a.first && touched && v < nn && f0 < a.Fk) {
+                const bool h0 = nbl == 1 || bi == nbl - 2, h1 = bi == nbl - 1;
+                if (!pfirst && touched && v < nn && f0 < a.Fk) {
                     const float* sp = a.scratch + (size_t)(t0 + v) * a.Fk + f0;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
@@ -771,7 +787,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                         }
                     }
                 }
-                if (h1 && a.last && v < nn) nrm = __ldg(a.xnorm + t0 + v);
+                if (h1 && plast && v < nn) nrm = __ldg(a.xnorm + t0 + v);
             }
             // the issuing thread alone polls for completion, everybody else sleeps in the hardware barrier: 511 threads
             // spinning on try_wait take issue slots from the one thread that feeds the tensor core
@@ -782,7 +798,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
             MK_PH(6);                                     // MMA completion
             // the tensor cores are done with Wt and this block's images: fetch the images of a later use, clear Wt
             for (int i = tid * 16; i < 2 * WT_ONE; i += TB_THREADS * 16) *reinterpret_cast<uint4*>(wt + i) = make_uint4(0, 0, 0, 0);
-            if (bi + 1 < a.nbl) __syncthreads();              // Wt cleared before the next block's scatter
+            if (bi + 1 < nbl) __syncthreads();              // Wt cleared before the next block's scatter
             MK_PH(7);                                     // Wt clear
         }
         fresh = false;
@@ -807,7 +823,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
 #pragma unroll
                 for (int i = 0; i < 32; ++i) { asm volatile("" : "+r"(u[i])); dv[i] = fmaf(__uint_as_float(u[i]), scale, dv[i]); }
             }
-            if (!a.last) {
+            if (!plast) {
                 if (tid == 0 && tnext < a.n_tiles) {
                     if (!a.dbuf) tb_issue_meta(a, smem, cur ^ 1, tnext, np_next, &bar_cp[cur ^ 1]);
                     tb_issue_x(a, smem, tnext, &bar_xi);
@@ -824,7 +840,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
                 float dot = 0.f;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) xh[i] = 0.f;
-                tc::mbar_wait(&bar_xi, (uint32_t)wk & 1u);                    // (complete since the first G MMA; acquire for this thread)
+                tc::mbar_wait(&bar_xi, (xi_base + (uint32_t)wk) & 1u);        // (complete since the first G MMA; acquire for this thread)
                 if (colok) {
                     const unsigned char* Xhi = smem + a.sm_x;
                     const unsigned char* Xlo = Xhi + a.x_one;
@@ -892,6 +908,7 @@ __global__ void __launch_bounds__(TB_THREADS, 1) k_conv_bwd_tile(const __grid_co
     tc::fence_before_sync();
     __syncthreads();
     MK_PH(9);                                             // G partial sums -> global
+  }
     MK_PH_FLUSH(g_ph_bwd);
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
@@ -1630,23 +1647,37 @@ int launch_conv_bwd_tile(const molkgnn_plan_t* plan, const molkgnn_layer_t* laye
         MK_CHECK_CUDA(cudaGetLastError());
     }
     MK_REQUIRE(nlaunch == 1 || scratch, "conv_bwd_tile: scratch is required for layers with more than two kernel blocks");
-    for (int l = 0; l < nlaunch; ++l) {
-        // blocks {0, 1} first (base model: the two degree-4 blocks, whose partial dxh touches the fewest rows), then {2, 3}
-        for (int i = 0; i < 4; ++i) a.blist[i] = 0;
-        if (one_launch) {
-            a.nbl = a.tb.nb;
-            for (int i = 0; i < a.tb.nb; ++i) a.blist[i] = i;
-            a.gstride = a.tb.nb <= 2 ? 128 : a.Fk;
-            a.dxcol = a.tb.nb <= 2 ? 256 : a.tb.nb * a.Fk;
-        } else if (a.tb.nb == 3) { a.nbl = l == 0 ? 2 : 1; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 2; }
-        else { a.nbl = 2; a.blist[0] = l == 0 ? 0 : 2; a.blist[1] = l == 0 ? 1 : 3; }
-        if (!one_launch) { a.gstride = 128; a.dxcol = 256; }
-        if (l == 0) {
-            a.dmask_first = 0;
-            for (int i = 0; i < a.nbl; ++i)
-                for (int si = 0; si < a.tb.nseg[a.blist[i]]; ++si) a.dmask_first |= 1 << a.tb.seg[a.blist[i]][si].d;
+    // Kernel blocks of the layer in (at most) two groups: {0, 1} first (base model: the two degree-4 blocks, whose partial dxh touches
+    // the fewest rows), then {2, 3}.  k_conv_bwd_tile runs both groups as two PASSES of one launch (MOLKGNN_BWD_FUSE=0 and the
+    // pipelined kernel: two launches).
+    int g_nbl[2] = {0, 0}, g_blist[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    if (one_launch) {
+        g_nbl[0] = a.tb.nb;
+        for (int i = 0; i < a.tb.nb; ++i) g_blist[0][i] = i;
+        a.gstride = a.tb.nb <= 2 ? 128 : a.Fk;
+        a.dxcol = a.tb.nb <= 2 ? 256 : a.tb.nb * a.Fk;
+    } else {
+        g_nbl[0] = 2; g_blist[0][0] = 0; g_blist[0][1] = 1;
+        g_nbl[1] = a.tb.nb - 2; g_blist[1][0] = 2; g_blist[1][1] = a.tb.nb == 3 ? 2 : 3;
+        a.gstride = 128; a.dxcol = 256;
+    }
+    a.dmask_first = 0;
+    for (int i = 0; i < g_nbl[0]; ++i)
+        for (int si = 0; si < a.tb.nseg[g_blist[0][i]]; ++si) a.dmask_first |= 1 << a.tb.seg[g_blist[0][i]][si].d;
+    static int s_fuse = -1;
+    if (s_fuse < 0) { const char* e = getenv("MOLKGNN_BWD_FUSE"); s_fuse = (e && e[0] == '0') ? 0 : 1; }
+    const bool fuse = nlaunch == 2 && s_fuse && !use_pipe;
+    const int nl_eff = fuse ? 1 : nlaunch;
+    for (int l = 0; l < nl_eff; ++l) {
+        a.npass = fuse ? 2 : 1;
+        for (int ps = 0; ps < 2; ++ps) {
+            const int g = fuse ? ps : l;
+            a.p_nbl[ps] = ps < a.npass ? g_nbl[g] : 0;
+            for (int i = 0; i < 4; ++i) a.p_blist[ps][i] = ps < a.npass ? g_blist[g][i] : 0;
         }
-        a.first = l == 0; a.last = l == nlaunch - 1;
+        a.nbl = g_nbl[l];
+        for (int i = 0; i < 4; ++i) a.blist[i] = g_blist[l][i];
+        a.first = fuse || l == 0; a.last = fuse || l == nlaunch - 1;
         count_launches(1);
         ProfScope prof("conv_bwd_tile", st);
         if (use_pipe) {
