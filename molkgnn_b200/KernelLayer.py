@@ -6,6 +6,8 @@ buckets rebuilt on the GPU from ``edge_index`` in one pass per batch.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch.nn import Module, ModuleList
 
@@ -119,7 +121,34 @@ class MolGCN(Module):
         aux = kwargv.get('aux', None)
         if save_score and aux is None:
             aux = {}
-        h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), aux, *flat)
+        # Parameter gradients: by default NOT through 72 autograd edges (72 view tensors, output checks and AccumulateGrad nodes per
+        # step cost ~0.3 ms of host time, a third of the step's host budget and what the 8-GPU runs were bound by) -- the backward
+        # writes / accumulates p.grad itself (functional.MolGCNFn, direct mode).  `loss.backward()` and optimizers see the same
+        # .grad tensors; torch.autograd.grad w.r.t. the kernel parameters and tensor hooks on them need the autograd edges:
+        # set `module.direct_param_grads = False` (or MOLKGNN_PARAM_GRADS=autograd); parameters that carry hooks switch it off
+        # by themselves.
+        direct = self.__dict__.get('direct_param_grads')
+        if direct is None:
+            direct = os.environ.get('MOLKGNN_PARAM_GRADS', 'direct') != 'autograd'
+            self.__dict__['direct_param_grads'] = direct
+        if direct:
+            for t in flat:
+                if t is not None and (t._backward_hooks or getattr(t, '_post_accumulate_grad_hooks', None)):
+                    direct = False
+                    break
+        if direct:
+            stack.direct_params = flat
+            args = ()
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in flat):
+                anchor = self.__dict__.get('_anchor')
+                if anchor is None or anchor.device != x.device:
+                    anchor = torch.zeros((), device=x.device, requires_grad=True)   # makes the graph reach the backward
+                    self.__dict__['_anchor'] = anchor
+                args = (anchor,)
+            h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), aux, *args)
+        else:
+            stack.direct_params = None
+            h = MolGCNFn.apply(x, plan, stack, kwargv.get('argmax_in', None), aux, *flat)
         if save_score:
             # KernelLayer.py:117 hands save_score to every layer, each of which dumps its [N, K] score matrix (kernels.py:749-750,
             # 594-608: scores.csv, rewritten layer after layer).  The stack keeps the compact scores; expand and dump them here.

@@ -353,6 +353,23 @@ class StackPack(object):
         check(_lib.lib().molkgnn_stack_layout(C.byref(plan.c), self.arr, self.nl, flags, C.byref(lay)))
         return lay
 
+    def persistent_grad_flat(self, lay, dev):
+        """The stack's own flat gradient buffer (direct mode): allocated once, rewritten by every backward that finds no
+        parameter holding a gradient."""
+        f = self.__dict__.get("_pflat")
+        if f is None or f.numel() != lay.grad_floats or f.device != dev:
+            f = torch.empty(lay.grad_floats, dtype=torch.float32, device=dev)
+            self._pflat = f
+            self._pviews = None
+        return f
+
+    def persistent_grad_views(self, lay):
+        v = self.__dict__.get("_pviews")
+        if v is None:
+            v = self.grad_views(lay, self._pflat)
+            self._pviews = v
+        return v
+
     def grad_views(self, lay, flat):
         """Views of the flat gradient buffer in flat_params() order (None for parameters without a gradient)."""
         specs = self.__dict__.get("_view_specs")
@@ -383,6 +400,9 @@ class MolGCNFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, plan, stack, argmax_in, aux, *flat):
+        # direct mode (see MolGCN.forward / DESIGN.md 5): `flat` is ONE anchor tensor (or nothing), the parameters themselves are in
+        # stack.direct_params and backward() writes their .grad itself instead of returning 72 tensors to the autograd engine
+        ctx.direct = getattr(stack, "direct_params", None) if len(flat) <= 1 else None
         L = _lib.lib()
         dev = x.device
         nl = stack.nl
@@ -453,15 +473,41 @@ class MolGCNFn(torch.autograd.Function):
         if g.stride(1) != 1 or g.data_ptr() % 16:
             g = g.contiguous()
         need_gp = any(ctx.needs_input_grad[5:])
+        direct = ctx.direct
+        accumulate = False
+        if direct is not None and need_gp:
+            # Direct mode.  If no parameter holds a gradient (zero_grad(set_to_none=True) / first step) the gradients are written
+            # into the stack's PERSISTENT flat buffer and every p.grad becomes its cached view of it: no allocation, no 72 new
+            # view tensors, no 72 AccumulateGrad nodes per step.  The buffer is overwritten by the next such backward -- the
+            # semantics of DDP's gradient_as_bucket_view=True.  If some parameter still holds a gradient (accumulation over
+            # micro-batches, a second backward through the same graph) a fresh buffer is used and added to the existing .grad.
+            accumulate = any(t is not None and t.grad is not None for t in direct)
         bs = torch.empty(lay.bwd_bytes, dtype=torch.uint8, device=dev)
-        gflat = torch.empty(lay.grad_floats, dtype=torch.float32, device=dev) if need_gp else None
+        if not need_gp:
+            gflat = None
+        elif direct is not None and not accumulate:
+            gflat = stack.persistent_grad_flat(lay, dev)
+        else:
+            gflat = torch.empty(lay.grad_floats, dtype=torch.float32, device=dev)
         Fp0 = stack.packs[0].Fp
         gx = torch.empty(plan.N, Fp0, dtype=torch.float32, device=dev) if ctx.need_gx else None
         check(L.molkgnn_stack_bwd(C.byref(plan.c), stack.arr, stack.nl, C.byref(lay), ptr(ws), ptr(bs), ptr(g), g.stride(0),
                                   ptr(gx), ptr(gflat), ctx.tile_fwd, stream_ptr()))
-        flat_all = stack.grad_views(lay, gflat) if need_gp else [None] * (stack.nl * 28)
         stack.last_grad_flat = gflat                # dp.GradBucket all-reduces this buffer in place
-        return (gx[:, :ctx.F0] if gx is not None else None, None, None, None, None, *flat_all)
+        gx_out = gx[:, :ctx.F0] if gx is not None else None
+        if direct is not None:
+            if need_gp:
+                views = stack.persistent_grad_views(lay) if not accumulate else stack.grad_views(lay, gflat)
+                for t, v in zip(direct, views):
+                    if t is None or v is None or not t.requires_grad:
+                        continue
+                    if t.grad is None:
+                        t.grad = v
+                    else:
+                        t.grad.add_(v)
+            return (gx_out, None, None, None, None) + ((None,) if len(ctx.needs_input_grad) > 5 else ())
+        flat_all = stack.grad_views(lay, gflat) if need_gp else [None] * (stack.nl * 28)
+        return (gx_out, None, None, None, None, *flat_all)
 
 
 def flat_params(params):
