@@ -336,6 +336,8 @@ int molkgnn_oneshot_ipc_handle(void* handle, void* out64);
 int molkgnn_oneshot_open(void* handle, const void* handles /* world x 64 bytes in rank order */);
 int molkgnn_oneshot_allreduce(void* handle, float* flat, int64_t n, int32_t average, void* stream);
 int molkgnn_oneshot_error(void* handle);      /* 0, or r + 1 if rank r's flag timed out since the last call; synchronises */
+/* queues a copy of the error word (same encoding) into 4 bytes of page-locked host memory behind the work on `stream`; no synchronisation */
+int molkgnn_oneshot_error_async(void* handle, void* pinned_host4, void* stream);
 int molkgnn_oneshot_destroy(void* handle);
 
 #ifdef __cplusplus

@@ -95,6 +95,7 @@ EXPORTS = {
     "molkgnn_oneshot_open": (C.c_int, [vp, vp]),
     "molkgnn_oneshot_allreduce": (C.c_int, [vp, vp, i64, i32, vp]),
     "molkgnn_oneshot_error": (C.c_int, [vp]),
+    "molkgnn_oneshot_error_async": (C.c_int, [vp, vp, vp]),
     "molkgnn_oneshot_destroy": (C.c_int, [vp]),
     "molkgnn_profile_enable": (C.c_int, [C.c_int]),
     "molkgnn_profile_only": (C.c_int, [C.c_char_p]),

@@ -198,6 +198,16 @@ extern "C" int molkgnn_oneshot_error(void* handle) {
     return (int)e;
 }
 
+// Non-blocking variant for the training loop: queues a copy of the error word into `pinned_host4` (4 bytes of page-locked host
+// memory) behind the work already on `stream`; the caller reads it once the stream has passed that point (an event it records
+// itself) -- no device synchronisation inside the step loop.
+extern "C" int molkgnn_oneshot_error_async(void* handle, void* pinned_host4, void* stream) {
+    OneShot* h = reinterpret_cast<OneShot*>(handle);
+    MK_REQUIRE(h && pinned_host4, "oneshot_error_async: bad arguments");
+    MK_CHECK_CUDA(cudaMemcpyAsync(pinned_host4, h->local + 65 * 4, 4, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return 0;
+}
+
 extern "C" int molkgnn_oneshot_destroy(void* handle) {
     OneShot* h = reinterpret_cast<OneShot*>(handle);
     if (!h) return 0;

@@ -99,6 +99,26 @@ class OneShotAllReduce(object):
         if e:
             raise _lib.MolKGNNError(f"OneShotAllReduce: the flag of rank {e - 1} did not arrive within the time limit")
 
+    def check_async(self):
+        """The periodic check of the step loop, without a device synchronisation: queues a copy of the error word into pinned host
+        memory behind the work on the current stream and examines the copy queued by the PREVIOUS call (its event completed
+        long ago).  An error therefore surfaces one period late -- the gradients were NaN-poisoned in the meantime."""
+        from . import _lib
+        prev = self.__dict__.get("_pending_err")
+        if prev is not None:
+            buf, ev = prev
+            ev.synchronize()
+            e = int(buf.item())
+            if e:
+                _lib.lib().molkgnn_oneshot_error(self.handle)       # (clears the word)
+                raise _lib.MolKGNNError(f"OneShotAllReduce: the flag of rank {e - 1} did not arrive within the time limit")
+        else:
+            buf = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _lib.check(_lib.lib().molkgnn_oneshot_error_async(self.handle, buf.data_ptr(), _lib.stream_ptr()))
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending_err = (buf, ev)
+
     def close(self):
         from . import _lib
         if self.handle is not None and self.handle.value:
@@ -146,7 +166,8 @@ class GradBucket(object):
     def check(self):
         """Raises if the one-shot exchange ever timed out (a rank that died or raised before its launch leaves the others
         with NaN-poisoned gradients, csrc/oneshot.cu).  Synchronises the device: call it where the loop synchronises anyway
-        (logging, before a checkpoint); ``allreduce`` itself calls it every ``check_every`` steps."""
+        (logging, before a checkpoint); ``allreduce`` itself polls the error word every ``check_every`` steps without synchronising
+        (``OneShotAllReduce.check_async``: an error surfaces one period late)."""
         if self.oneshot is not None:
             self.oneshot.check()
 
@@ -177,7 +198,7 @@ class GradBucket(object):
                 self.oneshot.allreduce(flat, self.average)
                 self._steps += 1
                 if self.check_every > 0 and self._steps % self.check_every == 0:
-                    self.check()
+                    self.oneshot.check_async()      # no device synchronisation inside the step loop
             elif self.world > 1:
                 if self.average and flat.is_cuda:
                     # NCCL averages inside the collective: no separate scaling kernel behind it
