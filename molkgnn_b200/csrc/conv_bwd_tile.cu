@@ -17,13 +17,16 @@
 //   k_coef_bond      streaming pre-pass in bucket order: coef = chi * g per (node, kernel) pair (the gather of the
 //                    incoming gradient rows stays out of the tile kernel's critical path) and the bond-attribute support
 //                    gradients (8 floats per support row) as one partial copy per CTA
-//   k_conv_bwd_tile  tile-major persistent kernel over a subset of <= 2 kernel blocks (TMEM: 2 x G_b + dxh = 336 of the
-//                    512 columns; a layer with 4 blocks runs it twice and the first launch hands its partial dxh to the
-//                    second through `scratch`).  Per (tile, block): Wt by scatter with one thread per (node, kernel) pair;
-//                    neighbour slots are pre-grouped by collision rank (k_tile_meta, bucket.cu) so that rank 0 is a plain
-//                    store and the few higher ranks read-modify-write after a barrier -- deterministic, no atomics;
-//                    then 48 UMMAs.  The block's images stream through shared memory by bulk copy.  Per tile one dxh
-//                    epilogue; the last launch applies d(x/|x|)/dx and writes grad_x.
+//   k_conv_bwd_tile  tile-major persistent kernel, ONE launch per layer.  TMEM holds 2 x G_b + dxh = 336 of the 512 columns, so a
+//                    layer with 4 blocks at Fk = 112 is two PASSES over the CTA's tiles inside the launch -- blocks {0, 1} (base
+//                    model: the degree-4 blocks), flush of their G, blocks {2, 3} -- and the first pass hands its partial dxh to the
+//                    second through `scratch` (only the rows its blocks touch; written and re-read by the same thread); layer 0
+//                    (Fk = 32) holds all accumulators at once.  Per (tile, block): Wt by scatter with one thread per (node,
+//                    kernel) pair; neighbour slots are pre-grouped by collision rank (k_tile_meta, bucket.cu) so that rank 0 is a
+//                    plain store and the followers of a collision chain are added by one thread per kernel after a barrier --
+//                    deterministic, no atomics; then 48 UMMAs from two issuing threads.  The block's images stream through
+//                    shared memory by bulk copy; metadata / coefficients are double buffered and fetched a tile ahead.  Per tile
+//                    one dxh epilogue; the last pass applies d(x/|x|)/dx and writes grad_x.
 // k_param_finalize (params.cu) reduces the per-CTA copies in fixed order.
 #include <algorithm>
 #include <cstring>
