@@ -100,3 +100,23 @@ def test_hooks_and_autograd_grad_use_the_autograd_edges():
     q0 = net2.layers[0].trainable_kernelconv_set[2].x_center
     (g,) = torch.autograd.grad((h * wout2).sum(), [q0])
     assert g.shape == q0.shape and float(g.abs().sum()) > 0 and q0.grad is None
+
+
+def test_parameters_get_gradients_when_x_needs_none():
+    """x without requires_grad: the graph reaches the backward through the anchor tensor alone."""
+    net, t, wout = _setup()
+    h = net(x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False)
+    assert h.requires_grad
+    (h * wout).sum().backward()
+    g_direct = _grads(net)
+    net.zero_grad(set_to_none=True)
+    net.direct_param_grads = False
+    h = net(x=t["x"], edge_index=t["edge_index"], edge_attr=t["edge_attr"], p=t["p"], save_score=False)
+    (h * wout).sum().backward()
+    n_with = 0
+    for n, p in net.named_parameters():
+        assert (p.grad is None) == (g_direct[n] is None), n
+        if p.grad is not None:
+            assert torch.equal(p.grad, g_direct[n]), n
+            n_with += 1
+    assert n_with >= 3 * 4 * 6
