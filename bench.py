@@ -317,6 +317,12 @@ def main():
     breakdown = Fn.profile_stop()
     breakdown.pop("bucket_count", None)      # contains the host round trip of the bucket sizes, not a kernel time
     top = max(breakdown, key=lambda k: breakdown[k][1])
+    # Host hygiene of a latency-bound loop: everything allocated so far (torch, the model, the batch) moves to the permanent
+    # generation, so that a full garbage collection inside the timed region does not walk it -- with N ranks coupled by the
+    # all-reduce, one rank's multi-millisecond collection pause is every rank's pause.
+    import gc
+    gc.collect()
+    gc.freeze()
 
     # ---- timed region: device-resident inputs ----
     sampler = ClockSampler(local) if rank == 0 else None
