@@ -159,3 +159,32 @@ def test_tile_image_sizes_for_base_wide_and_oversized_layers():
         want = nb * (Fk // 32) * 16384 + (es + 127) // 128 * 128 + nb * 8 * Fk * 64
         assert got == want, (F, got, want)
     assert lib.molkgnn_tile_img_bytes(C.byref(layer(440, (400, 800, 1200, 2000)))) == 0
+
+
+def test_bench_clock_sampler_window():
+    """bench.ClockSampler.stop: the lines inside the timed region count; if the region was shorter than nvidia-smi's first period
+    (no line inside), the lines next to it are used and the record says so -- never an empty `clocks` record while lines exist."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    class _P(object):
+        def terminate(self):
+            pass
+
+    def sampler(rows):
+        s = bench.ClockSampler.__new__(bench.ClockSampler)
+        s.rows, s.p = rows, _P()
+        return s
+
+    line = "1965, 1965, 400.0, Not Active, Not Active, Not Active, Not Active"
+    hot = "1200, 1965, 700.0, Not Active, Active, Not Active, Active"
+    r = sampler([(9.0, line), (10.01, line), (10.1, hot), (10.19, line), (11.0, line)]).stop(10.0, 10.2)
+    assert r["samples"] == 3 and r["window_s"] == 0.05 and r["sm_max_mhz"] == 1965.0
+    assert r["reasons"] == ["hw_thermal_slowdown", "sw_power_cap"]
+    r = sampler([(9.8, line), (10.4, line), (12.0, hot)]).stop(10.0, 10.02)        # nothing inside: the neighbours, not the far line
+    assert r["samples"] == 2 and r["window_s"] == 0.5 and r["sm_mhz"] == 1965.0 and r["reasons"] == []
+    r = sampler([]).stop(10.0, 10.2)
+    assert r["samples"] == 0 and r["sm_mhz"] is None
