@@ -318,7 +318,10 @@ def main():
     # ---- warm-up (also: find the dominant kernel with the event profiler) ----
     step(devt)                                   # the unpipelined path once (plan built inside the forward)
     zero_grads()
-    run_steps(max(args.warmup, 3))
+    # (warm-up runs have an ODD number of steps, and there are two of them: the prefetcher alternates between two side streams, each
+    # with its own pool in torch's caching allocator, and the start of a run needs one more cached segment on the stream its fourth
+    # batch lands on -- after two odd runs both pools have it; otherwise the timed run pays a 2 ms cudaMalloc in its second step)
+    run_steps(max(args.warmup, 3) | 1)
     Fn.profile_start()
     run_steps(3)
     breakdown = Fn.profile_stop()
@@ -388,6 +391,7 @@ def main():
         pending[1].synchronize()
         float(pending[0].view(-1)[0])
 
+    e2e_run(max(args.warmup, 3) | 1)             # two odd warm-up runs: both side-stream pools of the allocator are warm (see above)
     e2e_run(3)
     sync_all()
     e0.record()
@@ -440,6 +444,7 @@ def main():
             pending[1].synchronize()
             float(pending[0].view(-1)[0])
 
+        store_run(3)
         store_run(3)
         sync_all()
         e0.record()
