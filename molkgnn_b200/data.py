@@ -24,6 +24,9 @@ class DevicePrefetcher(object):
         # one side stream per slot, because finishing a plan synchronises the host with ITS stream -- with one stream the host
         # would also wait for the copies of the batch staged after it.  With depth 1 the host waits ~0.4 ms per step for the
         # 22 MB copy that could only start when the step before the previous one had finished.
+        # (Each side stream has its own pool in torch's caching allocator: the first few batches of a run allocate their staging
+        # and plan buffers with cudaMalloc -- ~2 ms each, once per stream and size; a loop that is timed from its first step
+        # should have run a handful of steps before, cf. bench.py.)
         self.depth = max(1, int(depth))
         self.streams = [torch.cuda.Stream(self.device) for _ in range(self.depth)]
         self.stream = self.streams[0]
